@@ -1,0 +1,117 @@
+/* weasal_b200 — C ABI of the B200 (sm_100a) KPConv hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / numpy types. Each entry point names the
+ * reference interface it replaces (paths relative to the WeaSAL repository root). INTEGRATION.md shows the
+ * reference-side binding (the Python modules cpp_wrappers.cpp_neighbors.radius_neighbors,
+ * cpp_wrappers.cpp_subsampling.grid_subsampling and the class models.blocks.KPConv) on top of these calls.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative kp_status; kp_last_error() returns the message of the
+ *     calling thread's last failure;
+ *   - "_host" entry points take HOST buffers and do their own host<->device copies (this is what the reference's
+ *     numpy-facing extension modules bind); "_dev" entry points take DEVICE pointers plus a cudaStream_t passed as
+ *     void* (what the torch-facing KPConv module and the device pyramid builder bind);
+ *   - batch-length arrays (q_batches, s_batches, batches) and rotation matrices are always HOST pointers;
+ *   - there is no CPU fallback: without a CUDA device every compute entry fails with KP_ERR_CUDA.
+ */
+#ifndef WEASAL_B200_H
+#define WEASAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum kp_status {
+    KP_OK = 0,
+    KP_ERR_CUDA = -1,        /* CUDA runtime failure */
+    KP_ERR_ARG = -2,         /* malformed argument */
+    KP_ERR_CAPACITY = -3,    /* caller buffer too small */
+    KP_ERR_TOO_DENSE = -4,   /* > 1024 neighbours for one query */
+    KP_ERR_EMPTY = -5,       /* empty result; the reference raises RuntimeError("Error") here */
+    KP_ERR_UNSUPPORTED = -6
+};
+
+const char* kp_last_error(void);
+int kp_version(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+long long kp_launch_count(void);
+void kp_free_host(void* p);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Batch radius search.
+ * Replaces: cpp_wrappers/cpp_neighbors/wrapper.cpp:58-238 `batch_query(queries, supports, q_batches, s_batches,
+ *           radius)` -> neighbors.cpp:211-332 batch_nanoflann_neighbors; called from datasets/common.py:185-196.
+ * Result rows: same-batch supports with d2 < radius^2 (f32, unfused), sorted by (d2, support index) ascending,
+ * global indices, padded with Ns.
+ *
+ * kp_batch_query_host: *out is malloc'd int32 [nq, *hmax] (free with kp_free_host), hmax = max neighbour count.
+ *   nq == 0 or hmax == 0 returns KP_ERR_EMPTY like the reference's RuntimeError("Error") (wrapper.cpp:201-205).
+ * kp_batch_query_dev: out is a device buffer [nq, cap] of int32 (out_is_i64 = 0) or int64 (= 1). Rows keep their
+ *   `cap` closest neighbours (the crop datasets/common.py:336-346 applies afterwards); *hmax receives the true
+ *   maximum count so the caller can slice [:, :min(hmax, cap)]. Synchronises the stream once.
+ */
+int kp_batch_query_host(const float* queries, int nq, const float* supports, int ns, const int* q_batches,
+                        const int* s_batches, int nb, float radius, int** out, int* hmax);
+int kp_batch_query_dev(const float* queries, int nq, const float* supports, int ns, const int* q_batches,
+                       const int* s_batches, int nb, float radius, void* out, int out_is_i64, int cap, int* hmax,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Grid subsampling.
+ * Replaces: cpp_wrappers/cpp_subsampling/wrapper.cpp:62-333 `subsample_batch(points, batches, features, classes,
+ *           sampleDl, method, max_p, verbose)` -> grid_subsampling.cpp:109-211, and wrapper.cpp:338-566
+ *           `subsample(points, features, classes, sampleDl, method, verbose)` -> grid_subsampling.cpp:5-106
+ *           (= nb 1, max_p 0); called from datasets/common.py:44-182.
+ * order: 1 = the reference's output order (iteration order of libstdc++'s unordered_map, reproduced exactly for the
+ *        libstdc++ this library is built against); 0 = first-occurrence order of the voxels (cheaper).
+ * rot:   optional HOST [nb,3,3] f32 — the per-element random grid orientation datasets/common.py:89-135 applies
+ *        around the call: points are rotated by R before voxelisation and barycentres by R^T afterwards, in the
+ *        same f32 order numpy uses. NULL = no rotation.
+ * features [n,fdim] / classes [n,ldim] may be NULL.
+ *
+ * _host: outputs are malloc'd ([m,3], [m,fdim], [m,ldim]); out_batches is a caller array [nb]; KP_ERR_EMPTY when
+ *        no voxel is produced (wrapper.cpp:266-270).
+ * _dev:  output buffers are caller-allocated device arrays with n rows; *m receives the voxel count; out_batches
+ *        is a HOST array [nb]. Synchronises the stream once.
+ */
+int kp_grid_subsample_host(const float* points, int n, const int* batches, int nb, const float* features, int fdim,
+                           const int* classes, int ldim, float sampleDl, int max_p, int order, const float* rot,
+                           float** out_points, int* out_batches, float** out_features, int** out_classes, int* m);
+int kp_grid_subsample_dev(const float* points, int n, const int* batches, int nb, const float* features, int fdim,
+                          const int* classes, int ldim, float sampleDl, int max_p, int order, const float* rot,
+                          float* out_points, int* out_batches, float* out_features, int* out_classes, int* m,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * KPConv (rigid, 'linear' influence, 'sum' aggregation), forward and backward.
+ * Replaces: models/blocks.py:238-374 `KPConv.forward(q_pts, s_pts, neighb_inds, x)` and the autograd backward of
+ *           that expression (gradients w.r.t. x and weights only; blocks.py:235-236).
+ *   q_pts [nq,3] f32, s_pts [ns,3] f32, neighb_inds [nq,H] int32/int64 with row stride idx_stride (elements),
+ *   shadow index == ns, x [ns,cin] f32, weights [K,cin,cout] f32, kernel_points [K,3] f32, out [nq,cout] f32.
+ * All pointers are device pointers. precision: 0 = TF32 tensor-core contraction with fp32 accumulation (inputs
+ * rounded to nearest TF32), 1 = fp32 CUDA-core cross-check path (slow; needs the `work` buffer, see below).
+ */
+int kp_kpconv_forward_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                          int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,
+                          int cout, const float* kernel_points, int K, float KP_extent, float* out, void* stream);
+/* d_x [ns,cin] and d_weights [K,cin,cout] are overwritten (not accumulated). */
+int kp_kpconv_backward_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                           int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,
+                           int cout, const float* kernel_points, int K, float KP_extent, const float* d_out,
+                           float* d_x, float* d_weights, void* stream);
+
+/* fp32 CUDA-core pieces (bring-up / cross-check of the tensor-core path; not the product path):
+ *   wf [nq, K*cin] = kernel-point-weighted neighbour features; dx [ns,cin] += adjoint scatter of dwf [nq,K*cin]. */
+int kp_kpconv_wf_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds, int idx_is_i64,
+                     int H, int idx_stride, const float* x, int cin, const float* kernel_points, int K,
+                     float KP_extent, float* wf, void* stream);
+int kp_kpconv_dx_atomic_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                            int idx_is_i64, int H, int idx_stride, const float* dwf, int cin,
+                            const float* kernel_points, int K, float KP_extent, float* dx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WEASAL_B200_H */

@@ -1,0 +1,372 @@
+"""GPU parity tests (run with ``-m gpu`` on the B200 box). Everything goes through the C-ABI library; the CPU oracle
+is only the checker. Bars: bit-exact for indices / voxel membership / barycentres; 1e-3 relative
+(max-abs error over max-abs reference, and L2 norm-wise) for KPConv features and gradients, TF32 operands with fp32
+accumulation against the f64-accumulating oracle and the reference's own fp32 outputs."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN, load_case
+from weasal_b200.synthetic import make_als_tile, make_batch
+
+pytestmark = pytest.mark.gpu
+
+KP_TOL = 1e-3
+
+
+def rel_max(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def pre_golden():
+    return np.load(os.path.join(GOLDEN, "precompute_ref.npz"))
+
+
+@pytest.fixture(scope="module")
+def kp_golden():
+    return np.load(os.path.join(GOLDEN, "kpconv_ref.npz"))
+
+
+# ------------------------------------------------------------------------------------------------------ radius search
+def test_batch_query_golden(pre_golden, torch_cuda):
+    from weasal_b200 import radius_neighbors as rn
+    g = pre_golden
+    pts, lens = g["pts"], g["lens"]
+    got = rn.batch_query(pts, pts, lens, lens, radius=0.6)
+    assert got.dtype == np.int32
+    assert np.array_equal(got, g["nbr_r0.6_ordered"])
+    sp, sl = g["sub0.48_pts"], g["sub0.48_lens"]
+    pool = rn.batch_query(sp, pts, sl, lens, radius=0.6)
+    assert pool.shape == g["pool_r0.6_nanoflann"].shape
+    assert np.array_equal(np.sort(pool, 1), np.sort(g["pool_r0.6_nanoflann"], 1))
+    assert np.array_equal(pool, oracle.batch_neighbors(sp, pts, sl, lens, 0.6))
+    up = rn.batch_query(pts, sp, lens, sl, radius=1.2)
+    assert np.array_equal(up, oracle.batch_neighbors(pts, sp, lens, sl, 1.2))
+
+
+@pytest.mark.parametrize("seed,radius,nb", [(0, 0.6, 1), (1, 0.6, 4), (2, 1.2, 3), (3, 2.4, 2), (4, 0.05, 2)])
+def test_batch_query_vs_oracle(seed, radius, nb, torch_cuda):
+    from weasal_b200 import radius_neighbors as rn
+    b = make_batch("vaihingen_pl", seed=seed, batch_num=nb, in_radius=6.0)
+    P, L = b["points"], b["lengths"]
+    want = oracle.batch_neighbors(P, P, L, L, radius)
+    got = rn.batch_query(P, P, L, L, radius=radius)
+    assert np.array_equal(got, want)
+    assert (got[:, 0] == np.arange(len(P))).all()  # self is neighbour 0 when q is s (d2 = 0)
+
+
+def test_batch_query_ragged_and_empty(torch_cuda):
+    from weasal_b200 import radius_neighbors as rn
+    rng = np.random.default_rng(0)
+    q = rng.uniform(0, 3, (50, 3)).astype(np.float32)
+    s = rng.uniform(0, 3, (70, 3)).astype(np.float32)
+    qb, sb = np.array([20, 0, 30], np.int32), np.array([0, 40, 30], np.int32)  # empty elements on both sides
+    got = rn.batch_query(q, s, qb, sb, radius=1.0)
+    assert np.array_equal(got, oracle.batch_neighbors(q, s, qb, sb, 1.0))
+    assert (got[:20] == 70).all()  # queries whose batch element has no supports: all shadow
+    with pytest.raises(RuntimeError, match="^Error$"):
+        rn.batch_query(q, s + 100.0, qb, sb, radius=0.01)  # no neighbour at all -> the reference's "Error"
+    with pytest.raises(RuntimeError, match="^Error$"):
+        rn.batch_query(np.zeros((0, 3), np.float32), s, np.array([0], np.int32), np.array([70], np.int32), radius=1.0)
+    with pytest.raises(RuntimeError, match="query.shape"):
+        rn.batch_query(q[:, :2], s, qb, sb, radius=1.0)
+
+
+def test_batch_query_dense_rows_exceed_first_capacity(torch_cuda):
+    from weasal_b200 import radius_neighbors as rn
+    rng = np.random.default_rng(1)
+    s = rng.uniform(0, 1, (900, 3)).astype(np.float32)  # ~250 neighbours per query: beyond the first 64-wide buffer
+    L = np.array([900], np.int32)
+    got = rn.batch_query(s, s, L, L, radius=0.45)
+    assert got.shape[1] > 64
+    assert np.array_equal(got, oracle.batch_neighbors(s, s, L, L, 0.45))
+
+
+def test_batch_query_duplicate_points_tie_break(torch_cuda):
+    from weasal_b200 import radius_neighbors as rn
+    base = np.random.default_rng(2).uniform(0, 2, (100, 3)).astype(np.float32)
+    s = np.concatenate([base, base, base[:30]], 0)  # exact duplicates => exact d2 ties
+    L = np.array([len(s)], np.int32)
+    got = rn.batch_query(s, s, L, L, radius=0.5)
+    assert np.array_equal(got, oracle.batch_neighbors(s, s, L, L, 0.5))
+
+
+def test_batch_query_device_limit_and_int64(torch_cuda):
+    torch = torch_cuda
+    from weasal_b200 import ops
+    b = make_batch("vaihingen_pl", seed=5, batch_num=2, in_radius=6.0)
+    P, L = b["points"], b["lengths"]
+    want = oracle.batch_neighbors(P, P, L, L, 0.9)
+    dP = torch.from_numpy(P).cuda()
+    full = ops.batch_query(dP, dP, L, L, 0.9)
+    assert full.dtype == torch.int64 and np.array_equal(full.cpu().numpy(), want)
+    lim = 7
+    crop = ops.batch_query(dP, dP, L, L, 0.9, limit=lim, dtype=torch.int32)
+    assert np.array_equal(crop.cpu().numpy(), want[:, :lim])  # big_neighborhood_filter keeps the closest `limit`
+
+
+# -------------------------------------------------------------------------------------------------- grid subsampling
+def test_subsample_golden(pre_golden, torch_cuda):
+    from weasal_b200 import grid_subsampling as gs
+    g = pre_golden
+    sp, sl = gs.subsample_batch(g["pts"], g["lens"], sampleDl=0.48)
+    assert np.array_equal(sl, g["sub0.48_lens"])
+    assert np.array_equal(sp, g["sub0.48_pts"])
+    p2, f2, c2 = gs.subsample(g["pts"], features=g["feats"], classes=g["labels"], sampleDl=0.9)
+    assert np.array_equal(p2, g["sub0.9_pts"])
+    assert np.array_equal(f2, g["sub0.9_feats"])
+    assert c2.shape == g["sub0.9_classes"].shape and np.array_equal(c2, g["sub0.9_classes"])
+
+
+@pytest.mark.parametrize("seed,dl,n_side", [(0, 0.24, 25.0), (1, 0.4, 40.0), (2, 1.3, 40.0), (3, 2.4, 60.0)])
+def test_subsample_vs_oracle(seed, dl, n_side, torch_cuda):
+    from weasal_b200 import grid_subsampling as gs
+    pts, inten, lab = make_als_tile(seed, n_side, 12.0)
+    feats = np.stack([inten, pts[:, 2], pts[:, 0]], 1)
+    for order in ("reference", "first"):
+        want = oracle.grid_subsample(pts, features=feats, classes=lab, sampleDl=dl, order=order)
+        got = gs.subsample(pts, features=feats, classes=lab, sampleDl=dl, order=order)
+        for w, g_ in zip(want, got):
+            assert w.shape == g_.shape and np.array_equal(w, g_)
+    only_pts = gs.subsample(pts, sampleDl=dl)
+    assert np.array_equal(only_pts, oracle.grid_subsample(pts, sampleDl=dl))
+
+
+def test_subsample_batch_max_p_and_rotation(torch_cuda):
+    from weasal_b200 import grid_subsampling as gs
+    from weasal_b200.pyramid import random_grid_rotations
+    b = make_batch("vaihingen_pl", seed=7, batch_num=3, in_radius=5.0)
+    P, L = b["points"], b["lengths"]
+    want_p, want_l = oracle.grid_subsample_batch(P, L, sampleDl=0.5, max_p=200)
+    got_p, got_l = gs.subsample_batch(P, L, sampleDl=0.5, max_p=200)
+    assert np.array_equal(got_l, want_l) and np.array_equal(got_p, want_p)
+    np.random.seed(11)
+    R = random_grid_rotations(len(L))
+    rot = P.copy()
+    i0 = 0
+    for bi, n in enumerate(L):
+        rot[i0:i0 + n] = oracle.rotate(P[i0:i0 + n], R[bi])
+        i0 += n
+    wp, wl = oracle.grid_subsample_batch(rot, L, sampleDl=0.5)
+    i0 = 0
+    for bi, n in enumerate(wl):
+        wp[i0:i0 + n] = oracle.rotate(wp[i0:i0 + n], R[bi], transpose=True)
+        i0 += n
+    gp, gl = gs.subsample_batch(P, L, sampleDl=0.5, rot=R)
+    assert np.array_equal(gl, wl) and np.array_equal(gp, wp)
+
+
+def test_subsample_labels_many_classes_and_ties(torch_cuda):
+    from weasal_b200 import grid_subsampling as gs
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(0, 4, (4000, 3)).astype(np.float32)
+    lab = rng.integers(-3, 40, 4000).astype(np.int32)  # > 13 distinct labels per voxel: histogram rehash path
+    wp, wc = oracle.grid_subsample(pts, classes=lab, sampleDl=1.0)
+    gp, gc = gs.subsample(pts, classes=lab, sampleDl=1.0)
+    assert np.array_equal(gp, wp) and np.array_equal(gc, wc)
+
+
+def test_subsample_edge_cases(torch_cuda):
+    from weasal_b200 import grid_subsampling as gs
+    one = np.array([[1.5, -2.0, 3.0]], np.float32)
+    assert np.array_equal(gs.subsample(one, sampleDl=0.3), oracle.grid_subsample(one, sampleDl=0.3))
+    same = np.repeat(one, 50, 0)
+    assert np.array_equal(gs.subsample(same, sampleDl=0.3), oracle.grid_subsample(same, sampleDl=0.3))
+    with pytest.raises(RuntimeError, match="^Error$"):
+        gs.subsample(np.zeros((0, 3), np.float32), sampleDl=0.3)
+    with pytest.raises(RuntimeError, match="points.shape"):
+        gs.subsample(np.zeros((5, 2), np.float32), sampleDl=0.3)
+    rng = np.random.default_rng(3)
+    P = rng.uniform(0, 5, (300, 3)).astype(np.float32)
+    L = np.array([100, 0, 200], np.int32)  # an empty batch element in the middle
+    wp, wl = oracle.grid_subsample_batch(P, L, sampleDl=0.8)
+    gp, gl = gs.subsample_batch(P, L, sampleDl=0.8)
+    assert np.array_equal(gl, wl) and np.array_equal(gp, wp)
+
+
+def test_subsample_large_properties(torch_cuda):
+    """Full-size (1M raw points, config 5) checks through size-independent properties."""
+    from weasal_b200 import grid_subsampling as gs
+    pts, inten, _ = make_als_tile(9, 250.0, 16.0)
+    dl = 0.4
+    sp, sf = gs.subsample(pts, features=np.ones((len(pts), 1), np.float32) * 2.0, sampleDl=dl)
+    # one barycentre per occupied voxel, each inside (or on the edge of) its own voxel, features averaged exactly
+    org = np.floor(pts.min(0) * np.float32(1 / np.float32(dl))) * np.float32(dl)
+    vox = np.floor((pts - org) / np.float32(dl)).astype(np.int64)
+    n_vox = len(np.unique(vox, axis=0))
+    assert len(sp) == n_vox
+    svox = np.floor((sp - org) / np.float32(dl) + 1e-3).astype(np.int64)
+    assert len(np.unique(svox, axis=0)) >= 0.999 * n_vox
+    assert np.array_equal(sf, np.full((len(sp), 1), 2.0, np.float32))
+    first = gs.subsample(pts, sampleDl=dl, order="first")
+    assert np.array_equal(first[np.lexsort(first.T)], sp[np.lexsort(sp.T)])  # same set, different order
+
+
+# ------------------------------------------------------------------------------------------------------------ KPConv
+def _run_kpconv(torch, a, idx_dtype, stride_pad=0):
+    from weasal_b200 import ops
+    dev = "cuda"
+    q = torch.from_numpy(a["q_pts"]).to(dev)
+    s = torch.from_numpy(a["s_pts"]).to(dev)
+    idx_np = a["idx"].astype(np.int64 if idx_dtype == torch.int64 else np.int32)
+    if stride_pad:
+        buf = torch.full((idx_np.shape[0], idx_np.shape[1] + stride_pad), len(a["s_pts"]), dtype=idx_dtype, device=dev)
+        buf[:, :idx_np.shape[1]] = torch.from_numpy(idx_np).to(dev)
+        idx = buf[:, :idx_np.shape[1]]  # strided view, like the radius-search output
+    else:
+        idx = torch.from_numpy(idx_np).to(dev)
+    x = torch.from_numpy(a["x"]).to(dev).requires_grad_(True)
+    w = torch.from_numpy(a["weights"]).to(dev).requires_grad_(True)
+    kp = torch.from_numpy(a["kernel_points"]).to(dev)
+    out = ops.kpconv(q, s, idx, x, w, kp, float(a["extent"]))
+    out.backward(torch.from_numpy(a["d_out"]).to(dev))
+    torch.cuda.synchronize()
+    return out.detach().cpu().numpy(), x.grad.cpu().numpy(), w.grad.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", ["c4_32", "c16_16", "c64_64", "c32_128", "c3_64", "strided16"])
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_kpconv_golden(kp_golden, name, impl, torch_cuda, monkeypatch):
+    torch = torch_cuda
+    monkeypatch.setenv("WEASAL_KPCONV_IMPL", impl)
+    a = load_case(kp_golden, name)
+    out, dx, dw = _run_kpconv(torch, a, torch.int64)
+    o_out = oracle.kpconv_forward(a["q_pts"], a["s_pts"], a["idx"], a["x"], a["weights"], a["kernel_points"], float(a["extent"]))
+    o_dx, o_dw = oracle.kpconv_backward(a["q_pts"], a["s_pts"], a["idx"], a["x"], a["weights"], a["kernel_points"],
+                                        float(a["extent"]), a["d_out"])
+    for got, ref, orc in ((out, a["out"], o_out), (dx, a["dx"], o_dx), (dw, a["dw"], o_dw)):
+        assert got.shape == ref.shape
+        assert rel_max(got, ref) < KP_TOL and rel_l2(got, ref) < KP_TOL      # vs the reference's own fp32 KPConv
+        assert rel_max(got, orc) < KP_TOL and rel_l2(got, orc) < KP_TOL      # vs the f64-accumulating oracle
+
+
+def test_kpconv_int32_indices_and_strided_rows(kp_golden, torch_cuda):
+    torch = torch_cuda
+    a = load_case(kp_golden, "c16_16")
+    ref = _run_kpconv(torch, a, torch.int64)
+    alt = _run_kpconv(torch, a, torch.int32, stride_pad=5)
+    for r, t in zip(ref, alt):
+        assert rel_max(t, r) < 1e-6
+
+
+@pytest.mark.parametrize("cin,cout,H", [(8, 24, 9), (64, 256, 20), (256, 64, 33), (128, 512, 17), (20, 10, 40)])
+def test_kpconv_random_shapes_vs_oracle(cin, cout, H, torch_cuda):
+    torch = torch_cuda
+    rng = np.random.default_rng(cin * 1000 + cout)
+    nq, ns = 300, 450
+    s = rng.uniform(0, 3, (ns, 3)).astype(np.float32)
+    q = s[rng.choice(ns, nq, replace=False)] + rng.normal(0, 0.05, (nq, 3)).astype(np.float32)
+    L = np.array([nq], np.int32), np.array([ns], np.int32)
+    idx = oracle.batch_neighbors(q, s, L[0], L[1], 0.9)[:, :H]
+    a = dict(q_pts=q, s_pts=s, idx=idx, x=rng.normal(size=(ns, cin)).astype(np.float32),
+             weights=(rng.normal(size=(15, cin, cout)) / np.sqrt(cin)).astype(np.float32),
+             kernel_points=(rng.normal(size=(15, 3)) * 0.4).astype(np.float32), extent=np.float32(0.36),
+             d_out=rng.normal(size=(nq, cout)).astype(np.float32))
+    out, dx, dw = _run_kpconv(torch, a, torch.int64)
+    o_out = oracle.kpconv_forward(q, s, idx, a["x"], a["weights"], a["kernel_points"], 0.36)
+    o_dx, o_dw = oracle.kpconv_backward(q, s, idx, a["x"], a["weights"], a["kernel_points"], 0.36, a["d_out"])
+    assert rel_max(out, o_out) < KP_TOL and rel_l2(out, o_out) < KP_TOL
+    assert rel_max(dx, o_dx) < KP_TOL and rel_l2(dx, o_dx) < KP_TOL
+    assert rel_max(dw, o_dw) < KP_TOL and rel_l2(dw, o_dw) < KP_TOL
+
+
+def test_kpconv_all_shadow_rows_and_linearity(torch_cuda):
+    torch = torch_cuda
+    from weasal_b200 import ops
+    rng = np.random.default_rng(0)
+    ns, nq, cin, cout, H = 200, 130, 16, 32, 6
+    s = torch.from_numpy(rng.uniform(0, 2, (ns, 3)).astype(np.float32)).cuda()
+    q = s[:nq].clone()
+    idx = torch.full((nq, H), ns, dtype=torch.int64, device="cuda")  # every neighbour is the shadow point
+    x = torch.randn(ns, cin, device="cuda")
+    w = torch.randn(15, cin, cout, device="cuda")
+    kp = torch.randn(15, 3, device="cuda") * 0.3
+    assert float(ops.kpconv(q, s, idx, x, w, kp, 0.3).abs().max()) == 0.0
+    idx2 = torch.from_numpy(oracle.batch_neighbors(q.cpu().numpy(), s.cpu().numpy(), [nq], [ns], 0.6).astype(np.int64)).cuda()
+    y1 = ops.kpconv(q, s, idx2, x, w, kp, 0.3)
+    y2 = ops.kpconv(q, s, idx2, 2.0 * x, w, kp, 0.3)
+    assert float((y2 - 2.0 * y1).abs().max()) <= 2e-3 * float(y1.abs().max())  # linear in x up to TF32 rounding
+
+
+# ----------------------------------------------------------------------------------------------------------- pyramid
+def test_pyramid_matches_reference_segmentation_inputs(torch_cuda):
+    """Whole device pyramid against the reference's segmentation_inputs (golden, random grid orientation included):
+    points bit-exact; index matrices identical where the reference's order is defined, i.e. up to permutations
+    inside groups of exactly equal d2 (nanoflann's unstable std::sort)."""
+    torch = torch_cuda
+    from weasal_b200 import pyramid
+    g = np.load(os.path.join(GOLDEN, "pyramid_ref.npz"))
+
+    class Cfg:
+        first_subsampling_dl = 0.24
+        conv_radius = 2.5
+        deform_radius = 6.0
+        architecture = ['simple', 'resnetb', 'resnetb_strided', 'resnetb', 'resnetb_strided', 'resnetb',
+                        'resnetb_strided', 'resnetb', 'nearest_upsample', 'unary', 'nearest_upsample', 'unary',
+                        'nearest_upsample', 'unary']
+
+    np.random.seed(int(g["seed"]))
+    li = pyramid.segmentation_inputs(g["in_pts"], None, None, g["in_lens"], Cfg(), neighborhood_limits=list(g["limits"]))
+    L = int(g["L"])
+    assert (len(li) - 2) // 5 == L
+    for l in range(L):
+        pts = li[l].cpu().numpy()
+        assert np.array_equal(pts, g[f"points{l}"]), f"points layer {l}"
+        assert np.array_equal(li[4 * L + l].cpu().numpy(), g[f"lengths{l}"])
+        for off, nm in ((L, "neighbors"), (2 * L, "pools"), (3 * L, "upsamples")):
+            got, ref = li[off + l].cpu().numpy(), g[f"{nm}{l}"]
+            assert got.shape == ref.shape, f"{nm}{l} shape {got.shape} vs {ref.shape}"
+            assert li[off + l].dtype == torch.int64
+            if ref.size:
+                assert (np.sort(got, 1) == np.sort(ref, 1)).mean() > 0.999
+                frac_rows_equal = (got == ref).all(1).mean()
+                assert frac_rows_equal > 0.995, f"{nm}{l}: {frac_rows_equal}"
+
+
+def test_full_size_vaihingen_batch_properties(torch_cuda):
+    """BASELINE config sizes (4 spheres of radius 24 m, ~40k points): properties instead of the O(N^2) oracle."""
+    torch = torch_cuda
+    from weasal_b200 import ops
+    b = make_batch("vaihingen_pl", seed=0)
+    P = torch.from_numpy(b["points"]).cuda()
+    L = b["lengths"]
+    r = 0.6
+    nb = ops.batch_query(P, P, L, L, r).cpu().numpy()
+    Pn = b["points"]
+    n = len(Pn)
+    assert (nb[:, 0] == np.arange(n)).all()
+    pad = np.vstack([Pn, np.full((1, 3), 1e9, np.float32)])
+    d2 = ((pad[nb] - Pn[:, None, :]) ** 2).sum(2)
+    real = nb < n
+    assert (d2[real] < r * r * (1 + 1e-5)).all()
+    assert (np.diff(np.where(real, d2, np.inf), axis=1) >= -1e-9).all()  # rows sorted by distance, shadows last
+    # symmetry of the neighbour relation for q == s (checked on a sample of pairs)
+    src = np.repeat(np.arange(n), nb.shape[1])[real.ravel()]
+    dst = nb[real]
+    sel = np.random.default_rng(1).choice(len(src), 5000, replace=False)
+    for i, j in zip(src[sel], dst[sel]):
+        assert i in nb[j]
+    offs = np.concatenate([[0], np.cumsum(L)])
+    bid = np.searchsorted(offs, np.arange(n), side="right") - 1
+    assert (bid[nb[real]] == np.repeat(bid, nb.shape[1])[real.ravel()]).all()  # never crosses batch elements
+    # sampled rows against the oracle
+    rows = np.random.default_rng(0).choice(n, 300, replace=False)
+    for i in rows:
+        lo, hi = offs[bid[i]], offs[bid[i] + 1]
+        want = oracle.batch_neighbors(Pn[i:i + 1], Pn[lo:hi], [1], [hi - lo], r)[0] + lo
+        k = len(want)
+        assert np.array_equal(nb[i, :k], want) and (nb[i, k:] == n).all()

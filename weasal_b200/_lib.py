@@ -1,0 +1,64 @@
+"""ctypes loader for libweasal_b200.so (the C-ABI declared in include/weasal_b200.h).
+
+There is no CPU fallback: if the library cannot be loaded (and cannot be built because nvcc is absent) importing any
+compute entry point raises; if it loads but no CUDA device is present every compute call returns KP_ERR_CUDA, which
+:func:`check` turns into a RuntimeError.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libweasal_b200.so")
+_lib = None
+
+c_f32p = C.POINTER(C.c_float)
+c_i32p = C.POINTER(C.c_int)
+vp = C.c_void_p
+
+KP_OK, KP_ERR_CUDA, KP_ERR_ARG, KP_ERR_CAPACITY, KP_ERR_TOO_DENSE, KP_ERR_EMPTY, KP_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+
+# every symbol include/weasal_b200.h declares (tests check the library exports all of them)
+SYMBOLS = ["kp_last_error", "kp_version", "kp_launch_count", "kp_free_host", "kp_batch_query_host",
+           "kp_batch_query_dev", "kp_grid_subsample_host", "kp_grid_subsample_dev", "kp_kpconv_forward_dev",
+           "kp_kpconv_backward_dev", "kp_kpconv_wf_dev", "kp_kpconv_dx_atomic_dev"]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    L = C.CDLL(LIB_PATH)
+    L.kp_last_error.restype = C.c_char_p
+    L.kp_launch_count.restype = C.c_longlong
+    L.kp_free_host.argtypes = [vp]
+    L.kp_batch_query_host.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_float, C.POINTER(c_i32p), c_i32p]
+    L.kp_batch_query_dev.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_float, vp, C.c_int, C.c_int,
+                                     c_i32p, vp]
+    L.kp_grid_subsample_host.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_float, C.c_int,
+                                         C.c_int, vp, C.POINTER(c_f32p), vp, C.POINTER(c_f32p), C.POINTER(c_i32p),
+                                         c_i32p]
+    L.kp_grid_subsample_dev.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_float, C.c_int,
+                                        C.c_int, vp, vp, vp, vp, vp, c_i32p, vp]
+    conv_common = [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+    L.kp_kpconv_forward_dev.argtypes = conv_common + [vp, C.c_int, vp, C.c_int, C.c_float, vp, vp]
+    L.kp_kpconv_backward_dev.argtypes = conv_common + [vp, C.c_int, vp, C.c_int, C.c_float, vp, vp, vp, vp]
+    L.kp_kpconv_wf_dev.argtypes = conv_common + [vp, C.c_int, C.c_float, vp, vp]
+    L.kp_kpconv_dx_atomic_dev.argtypes = conv_common + [vp, C.c_int, C.c_float, vp, vp]
+    _lib = L
+    return L
+
+
+def last_error():
+    return lib().kp_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != KP_OK:
+        raise RuntimeError(f"{what}: {last_error()} (status {rc})")
+
+
+def launch_count():
+    return int(lib().kp_launch_count())

@@ -1,0 +1,158 @@
+// extern "C" surface of libweasal_b200.so — see include/weasal_b200.h for the contract of every entry point.
+#include "../../include/weasal_b200.h"
+#include "common.cuh"
+
+#include <cstdlib>
+#include <vector>
+
+namespace kp {
+int batch_query_device(const float* q, int nq, const float* s, int ns, const int* qb_host, const int* sb_host, int nb,
+                       float radius, void* out, int out_is_i64, int cap, int* hmax_host, cudaStream_t stream);
+int grid_subsample_device(const float* pts, int n, const int* lens_host, int nb, const float* feats, int fdim,
+                          const int* classes, int ldim, float dl, int max_p, int order_mode, const float* rot_host,
+                          float* out_pts, int* out_lens_host, float* out_feats, int* out_classes, int* m_host,
+                          cudaStream_t stream);
+int kpconv_wf_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
+                     int idx_stride, const float* x, int cin, const float* kp, int K, float extent, float* wf,
+                     cudaStream_t stream);
+int kpconv_dx_atomic_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
+                            int idx_stride, const float* dwf, int cin, const float* kp, int K, float extent, float* dx,
+                            cudaStream_t stream);
+int kpconv_forward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
+                          int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
+                          float extent, float* out, cudaStream_t stream);
+int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
+                           int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
+                           float extent, const float* dout, float* dx, float* dw, cudaStream_t stream);
+}  // namespace kp
+
+using namespace kp;
+
+namespace {
+struct DevBuf {  // synchronous device buffer for the host-facing entry points
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        KP_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
+        return KP_OK;
+    }
+};
+}  // namespace
+
+extern "C" {
+
+const char* kp_last_error(void) { return g_last_error.c_str(); }
+int kp_version(void) { return 100; }
+long long kp_launch_count(void) { return g_launch_count.load(); }
+void kp_free_host(void* p) { free(p); }
+
+int kp_batch_query_dev(const float* queries, int nq, const float* supports, int ns, const int* q_batches,
+                       const int* s_batches, int nb, float radius, void* out, int out_is_i64, int cap, int* hmax,
+                       void* stream) {
+    return batch_query_device(queries, nq, supports, ns, q_batches, s_batches, nb, radius, out, out_is_i64, cap, hmax,
+                              (cudaStream_t)stream);
+}
+
+int kp_batch_query_host(const float* queries, int nq, const float* supports, int ns, const int* q_batches,
+                        const int* s_batches, int nb, float radius, int** out, int* hmax) {
+    *out = nullptr;
+    *hmax = 0;
+    if (nq <= 0) return fail(KP_ERR_EMPTY, "Error");
+    DevBuf dq, ds, dout;
+    int rc;
+    if ((rc = dq.alloc((size_t)nq * 12)) || (rc = ds.alloc((size_t)ns * 12))) return rc;
+    KP_CUDA(cudaMemcpy(dq.p, queries, (size_t)nq * 12, cudaMemcpyHostToDevice));
+    if (ns > 0) KP_CUDA(cudaMemcpy(ds.p, supports, (size_t)ns * 12, cudaMemcpyHostToDevice));
+    int cap = 64;
+    while (true) {
+        if ((rc = dout.alloc((size_t)nq * cap * sizeof(int)))) return rc;
+        rc = batch_query_device((const float*)dq.p, nq, (const float*)ds.p, ns, q_batches, s_batches, nb, radius, dout.p,
+                                0, cap, hmax, 0);
+        if (rc != KP_OK) return rc;
+        if (*hmax <= cap) break;
+        cap = *hmax;  // rare: a row was wider than the first guess, redo with the exact width
+        cudaFree(dout.p);
+        dout.p = nullptr;
+    }
+    if (*hmax == 0) return fail(KP_ERR_EMPTY, "Error");
+    *out = (int*)malloc((size_t)nq * (*hmax) * sizeof(int));
+    KP_CUDA(cudaMemcpy2D(*out, (size_t)(*hmax) * sizeof(int), dout.p, (size_t)cap * sizeof(int),
+                         (size_t)(*hmax) * sizeof(int), nq, cudaMemcpyDeviceToHost));
+    return KP_OK;
+}
+
+int kp_grid_subsample_dev(const float* points, int n, const int* batches, int nb, const float* features, int fdim,
+                          const int* classes, int ldim, float sampleDl, int max_p, int order, const float* rot,
+                          float* out_points, int* out_batches, float* out_features, int* out_classes, int* m,
+                          void* stream) {
+    return grid_subsample_device(points, n, batches, nb, features, fdim, classes, ldim, sampleDl, max_p, order, rot,
+                                 out_points, out_batches, out_features, out_classes, m, (cudaStream_t)stream);
+}
+
+int kp_grid_subsample_host(const float* points, int n, const int* batches, int nb, const float* features, int fdim,
+                           const int* classes, int ldim, float sampleDl, int max_p, int order, const float* rot,
+                           float** out_points, int* out_batches, float** out_features, int** out_classes, int* m) {
+    *out_points = nullptr;
+    if (out_features) *out_features = nullptr;
+    if (out_classes) *out_classes = nullptr;
+    *m = 0;
+    if (n <= 0) return fail(KP_ERR_EMPTY, "Error");
+    DevBuf dp, df, dc, op, of, oc;
+    int rc;
+    if ((rc = dp.alloc((size_t)n * 12)) || (rc = op.alloc((size_t)n * 12))) return rc;
+    KP_CUDA(cudaMemcpy(dp.p, points, (size_t)n * 12, cudaMemcpyHostToDevice));
+    if (features) {
+        if ((rc = df.alloc((size_t)n * fdim * 4)) || (rc = of.alloc((size_t)n * fdim * 4))) return rc;
+        KP_CUDA(cudaMemcpy(df.p, features, (size_t)n * fdim * 4, cudaMemcpyHostToDevice));
+    }
+    if (classes) {
+        if ((rc = dc.alloc((size_t)n * ldim * 4)) || (rc = oc.alloc((size_t)n * ldim * 4))) return rc;
+        KP_CUDA(cudaMemcpy(dc.p, classes, (size_t)n * ldim * 4, cudaMemcpyHostToDevice));
+    }
+    rc = grid_subsample_device((const float*)dp.p, n, batches, nb, (const float*)df.p, fdim, (const int*)dc.p, ldim,
+                               sampleDl, max_p, order, rot, (float*)op.p, out_batches, (float*)of.p, (int*)oc.p, m, 0);
+    if (rc != KP_OK) return rc;
+    if (*m <= 0) return fail(KP_ERR_EMPTY, "Error");
+    *out_points = (float*)malloc((size_t)(*m) * 12);
+    KP_CUDA(cudaMemcpy(*out_points, op.p, (size_t)(*m) * 12, cudaMemcpyDeviceToHost));
+    if (features) {
+        *out_features = (float*)malloc((size_t)(*m) * fdim * 4);
+        KP_CUDA(cudaMemcpy(*out_features, of.p, (size_t)(*m) * fdim * 4, cudaMemcpyDeviceToHost));
+    }
+    if (classes) {
+        *out_classes = (int*)malloc((size_t)(*m) * ldim * 4);
+        KP_CUDA(cudaMemcpy(*out_classes, oc.p, (size_t)(*m) * ldim * 4, cudaMemcpyDeviceToHost));
+    }
+    return KP_OK;
+}
+
+int kp_kpconv_wf_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds, int idx_is_i64,
+                     int H, int idx_stride, const float* x, int cin, const float* kernel_points, int K,
+                     float KP_extent, float* wf, void* stream) {
+    return kpconv_wf_device(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, kernel_points, K,
+                            KP_extent, wf, (cudaStream_t)stream);
+}
+
+int kp_kpconv_dx_atomic_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                            int idx_is_i64, int H, int idx_stride, const float* dwf, int cin,
+                            const float* kernel_points, int K, float KP_extent, float* dx, void* stream) {
+    return kpconv_dx_atomic_device(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, dwf, cin,
+                                   kernel_points, K, KP_extent, dx, (cudaStream_t)stream);
+}
+
+int kp_kpconv_forward_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                          int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,
+                          int cout, const float* kernel_points, int K, float KP_extent, float* out, void* stream) {
+    return kpconv_forward_device(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, weights, cout,
+                                 kernel_points, K, KP_extent, out, (cudaStream_t)stream);
+}
+
+int kp_kpconv_backward_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                           int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,
+                           int cout, const float* kernel_points, int K, float KP_extent, const float* d_out,
+                           float* d_x, float* d_weights, void* stream) {
+    return kpconv_backward_device(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, weights, cout,
+                                  kernel_points, K, KP_extent, d_out, d_x, d_weights, (cudaStream_t)stream);
+}
+
+}  // extern "C"

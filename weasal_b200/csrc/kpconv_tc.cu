@@ -1,0 +1,816 @@
+// KPConv forward / backward for sm_100a: sparse kernel-point gather on CUDA cores feeding tcgen05 (TF32 in,
+// FP32 accumulate in TMEM) — replaces models/blocks.py:238-374 (rigid, 'linear' influence, 'sum' aggregation) and the
+// autograd backward of that expression.
+//
+//   out[i,:] = sum_k ( sum_h w[i,k,h] * x[idx[i,h],:] ) @ W[k],   w = max(0, 1 - ||(s[idx[i,h]] - q[i]) - kp[k]|| / ext)
+//
+// Facts the design rests on (measured on ALS spheres):
+//   * w is ~93 % zeros: a neighbour lies within KP_extent of ~1.03 kernel points (max 3). So the first contraction
+//     is done sparsely in fp32 on CUDA cores (exact, ~15x fewer FMAs than the dense [K x H] x [H x Cin] product),
+//     and only the dense second contraction [P x (K*Cin)] x [(K*Cin) x Cout] goes to the tensor cores.
+//   * bf16 operands give ~1.6e-3 relative error on that contraction, above the 1e-3 parity bar; TF32 operands
+//     rounded to nearest give ~4e-4. Hence kind::tf32.
+//
+// Kernels
+//   kp_influence   one warp per centre point: influence weights of every (neighbour, kernel point) pair, compacted
+//                  into per-point entry lists grouped by kernel point: entry = (neighbour index | k << 27, weight).
+//   kp_pack_w      W[k,c,o] -> TF32-rounded B-operand images, one per 128-column chunk of the (k,c) reduction axis,
+//                  already in the UMMA K-major core-matrix layout (so a CTA fetches a chunk with one bulk copy).
+//   kp_fwd         one CTA per 128 points. Per chunk: warps assemble the A tile [128 x 128] in shared memory from the
+//                  entry lists (gathered float4 rows of x, all loads of a batch in flight together), one thread issues
+//                  16 tcgen05.mma (M128 x N x K8) accumulating into TMEM; epilogue tcgen05.ld -> global.
+//                  Backward-dX is the same kernel run on the transposed neighbour table with W^T and -kp
+//                  (atomics-free segmented scatter).
+//   kp_dw          dW[(k,c),o] = sum_i WF[i,(k,c)] * dOut[i,o]: the same A tile consumed MN-major (M = (k,c) rows,
+//                  K = points) against the dOut tile, accumulated in TMEM across a CTA's point tiles, then added to dW.
+#include "common.cuh"
+
+#include <vector>
+
+namespace kp {
+
+// ------------------------------------------------------------------------------------------------------- constants
+constexpr int TILE_M = 128;      // points per CTA tile (= UMMA M)
+constexpr int CK = 128;          // reduction columns per chunk
+constexpr int FWD_THREADS = 256;
+constexpr int KOFF = 16;         // per-point cumulative entry counts per kernel point (K <= 15)
+constexpr int K_SHIFT = 27;      // entry.x = neighbour index | (kernel point << 27)
+constexpr unsigned J_MASK = (1u << K_SHIFT) - 1u;
+// A tile, UMMA canonical no-swizzle layout: element (row p, col c) at
+//   (p/8)*A_SBO + (c/4)*A_LBO + (p%8)*16 + (c%4)*4     (8 rows x 16 bytes core matrices)
+// A_LBO carries 16 bytes of padding so that a warp writing one row (32 lanes x 16 B) is bank-conflict free.
+constexpr int A_SBO = 128;
+constexpr int A_LBO = 16 * 128 + 16;          // 2064
+constexpr int A_BYTES = (CK / 4) * A_LBO;     // 66048
+constexpr int B_SBO = 128;
+
+// --------------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // bounded spin: a barrier that never completes (a malformed descriptor, a lost bulk copy) traps instead of
+    // hanging the GPU; 2^26 polls is seconds, far beyond any legitimate wait here
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); spins++)
+        if (spins > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {  // 32 lanes x 16 columns, one row per thread
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float to_tf32(float f) {  // round to nearest, ties away (the MMA itself truncates)
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(f));
+    return __uint_as_float(u);
+}
+
+// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor, version 1):
+// [0,14) start>>4, [16,30) leading (K-direction) byte offset>>4, [32,46) stride (M/N-direction) byte offset>>4
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+           (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ influence lists
+struct Table {           // neighbour table of the centre points
+    const void* idx;     // padded rows [nc, H] (row stride `stride`), or CSR column indices when rowptr != null
+    const int* rowptr;   // CSR row pointers [nc+1] or null
+    int H, stride, is_i64;
+};
+
+__device__ __forceinline__ long long table_get(const Table& T, size_t pos) {
+    return T.is_i64 ? ((const long long*)T.idx)[pos] : (long long)((const int*)T.idx)[pos];
+}
+
+__device__ __forceinline__ float influence_w(float rx, float ry, float rz, float kx, float ky, float kz, float inv_ext) {
+    const float dx = rx - kx, dy = ry - ky, dz = rz - kz;
+    return fmaxf(0.f, 1.f - sqrtf(dx * dx + dy * dy + dz * dz) * inv_ext);
+}
+
+// one warp per centre; lanes = neighbours; two passes (count, then write) so that entries land grouped by kernel point
+__global__ void __launch_bounds__(128) kp_influence_kernel(const float* __restrict__ centres, int nc,
+                                                          const float* __restrict__ others, int no, Table T,
+                                                          const float* __restrict__ kp, int K, float kp_sign,
+                                                          float inv_ext, int* __restrict__ ebase,
+                                                          unsigned short* __restrict__ koff, int2* __restrict__ entries,
+                                                          long long capacity, unsigned long long* __restrict__ counter,
+                                                          int* __restrict__ err) {
+    __shared__ float s_kp[16 * 3];
+    if (threadIdx.x < 48) s_kp[threadIdx.x] = (threadIdx.x < 3 * K) ? kp_sign * kp[threadIdx.x] : 1e30f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= nc) return;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float cx = centres[3 * (size_t)i], cy = centres[3 * (size_t)i + 1], cz = centres[3 * (size_t)i + 2];
+    size_t row0;
+    int cnt_row;
+    if (T.rowptr) { row0 = (size_t)T.rowptr[i]; cnt_row = T.rowptr[i + 1] - T.rowptr[i]; }
+    else { row0 = (size_t)i * T.stride; cnt_row = T.H; }
+
+    int cnt[15];
+#pragma unroll
+    for (int k = 0; k < 15; k++) cnt[k] = 0;
+    for (int hb = 0; hb < cnt_row; hb += 32) {
+        const int h = hb + lane;
+        long long j = (h < cnt_row) ? table_get(T, row0 + h) : -1;
+        const bool valid = j >= 0 && j < no;
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        float rx = 0.f, ry = 0.f, rz = 0.f;
+        if (valid) { rx = others[3 * j] - cx; ry = others[3 * j + 1] - cy; rz = others[3 * j + 2] - cz; }
+#pragma unroll
+        for (int k = 0; k < 15; k++) {
+            const float w = valid ? influence_w(rx, ry, rz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext) : 0.f;
+            cnt[k] += __popc(__ballot_sync(0xffffffffu, w > 0.f));
+        }
+    }
+    int run[16];
+    int total = 0;
+#pragma unroll
+    for (int k = 0; k < 15; k++) { run[k] = total; total += cnt[k]; }
+    run[15] = total;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(counter, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    bool ok = true;
+    if (total > 65535 || base + (unsigned long long)total > (unsigned long long)capacity || base > 0x7fffffffULL) {
+        if (lane == 0) atomicOr(err, 1);
+        ok = false;
+    }
+    if (lane == 0) ebase[i] = ok ? (int)base : 0;
+    if (lane < 16) koff[(size_t)i * KOFF + lane] = ok ? (unsigned short)run[lane] : (unsigned short)0;
+    if (!ok || total == 0) return;
+    for (int hb = 0; hb < cnt_row; hb += 32) {
+        const int h = hb + lane;
+        long long j = (h < cnt_row) ? table_get(T, row0 + h) : -1;
+        const bool valid = j >= 0 && j < no;
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        float rx = 0.f, ry = 0.f, rz = 0.f;
+        if (valid) { rx = others[3 * j] - cx; ry = others[3 * j + 1] - cy; rz = others[3 * j + 2] - cz; }
+#pragma unroll
+        for (int k = 0; k < 15; k++) {
+            const float w = valid ? influence_w(rx, ry, rz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext) : 0.f;
+            const unsigned m = __ballot_sync(0xffffffffu, w > 0.f);
+            if (w > 0.f) {
+                int2 e;
+                e.x = (int)((unsigned)j | ((unsigned)k << K_SHIFT));
+                e.y = __float_as_int(w);
+                entries[base + run[k] + __popc(m & lt_mask)] = e;
+            }
+            run[k] += __popc(m);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- weight pack
+// images[chunk][nblk] : NB rows (output channels) x CK reduction columns, K-major core-matrix layout:
+//   element (n, col) at (n/8)*128 + (col/4)*(NB*16) + (n%8)*16 + (col%4)*4 bytes.  col <-> (k, c) = (col / cin_p, col % cin_p)
+// value = tf32(W[k*sk + c*sc + n*sn]) inside the valid range, else 0.
+__global__ void __launch_bounds__(256) kp_pack_w_kernel(const float* __restrict__ W, int K, int cin, int cin_p, int cout,
+                                                       long long sk, long long sc, long long sn, int NB, int n_nblk,
+                                                       int n_chunks, float* __restrict__ images) {
+    const long long total = (long long)n_chunks * n_nblk * NB * CK;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        // t enumerates destination floats linearly (coalesced stores)
+        const long long img = t / ((long long)NB * CK);
+        const int r = (int)(t % ((long long)NB * CK));
+        const int chunk = (int)(img / n_nblk), nblk = (int)(img % n_nblk);
+        const int word = r;                    // float index inside the image
+        const int j = word / (NB * 4);         // 16-byte K chunk
+        const int rem = word % (NB * 4);
+        const int n8 = rem / 32, in8 = rem % 32;
+        const int n = n8 * 8 + in8 / 4, e = in8 % 4;
+        const int col = chunk * CK + j * 4 + e;
+        const int k = col / cin_p, c = col % cin_p;
+        const int ng = nblk * NB + n;
+        float v = 0.f;
+        if (k < K && c < cin && ng < cout) v = to_tf32(W[k * sk + c * sc + ng * sn]);
+        images[t] = v;
+    }
+}
+
+// zero-pad the channel dimension to a multiple of 4 (float4 gathers)
+__global__ void __launch_bounds__(256) kp_pad_cols_kernel(const float* __restrict__ src, long long rows, int c, int c_p,
+                                                         float* __restrict__ dst) {
+    const long long total = rows * c_p;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / c_p;
+        const int cc = (int)(t % c_p);
+        dst[t] = cc < c ? src[r * c + cc] : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------- A-tile assembly (shared by fwd, dW)
+// Warp `warp` owns tile rows [warp*16, warp*16+16). For chunk `chunk` it zeroes them, walks the entry lists of its 16
+// points restricted to the chunk's kernel points, gathers float4 feature rows (U loads in flight per lane) and
+// accumulates w * x into the rows, then rounds the rows to TF32.
+template <int U>
+__device__ __forceinline__ void assemble_rows(unsigned char* sA, int warp, int lane, int chunk, int cin_p, int K,
+                                              const int* s_ebase, const unsigned short* s_koff,
+                                              const int2* __restrict__ entries, const float* __restrict__ x) {
+    const int col0 = chunk * CK;
+    const int kfirst = col0 / cin_p;
+    const int klast = min(K - 1, (col0 + CK - 1) / cin_p);
+    const int my_col = col0 + 4 * lane;
+    const int k_l = my_col / cin_p, c_l = my_col % cin_p;
+    const int p0 = warp * 16;
+    unsigned char* my = sA + lane * A_LBO;  // + (p/8)*128 + (p%8)*16
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const int p = p0 + r;
+        *reinterpret_cast<float4*>(my + (p >> 3) * A_SBO + (p & 7) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    int start = 0, cnt = 0;
+    if (lane < 16 && kfirst < K) {
+        const unsigned short* ko = s_koff + (p0 + lane) * KOFF;
+        start = s_ebase[p0 + lane] + ko[kfirst];
+        cnt = (int)ko[klast + 1] - (int)ko[kfirst];
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int E = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - cnt;
+    for (int b0 = 0; b0 < E; b0 += 32) {
+        const int e = b0 + lane;
+        int pt = 0;
+#pragma unroll
+        for (int t = 0; t < 16; t++) pt += (__shfl_sync(0xffffffffu, incl, t) <= e) ? 1 : 0;
+        pt = min(pt, 15);
+        const int pstart = __shfl_sync(0xffffffffu, start, pt);
+        const int pexcl = __shfl_sync(0xffffffffu, excl, pt);
+        int2 rec = make_int2(0, 0);
+        if (e < E) rec = entries[pstart + (e - pexcl)];
+        const int nb = min(32, E - b0);
+        for (int g = 0; g < nb; g += U) {
+            float4 xv[U];
+            float wv[U];
+            int pv[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int ee = min(g + u, 31);
+                const unsigned jk = (unsigned)__shfl_sync(0xffffffffu, rec.x, ee);
+                const float w = __int_as_float(__shfl_sync(0xffffffffu, rec.y, ee));
+                pv[u] = __shfl_sync(0xffffffffu, pt, ee);
+                const bool mine = (g + u < nb) && ((int)(jk >> K_SHIFT) == k_l);
+                wv[u] = mine ? w : 0.f;
+                xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (mine) xv[u] = __ldg(reinterpret_cast<const float4*>(x + (size_t)(jk & J_MASK) * cin_p + c_l));
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (wv[u] != 0.f) {
+                    const int p = p0 + pv[u];
+                    float4* a = reinterpret_cast<float4*>(my + (p >> 3) * A_SBO + (p & 7) * 16);
+                    float4 v = *a;
+                    v.x = fmaf(wv[u], xv[u].x, v.x); v.y = fmaf(wv[u], xv[u].y, v.y);
+                    v.z = fmaf(wv[u], xv[u].z, v.z); v.w = fmaf(wv[u], xv[u].w, v.w);
+                    *a = v;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const int p = p0 + r;
+        float4* a = reinterpret_cast<float4*>(my + (p >> 3) * A_SBO + (p & 7) * 16);
+        float4 v = *a;
+        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+        *a = v;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------- forward
+struct FwdParams {
+    int nq;              // centre points (rows of out)
+    const float* x;      // [n_other, cin_p] features gathered through the entry lists
+    int cin_p, K;
+    const int* ebase;
+    const unsigned short* koff;
+    const int2* entries;
+    const float* images; // packed weights [n_chunks][n_nblk][NB*CK]
+    int NB, n_nblk, n_chunks;
+    float* out;          // [nq, cout]
+    int cout;
+    uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(FWD_THREADS) kp_fwd_kernel(FwdParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + A_BYTES;
+    const int b_bytes = P.NB * CK * 4;
+    unsigned short* s_koff = reinterpret_cast<unsigned short*>(sB + b_bytes);
+    int* s_ebase = reinterpret_cast<int*>(s_koff + TILE_M * KOFF);
+    uint64_t* bar_b = reinterpret_cast<uint64_t*>(s_ebase + TILE_M);
+    uint64_t* bar_mma = bar_b + 1;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_base = blockIdx.x * TILE_M;
+
+    if (tid == 0) {
+        mbar_init(bar_b, 1);
+        mbar_init(bar_mma, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(s_tmem, P.tmem_cols);
+    for (int t = tid; t < TILE_M; t += FWD_THREADS) {
+        const int i = tile_base + t;
+        s_ebase[t] = (i < P.nq) ? P.ebase[i] : 0;
+    }
+    for (int t = tid; t < TILE_M * KOFF; t += FWD_THREADS) {
+        const int i = tile_base + t / KOFF;
+        s_koff[t] = (i < P.nq) ? P.koff[(size_t)i * KOFF + (t % KOFF)] : (unsigned short)0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t idesc = make_idesc(TILE_M, P.NB, 0, 0);
+    const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+    const uint32_t b_lbo = (uint32_t)P.NB * 16u;
+
+    int step = 0;  // one MMA group (chunk, nblk) per step; bar_b / bar_mma complete once per step
+    for (int chunk = 0; chunk < P.n_chunks; chunk++) {
+        for (int nblk = 0; nblk < P.n_nblk; nblk++, step++) {
+            if (step > 0) mbar_wait(bar_mma, (uint32_t)((step - 1) & 1));  // previous MMAs done: A and B reusable
+            if (tid == 0) {
+                mbar_expect_tx(bar_b, (uint32_t)b_bytes);
+                bulk_g2s(sB, P.images + ((size_t)chunk * P.n_nblk + nblk) * (size_t)P.NB * CK, (uint32_t)b_bytes, bar_b);
+            }
+            if (nblk == 0) {
+                assemble_rows<8>(sA, warp, lane, chunk, P.cin_p, P.K, s_ebase, s_koff, P.entries, P.x);
+                fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
+            }
+            __syncthreads();
+            if (tid == 0) {
+                mbar_wait(bar_b, (uint32_t)(step & 1));
+                tc_fence_after();
+#pragma unroll 1
+                for (int kk = 0; kk < CK / 8; kk++) {  // K = 8 per tf32 MMA = two 16-byte K chunks
+                    const uint64_t ad = make_desc(a_addr + kk * 2 * A_LBO, A_LBO, A_SBO);
+                    const uint64_t bd = make_desc(b_addr + kk * 2 * b_lbo, b_lbo, B_SBO);
+                    umma_tf32(tmem + (uint32_t)(nblk * P.NB), ad, bd, idesc, (chunk > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(bar_mma);
+            }
+        }
+    }
+    mbar_wait(bar_mma, (uint32_t)((step - 1) & 1));
+    tc_fence_after();
+
+    // epilogue: warp w reads TMEM lanes 32*(w%4).., column blocks of 16 interleaved between the two warpgroups
+    const int row = tile_base + 32 * (warp & 3) + lane;
+    const int n_cb = (P.n_nblk * P.NB) / 16;
+    for (int cb = warp >> 2; cb < n_cb; cb += 2) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cb * 16), v);
+        if (row < P.nq) {
+            float* o = P.out + (size_t)row * P.cout + cb * 16;
+            if ((P.cout & 3) == 0) {
+#pragma unroll
+                for (int t = 0; t < 16; t += 4)
+                    if (cb * 16 + t < P.cout) *reinterpret_cast<float4*>(o + t) = make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 16; t++)
+                    if (cb * 16 + t < P.cout) o[t] = v[t];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, P.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------------- dW
+// B tile = dOut[tile points, NB outputs] MN-major: element (n, p) at (n/4)*DW_B_SBO + (p/8)*128 + (p%8)*16 + (n%4)*4
+constexpr int DW_B_SBO = 16 * 128 + 16;  // 2064
+
+struct DwParams {
+    int nq;
+    const float* x;      // [ns, cin_p]
+    int cin, cin_p, K;
+    const int* ebase;
+    const unsigned short* koff;
+    const int2* entries;
+    const float* dout;   // [nq, cout]
+    int cout, NB;        // NB = output columns handled per CTA (<= 256), slice index = blockIdx.z
+    int n_tiles, n_splits;
+    float* dw;           // [K, cin, cout], pre-zeroed
+    uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(FWD_THREADS) kp_dw_kernel(DwParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + A_BYTES;
+    const int b_bytes = (P.NB / 4) * DW_B_SBO;
+    unsigned short* s_koff = reinterpret_cast<unsigned short*>(sB + b_bytes);
+    int* s_ebase = reinterpret_cast<int*>(s_koff + TILE_M * KOFF);
+    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(s_ebase + TILE_M);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = blockIdx.x, split = blockIdx.y, n0 = blockIdx.z * P.NB;
+    if (split >= P.n_tiles) return;  // uniform: nothing to do for this CTA
+
+    if (tid == 0) {
+        mbar_init(bar_mma, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(s_tmem, P.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t idesc = make_idesc(TILE_M, P.NB, 1, 1);
+    const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+
+    int step = 0;
+    for (int tile = split; tile < P.n_tiles; tile += P.n_splits, step++) {
+        const int tile_base = tile * TILE_M;
+        if (step > 0) mbar_wait(bar_mma, (uint32_t)((step - 1) & 1));
+        for (int t = tid; t < TILE_M; t += FWD_THREADS) {
+            const int i = tile_base + t;
+            s_ebase[t] = (i < P.nq) ? P.ebase[i] : 0;
+        }
+        for (int t = tid; t < TILE_M * KOFF; t += FWD_THREADS) {
+            const int i = tile_base + t / KOFF;
+            s_koff[t] = (i < P.nq) ? P.koff[(size_t)i * KOFF + (t % KOFF)] : (unsigned short)0;
+        }
+        // dOut tile -> B (TF32), warp per point row, lane per group of 4 outputs
+        for (int r = 0; r < 16; r++) {
+            const int p = warp * 16 + r;
+            const int i = tile_base + p;
+            for (int n4 = lane; n4 < P.NB / 4; n4 += 32) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int n = n0 + n4 * 4;
+                if (i < P.nq) {
+                    const float* src = P.dout + (size_t)i * P.cout + n;
+                    if ((P.cout & 3) == 0) {
+                        if (n < P.cout) v = __ldg(reinterpret_cast<const float4*>(src));
+                    } else {
+                        if (n < P.cout) v.x = src[0];
+                        if (n + 1 < P.cout) v.y = src[1];
+                        if (n + 2 < P.cout) v.z = src[2];
+                        if (n + 3 < P.cout) v.w = src[3];
+                    }
+                }
+                v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                *reinterpret_cast<float4*>(sB + n4 * DW_B_SBO + (p >> 3) * 128 + (p & 7) * 16) = v;
+            }
+        }
+        __syncthreads();  // s_ebase / s_koff ready
+        assemble_rows<8>(sA, warp, lane, chunk, P.cin_p, P.K, s_ebase, s_koff, P.entries, P.x);
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll 1
+            for (int kk = 0; kk < TILE_M / 8; kk++) {  // K = 8 points per MMA
+                // MN-major: K-direction (8-point groups) stride 128 B, M/N-direction (4-element groups) stride 2064 B
+                const uint64_t ad = make_desc(a_addr + kk * A_SBO, A_SBO, A_LBO);
+                const uint64_t bd = make_desc(b_addr + kk * 128, 128, DW_B_SBO);
+                umma_tf32(tmem, ad, bd, idesc, (step > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(bar_mma);
+        }
+    }
+    mbar_wait(bar_mma, (uint32_t)((step - 1) & 1));
+    tc_fence_after();
+
+    // epilogue: TMEM lane r = reduction column chunk*CK + r = (k, c); add into dW[k, c, n0 + col]
+    const int r = 32 * (warp & 3) + lane;
+    const int col = chunk * CK + r;
+    const int k = col / P.cin_p, c = col % P.cin_p;
+    const bool row_ok = k < P.K && c < P.cin;
+    for (int cb = warp >> 2; cb < P.NB / 16; cb += 2) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cb * 16), v);
+        if (row_ok) {
+            float* o = P.dw + ((size_t)k * P.cin + c) * P.cout + n0 + cb * 16;
+#pragma unroll
+            for (int t = 0; t < 16; t++)
+                if (n0 + cb * 16 + t < P.cout) atomicAdd(o + t, v[t]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, P.tmem_cols);
+}
+
+// ----------------------------------------------------------------------------------------- transposed neighbour table
+template <typename IdxT>
+__global__ void __launch_bounds__(256) kp_tr_count_kernel(const IdxT* __restrict__ idx, int nq, int H, int stride, int ns,
+                                                         int* __restrict__ deg) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)nq * H) return;
+    const long long j = (long long)idx[(t / H) * stride + (t % H)];
+    if (j >= 0 && j < ns) atomicAdd(&deg[j], 1);
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256) kp_tr_fill_kernel(const IdxT* __restrict__ idx, int nq, int H, int stride, int ns,
+                                                        const int* __restrict__ rowptr, int* __restrict__ cursor,
+                                                        int* __restrict__ col) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)nq * H) return;
+    const long long j = (long long)idx[(t / H) * stride + (t % H)];
+    if (j >= 0 && j < ns) col[rowptr[j] + atomicAdd(&cursor[j], 1)] = (int)(t / H);
+}
+
+// each row's centre list sorted ascending so that the dX sums run in a fixed order (rows are short)
+__global__ void __launch_bounds__(256) kp_tr_sort_kernel(const int* __restrict__ rowptr, int ns, int* __restrict__ col) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ns) return;
+    const int a = rowptr[j], b = rowptr[j + 1];
+    for (int u = a + 1; u < b; u++) {
+        const int v = col[u];
+        int t = u - 1;
+        while (t >= a && col[t] > v) { col[t + 1] = col[t]; t--; }
+        col[t + 1] = v;
+    }
+}
+
+__global__ void kp_set_last_kernel(int* rowptr, int n, const int* total) { rowptr[n] = *total; }
+
+// ---------------------------------------------------------------------------------------------------------- host side
+static long long entry_capacity(long long n_pairs) {
+    long long cap = n_pairs * 15;
+    const long long limit = 1LL << 29;  // 4 GiB of entries
+    if (cap > limit) cap = n_pairs * 4 > limit ? limit : n_pairs * 4;
+    return cap > 0 ? cap : 1;
+}
+
+struct Lists {
+    int* ebase;
+    unsigned short* koff;
+    int2* entries;
+};
+
+static int build_lists(Scratch& S, const float* centres, int nc, const float* others, int no, const Table& T,
+                       long long n_pairs, const float* kp, int K, float kp_sign, float extent, int* d_err, Lists* L,
+                       cudaStream_t stream) {
+    const long long cap = entry_capacity(n_pairs);
+    L->ebase = S.alloc<int>(nc);
+    L->koff = S.alloc<unsigned short>((size_t)nc * KOFF);
+    L->entries = S.alloc<int2>((size_t)cap);
+    unsigned long long* counter = S.alloc<unsigned long long>(1);
+    if (S.status != KP_OK) return S.status;
+    KP_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+    kp_influence_kernel<<<ceil_div(nc, 4), 128, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, 1.f / extent,
+                                                            L->ebase, L->koff, L->entries, cap, counter, d_err);
+    KP_CHECK_LAUNCH();
+    return KP_OK;
+}
+
+static int pad4(int c) { return (c + 3) & ~3; }
+
+// out[nc, cout] = sum over entry lists of w * x[j, :] contracted with W (strides sk, sc, sn over (k, c_in, n_out))
+static int run_forward(Scratch& S, int nc, const float* x, int n_x_rows, int cin, const Lists& L, const float* W,
+                       long long sk, long long sc, long long sn, int cout, int K, float* out, cudaStream_t stream) {
+    const int cin_p = pad4(cin);
+    const float* xg = x;
+    if (cin_p != cin) {
+        float* xp = S.alloc<float>((size_t)n_x_rows * cin_p);
+        if (S.status != KP_OK) return S.status;
+        kp_pad_cols_kernel<<<ceil_div((long long)n_x_rows * cin_p, 256) < 2048 ? ceil_div((long long)n_x_rows * cin_p, 256) : 2048,
+                             256, 0, stream>>>(x, n_x_rows, cin, cin_p, xp);
+        KP_CHECK_LAUNCH();
+        xg = xp;
+    }
+    const int cout_p = (cout + 15) & ~15;
+    const int NB = cout_p < 256 ? cout_p : 256;
+    const int n_nblk = ceil_div(cout_p, NB);
+    if (n_nblk * NB > 512) return fail(KP_ERR_UNSUPPORTED, "kpconv: out_channels > 512");
+    const int n_chunks = ceil_div((long long)K * cin_p, CK);
+    float* images = S.alloc<float>((size_t)n_chunks * n_nblk * NB * CK);
+    if (S.status != KP_OK) return S.status;
+    {
+        const long long total = (long long)n_chunks * n_nblk * NB * CK;
+        const int grid = ceil_div(total, 256) < 4096 ? ceil_div(total, 256) : 4096;
+        kp_pack_w_kernel<<<grid, 256, 0, stream>>>(W, K, cin, cin_p, cout, sk, sc, sn, NB, n_nblk, n_chunks, images);
+        KP_CHECK_LAUNCH();
+    }
+    FwdParams P;
+    P.nq = nc; P.x = xg; P.cin_p = cin_p; P.K = K;
+    P.ebase = L.ebase; P.koff = L.koff; P.entries = L.entries;
+    P.images = images; P.NB = NB; P.n_nblk = n_nblk; P.n_chunks = n_chunks;
+    P.out = out; P.cout = cout;
+    uint32_t cols = 32;
+    while ((int)cols < n_nblk * NB) cols <<= 1;
+    P.tmem_cols = cols;
+    const size_t smem = (size_t)A_BYTES + (size_t)NB * CK * 4 + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
+    KP_CUDA(cudaFuncSetAttribute(kp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kp_fwd_kernel<<<ceil_div(nc, TILE_M), FWD_THREADS, smem, stream>>>(P);
+    KP_CHECK_LAUNCH();
+    return KP_OK;
+}
+
+static int check_args(int nq, int ns, int H, int idx_stride, int cin, int cout, int K, float extent) {
+    if (nq < 0 || ns < 0 || H < 0 || idx_stride < H || cin <= 0 || cout <= 0) return fail(KP_ERR_ARG, "kpconv: bad sizes");
+    if (K <= 0 || K > 15) return fail(KP_ERR_UNSUPPORTED, "kpconv: kernel_size must be 1..15");
+    if (!(extent > 0.f)) return fail(KP_ERR_ARG, "kpconv: KP_extent must be positive");
+    if ((long long)ns >= (1LL << K_SHIFT) || (long long)nq >= (1LL << K_SHIFT))
+        return fail(KP_ERR_UNSUPPORTED, "kpconv: more than 2^27 points in one call");
+    return KP_OK;
+}
+
+static int check_err_flag(int* d_err, cudaStream_t stream, bool sync_now) {
+    // The entry-list capacity is an exact upper bound for every realistic shape (15 entries per neighbour);
+    // only the capped case can overflow, and that one is checked synchronously.
+    if (!sync_now) return KP_OK;
+    int h = 0;
+    KP_CUDA(cudaMemcpyAsync(&h, d_err, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    KP_CUDA(cudaStreamSynchronize(stream));
+    if (h) return fail(KP_ERR_UNSUPPORTED, "kpconv: influence entry list overflow");
+    return KP_OK;
+}
+
+int kpconv_forward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
+                          int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
+                          float extent, float* out, cudaStream_t stream) {
+    int rc = check_args(nq, ns, H, idx_stride, cin, cout, K, extent);
+    if (rc != KP_OK) return rc;
+    if (nq == 0) return KP_OK;
+    if (ns == 0 || H == 0) {
+        KP_CUDA(cudaMemsetAsync(out, 0, (size_t)nq * cout * sizeof(float), stream));
+        return KP_OK;
+    }
+    Scratch S(stream);
+    int* d_err = S.alloc<int>(1);
+    if (S.status != KP_OK) return S.status;
+    KP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), stream));
+    Table T;
+    T.idx = idx; T.rowptr = nullptr; T.H = H; T.stride = idx_stride; T.is_i64 = idx_is_i64;
+    Lists L;
+    const long long n_pairs = (long long)nq * H;
+    rc = build_lists(S, q, nq, s, ns, T, n_pairs, kp, K, 1.f, extent, d_err, &L, stream);
+    if (rc != KP_OK) return rc;
+    rc = run_forward(S, nq, x, ns, cin, L, w, (long long)cin * cout, cout, 1, cout, K, out, stream);
+    if (rc != KP_OK) return rc;
+    return check_err_flag(d_err, stream, entry_capacity(n_pairs) < n_pairs * 15);
+}
+
+int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
+                           int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
+                           float extent, const float* dout, float* dx, float* dw, cudaStream_t stream) {
+    int rc = check_args(nq, ns, H, idx_stride, cin, cout, K, extent);
+    if (rc != KP_OK) return rc;
+    KP_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * cin * cout * sizeof(float), stream));
+    if (ns > 0) KP_CUDA(cudaMemsetAsync(dx, 0, (size_t)ns * cin * sizeof(float), stream));
+    if (nq == 0 || ns == 0 || H == 0) return KP_OK;
+    Scratch S(stream);
+    int* d_err = S.alloc<int>(1);
+    if (S.status != KP_OK) return S.status;
+    KP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), stream));
+    const long long n_pairs = (long long)nq * H;
+
+    // ---- dW: entry lists centred on the queries (same as forward)
+    {
+        Table T;
+        T.idx = idx; T.rowptr = nullptr; T.H = H; T.stride = idx_stride; T.is_i64 = idx_is_i64;
+        Lists L;
+        rc = build_lists(S, q, nq, s, ns, T, n_pairs, kp, K, 1.f, extent, d_err, &L, stream);
+        if (rc != KP_OK) return rc;
+        const int cin_p = pad4(cin);
+        const float* xg = x;
+        if (cin_p != cin) {
+            float* xp = S.alloc<float>((size_t)ns * cin_p);
+            if (S.status != KP_OK) return S.status;
+            const int grid = ceil_div((long long)ns * cin_p, 256) < 2048 ? ceil_div((long long)ns * cin_p, 256) : 2048;
+            kp_pad_cols_kernel<<<grid, 256, 0, stream>>>(x, ns, cin, cin_p, xp);
+            KP_CHECK_LAUNCH();
+            xg = xp;
+        }
+        const int cout_p = (cout + 15) & ~15;
+        DwParams P;
+        P.nq = nq; P.x = xg; P.cin = cin; P.cin_p = cin_p; P.K = K;
+        P.ebase = L.ebase; P.koff = L.koff; P.entries = L.entries;
+        P.dout = dout; P.cout = cout;
+        P.NB = cout_p < 256 ? cout_p : 256;
+        const int n_slices = ceil_div(cout_p, P.NB);
+        const int n_chunks = ceil_div((long long)K * cin_p, CK);
+        P.n_tiles = ceil_div(nq, TILE_M);
+        int splits = (2 * 148) / (n_chunks * n_slices);
+        if (splits < 1) splits = 1;
+        if (splits > P.n_tiles) splits = P.n_tiles;
+        P.n_splits = splits;
+        P.dw = dw;
+        uint32_t cols = 32;
+        while ((int)cols < P.NB) cols <<= 1;
+        P.tmem_cols = cols;
+        const size_t smem = (size_t)A_BYTES + (size_t)(P.NB / 4) * DW_B_SBO + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
+        KP_CUDA(cudaFuncSetAttribute(kp_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kp_dw_kernel<<<dim3(n_chunks, splits, n_slices), FWD_THREADS, smem, stream>>>(P);
+        KP_CHECK_LAUNCH();
+    }
+
+    // ---- dX: the forward kernel on the transposed table, with W^T and -kp
+    {
+        int* deg = S.alloc<int>(ns + 1);
+        int* rowptr = S.alloc<int>(ns + 1);
+        int* cursor = S.alloc<int>(ns);
+        int* total = S.alloc<int>(1);
+        int* scan_tmp = S.alloc<int>(scan_tmp_ints(ns));
+        int* col = S.alloc<int>((size_t)n_pairs);
+        if (S.status != KP_OK) return S.status;
+        KP_CUDA(cudaMemsetAsync(deg, 0, (size_t)(ns + 1) * sizeof(int), stream));
+        KP_CUDA(cudaMemsetAsync(cursor, 0, (size_t)ns * sizeof(int), stream));
+        const int grid = ceil_div(n_pairs, 256);
+        if (idx_is_i64) kp_tr_count_kernel<long long><<<grid, 256, 0, stream>>>((const long long*)idx, nq, H, idx_stride, ns, deg);
+        else kp_tr_count_kernel<int><<<grid, 256, 0, stream>>>((const int*)idx, nq, H, idx_stride, ns, deg);
+        KP_CHECK_LAUNCH();
+        rc = exclusive_scan(deg, rowptr, ns, total, scan_tmp, stream);
+        if (rc != KP_OK) return rc;
+        kp_set_last_kernel<<<1, 1, 0, stream>>>(rowptr, ns, total);
+        KP_CHECK_LAUNCH();
+        if (idx_is_i64) kp_tr_fill_kernel<long long><<<grid, 256, 0, stream>>>((const long long*)idx, nq, H, idx_stride, ns, rowptr, cursor, col);
+        else kp_tr_fill_kernel<int><<<grid, 256, 0, stream>>>((const int*)idx, nq, H, idx_stride, ns, rowptr, cursor, col);
+        KP_CHECK_LAUNCH();
+        kp_tr_sort_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(rowptr, ns, col);
+        KP_CHECK_LAUNCH();
+        Table T;
+        T.idx = col; T.rowptr = rowptr; T.H = 0; T.stride = 0; T.is_i64 = 0;
+        Lists L;
+        rc = build_lists(S, s, ns, q, nq, T, n_pairs, kp, K, -1.f, extent, d_err, &L, stream);
+        if (rc != KP_OK) return rc;
+        // W'[k][c' = o][n' = c] = W[k][c][o]
+        rc = run_forward(S, ns, dout, nq, cout, L, w, (long long)cin * cout, 1, cout, cin, K, dx, stream);
+        if (rc != KP_OK) return rc;
+    }
+    return check_err_flag(d_err, stream, entry_capacity(n_pairs) < n_pairs * 15);
+}
+
+}  // namespace kp

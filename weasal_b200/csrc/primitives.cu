@@ -1,0 +1,217 @@
+// Device-wide building blocks used by the precompute kernels: exclusive scan and a stable LSD radix sort.
+// Hand-written (no CUB / Thrust): the sizes on this path (10^3 .. 10^7 keys, 8..24 significant bits) are
+// launch- and HBM-bound, so the kernels are kept few and fat: one histogram, one single-CTA scan and one
+// ranked scatter per 8-bit digit.
+#include "common.cuh"
+
+namespace kp {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launch_count{0};
+
+int pool_init_once() {
+    static thread_local int done_dev = -1;
+    int dev = 0;
+    KP_CUDA(cudaGetDevice(&dev));
+    if (done_dev == dev) return KP_OK;
+    cudaMemPool_t pool;
+    KP_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long thr = ~0ULL;
+    KP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    done_dev = dev;
+    return KP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------ scan
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const int* __restrict__ in, int* __restrict__ out,
+                                                                  int n, int* __restrict__ block_sums,
+                                                                  int* __restrict__ total_out) {
+    __shared__ int s_warp[33];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        v[i] = (base + i < n) ? in[base + i] : 0;
+        sum += v[i];
+    }
+    int total;
+    int excl = block_exclusive_scan(sum, s_warp, &total);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        if (base + i < n) out[base + i] = excl;
+        excl += v[i];
+    }
+    if (threadIdx.x == 0) {
+        if (block_sums) block_sums[blockIdx.x] = total;
+        if (gridDim.x == 1 && total_out) *total_out = total;
+    }
+}
+
+// single CTA: exclusive scan of m values in place (m <= 1024 * chunk)
+__global__ void __launch_bounds__(SCAN_THREADS) scan_single_kernel(int* __restrict__ data, int m,
+                                                                  int* __restrict__ total_out) {
+    __shared__ int s_warp[33];
+    const int chunk = (m + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int lo = threadIdx.x * chunk, hi = min(lo + chunk, m);
+    int sum = 0;
+    for (int i = lo; i < hi; i++) sum += data[i];
+    int total;
+    int excl = block_exclusive_scan(sum, s_warp, &total);
+    for (int i = lo; i < hi; i++) {
+        int v = data[i];
+        data[i] = excl;
+        excl += v;
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(int* __restrict__ out, int n,
+                                                               const int* __restrict__ block_sums) {
+    const int off = block_sums[blockIdx.x];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++)
+        if (base + i < n) out[base + i] += off;
+}
+
+size_t scan_tmp_ints(int n) { return (size_t)ceil_div(n > 0 ? n : 1, SCAN_TILE) + 1; }
+
+int exclusive_scan(const int* d_in, int* d_out, int n, int* d_total, int* tmp, cudaStream_t stream) {
+    if (n <= 0) {
+        if (d_total) KP_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int), stream));
+        return KP_OK;
+    }
+    const int nblk = ceil_div(n, SCAN_TILE);
+    scan_tiles_kernel<<<nblk, SCAN_THREADS, 0, stream>>>(d_in, d_out, n, nblk > 1 ? tmp : nullptr, d_total);
+    KP_CHECK_LAUNCH();
+    if (nblk > 1) {
+        scan_single_kernel<<<1, SCAN_THREADS, 0, stream>>>(tmp, nblk, d_total);
+        KP_CHECK_LAUNCH();
+        scan_add_kernel<<<nblk, SCAN_THREADS, 0, stream>>>(d_out, n, tmp);
+        KP_CHECK_LAUNCH();
+    }
+    return KP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------ radix sort
+constexpr int RS_THREADS = 512;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ROUNDS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;  // 4096 keys
+constexpr int RS_MAX_BLOCKS = 296;               // 2 CTAs per SM on 148 SMs
+
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned* __restrict__ keys, int n, int shift,
+                                                            int tiles_per_block, int* __restrict__ hist) {
+    __shared__ int s_hist[256];
+    for (int i = threadIdx.x; i < 256; i += RS_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    const long long lo = (long long)blockIdx.x * tiles_per_block * RS_TILE;
+    const long long hi = min((long long)n, lo + (long long)tiles_per_block * RS_TILE);
+    for (long long i = lo + threadIdx.x; i < hi; i += RS_THREADS) atomicAdd(&s_hist[(keys[i] >> shift) & 255u], 1);
+    __syncthreads();
+    for (int d = threadIdx.x; d < 256; d += RS_THREADS) hist[d * gridDim.x + blockIdx.x] = s_hist[d];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned* __restrict__ keys_in,
+                                                               const unsigned* __restrict__ vals_in,
+                                                               unsigned* __restrict__ keys_out,
+                                                               unsigned* __restrict__ vals_out, int n, int shift,
+                                                               int tiles_per_block, const int* __restrict__ offs) {
+    __shared__ int s_run[256];
+    __shared__ int s_wcnt[RS_WARPS][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int d = threadIdx.x; d < 256; d += RS_THREADS) s_run[d] = offs[d * gridDim.x + blockIdx.x];
+    for (int t = 0; t < tiles_per_block; t++) {
+        const long long tile_base = ((long long)blockIdx.x * tiles_per_block + t) * RS_TILE;
+        if (tile_base >= n) break;
+        for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&s_wcnt[0][0])[i] = 0;
+        __syncthreads();
+        unsigned k[RS_ROUNDS], v[RS_ROUNDS];
+        const long long seg = tile_base + warp * (32 * RS_ROUNDS);
+#pragma unroll
+        for (int r = 0; r < RS_ROUNDS; r++) {
+            const long long i = seg + r * 32 + lane;
+            const bool ok = i < n;
+            k[r] = ok ? keys_in[i] : 0xffffffffu;
+            v[r] = ok ? vals_in[i] : 0u;
+            const unsigned d = ok ? ((k[r] >> shift) & 255u) : 256u;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            if (ok && (peers & lt_mask) == 0) s_wcnt[warp][d] += __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            int o = s_run[threadIdx.x];
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; w++) {
+                int c = s_wcnt[w][threadIdx.x];
+                s_wcnt[w][threadIdx.x] = o;
+                o += c;
+            }
+            s_run[threadIdx.x] = o;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < RS_ROUNDS; r++) {
+            const long long i = seg + r * 32 + lane;
+            const bool ok = i < n;
+            const unsigned d = ok ? ((k[r] >> shift) & 255u) : 256u;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            int pos = 0;
+            if (ok) pos = s_wcnt[warp][d] + __popc(peers & lt_mask);
+            __syncwarp();
+            if (ok && (peers & lt_mask) == 0) s_wcnt[warp][d] += __popc(peers);
+            __syncwarp();
+            if (ok) {
+                keys_out[pos] = k[r];
+                vals_out[pos] = v[r];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+size_t sort_tmp_ints(int n) {
+    (void)n;
+    return (size_t)256 * RS_MAX_BLOCKS + 8;
+}
+
+int stable_sort_pairs(const unsigned* keys_in, const unsigned* vals_in, unsigned* keys_out, unsigned* vals_out,
+                      unsigned* keys_alt, unsigned* vals_alt, int n, int nbits, int* tmp, cudaStream_t stream) {
+    if (n <= 0) return KP_OK;
+    const int passes = (nbits + 7) / 8;
+    const int ntiles = ceil_div(n, RS_TILE);
+    const int grid = ntiles < RS_MAX_BLOCKS ? ntiles : RS_MAX_BLOCKS;
+    const int tpb = ceil_div(ntiles, grid);
+    const int grid2 = ceil_div(ntiles, tpb);
+    if (passes == 0) {
+        KP_CUDA(cudaMemcpyAsync(keys_out, keys_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+        KP_CUDA(cudaMemcpyAsync(vals_out, vals_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+        return KP_OK;
+    }
+    // ping-pong so that the last pass lands in (keys_out, vals_out)
+    const unsigned* src_k = keys_in;
+    const unsigned* src_v = vals_in;
+    for (int p = 0; p < passes; p++) {
+        const bool to_out = ((passes - 1 - p) % 2) == 0;
+        unsigned* dst_k = to_out ? keys_out : keys_alt;
+        unsigned* dst_v = to_out ? vals_out : vals_alt;
+        rs_hist_kernel<<<grid2, RS_THREADS, 0, stream>>>(src_k, n, p * 8, tpb, tmp);
+        KP_CHECK_LAUNCH();
+        scan_single_kernel<<<1, SCAN_THREADS, 0, stream>>>(tmp, 256 * grid2, nullptr);
+        KP_CHECK_LAUNCH();
+        rs_scatter_kernel<<<grid2, RS_THREADS, 0, stream>>>(src_k, src_v, dst_k, dst_v, n, p * 8, tpb, tmp);
+        KP_CHECK_LAUNCH();
+        src_k = dst_k;
+        src_v = dst_v;
+    }
+    return KP_OK;
+}
+
+}  // namespace kp

@@ -1,0 +1,318 @@
+// Batch radius search on the GPU — replaces cpp_wrappers/cpp_neighbors (neighbors.cpp:211-332 as wired in at
+// wrapper.cpp:197-198; ordering contract of neighbors.cpp:125-208).
+//
+// Semantics reproduced bit-exactly: neighbours of query i = supports j of the SAME batch element with
+// d2 = ((qx-sx)^2 + (qy-sy)^2) + (qz-sz)^2 < r2 = radius*radius, all in unfused f32 (nanoflann.hpp:432-440,
+// neighbors.cpp:226), strict '<' (nanoflann.hpp:249-251); rows sorted by d2 ascending; global support indices;
+// rows padded with Ns (neighbors.cpp:322-324).
+// Stated tie-break: (d2 ascending, support index ascending) — that of batch_ordered_neighbors (upper_bound
+// insertion, neighbors.cpp:176-181). The wired-in nanoflann path sorts by d2 only (std::sort, nanoflann.hpp:208-214),
+// so it can differ from this order only inside groups of exactly equal d2.
+//
+// Design: uniform hash grid over the supports (cell edge slightly above the radius so that every neighbour lies in
+// the 27 cells around the query's cell), supports scattered into cell-contiguous order as float4 (x,y,z,index),
+// one warp per query: 27 lanes probe the 27 cells, the warp sweeps each non-empty cell 32 candidates at a time,
+// ballot-compacts the hits into shared memory, rank-sorts them by (d2, index) and writes the row.
+// The row buffer is [Nq, cap]; rows keep their `cap` closest neighbours (what big_neighborhood_filter,
+// datasets/common.py:336-346, does afterwards) and the true maximum count is returned for the caller to slice.
+#include "common.cuh"
+
+#include <vector>
+
+namespace kp {
+
+constexpr unsigned long long CELL_EMPTY = ~0ULL;
+constexpr int RS_WARPS_PER_CTA = 4;
+constexpr int RS_MAX_HITS = 1024;  // hits staged per query (8 KB of shared memory per warp)
+
+struct GridPlan {   // written by the plan kernel, read by the others
+    float inv_cell;
+    float pad0, pad1, pad2;
+};
+
+struct SearchParams {
+    const float* q; int nq;
+    const float* s; int ns;
+    const int* q_off; const int* s_off; int nb;
+    float r2;
+};
+
+__global__ void rs_bbox_init_kernel(unsigned* bbox, int nb) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nb * 6) bbox[i] = ((i % 6) < 3) ? 0xffffffffu : 0u;
+}
+
+__global__ void __launch_bounds__(256) rs_bbox_kernel(const float* __restrict__ s, int ns,
+                                                     const int* __restrict__ s_off, int nb,
+                                                     unsigned* __restrict__ bbox) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = i < ns;
+    int b = -1;
+    unsigned v[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    if (ok) {
+        b = batch_of(s_off, nb, i);
+        v[0] = v[3] = f2ord(s[3 * (size_t)i]);
+        v[1] = v[4] = f2ord(s[3 * (size_t)i + 1]);
+        v[2] = v[5] = f2ord(s[3 * (size_t)i + 2]);
+    }
+    const int b0 = __shfl_sync(0xffffffffu, b, 0);
+    const bool uniform = __all_sync(0xffffffffu, b == b0 || !ok) && b0 >= 0;
+    if (uniform) {
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            unsigned r = (a < 3) ? __reduce_min_sync(0xffffffffu, v[a]) : __reduce_max_sync(0xffffffffu, v[a]);
+            if ((threadIdx.x & 31) == 0) {
+                if (a < 3) atomicMin(&bbox[b0 * 6 + a], r); else atomicMax(&bbox[b0 * 6 + a], r);
+            }
+        }
+    } else if (ok) {
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            if (a < 3) atomicMin(&bbox[b * 6 + a], v[a]); else atomicMax(&bbox[b * 6 + a], v[a]);
+        }
+    }
+}
+
+// Cell edge = radius * (1 + slack). The slack covers the f32 rounding of (p - origin) * inv_cell, which grows with
+// the cell coordinate: |error| <= ~4 * Vmax * 2^-24 cells, so slack = 2^-10 + Vmax * 2^-20 keeps every true
+// neighbour within +-1 cell on each axis.
+__global__ void rs_plan_kernel(const unsigned* __restrict__ bbox, int nb, float radius, GridPlan* plan,
+                               int* __restrict__ err) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float ext = 0.f;
+    for (int b = 0; b < nb; b++)
+        for (int a = 0; a < 3; a++) {
+            const unsigned lo = bbox[b * 6 + a], hi = bbox[b * 6 + 3 + a];
+            if (lo == 0xffffffffu) continue;  // empty batch element
+            ext = fmaxf(ext, ord2f(hi) - ord2f(lo));
+        }
+    const float vmax = ext / radius + 2.f;
+    const float slack = 0.0009765625f + vmax * 9.5367431640625e-07f;
+    const float cell = radius * (1.f + slack);
+    plan->inv_cell = 1.f / cell;
+    if (!(vmax < 260000.f)) atomicOr(err, 1);  // 18 bits per axis in the cell key
+}
+
+__device__ __forceinline__ int cell_coord(float p, float origin, float inv_cell) {
+    float v = floorf((p - origin) * inv_cell);
+    v = fminf(fmaxf(v, -4.f), 262150.f);
+    return (int)v;
+}
+
+__device__ __forceinline__ unsigned long long cell_key(int b, int cx, int cy, int cz) {
+    return ((unsigned long long)b << 54) | ((unsigned long long)cz << 36) | ((unsigned long long)cy << 18) |
+           (unsigned long long)cx;
+}
+
+__global__ void rs_table_init_kernel(unsigned long long* tkeys, int* tcount, int tsize) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < tsize) { tkeys[i] = CELL_EMPTY; tcount[i] = 0; }
+}
+
+__global__ void __launch_bounds__(256) rs_insert_kernel(const float* __restrict__ s, int ns,
+                                                       const int* __restrict__ s_off, int nb,
+                                                       const unsigned* __restrict__ bbox,
+                                                       const GridPlan* __restrict__ plan,
+                                                       unsigned long long* __restrict__ tkeys,
+                                                       int* __restrict__ tcount, int tmask, int* __restrict__ sslot,
+                                                       int* __restrict__ srank) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    const int b = batch_of(s_off, nb, i);
+    const float inv = plan->inv_cell;
+    const int cx = cell_coord(s[3 * (size_t)i], ord2f(bbox[b * 6 + 0]), inv);
+    const int cy = cell_coord(s[3 * (size_t)i + 1], ord2f(bbox[b * 6 + 1]), inv);
+    const int cz = cell_coord(s[3 * (size_t)i + 2], ord2f(bbox[b * 6 + 2]), inv);
+    const unsigned long long key = cell_key(b, cx, cy, cz);
+    unsigned slot = (unsigned)mix64(key) & (unsigned)tmask;
+    while (true) {
+        unsigned long long cur = tkeys[slot];
+        if (cur == CELL_EMPTY) cur = atomicCAS(&tkeys[slot], CELL_EMPTY, key);
+        if (cur == CELL_EMPTY || cur == key) break;
+        slot = (slot + 1) & (unsigned)tmask;
+    }
+    sslot[i] = (int)slot;
+    srank[i] = atomicAdd(&tcount[slot], 1);
+}
+
+__global__ void __launch_bounds__(256) rs_fill_kernel(const float* __restrict__ s, int ns,
+                                                     const int* __restrict__ sslot, const int* __restrict__ srank,
+                                                     const int* __restrict__ tstart, float4* __restrict__ sorted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    float4 v;
+    v.x = s[3 * (size_t)i]; v.y = s[3 * (size_t)i + 1]; v.z = s[3 * (size_t)i + 2];
+    v.w = __int_as_float(i);
+    sorted[tstart[sslot[i]] + srank[i]] = v;
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32) rs_search_kernel(
+    SearchParams P, const unsigned* __restrict__ bbox, const GridPlan* __restrict__ plan,
+    const unsigned long long* __restrict__ tkeys, const int* __restrict__ tcount, const int* __restrict__ tstart,
+    int tmask, const float4* __restrict__ sorted, OutT* __restrict__ out, int cap, int* __restrict__ hmax,
+    int* __restrict__ err) {
+    __shared__ float s_d2[RS_WARPS_PER_CTA][RS_MAX_HITS];
+    __shared__ int s_idx[RS_WARPS_PER_CTA][RS_MAX_HITS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int qi = blockIdx.x * RS_WARPS_PER_CTA + warp;
+    if (qi >= P.nq) return;
+    float* hd = s_d2[warp];
+    int* hi = s_idx[warp];
+
+    const float qx = P.q[3 * (size_t)qi], qy = P.q[3 * (size_t)qi + 1], qz = P.q[3 * (size_t)qi + 2];
+    const int b = batch_of(P.q_off, P.nb, qi);
+    int count = 0;
+    if (P.s_off[b + 1] > P.s_off[b]) {
+        const float inv = plan->inv_cell;
+        const int cx = cell_coord(qx, ord2f(bbox[b * 6 + 0]), inv);
+        const int cy = cell_coord(qy, ord2f(bbox[b * 6 + 1]), inv);
+        const int cz = cell_coord(qz, ord2f(bbox[b * 6 + 2]), inv);
+        // lanes 0..26 look up the 27 surrounding cells
+        int c_start = 0, c_cnt = 0;
+        if (lane < 27) {
+            const int nx = cx + (lane % 3) - 1, ny = cy + ((lane / 3) % 3) - 1, nz = cz + (lane / 9) - 1;
+            if (nx >= 0 && ny >= 0 && nz >= 0 && nx < 262144 && ny < 262144 && nz < 262144) {
+                const unsigned long long key = cell_key(b, nx, ny, nz);
+                unsigned slot = (unsigned)mix64(key) & (unsigned)tmask;
+                while (true) {
+                    const unsigned long long cur = tkeys[slot];
+                    if (cur == key) { c_start = tstart[slot]; c_cnt = tcount[slot]; break; }
+                    if (cur == CELL_EMPTY) break;
+                    slot = (slot + 1) & (unsigned)tmask;
+                }
+            }
+        }
+        unsigned cells = __ballot_sync(0xffffffffu, c_cnt > 0);
+        while (cells) {
+            const int l = __ffs(cells) - 1;
+            cells &= cells - 1;
+            const int st = __shfl_sync(0xffffffffu, c_start, l);
+            const int cn = __shfl_sync(0xffffffffu, c_cnt, l);
+            for (int base = 0; base < cn; base += 32) {
+                const int c = base + lane;
+                bool hit = false;
+                float d2 = 0.f;
+                int sj = 0;
+                if (c < cn) {
+                    const float4 sp = sorted[st + c];
+                    d2 = sq_dist_ref(qx, qy, qz, sp.x, sp.y, sp.z);
+                    sj = __float_as_int(sp.w);
+                    hit = d2 < P.r2;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (hit) {
+                    const int pos = count + __popc(m & lt_mask);
+                    if (pos < RS_MAX_HITS) { hd[pos] = d2; hi[pos] = sj; }
+                }
+                count += __popc(m);
+            }
+        }
+    }
+    if (count > RS_MAX_HITS) {
+        if (lane == 0) atomicOr(err, 2);
+        count = RS_MAX_HITS;
+    }
+    if (lane == 0 && count > *(volatile int*)hmax) atomicMax(hmax, count);
+    __syncwarp();
+    // rank sort by (d2, index): stable, O(n^2 / 32) per query, n is a few dozen
+    OutT* row = out + (size_t)qi * cap;
+    for (int i = lane; i < count; i += 32) {
+        const float di = hd[i];
+        const int ii = hi[i];
+        int rank = 0;
+        for (int j = 0; j < count; j++) {
+            const float dj = hd[j];
+            rank += (dj < di || (dj == di && hi[j] < ii)) ? 1 : 0;
+        }
+        if (rank < cap) row[rank] = (OutT)ii;
+    }
+    for (int h = count + lane; h < cap; h += 32) row[h] = (OutT)P.ns;
+}
+
+// ---------------------------------------------------------------------------------------------------------- host side
+// q, s, out are device pointers; qb_host / sb_host are host batch lengths. out is [nq, cap] (int32 or int64).
+// *hmax_host receives the true maximum neighbour count (may exceed cap: rows then hold their cap closest).
+int batch_query_device(const float* q, int nq, const float* s, int ns, const int* qb_host, const int* sb_host, int nb,
+                       float radius, void* out, int out_is_i64, int cap, int* hmax_host, cudaStream_t stream) {
+    if (nq < 0 || ns < 0 || nb <= 0 || cap < 0 || !(radius > 0.f)) return fail(KP_ERR_ARG, "batch_query: bad sizes / radius");
+    if (nb > 1023) return fail(KP_ERR_UNSUPPORTED, "batch_query: more than 1023 batch elements");
+    std::vector<int> qoff(nb + 1, 0), soff(nb + 1, 0);
+    for (int b = 0; b < nb; b++) {
+        if (qb_host[b] < 0 || sb_host[b] < 0) return fail(KP_ERR_ARG, "batch_query: negative batch length");
+        qoff[b + 1] = qoff[b] + qb_host[b];
+        soff[b + 1] = soff[b] + sb_host[b];
+    }
+    if (qoff[nb] != nq || soff[nb] != ns) return fail(KP_ERR_ARG, "batch_query: batch lengths do not sum to N");
+    *hmax_host = 0;
+    if (nq == 0) return KP_OK;
+
+    Scratch S(stream);
+    int* d_qoff = S.alloc<int>(nb + 1);
+    int* d_soff = S.alloc<int>(nb + 1);
+    unsigned* d_bbox = S.alloc<unsigned>((size_t)nb * 6);
+    GridPlan* d_plan = S.alloc<GridPlan>(1);
+    int tsize = 1024;
+    while (tsize < 2 * ns) tsize <<= 1;
+    unsigned long long* d_tkeys = S.alloc<unsigned long long>(tsize);
+    int* d_tcount = S.alloc<int>(tsize);
+    int* d_tstart = S.alloc<int>(tsize);
+    int* d_scan_tmp = S.alloc<int>(scan_tmp_ints(tsize));
+    int* d_sslot = S.alloc<int>(ns);
+    int* d_srank = S.alloc<int>(ns);
+    float4* d_sorted = S.alloc<float4>(ns);
+    int* d_hmax = S.alloc<int>(2);
+    if (S.status != KP_OK) return S.status;
+    int* d_err = d_hmax + 1;
+
+    KP_CUDA(cudaMemcpyAsync(d_qoff, qoff.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    KP_CUDA(cudaMemcpyAsync(d_soff, soff.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    KP_CUDA(cudaMemsetAsync(d_hmax, 0, 2 * sizeof(int), stream));
+
+    if (ns > 0) {
+        rs_bbox_init_kernel<<<ceil_div(nb * 6, 256), 256, 0, stream>>>(d_bbox, nb);
+        KP_CHECK_LAUNCH();
+        rs_bbox_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(s, ns, d_soff, nb, d_bbox);
+        KP_CHECK_LAUNCH();
+        rs_plan_kernel<<<1, 32, 0, stream>>>(d_bbox, nb, radius, d_plan, d_err);
+        KP_CHECK_LAUNCH();
+        rs_table_init_kernel<<<ceil_div(tsize, 256), 256, 0, stream>>>(d_tkeys, d_tcount, tsize);
+        KP_CHECK_LAUNCH();
+        rs_insert_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(s, ns, d_soff, nb, d_bbox, d_plan, d_tkeys, d_tcount,
+                                                              tsize - 1, d_sslot, d_srank);
+        KP_CHECK_LAUNCH();
+        int rc = exclusive_scan(d_tcount, d_tstart, tsize, nullptr, d_scan_tmp, stream);
+        if (rc != KP_OK) return rc;
+        rs_fill_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(s, ns, d_sslot, d_srank, d_tstart, d_sorted);
+        KP_CHECK_LAUNCH();
+    } else {
+        rs_table_init_kernel<<<ceil_div(tsize, 256), 256, 0, stream>>>(d_tkeys, d_tcount, tsize);
+        KP_CHECK_LAUNCH();
+        rs_bbox_init_kernel<<<ceil_div(nb * 6, 256), 256, 0, stream>>>(d_bbox, nb);
+        KP_CHECK_LAUNCH();
+        KP_CUDA(cudaMemsetAsync(d_plan, 0, sizeof(GridPlan), stream));
+    }
+
+    SearchParams P;
+    P.q = q; P.nq = nq; P.s = s; P.ns = ns; P.q_off = d_qoff; P.s_off = d_soff; P.nb = nb;
+    P.r2 = radius * radius;  // neighbors.cpp:226, f32
+    const int grid = ceil_div(nq, RS_WARPS_PER_CTA);
+    if (out_is_i64)
+        rs_search_kernel<long long><<<grid, RS_WARPS_PER_CTA * 32, 0, stream>>>(
+            P, d_bbox, d_plan, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (long long*)out, cap, d_hmax, d_err);
+    else
+        rs_search_kernel<int><<<grid, RS_WARPS_PER_CTA * 32, 0, stream>>>(
+            P, d_bbox, d_plan, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (int*)out, cap, d_hmax, d_err);
+    KP_CHECK_LAUNCH();
+
+    int h[2] = {0, 0};
+    KP_CUDA(cudaMemcpyAsync(h, d_hmax, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    KP_CUDA(cudaStreamSynchronize(stream));
+    if (h[1] & 1) return fail(KP_ERR_UNSUPPORTED, "batch_query: cloud extent / radius exceeds 2^18 cells per axis");
+    if (h[1] & 2) return fail(KP_ERR_TOO_DENSE, "batch_query: more than 1024 neighbours for one query");
+    *hmax_host = h[0];
+    return KP_OK;
+}
+
+}  // namespace kp

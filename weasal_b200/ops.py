@@ -1,0 +1,173 @@
+"""Torch-tensor front ends of the device C-ABI (``*_dev`` entry points of include/weasal_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; all arithmetic happens in the hand-written
+kernels of libweasal_b200.so. Tensors must live on a CUDA device; there is no CPU path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("weasal_b200: tensors must be CUDA tensors (there is no CPU fallback)")
+
+
+def _f32c(t):
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+def _lens(a):
+    if torch.is_tensor(a):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(a, dtype=np.int32).reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------------------ radius search
+def batch_query(queries, supports, q_batches, s_batches, radius, limit=None, dtype=torch.int64, cap_hint=96):
+    """GPU ``batch_neighbors`` (datasets/common.py:185-196) on device tensors.
+
+    Returns ``[Nq, min(Hmax, limit)]`` indices (``dtype`` int64 like the collated batch, or int32), sorted by
+    (d2, index), padded with ``Ns``. ``limit`` is the ``neighborhood_limits`` crop of common.py:336-346.
+    The result is a column-sliced view of the row buffer when Hmax < capacity (row stride != width).
+    """
+    _need_cuda(queries, supports)
+    q, s = _f32c(queries), _f32c(supports)
+    qb, sb = _lens(q_batches), _lens(s_batches)
+    nq, ns = q.shape[0], s.shape[0]
+    L = _lib.lib()
+    cap = int(limit) if limit is not None else int(cap_hint)
+    i64 = dtype == torch.int64
+    while True:
+        out = torch.empty((nq, max(cap, 1)), dtype=dtype, device=q.device)
+        hmax = C.c_int(0)
+        rc = L.kp_batch_query_dev(q.data_ptr(), nq, s.data_ptr(), ns, qb.ctypes.data, sb.ctypes.data, len(qb),
+                                  float(radius), out.data_ptr(), 1 if i64 else 0, cap, C.byref(hmax), _stream())
+        _lib.check(rc, "batch_query")
+        if limit is not None or hmax.value <= cap:
+            break
+        cap = hmax.value
+    width = hmax.value if limit is None else min(hmax.value, cap)
+    return out[:, :width]
+
+
+# -------------------------------------------------------------------------------------------------- grid subsampling
+def grid_subsample(points, batches, features=None, classes=None, sampleDl=0.1, max_p=0, order="reference", rot=None):
+    """GPU ``batch_grid_subsampling`` core (datasets/common.py:77-182 minus the numpy rotation, which ``rot`` folds
+    in). Returns (s_points, s_batches(np.int32)[, s_features][, s_classes]) as device tensors."""
+    _need_cuda(points, features, classes)
+    p = _f32c(points)
+    b = _lens(batches)
+    n = p.shape[0]
+    f = _f32c(features) if features is not None else None
+    c = classes.to(torch.int32).contiguous() if classes is not None else None
+    fdim = f.shape[1] if f is not None else 0
+    ldim = (c.shape[1] if c.dim() == 2 else 1) if c is not None else 0
+    op = torch.empty((max(n, 1), 3), dtype=torch.float32, device=p.device)
+    of = torch.empty((max(n, 1), fdim), dtype=torch.float32, device=p.device) if f is not None else None
+    oc = torch.empty((max(n, 1), ldim), dtype=torch.int32, device=p.device) if c is not None else None
+    ob = np.zeros(len(b), np.int32)
+    m = C.c_int(0)
+    r = np.ascontiguousarray(rot, np.float32) if rot is not None else None
+    rc = _lib.lib().kp_grid_subsample_dev(p.data_ptr(), n, b.ctypes.data, len(b), f.data_ptr() if f is not None else None,
+                                          fdim, c.data_ptr() if c is not None else None, ldim, float(sampleDl),
+                                          int(max_p), 1 if order == "reference" else 0,
+                                          r.ctypes.data if r is not None else None, op.data_ptr(), ob.ctypes.data,
+                                          of.data_ptr() if of is not None else None,
+                                          oc.data_ptr() if oc is not None else None, C.byref(m), _stream())
+    _lib.check(rc, "grid_subsample")
+    M = m.value
+    res = [op[:M], ob]
+    if f is not None:
+        res.append(of[:M])
+    if c is not None:
+        res.append(oc[:M])
+    return tuple(res)
+
+
+# ------------------------------------------------------------------------------------------------------------ KPConv
+def _idx_args(idx):
+    if idx.dtype not in (torch.int32, torch.int64):
+        idx = idx.long()
+    if idx.dim() != 2:
+        raise RuntimeError("neighb_inds must be [Nq, H]")
+    if idx.shape[1] > 0 and idx.stride(1) != 1:
+        idx = idx.contiguous()
+    stride = idx.stride(0) if idx.shape[0] > 1 else max(idx.shape[1], 1)
+    if stride < idx.shape[1]:
+        idx = idx.contiguous()
+        stride = idx.shape[1]
+    return idx, 1 if idx.dtype == torch.int64 else 0, idx.shape[1], stride
+
+
+def kpconv_impl():
+    return os.environ.get("WEASAL_KPCONV_IMPL", "tc")
+
+
+class KPConvFunction(torch.autograd.Function):
+    """Autograd node around kp_kpconv_forward_dev / kp_kpconv_backward_dev (gradients w.r.t. x and weights only,
+    like the reference: kernel_points has requires_grad=False and points carry no grad, blocks.py:235-236)."""
+
+    @staticmethod
+    def forward(ctx, q_pts, s_pts, neighb_inds, x, weights, kernel_points, KP_extent):
+        _need_cuda(q_pts, s_pts, neighb_inds, x, weights, kernel_points)
+        q, s, xx, w, kp = _f32c(q_pts), _f32c(s_pts), _f32c(x), _f32c(weights), _f32c(kernel_points)
+        idx, i64, H, stride = _idx_args(neighb_inds)
+        K, cin, cout = w.shape
+        nq, ns = q.shape[0], s.shape[0]
+        L = _lib.lib()
+        if kpconv_impl() == "simt":  # fp32 cross-check path (CUDA-core gather + library GEMM), not the product path
+            wf = torch.empty((nq, K * cin), dtype=torch.float32, device=q.device)
+            _lib.check(L.kp_kpconv_wf_dev(q.data_ptr(), nq, s.data_ptr(), ns, idx.data_ptr(), i64, H, stride,
+                                          xx.data_ptr(), cin, kp.data_ptr(), K, float(KP_extent), wf.data_ptr(),
+                                          _stream()), "kpconv_wf")
+            out = wf @ w.reshape(K * cin, cout)
+        else:
+            out = torch.empty((nq, cout), dtype=torch.float32, device=q.device)
+            _lib.check(L.kp_kpconv_forward_dev(q.data_ptr(), nq, s.data_ptr(), ns, idx.data_ptr(), i64, H, stride,
+                                               xx.data_ptr(), cin, w.data_ptr(), cout, kp.data_ptr(), K,
+                                               float(KP_extent), out.data_ptr(), _stream()), "kpconv_forward")
+        ctx.save_for_backward(q, s, idx, xx, w, kp)
+        ctx.meta = (i64, H, stride, float(KP_extent))
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        q, s, idx, xx, w, kp = ctx.saved_tensors
+        i64, H, stride, ext = ctx.meta
+        K, cin, cout = w.shape
+        nq, ns = q.shape[0], s.shape[0]
+        do = _f32c(d_out)
+        L = _lib.lib()
+        if kpconv_impl() == "simt":
+            wf = torch.empty((nq, K * cin), dtype=torch.float32, device=q.device)
+            _lib.check(L.kp_kpconv_wf_dev(q.data_ptr(), nq, s.data_ptr(), ns, idx.data_ptr(), i64, H, stride,
+                                          xx.data_ptr(), cin, kp.data_ptr(), K, ext, wf.data_ptr(), _stream()),
+                       "kpconv_wf")
+            dw = (wf.t() @ do).reshape(K, cin, cout)
+            dwf = (do @ w.reshape(K * cin, cout).t()).contiguous()
+            dx = torch.zeros((ns, cin), dtype=torch.float32, device=q.device)
+            _lib.check(L.kp_kpconv_dx_atomic_dev(q.data_ptr(), nq, s.data_ptr(), ns, idx.data_ptr(), i64, H, stride,
+                                                 dwf.data_ptr(), cin, kp.data_ptr(), K, ext, dx.data_ptr(), _stream()),
+                       "kpconv_dx")
+        else:
+            dx = torch.empty((ns, cin), dtype=torch.float32, device=q.device)
+            dw = torch.empty((K, cin, cout), dtype=torch.float32, device=q.device)
+            _lib.check(L.kp_kpconv_backward_dev(q.data_ptr(), nq, s.data_ptr(), ns, idx.data_ptr(), i64, H, stride,
+                                                xx.data_ptr(), cin, w.data_ptr(), cout, kp.data_ptr(), K, ext,
+                                                do.data_ptr(), dx.data_ptr(), dw.data_ptr(), _stream()),
+                       "kpconv_backward")
+        return None, None, None, dx, dw, None, None
+
+
+def kpconv(q_pts, s_pts, neighb_inds, x, weights, kernel_points, KP_extent):
+    return KPConvFunction.apply(q_pts, s_pts, neighb_inds, x, weights, kernel_points, KP_extent)
