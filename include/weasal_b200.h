@@ -38,6 +38,11 @@ int kp_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 long long kp_launch_count(void);
 void kp_free_host(void* p);
+/* Per-kernel timing for bench.py's roofline leg: while enabled, the library brackets its main kernels with CUDA
+ * events on the launching stream. kp_profile_read synchronises those events, writes "tag launches total_ms" lines
+ * into buf (returns the length, -1 if buf is too small) and clears the records. */
+void kp_profile_enable(int on);
+int kp_profile_read(char* buf, int buflen);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Batch radius search.
@@ -90,8 +95,8 @@ int kp_grid_subsample_dev(const float* points, int n, const int* batches, int nb
  *           that expression (gradients w.r.t. x and weights only; blocks.py:235-236).
  *   q_pts [nq,3] f32, s_pts [ns,3] f32, neighb_inds [nq,H] int32/int64 with row stride idx_stride (elements),
  *   shadow index == ns, x [ns,cin] f32, weights [K,cin,cout] f32, kernel_points [K,3] f32, out [nq,cout] f32.
- * All pointers are device pointers. precision: 0 = TF32 tensor-core contraction with fp32 accumulation (inputs
- * rounded to nearest TF32), 1 = fp32 CUDA-core cross-check path (slow; needs the `work` buffer, see below).
+ * All pointers are device pointers. The second contraction runs on tcgen05 tensor cores with TF32 operands
+ * (rounded to nearest) and fp32 accumulation; the kernel-point-weighted gather is exact fp32.
  */
 int kp_kpconv_forward_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
                           int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,

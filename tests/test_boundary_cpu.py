@@ -1,0 +1,218 @@
+"""CPU tests of the boundary and the host logic: the C-ABI library loads and exports every symbol
+include/weasal_b200.h declares (no compute without a GPU), the numpy shims validate arguments like the reference's
+wrappers, the KPConv module keeps the reference's parameter contract, the torch restatement of the reference
+operator is pinned to the reference's own outputs, and the data-parallel / sharded-voting plumbing works at
+world_size 2 over gloo."""
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import GOLDEN, ROOT, load_case
+
+
+def test_library_exports_every_declared_symbol():
+    from weasal_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "weasal_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(kp_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 12
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), f"libweasal_b200.so does not export {name}"
+    assert sorted(set(_lib.SYMBOLS)) == sorted(s for s in declared if s in _lib.SYMBOLS)
+    assert L.kp_version() >= 100
+    assert _lib.launch_count() >= 0
+
+
+def test_no_cpu_fallback_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from weasal_b200 import grid_subsampling as gs, ops, radius_neighbors as rn
+    p = np.random.default_rng(0).uniform(0, 1, (10, 3)).astype(np.float32)
+    with pytest.raises(RuntimeError, match="status -1"):
+        rn.batch_query(p, p, [10], [10], radius=0.5)
+    with pytest.raises(RuntimeError, match="status -1"):
+        gs.subsample(p, sampleDl=0.5)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.batch_query(torch.from_numpy(p), torch.from_numpy(p), [10], [10], 0.5)
+
+
+def test_shims_validate_like_the_reference_wrappers():
+    from weasal_b200 import grid_subsampling as gs, radius_neighbors as rn
+    p = np.zeros((5, 3), np.float32)
+    with pytest.raises(RuntimeError, match=r"query.shape is not \(N, 3\)"):
+        rn.batch_query(np.zeros((5, 2), np.float32), p, [5], [5], radius=1.0)
+    with pytest.raises(RuntimeError, match=r"support.shape is not \(N, 3\)"):
+        rn.batch_query(p, np.zeros((5,), np.float32), [5], [5], radius=1.0)
+    with pytest.raises(RuntimeError, match="Wrong number of batch elements"):
+        rn.batch_query(p, p, [5], [2, 3], radius=1.0)
+    with pytest.raises(TypeError):
+        rn.batch_query(p, p, [5], [5], 1.0)  # radius is keyword-only (format "OOOO|$f", wrapper.cpp:75)
+    with pytest.raises(RuntimeError, match=r"points.shape is not \(N, 3\)"):
+        gs.subsample(np.zeros((5, 4), np.float32), sampleDl=0.1)
+    with pytest.raises(RuntimeError, match=r"features.shape is not \(N, d\)"):
+        gs.subsample(p, features=np.zeros((4, 2), np.float32), sampleDl=0.1)
+    with pytest.raises(RuntimeError, match=r"classes.shape is not \(N,\) or \(N, d\)"):
+        gs.subsample_batch(p, [5], classes=np.zeros((3,), np.int32), sampleDl=0.1)
+    with pytest.raises(RuntimeError, match="Error parsing method"):
+        gs.subsample(p, sampleDl=0.1, method="nope")
+
+
+def test_kpconv_module_contract():
+    from weasal_b200.blocks import KPConv
+    np.random.seed(0)
+    torch.manual_seed(0)
+    m = KPConv(15, 3, 16, 32, 0.24, 0.6)
+    sd = m.state_dict()
+    assert list(sd.keys()) == ["weights", "kernel_points"]
+    assert sd["weights"].shape == (15, 16, 32) and sd["kernel_points"].shape == (15, 3)
+    assert m.weights.requires_grad and not m.kernel_points.requires_grad
+    assert (m.K, m.p_dim, m.in_channels, m.out_channels, m.radius, m.KP_extent) == (15, 3, 16, 32, 0.6, 0.24)
+    assert m.deformable is False and m.min_d2 is None and m.deformed_KP is None and m.offset_features is None
+    assert repr(m) == "KPConv(radius: 0.60, in_feat: 16, out_feat: 32)"
+    # same initialisation call as blocks.py:217-218 => same bound: U(-b, b), b = 1/sqrt(fan_in), fan_in = Cin*Cout
+    assert float(m.weights.abs().max()) <= 1.0 / np.sqrt(16 * 32) + 1e-7
+    kn = np.linalg.norm(m.kernel_points.numpy(), axis=1)
+    assert kn[0] < 0.05 * 0.6 and (kn[1:] > 0.5 * 0.6).all() and (kn[1:] < 0.8 * 0.6).all()
+    for bad in (dict(deformable=True), dict(KP_influence="gaussian"), dict(aggregation_mode="closest")):
+        with pytest.raises(NotImplementedError):
+            KPConv(15, 3, 16, 32, 0.24, 0.6, **bad)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(4, 3), torch.zeros(4, 3), torch.zeros(4, 2, dtype=torch.long), torch.zeros(4, 16))
+
+
+@pytest.mark.parametrize("name", ["c4_32", "c16_16", "c64_64", "strided16"])
+def test_torch_restatement_of_reference_operator(name):
+    from oracle.kpconv_torch import kpconv_reference_ops
+    a = load_case(np.load(os.path.join(GOLDEN, "kpconv_ref.npz")), name)
+    x = torch.from_numpy(a["x"]).requires_grad_(True)
+    w = torch.from_numpy(a["weights"]).requires_grad_(True)
+    out = kpconv_reference_ops(torch.from_numpy(a["q_pts"]), torch.from_numpy(a["s_pts"]),
+                               torch.from_numpy(a["idx"].astype(np.int64)), x, w,
+                               torch.from_numpy(a["kernel_points"]), float(a["extent"]))
+    out.backward(torch.from_numpy(a["d_out"]))
+    assert np.allclose(out.detach().numpy(), a["out"], rtol=0, atol=2e-6 * np.abs(a["out"]).max())
+    assert np.allclose(x.grad.numpy(), a["dx"], rtol=0, atol=2e-6 * np.abs(a["dx"]).max())
+    assert np.allclose(w.grad.numpy(), a["dw"], rtol=0, atol=2e-6 * np.abs(a["dw"]).max())
+
+
+def test_cpu_pyramid_restatement_matches_reference_golden():
+    from oracle.pyramid_ref import segmentation_inputs_cpu
+    g = np.load(os.path.join(GOLDEN, "pyramid_ref.npz"))
+
+    class Cfg:
+        first_subsampling_dl = 0.24
+        conv_radius = 2.5
+        deform_radius = 6.0
+        architecture = ['simple', 'resnetb', 'resnetb_strided', 'resnetb', 'resnetb_strided', 'resnetb',
+                        'resnetb_strided', 'resnetb', 'nearest_upsample', 'unary', 'nearest_upsample', 'unary',
+                        'nearest_upsample', 'unary']
+
+    np.random.seed(int(g["seed"]))
+    li = segmentation_inputs_cpu(g["in_pts"], None, None, g["in_lens"], Cfg(), neighborhood_limits=list(g["limits"]),
+                                 use_ref=oracle.ref_available())
+    L = int(g["L"])
+    for l in range(L):
+        assert np.array_equal(li[l], g[f"points{l}"])  # includes the grid rotations drawn from np.random
+        for off, nm in ((L, "neighbors"), (2 * L, "pools"), (3 * L, "upsamples")):
+            ref = g[f"{nm}{l}"]
+            assert li[off + l].shape == ref.shape
+            if oracle.ref_available():
+                assert np.array_equal(li[off + l], ref)
+            elif ref.size:
+                assert np.array_equal(np.sort(li[off + l], 1), np.sort(ref, 1))
+
+
+def test_harness_network_shapes_match_reference_architecture():
+    """Feature widths of the KPFCNN harness = the table derived from architectures.py:214-251."""
+    from oracle.kpconv_torch import KPConvTorch
+    from weasal_b200.net import KPFCNNHarness, net_config
+    np.random.seed(0)
+    net = KPFCNNHarness(net_config("vaihingen_pl"), KPConvTorch)
+    convs = [(b.conv.in_channels, b.conv.out_channels, b.layer, b.strided) for b in net.encoder]
+    assert convs == [(4, 32, 0, False), (16, 16, 0, False), (16, 16, 0, True), (32, 32, 1, False), (32, 32, 1, True),
+                     (64, 64, 2, False), (64, 64, 2, True), (128, 128, 3, False), (128, 128, 3, True),
+                     (256, 256, 4, False)]
+    unary_in = [m.mlp.in_features for m in net.decoder if hasattr(m, "mlp")]
+    assert unary_in == [1536, 768, 384, 192]
+    n_params = sum(p.numel() for p in net.parameters() if p.requires_grad)
+    assert 3.9e6 < n_params < 4.3e6  # the reference's KPFCNN has 4.10 M parameters
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _ddp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from weasal_b200.distributed import GradAllReducer, VoteAccumulator, shard_indices
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(6, 3)
+    unused = torch.nn.Parameter(torch.zeros(5))  # a parameter that never gets a gradient (BatchNorm quirk)
+    params = list(lin.parameters()) + [unused]
+    red = GradAllReducer(params)
+    x = torch.full((4, 6), float(rank + 1))
+    lin(x).sum().backward()
+    local = [p.grad.clone() for p in lin.parameters()]
+    red.step()
+    acc = VoteAccumulator(10, 3, "cpu")
+    mine = shard_indices(7, rank, world)
+    for s in mine:
+        acc.add(torch.tensor([s, (s + 1) % 10]), torch.full((2, 3), float(s)), w=1.0)
+    probs = acc.reduce()
+    q.put((rank, [g.numpy() for g in local], [p.grad.numpy() for p in lin.parameters()], unused.grad is None, mine,
+           probs.numpy()))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_and_vote_sharding_world_size_2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, l0, a0, u0, m0, p0), (_, l1, a1, u1, m1, p1) = res
+    for g0, g1, r0, r1 in zip(l0, l1, a0, a1):
+        assert np.allclose(r0, (g0 + g1) / 2) and np.allclose(r1, r0)  # averaged, identical on both ranks
+    assert u0 and u1  # the gradient-less parameter stays grad=None
+    assert m0 == [0, 2, 4, 6] and m1 == [1, 3, 5]
+    assert np.array_equal(p0, p1)
+    want = np.zeros((10, 3)); wsum = np.zeros(10)
+    for s in range(7):
+        for i in (s, (s + 1) % 10):
+            want[i] += s; wsum[i] += 1
+    assert np.allclose(p0, want / np.maximum(wsum, 1e-12)[:, None])
+
+
+def test_random_grid_rotations_replay_numpy_stream():
+    from weasal_b200.pyramid import axis_angle_rotations, random_grid_rotations
+    np.random.seed(3)
+    R = random_grid_rotations(4)
+    assert R.dtype == np.float32 and R.shape == (4, 3, 3)
+    for r in R:
+        assert np.allclose(r @ r.T, np.eye(3), atol=1e-6) and abs(np.linalg.det(r) - 1) < 1e-5
+    np.random.seed(3)
+    theta = np.random.rand(4) * 2 * np.pi
+    phi = (np.random.rand(4) - 0.5) * np.pi
+    alpha = np.random.rand(4) * 2 * np.pi
+    u = np.stack([np.cos(theta) * np.cos(phi), np.sin(theta) * np.cos(phi), np.sin(phi)], 1)
+    assert np.array_equal(R, axis_angle_rotations(u, alpha).astype(np.float32))
+    v = np.array([[0.0, 0.0, 1.0]])
+    Rz = axis_angle_rotations(v, np.array([np.pi / 2]))[0]
+    assert np.allclose(Rz @ np.array([1.0, 0, 0]), [0, 1, 0], atol=1e-12)

@@ -24,6 +24,7 @@ int kpconv_forward_device(const float* q, int nq, const float* s, int ns, const 
 int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
                            int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
                            float extent, const float* dout, float* dx, float* dw, cudaStream_t stream);
+int profile_read(char* buf, int buflen);
 }  // namespace kp
 
 using namespace kp;
@@ -45,6 +46,8 @@ const char* kp_last_error(void) { return g_last_error.c_str(); }
 int kp_version(void) { return 100; }
 long long kp_launch_count(void) { return g_launch_count.load(); }
 void kp_free_host(void* p) { free(p); }
+void kp_profile_enable(int on) { g_profile_on = on != 0; }
+int kp_profile_read(char* buf, int buflen) { return profile_read(buf, buflen); }
 
 int kp_batch_query_dev(const float* queries, int nq, const float* supports, int ns, const int* q_batches,
                        const int* s_batches, int nb, float radius, void* out, int out_is_i64, int cap, int* hmax,

@@ -35,6 +35,21 @@ extern std::atomic<long long> g_launch_count;
         KP_CUDA(cudaGetLastError());          \
     } while (0)
 
+// ---- optional per-kernel timing (bench.py's roofline leg): CUDA events recorded on the launching stream ---------------
+extern bool g_profile_on;
+void profile_push(const char* tag, cudaEvent_t a, cudaEvent_t b);
+struct ProfileScope {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t s;
+    const char* tag;
+    ProfileScope(const char* t, cudaStream_t st) : s(st), tag(t) {
+        if (g_profile_on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+    }
+    ~ProfileScope() {
+        if (a) { cudaEventRecord(b, s); profile_push(tag, a, b); }
+    }
+};
+
 // ---- stream-ordered scratch memory --------------------------------------------------------------------------------
 // Temporaries come from the device's default stream-ordered pool (cudaMallocAsync); the pool's release threshold
 // is raised once so that steady-state calls never hit the OS allocator.

@@ -463,6 +463,7 @@ int grid_subsample_device(const float* pts, int n, const int* lens_host, int nb,
     P.inv_dl = 1.0f / dl;  // grid_subsampling.cpp:27: `1/sampleDl` is an f32 division
     const int nblk = ceil_div(n, 256);
 
+    ProfileScope* ps = new ProfileScope("gs_hash", stream);
     gs_bbox_init_kernel<<<ceil_div(nb * 6, 256), 256, 0, stream>>>(d_bbox, nb);
     KP_CHECK_LAUNCH();
     gs_bbox_kernel<<<nblk, 256, 0, stream>>>(P, d_bbox);
@@ -480,6 +481,7 @@ int grid_subsample_device(const float* pts, int n, const int* lens_host, int nb,
                                                                              d_seq_start);
     KP_CHECK_LAUNCH();
 
+    delete ps;
     int* d_pos_local = nullptr;
     if (order_mode == 1) {
         Sched sched = make_schedule(n);
@@ -497,10 +499,12 @@ int grid_subsample_device(const float* pts, int n, const int* lens_host, int nb,
         d_pos_local = S.alloc<int>(n);
         if (S.status != KP_OK) return S.status;
         KP_CUDA(cudaMemcpyAsync(d_soff, soff.data(), nb * sizeof(long long), cudaMemcpyHostToDevice, stream));
+        ProfileScope pso("gs_order", stream);
         gs_order_kernel<<<nb, ORD_THREADS, 0, stream>>>(d_seq_key, d_seq_start, sched, d_scratch, d_soff, d_offs,
                                                        d_pos_local);
         KP_CHECK_LAUNCH();
     }
+    ProfileScope* ps3 = new ProfileScope("gs_sort", stream);
     const int invalid = n;  // sort key of points whose voxel was truncated by max_p
     gs_outpos_kernel<<<ceil_div(n > nb ? n : nb + 1, 256), 256, 0, stream>>>(nb, d_seq_start, d_seq_slot, d_pos_local,
                                                                            max_p, d_slot_outpos, d_out_lens, invalid);
@@ -511,6 +515,7 @@ int grid_subsample_device(const float* pts, int n, const int* lens_host, int nb,
                            d_sort_tmp, stream);
     if (rc != KP_OK) return rc;
     gs_segment_kernel<<<nblk, 256, 0, stream>>>(n, d_skey2, invalid, d_seg_start);
+    delete ps3;
     KP_CHECK_LAUNCH();
 
     // the voxel count decides the reduce grid: the one host sync of this call
@@ -523,6 +528,7 @@ int grid_subsample_device(const float* pts, int n, const int* lens_host, int nb,
     const int m_total = h_lens[nb];
     Sched lsched = make_schedule(MAX_LABELS + 1);
     if (m_total > 0) {
+        ProfileScope psr("gs_reduce", stream);
         gs_reduce_kernel<<<ceil_div(m_total, 128), 128, 0, stream>>>(P, m_total, d_skey2, d_sval2, d_seg_start, feats,
                                                                     fdim, classes, ldim, lsched, out_pts, out_feats,
                                                                     out_classes, d_err);

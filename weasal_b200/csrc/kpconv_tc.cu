@@ -629,6 +629,7 @@ static int build_lists(Scratch& S, const float* centres, int nc, const float* ot
     unsigned long long* counter = S.alloc<unsigned long long>(1);
     if (S.status != KP_OK) return S.status;
     KP_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+    ProfileScope ps("kp_influence", stream);
     kp_influence_kernel<<<ceil_div(nc, 4), 128, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, 1.f / extent,
                                                             L->ebase, L->koff, L->entries, cap, counter, d_err);
     KP_CHECK_LAUNCH();
@@ -638,7 +639,7 @@ static int build_lists(Scratch& S, const float* centres, int nc, const float* ot
 static int pad4(int c) { return (c + 3) & ~3; }
 
 // out[nc, cout] = sum over entry lists of w * x[j, :] contracted with W (strides sk, sc, sn over (k, c_in, n_out))
-static int run_forward(Scratch& S, int nc, const float* x, int n_x_rows, int cin, const Lists& L, const float* W,
+static int run_forward(const char* tag, Scratch& S, int nc, const float* x, int n_x_rows, int cin, const Lists& L, const float* W,
                        long long sk, long long sc, long long sn, int cout, int K, float* out, cudaStream_t stream) {
     const int cin_p = pad4(cin);
     const float* xg = x;
@@ -660,6 +661,7 @@ static int run_forward(Scratch& S, int nc, const float* x, int n_x_rows, int cin
     {
         const long long total = (long long)n_chunks * n_nblk * NB * CK;
         const int grid = ceil_div(total, 256) < 4096 ? ceil_div(total, 256) : 4096;
+        ProfileScope ps("kp_pack_w", stream);
         kp_pack_w_kernel<<<grid, 256, 0, stream>>>(W, K, cin, cin_p, cout, sk, sc, sn, NB, n_nblk, n_chunks, images);
         KP_CHECK_LAUNCH();
     }
@@ -673,7 +675,10 @@ static int run_forward(Scratch& S, int nc, const float* x, int n_x_rows, int cin
     P.tmem_cols = cols;
     const size_t smem = (size_t)A_BYTES + (size_t)NB * CK * 4 + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
     KP_CUDA(cudaFuncSetAttribute(kp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kp_fwd_kernel<<<ceil_div(nc, TILE_M), FWD_THREADS, smem, stream>>>(P);
+    {
+        ProfileScope ps(tag, stream);
+        kp_fwd_kernel<<<ceil_div(nc, TILE_M), FWD_THREADS, smem, stream>>>(P);
+    }
     KP_CHECK_LAUNCH();
     return KP_OK;
 }
@@ -718,7 +723,7 @@ int kpconv_forward_device(const float* q, int nq, const float* s, int ns, const 
     const long long n_pairs = (long long)nq * H;
     rc = build_lists(S, q, nq, s, ns, T, n_pairs, kp, K, 1.f, extent, d_err, &L, stream);
     if (rc != KP_OK) return rc;
-    rc = run_forward(S, nq, x, ns, cin, L, w, (long long)cin * cout, cout, 1, cout, K, out, stream);
+    rc = run_forward("kp_fwd", S, nq, x, ns, cin, L, w, (long long)cin * cout, cout, 1, cout, K, out, stream);
     if (rc != KP_OK) return rc;
     return check_err_flag(d_err, stream, entry_capacity(n_pairs) < n_pairs * 15);
 }
@@ -773,7 +778,10 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
         P.tmem_cols = cols;
         const size_t smem = (size_t)A_BYTES + (size_t)(P.NB / 4) * DW_B_SBO + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
         KP_CUDA(cudaFuncSetAttribute(kp_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kp_dw_kernel<<<dim3(n_chunks, splits, n_slices), FWD_THREADS, smem, stream>>>(P);
+        {
+            ProfileScope ps("kp_dw", stream);
+            kp_dw_kernel<<<dim3(n_chunks, splits, n_slices), FWD_THREADS, smem, stream>>>(P);
+        }
         KP_CHECK_LAUNCH();
     }
 
@@ -789,6 +797,7 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
         KP_CUDA(cudaMemsetAsync(deg, 0, (size_t)(ns + 1) * sizeof(int), stream));
         KP_CUDA(cudaMemsetAsync(cursor, 0, (size_t)ns * sizeof(int), stream));
         const int grid = ceil_div(n_pairs, 256);
+        ProfileScope* pst = new ProfileScope("kp_transpose", stream);
         if (idx_is_i64) kp_tr_count_kernel<long long><<<grid, 256, 0, stream>>>((const long long*)idx, nq, H, idx_stride, ns, deg);
         else kp_tr_count_kernel<int><<<grid, 256, 0, stream>>>((const int*)idx, nq, H, idx_stride, ns, deg);
         KP_CHECK_LAUNCH();
@@ -800,6 +809,7 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
         else kp_tr_fill_kernel<int><<<grid, 256, 0, stream>>>((const int*)idx, nq, H, idx_stride, ns, rowptr, cursor, col);
         KP_CHECK_LAUNCH();
         kp_tr_sort_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(rowptr, ns, col);
+        delete pst;
         KP_CHECK_LAUNCH();
         Table T;
         T.idx = col; T.rowptr = rowptr; T.H = 0; T.stride = 0; T.is_i64 = 0;
@@ -807,7 +817,7 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
         rc = build_lists(S, s, ns, q, nq, T, n_pairs, kp, K, -1.f, extent, d_err, &L, stream);
         if (rc != KP_OK) return rc;
         // W'[k][c' = o][n' = c] = W[k][c][o]
-        rc = run_forward(S, ns, dout, nq, cout, L, w, (long long)cin * cout, 1, cout, cin, K, dx, stream);
+        rc = run_forward("kp_fwd_dx", S, ns, dout, nq, cout, L, w, (long long)cin * cout, 1, cout, cin, K, dx, stream);
         if (rc != KP_OK) return rc;
     }
     return check_err_flag(d_err, stream, entry_capacity(n_pairs) < n_pairs * 15);

@@ -4,10 +4,49 @@
 // ranked scatter per 8-bit digit.
 #include "common.cuh"
 
+#include <map>
+#include <mutex>
+#include <vector>
+
 namespace kp {
 
 thread_local std::string g_last_error;
 std::atomic<long long> g_launch_count{0};
+bool g_profile_on = false;
+namespace {
+struct ProfRec { std::string tag; cudaEvent_t a, b; };
+std::vector<ProfRec> g_prof;
+std::mutex g_prof_mu;
+}  // namespace
+void profile_push(const char* tag, cudaEvent_t a, cudaEvent_t b) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back({tag, a, b});
+}
+// "tag count total_ms" lines; drains the record list
+int profile_read(char* buf, int buflen) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::map<std::string, std::pair<long long, double>> acc;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        cudaEventSynchronize(r.b);
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+        auto& e = acc[r.tag];
+        e.first++;
+        e.second += ms;
+    }
+    g_prof.clear();
+    std::string out;
+    for (auto& kv : acc) {
+        char line[160];
+        snprintf(line, sizeof line, "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if ((int)out.size() + 1 > buflen) return -1;
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return (int)out.size();
+}
 
 int pool_init_once() {
     static thread_local int done_dev = -1;

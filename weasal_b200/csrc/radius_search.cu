@@ -270,6 +270,7 @@ int batch_query_device(const float* q, int nq, const float* s, int ns, const int
     KP_CUDA(cudaMemcpyAsync(d_soff, soff.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
     KP_CUDA(cudaMemsetAsync(d_hmax, 0, 2 * sizeof(int), stream));
 
+    ProfileScope* ps = new ProfileScope("rs_build", stream);
     if (ns > 0) {
         rs_bbox_init_kernel<<<ceil_div(nb * 6, 256), 256, 0, stream>>>(d_bbox, nb);
         KP_CHECK_LAUNCH();
@@ -294,16 +295,19 @@ int batch_query_device(const float* q, int nq, const float* s, int ns, const int
         KP_CUDA(cudaMemsetAsync(d_plan, 0, sizeof(GridPlan), stream));
     }
 
+    delete ps;
     SearchParams P;
     P.q = q; P.nq = nq; P.s = s; P.ns = ns; P.q_off = d_qoff; P.s_off = d_soff; P.nb = nb;
     P.r2 = radius * radius;  // neighbors.cpp:226, f32
     const int grid = ceil_div(nq, RS_WARPS_PER_CTA);
+    ProfileScope* ps2 = new ProfileScope("rs_search", stream);
     if (out_is_i64)
         rs_search_kernel<long long><<<grid, RS_WARPS_PER_CTA * 32, 0, stream>>>(
             P, d_bbox, d_plan, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (long long*)out, cap, d_hmax, d_err);
     else
         rs_search_kernel<int><<<grid, RS_WARPS_PER_CTA * 32, 0, stream>>>(
             P, d_bbox, d_plan, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (int*)out, cap, d_hmax, d_err);
+    delete ps2;
     KP_CHECK_LAUNCH();
 
     int h[2] = {0, 0};
