@@ -19,23 +19,30 @@ def section(name):
 
 def main():
     import torch
-    print(torch.cuda.get_device_name(0), torch.version.cuda)
+    stages = sys.argv[1:] or ["pre", "simt", "tc", "timing"]
+    print(torch.cuda.get_device_name(0), torch.version.cuda, stages)
     from weasal_b200 import grid_subsampling as gs, ops, radius_neighbors as rn
 
     b = make_batch("vaihingen_pl", seed=0, batch_num=2, in_radius=6.0)
     P, L = b["points"], b["lengths"]
     section("radius search")
     try:
+        if "pre" not in stages:
+            raise KeyboardInterrupt
         want = oracle.batch_neighbors(P, P, L, L, 0.6)
         got = rn.batch_query(P, P, L, L, radius=0.6)
         print("shape", got.shape, want.shape, "equal", np.array_equal(got, want))
         if got.shape == want.shape and not np.array_equal(got, want):
             bad = np.nonzero((got != want).any(1))[0]
             print("bad rows", len(bad), bad[:5], got[bad[0]], want[bad[0]])
+    except KeyboardInterrupt:
+        pass
     except Exception:
         traceback.print_exc()
     section("grid subsample")
     try:
+        if "pre" not in stages:
+            raise KeyboardInterrupt
         for order in ("first", "reference"):
             wp, wl = oracle.grid_subsample_batch(P, L, sampleDl=0.48, order=order)
             gp, gl = gs.subsample_batch(P, L, sampleDl=0.48, order=order)
@@ -43,11 +50,13 @@ def main():
             if gp.shape == wp.shape and not np.array_equal(gp, wp):
                 same_set = np.array_equal(gp[np.lexsort(gp.T)], wp[np.lexsort(wp.T)])
                 print("   same set:", same_set, "first diff row", np.nonzero((gp != wp).any(1))[0][:5])
+    except KeyboardInterrupt:
+        pass
     except Exception:
         traceback.print_exc()
     section("kpconv")
     g = np.load(os.path.join(ROOT, "tests", "golden", "kpconv_ref.npz"))
-    for impl in ("simt", "tc"):
+    for impl in [s for s in ("simt", "tc") if s in stages]:
         os.environ["WEASAL_KPCONV_IMPL"] = impl
         for name in ["c4_32", "c16_16", "c64_64", "c32_128", "c3_64", "strided16"]:
             try:
@@ -70,6 +79,8 @@ def main():
     os.environ.pop("WEASAL_KPCONV_IMPL", None)
     section("timing (VPL batch)")
     try:
+        if "timing" not in stages:
+            return
         bb = make_batch("vaihingen_pl", seed=0)
         dP = torch.from_numpy(bb["points"]).cuda(); LL = bb["lengths"]
         for _ in range(3):
@@ -88,7 +99,7 @@ def main():
             x = torch.randn(len(dP), cin, device="cuda", requires_grad=True)
             w = torch.randn(15, cin, cout, device="cuda", requires_grad=True)
             kp = torch.randn(15, 3, device="cuda") * 0.25
-            for impl in ("simt", "tc"):
+            for impl in [s for s in ("simt", "tc") if s in stages]:
                 os.environ["WEASAL_KPCONV_IMPL"] = impl
                 for _ in range(3):
                     y = ops.kpconv(dP, dP, nb, x, w, kp, 0.24)

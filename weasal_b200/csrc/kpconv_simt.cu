@@ -71,15 +71,17 @@ __global__ void __launch_bounds__(128) kpconv_dx_atomic_kernel(const float* __re
             const float w = (lane < K) ? influence(rx, ry, rz, kx, ky, kz, inv_ext) : 0.f;
             const unsigned m0 = __ballot_sync(0xffffffffu, w > 0.f);
             if (!m0) continue;
-            for (int c = lane; c < cin; c += 32) {
+            for (int c0 = 0; c0 < cin; c0 += 32) {  // warp-uniform trip count: the shuffles below need all lanes
+                const int c = c0 + lane;
                 float v = 0.f;
                 unsigned m = m0;
                 while (m) {
                     const int k = __ffs(m) - 1;
                     m &= m - 1;
-                    v += __shfl_sync(0xffffffffu, w, k) * dwf[((size_t)i * K + k) * cin + c];
+                    const float wk = __shfl_sync(0xffffffffu, w, k);
+                    if (c < cin) v += wk * dwf[((size_t)i * K + k) * cin + c];
                 }
-                atomicAdd(&dx[(size_t)j * cin + c], v);
+                if (c < cin) atomicAdd(&dx[(size_t)j * cin + c], v);
             }
         }
     }

@@ -125,10 +125,11 @@ __device__ __forceinline__ float to_tf32(float f) {  // round to nearest, ties a
 
 // shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor, version 1):
 // [0,14) start>>4, [16,30) leading (K-direction) byte offset>>4, [32,46) stride (M/N-direction) byte offset>>4
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo, uint32_t layout_type = 0) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
-           (1ull << 46);
+           (1ull << 46) | ((uint64_t)layout_type << 61);
 }
+constexpr uint32_t LAYOUT_SW128_BASE32B = 1;  // cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -268,7 +269,24 @@ __global__ void __launch_bounds__(256) kp_pad_cols_kernel(const float* __restric
 // Warp `warp` owns tile rows [warp*16, warp*16+16). For chunk `chunk` it zeroes them, walks the entry lists of its 16
 // points restricted to the chunk's kernel points, gathers float4 feature rows (U loads in flight per lane) and
 // accumulates w * x into the rows, then rounds the rows to TF32.
-template <int U>
+// Where the 16 bytes (4 consecutive reduction columns 4*lane..4*lane+3) of tile row p live in shared memory.
+struct LayoutKMajor {  // forward: UMMA K-major, no swizzle (see A_SBO / A_LBO above)
+    static __device__ __forceinline__ int off(int p, int lane) { return lane * A_LBO + (p >> 3) * A_SBO + (p & 7) * 16; }
+};
+// dW: the same tile consumed MN-major (M = reduction column, K = point). For 32-bit operands the only MN-major shared
+// memory layout the tensor core accepts is SWIZZLE_128B_BASE32B (cute::UMMA::Layout_MN_SW128_32B_Atom): rows of 32
+// elements (128 B) along M, 4 consecutive K values = 4 consecutive rows (512 B atom), byte-address bits [5,7) XORed
+// with bits [7,9). Element (m, k) at
+//   (m/32)*MN_LBO + (k/4)*MN_SBO + (k%4)*128 + ((((m%32)/8) ^ (k%4))*32) + (m%8)*4
+constexpr int MN_SBO = 512;                     // next group of 4 K values (points)
+constexpr int MN_LBO = (TILE_M / 4) * MN_SBO;   // next group of 32 M values: 16 KiB
+struct LayoutMNMajor {
+    static __device__ __forceinline__ int off(int p, int lane) {
+        return (lane >> 3) * MN_LBO + (p >> 2) * MN_SBO + (p & 3) * 128 + ((((lane & 7) >> 1) ^ (p & 3)) << 5) + (lane & 1) * 16;
+    }
+};
+
+template <int U, class LAY>
 __device__ __forceinline__ void assemble_rows(unsigned char* sA, int warp, int lane, int chunk, int cin_p, int K,
                                               const int* s_ebase, const unsigned short* s_koff,
                                               const int2* __restrict__ entries, const float* __restrict__ x) {
@@ -278,12 +296,9 @@ __device__ __forceinline__ void assemble_rows(unsigned char* sA, int warp, int l
     const int my_col = col0 + 4 * lane;
     const int k_l = my_col / cin_p, c_l = my_col % cin_p;
     const int p0 = warp * 16;
-    unsigned char* my = sA + lane * A_LBO;  // + (p/8)*128 + (p%8)*16
 #pragma unroll
-    for (int r = 0; r < 16; r++) {
-        const int p = p0 + r;
-        *reinterpret_cast<float4*>(my + (p >> 3) * A_SBO + (p & 7) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int r = 0; r < 16; r++)
+        *reinterpret_cast<float4*>(sA + LAY::off(p0 + r, lane)) = make_float4(0.f, 0.f, 0.f, 0.f);
     int start = 0, cnt = 0;
     if (lane < 16 && kfirst < K) {
         const unsigned short* ko = s_koff + (p0 + lane) * KOFF;
@@ -327,8 +342,7 @@ __device__ __forceinline__ void assemble_rows(unsigned char* sA, int warp, int l
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 if (wv[u] != 0.f) {
-                    const int p = p0 + pv[u];
-                    float4* a = reinterpret_cast<float4*>(my + (p >> 3) * A_SBO + (p & 7) * 16);
+                    float4* a = reinterpret_cast<float4*>(sA + LAY::off(p0 + pv[u], lane));
                     float4 v = *a;
                     v.x = fmaf(wv[u], xv[u].x, v.x); v.y = fmaf(wv[u], xv[u].y, v.y);
                     v.z = fmaf(wv[u], xv[u].z, v.z); v.w = fmaf(wv[u], xv[u].w, v.w);
@@ -339,8 +353,7 @@ __device__ __forceinline__ void assemble_rows(unsigned char* sA, int warp, int l
     }
 #pragma unroll
     for (int r = 0; r < 16; r++) {
-        const int p = p0 + r;
-        float4* a = reinterpret_cast<float4*>(my + (p >> 3) * A_SBO + (p & 7) * 16);
+        float4* a = reinterpret_cast<float4*>(sA + LAY::off(p0 + r, lane));
         float4 v = *a;
         v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
         *a = v;
@@ -363,7 +376,7 @@ struct FwdParams {
 };
 
 __global__ void __launch_bounds__(FWD_THREADS) kp_fwd_kernel(FwdParams P) {
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;
     unsigned char* sB = smem + A_BYTES;
     const int b_bytes = P.NB * CK * 4;
@@ -408,7 +421,7 @@ __global__ void __launch_bounds__(FWD_THREADS) kp_fwd_kernel(FwdParams P) {
                 bulk_g2s(sB, P.images + ((size_t)chunk * P.n_nblk + nblk) * (size_t)P.NB * CK, (uint32_t)b_bytes, bar_b);
             }
             if (nblk == 0) {
-                assemble_rows<8>(sA, warp, lane, chunk, P.cin_p, P.K, s_ebase, s_koff, P.entries, P.x);
+                assemble_rows<8, LayoutKMajor>(sA, warp, lane, chunk, P.cin_p, P.K, s_ebase, s_koff, P.entries, P.x);
                 fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
             }
             __syncthreads();
@@ -453,8 +466,9 @@ __global__ void __launch_bounds__(FWD_THREADS) kp_fwd_kernel(FwdParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------------------- dW
-// B tile = dOut[tile points, NB outputs] MN-major: element (n, p) at (n/4)*DW_B_SBO + (p/8)*128 + (p%8)*16 + (n%4)*4
-constexpr int DW_B_SBO = 16 * 128 + 16;  // 2064
+// B tile = dOut[tile points, NB outputs], also MN-major SWIZZLE_128B_BASE32B: element (n, p) by the formula above
+// with m = n. Size = ceil(NB/32) * MN_LBO.
+__host__ __device__ constexpr int dw_b_bytes(int NB) { return ((NB + 31) / 32) * MN_LBO; }
 
 struct DwParams {
     int nq;
@@ -471,10 +485,10 @@ struct DwParams {
 };
 
 __global__ void __launch_bounds__(FWD_THREADS) kp_dw_kernel(DwParams P) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* sA = smem;
-    unsigned char* sB = smem + A_BYTES;
-    const int b_bytes = (P.NB / 4) * DW_B_SBO;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sA = smem;                       // 4 * MN_LBO = 64 KiB, 1024-aligned (swizzle uses address bits)
+    unsigned char* sB = smem + 4 * MN_LBO;
+    const int b_bytes = dw_b_bytes(P.NB);
     unsigned short* s_koff = reinterpret_cast<unsigned short*>(sB + b_bytes);
     int* s_ebase = reinterpret_cast<int*>(s_koff + TILE_M * KOFF);
     uint64_t* bar_mma = reinterpret_cast<uint64_t*>(s_ebase + TILE_M);
@@ -528,20 +542,21 @@ __global__ void __launch_bounds__(FWD_THREADS) kp_dw_kernel(DwParams P) {
                     }
                 }
                 v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-                *reinterpret_cast<float4*>(sB + n4 * DW_B_SBO + (p >> 3) * 128 + (p & 7) * 16) = v;
+                *reinterpret_cast<float4*>(sB + LayoutMNMajor::off(p, n4)) = v;
             }
         }
         __syncthreads();  // s_ebase / s_koff ready
-        assemble_rows<8>(sA, warp, lane, chunk, P.cin_p, P.K, s_ebase, s_koff, P.entries, P.x);
+        assemble_rows<8, LayoutMNMajor>(sA, warp, lane, chunk, P.cin_p, P.K, s_ebase, s_koff, P.entries, P.x);
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll 1
             for (int kk = 0; kk < TILE_M / 8; kk++) {  // K = 8 points per MMA
-                // MN-major: K-direction (8-point groups) stride 128 B, M/N-direction (4-element groups) stride 2064 B
-                const uint64_t ad = make_desc(a_addr + kk * A_SBO, A_SBO, A_LBO);
-                const uint64_t bd = make_desc(b_addr + kk * 128, 128, DW_B_SBO);
+                // MN-major swizzled descriptors: "leading" offset = next 32-element group along M/N, "stride" offset =
+                // next group of 4 K values; 8 points per MMA = two K groups = 1024 B
+                const uint64_t ad = make_desc(a_addr + kk * 2 * MN_SBO, MN_LBO, MN_SBO, LAYOUT_SW128_BASE32B);
+                const uint64_t bd = make_desc(b_addr + kk * 2 * MN_SBO, MN_LBO, MN_SBO, LAYOUT_SW128_BASE32B);
                 umma_tf32(tmem, ad, bd, idesc, (step > 0 || kk > 0) ? 1u : 0u);
             }
             umma_commit(bar_mma);
@@ -776,7 +791,7 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
         uint32_t cols = 32;
         while ((int)cols < P.NB) cols <<= 1;
         P.tmem_cols = cols;
-        const size_t smem = (size_t)A_BYTES + (size_t)(P.NB / 4) * DW_B_SBO + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
+        const size_t smem = (size_t)4 * MN_LBO + (size_t)dw_b_bytes(P.NB) + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
         KP_CUDA(cudaFuncSetAttribute(kp_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
             ProfileScope ps("kp_dw", stream);
