@@ -116,6 +116,21 @@ int kp_kpconv_dx_atomic_dev(const float* q_pts, int nq, const float* s_pts, int 
                             int idx_is_i64, int H, int idx_stride, const float* dwf, int cin,
                             const float* kernel_points, int K, float KP_extent, float* dx, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Pooling gathers next to KPConv (the callers' side of the path).
+ * Replaces: models/blocks.py:93-112 `max_pool(x, inds)` (shadow row = zeros, so a shadow entry contributes 0 to the
+ *           max) and models/blocks.py:77-90 `closest_pool(x, inds)` (first column only), plus their adjoints.
+ *   x [ns,channels] f32, inds [nq,H] int32/int64 (row stride idx_stride), out [nq,channels];
+ *   argmax [nq,channels] int32 receives the winning support row (-1 = the shadow zero) for the backward pass.
+ *   kp_closest_pool_dev: backward == 0: dst[nq,ch] = src[inds[:,0]];  backward != 0: dst[ns,ch] = scatter-add of src[nq,ch].
+ */
+int kp_max_pool_forward_dev(const float* x, int ns, int channels, const void* inds, int idx_is_i64, int nq, int H,
+                            int idx_stride, float* out, int* argmax, void* stream);
+int kp_max_pool_backward_dev(const float* d_out, const int* argmax, int nq, int channels, float* d_x, int ns,
+                             void* stream);
+int kp_closest_pool_dev(const float* src, int ns, int channels, const void* inds, int idx_is_i64, int nq,
+                        int idx_stride, float* dst, int backward, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -353,7 +353,7 @@ def test_full_size_vaihingen_batch_properties(torch_cuda):
     d2 = ((pad[nb] - Pn[:, None, :]) ** 2).sum(2)
     real = nb < n
     assert (d2[real] < r * r * (1 + 1e-5)).all()
-    assert (np.diff(np.where(real, d2, np.inf), axis=1) >= -1e-9).all()  # rows sorted by distance, shadows last
+    assert (np.diff(np.where(real, d2, np.float32(1e30)), axis=1) >= -1e-9).all()  # rows sorted by distance, shadows last
     # symmetry of the neighbour relation for q == s (checked on a sample of pairs)
     src = np.repeat(np.arange(n), nb.shape[1])[real.ravel()]
     dst = nb[real]
@@ -370,3 +370,37 @@ def test_full_size_vaihingen_batch_properties(torch_cuda):
         want = oracle.batch_neighbors(Pn[i:i + 1], Pn[lo:hi], [1], [hi - lo], r)[0] + lo
         k = len(want)
         assert np.array_equal(nb[i, :k], want) and (nb[i, k:] == n).all()
+
+
+# ----------------------------------------------------------------------------------------------------------- pooling
+def test_pooling_ops_match_reference_formulation(torch_cuda):
+    """max_pool / closest_pool (models/blocks.py:77-112) forward and backward against the reference's cat + gather
+    formulation evaluated by PyTorch."""
+    torch = torch_cuda
+    from weasal_b200 import ops
+    rng = np.random.default_rng(0)
+    ns, nq, C_, H = 500, 320, 48, 9
+    x = torch.from_numpy(rng.normal(size=(ns, C_)).astype(np.float32)).cuda()
+    idx_np = rng.integers(0, ns + 1, (nq, H))  # includes shadow entries (== ns)
+    idx_np[5] = ns                              # one row made of shadows only
+    idx = torch.from_numpy(idx_np).cuda()
+    g = torch.from_numpy(rng.normal(size=(nq, C_)).astype(np.float32)).cuda()
+
+    def ref_max(xx):
+        xp = torch.cat((xx, torch.zeros_like(xx[:1])), 0)
+        return xp[idx].max(dim=1)[0]
+
+    def ref_closest(xx):
+        xp = torch.cat((xx, torch.zeros_like(xx[:1])), 0)
+        return xp[idx[:, 0]]
+
+    for mine, ref in ((ops.max_pool, ref_max), (ops.closest_pool, ref_closest)):
+        x1 = x.clone().requires_grad_(True)
+        x2 = x.clone().requires_grad_(True)
+        y1, y2 = mine(x1, idx), ref(x2)
+        assert torch.equal(y1, y2)
+        y1.backward(g)
+        y2.backward(g)
+        assert torch.allclose(x1.grad, x2.grad, rtol=0, atol=1e-5)
+    y = ops.max_pool(x, idx.to(torch.int32))
+    assert torch.equal(y, ref_max(x))

@@ -20,7 +20,8 @@ KP_OK, KP_ERR_CUDA, KP_ERR_ARG, KP_ERR_CAPACITY, KP_ERR_TOO_DENSE, KP_ERR_EMPTY,
 # every symbol include/weasal_b200.h declares (tests check the library exports all of them)
 SYMBOLS = ["kp_last_error", "kp_version", "kp_launch_count", "kp_free_host", "kp_batch_query_host",
            "kp_batch_query_dev", "kp_grid_subsample_host", "kp_grid_subsample_dev", "kp_kpconv_forward_dev",
-           "kp_kpconv_backward_dev", "kp_kpconv_wf_dev", "kp_kpconv_dx_atomic_dev"]
+           "kp_kpconv_backward_dev", "kp_kpconv_wf_dev", "kp_kpconv_dx_atomic_dev", "kp_profile_enable",
+           "kp_profile_read", "kp_max_pool_forward_dev", "kp_max_pool_backward_dev", "kp_closest_pool_dev"]
 
 
 def lib():
@@ -47,6 +48,11 @@ def lib():
     L.kp_kpconv_backward_dev.argtypes = conv_common + [vp, C.c_int, vp, C.c_int, C.c_float, vp, vp, vp, vp]
     L.kp_kpconv_wf_dev.argtypes = conv_common + [vp, C.c_int, C.c_float, vp, vp]
     L.kp_kpconv_dx_atomic_dev.argtypes = conv_common + [vp, C.c_int, C.c_float, vp, vp]
+    L.kp_profile_enable.argtypes = [C.c_int]
+    L.kp_profile_read.argtypes = [C.c_char_p, C.c_int]
+    L.kp_max_pool_forward_dev.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.kp_max_pool_backward_dev.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.kp_closest_pool_dev.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
     _lib = L
     return L
 

@@ -25,6 +25,11 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
                            int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
                            float extent, const float* dout, float* dx, float* dw, cudaStream_t stream);
 int profile_read(char* buf, int buflen);
+int max_pool_fwd_device(const float* x, int ns, int C, const void* idx, int is_i64, int nq, int H, int stride,
+                        float* out, int* arg, cudaStream_t stream);
+int max_pool_bwd_device(const float* dout, const int* arg, int nq, int C, float* dx, int ns, cudaStream_t stream);
+int closest_pool_device(const float* src, int ns, int C, const void* idx, int is_i64, int nq, int stride, float* dst,
+                        int backward, cudaStream_t stream);
 }  // namespace kp
 
 using namespace kp;
@@ -156,6 +161,19 @@ int kp_kpconv_backward_dev(const float* q_pts, int nq, const float* s_pts, int n
                            float* d_x, float* d_weights, void* stream) {
     return kpconv_backward_device(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, weights, cout,
                                   kernel_points, K, KP_extent, d_out, d_x, d_weights, (cudaStream_t)stream);
+}
+
+int kp_max_pool_forward_dev(const float* x, int ns, int channels, const void* inds, int idx_is_i64, int nq, int H,
+                            int idx_stride, float* out, int* argmax, void* stream) {
+    return max_pool_fwd_device(x, ns, channels, inds, idx_is_i64, nq, H, idx_stride, out, argmax, (cudaStream_t)stream);
+}
+int kp_max_pool_backward_dev(const float* d_out, const int* argmax, int nq, int channels, float* d_x, int ns,
+                             void* stream) {
+    return max_pool_bwd_device(d_out, argmax, nq, channels, d_x, ns, (cudaStream_t)stream);
+}
+int kp_closest_pool_dev(const float* src, int ns, int channels, const void* inds, int idx_is_i64, int nq,
+                        int idx_stride, float* dst, int backward, void* stream) {
+    return closest_pool_device(src, ns, channels, inds, idx_is_i64, nq, idx_stride, dst, backward, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -16,14 +16,22 @@ import torch.nn.functional as F
 
 def max_pool(x, inds):
     """blocks.py:93-112: shadow row is zeros, so shadow entries contribute 0 to the max."""
-    xp = torch.cat((x, torch.zeros_like(x[:1, :])), 0)
-    return xp[inds].max(dim=1)[0]
+    if x.is_cuda:
+        from . import ops
+        return ops.max_pool(x, inds)
+    xp = torch.cat((x, torch.zeros_like(x[:1, :])), 0)  # CPU: the reference's own formulation (reference arm only)
+    idx = inds.unsqueeze(2).expand(-1, -1, xp.shape[1])
+    return xp.unsqueeze(1).expand(-1, inds.shape[1], -1).gather(0, idx).max(dim=1)[0]
 
 
 def closest_pool(x, inds):
     """blocks.py:77-90: nearest upsampling through the first (closest) neighbour column."""
+    if x.is_cuda:
+        from . import ops
+        return ops.closest_pool(x, inds)
     xp = torch.cat((x, torch.zeros_like(x[:1, :])), 0)
-    return xp[inds[:, 0]]
+    idx = inds[:, 0].unsqueeze(1).expand(-1, xp.shape[1])
+    return xp.gather(0, idx)
 
 
 class Unary(nn.Module):

@@ -171,3 +171,70 @@ class KPConvFunction(torch.autograd.Function):
 
 def kpconv(q_pts, s_pts, neighb_inds, x, weights, kernel_points, KP_extent):
     return KPConvFunction.apply(q_pts, s_pts, neighb_inds, x, weights, kernel_points, KP_extent)
+
+
+# ----------------------------------------------------------------------------------------------------------- pooling
+class MaxPoolFunction(torch.autograd.Function):
+    """models/blocks.py:93-112 as one gather-max kernel; backward routes each gradient to the winning support row."""
+
+    @staticmethod
+    def forward(ctx, x, inds):
+        _need_cuda(x, inds)
+        xx = _f32c(x)
+        idx, i64, H, stride = _idx_args(inds)
+        ns, C_ = xx.shape
+        nq = idx.shape[0]
+        out = torch.empty((nq, C_), dtype=torch.float32, device=xx.device)
+        arg = torch.empty((nq, C_), dtype=torch.int32, device=xx.device)
+        _lib.check(_lib.lib().kp_max_pool_forward_dev(xx.data_ptr(), ns, C_, idx.data_ptr(), i64, nq, H, stride,
+                                                      out.data_ptr(), arg.data_ptr(), _stream()), "max_pool")
+        ctx.save_for_backward(arg)
+        ctx.ns = ns
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (arg,) = ctx.saved_tensors
+        do = _f32c(d_out)
+        nq, C_ = arg.shape
+        dx = torch.empty((ctx.ns, C_), dtype=torch.float32, device=do.device)
+        _lib.check(_lib.lib().kp_max_pool_backward_dev(do.data_ptr(), arg.data_ptr(), nq, C_, dx.data_ptr(), ctx.ns,
+                                                       _stream()), "max_pool_backward")
+        return dx, None
+
+
+class ClosestPoolFunction(torch.autograd.Function):
+    """models/blocks.py:77-90: nearest upsampling through the first neighbour column."""
+
+    @staticmethod
+    def forward(ctx, x, inds):
+        _need_cuda(x, inds)
+        xx = _f32c(x)
+        idx, i64, H, stride = _idx_args(inds)
+        ns, C_ = xx.shape
+        nq = idx.shape[0]
+        out = torch.empty((nq, C_), dtype=torch.float32, device=xx.device)
+        _lib.check(_lib.lib().kp_closest_pool_dev(xx.data_ptr(), ns, C_, idx.data_ptr(), i64, nq, stride,
+                                                  out.data_ptr(), 0, _stream()), "closest_pool")
+        ctx.save_for_backward(idx)
+        ctx.meta = (ns, i64, stride)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (idx,) = ctx.saved_tensors
+        ns, i64, stride = ctx.meta
+        do = _f32c(d_out)
+        nq, C_ = do.shape
+        dx = torch.empty((ns, C_), dtype=torch.float32, device=do.device)
+        _lib.check(_lib.lib().kp_closest_pool_dev(do.data_ptr(), ns, C_, idx.data_ptr(), i64, nq, stride,
+                                                  dx.data_ptr(), 1, _stream()), "closest_pool_backward")
+        return dx, None
+
+
+def max_pool(x, inds):
+    return MaxPoolFunction.apply(x, inds)
+
+
+def closest_pool(x, inds):
+    return ClosestPoolFunction.apply(x, inds)
