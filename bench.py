@@ -143,6 +143,8 @@ def run_ours(args):
                            "(use --impl reference for the CPU reference arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # the harness network's Linear layers use the same operand precision as the KPConv contraction (TF32 in, fp32 out)
+    torch.backends.cuda.matmul.allow_tf32 = True
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -290,7 +292,8 @@ def run_ours(args):
                        "points_per_step_per_gpu": n0, "global_points_per_step": n0 * world,
                        "first_subsampling_dl": cfg["dl"], "layers": 5, "kpconv_per_forward": 10,
                        "parallelism": f"dp{world}", "l2": "flushed between steps (256 MB write)",
-                       "random_grid_orient": True, "neighborhood_limits": None},
+                       "random_grid_orient": True, "neighborhood_limits": None,
+                       "harness_linear_precision": "tf32"},
             "e2e": {"value": e2e_pts / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": int(gpu_launches), "gpu_launches_per_step": gpu_launches / max(K, 1),

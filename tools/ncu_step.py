@@ -16,6 +16,7 @@ from weasal_b200.net import CfgView, KPFCNNHarness, net_config  # noqa: E402
 
 cfg_name = sys.argv[1] if len(sys.argv) > 1 else "vaihingen_pl"
 dev = torch.device("cuda", 0)
+torch.backends.cuda.matmul.allow_tf32 = True
 cfg, batches = bench.build_batches(cfg_name, 0, 2,
                                    lambda p, f, l, dl: grid_subsampling.subsample(p, features=f, classes=l, sampleDl=dl))
 ncfg = net_config(cfg_name)

@@ -15,6 +15,7 @@ from weasal_b200.blocks import KPConv  # noqa: E402
 from weasal_b200.net import CfgView, KPFCNNHarness, net_config  # noqa: E402
 
 dev = torch.device("cuda", 0)
+torch.backends.cuda.matmul.allow_tf32 = True
 cfg, batches = bench.build_batches("vaihingen_pl", 0, 4,
                                    lambda p, f, l, dl: grid_subsampling.subsample(p, features=f, classes=l, sampleDl=dl))
 ncfg = net_config("vaihingen_pl")

@@ -14,6 +14,7 @@
 // Kernels
 //   kp_influence   one warp per centre point: influence weights of every (neighbour, kernel point) pair, compacted
 //                  into per-point entry lists grouped by kernel point: entry = (neighbour index | k << 27, weight).
+//                  A centre's list lives in its own slot of 15 entries per table column, so no allocation / atomics.
 //   kp_pack_w      W[k,c,o] -> TF32-rounded B-operand images, one per 128-column chunk of the (k,c) reduction axis,
 //                  already in the UMMA K-major core-matrix layout (so a CTA fetches a chunk with one bulk copy).
 //   kp_fwd         one CTA per 128 points. Per chunk: warps assemble the A tile [128 x 128] in shared memory from the
@@ -32,7 +33,10 @@ namespace kp {
 // ------------------------------------------------------------------------------------------------------- constants
 constexpr int TILE_M = 128;      // points per CTA tile (= UMMA M)
 constexpr int CK = 128;          // reduction columns per chunk
-constexpr int FWD_THREADS = 256;
+// Warps per CTA (template parameter NW of the kernels): the A-tile assembly is latency bound and wants as many warps in
+// flight as the SM holds. Shapes whose shared memory lets two CTAs share an SM run 8 warps per CTA (the second CTA's
+// assembly overlaps the first one's MMA / barrier phases); shapes with one CTA per SM run 16 warps.
+constexpr int SMEM_TWO_CTAS = 110 * 1024;
 constexpr int KOFF = 16;         // per-point cumulative entry counts per kernel point (K <= 15)
 constexpr int K_SHIFT = 27;      // entry.x = neighbour index | (kernel point << 27)
 constexpr unsigned J_MASK = (1u << K_SHIFT) - 1u;
@@ -152,14 +156,18 @@ __device__ __forceinline__ float influence_w(float rx, float ry, float rz, float
     return fmaxf(0.f, 1.f - sqrtf(dx * dx + dy * dy + dz * dz) * inv_ext);
 }
 
-// one warp per centre; lanes = neighbours; two passes (count, then write) so that entries land grouped by kernel point
-__global__ void __launch_bounds__(128) kp_influence_kernel(const float* __restrict__ centres, int nc,
+// Entry lists. Centre i owns the slot entries[15 * row0(i) ...), row0 = i*H (padded table) or rowptr[i] (CSR): 15
+// entries per table column is the exact worst case, so the list never overflows and needs no allocator. Inside the
+// slot the entries are packed, grouped by kernel point (koff[i][k] = first entry of kernel point k, koff[i][15] =
+// count), each group in table-column order.
+// One warp per centre, lanes = neighbours. NB > 0: the row fits NB batches of 32 and every weight is evaluated once
+// (kept in registers between counting and writing); NB == 0: any row length, two evaluation passes.
+template <int NB>
+__global__ void __launch_bounds__(256) kp_influence_kernel(const float* __restrict__ centres, int nc,
                                                           const float* __restrict__ others, int no, Table T,
                                                           const float* __restrict__ kp, int K, float kp_sign,
-                                                          float inv_ext, int* __restrict__ ebase,
-                                                          unsigned short* __restrict__ koff, int2* __restrict__ entries,
-                                                          long long capacity, unsigned long long* __restrict__ counter,
-                                                          int* __restrict__ err) {
+                                                          float inv_ext, unsigned short* __restrict__ koff,
+                                                          int2* __restrict__ entries) {
     __shared__ float s_kp[16 * 3];
     if (threadIdx.x < 48) s_kp[threadIdx.x] = (threadIdx.x < 3 * K) ? kp_sign * kp[threadIdx.x] : 1e30f;
     __syncthreads();
@@ -168,61 +176,105 @@ __global__ void __launch_bounds__(128) kp_influence_kernel(const float* __restri
     if (i >= nc) return;
     const unsigned lt_mask = (1u << lane) - 1u;
     const float cx = centres[3 * (size_t)i], cy = centres[3 * (size_t)i + 1], cz = centres[3 * (size_t)i + 2];
-    size_t row0;
+    size_t row0, pos0;
     int cnt_row;
-    if (T.rowptr) { row0 = (size_t)T.rowptr[i]; cnt_row = T.rowptr[i + 1] - T.rowptr[i]; }
-    else { row0 = (size_t)i * T.stride; cnt_row = T.H; }
+    if (T.rowptr) { row0 = (size_t)T.rowptr[i]; pos0 = row0; cnt_row = T.rowptr[i + 1] - T.rowptr[i]; }
+    else { row0 = (size_t)i * T.H; pos0 = (size_t)i * T.stride; cnt_row = T.H; }
+    int2* my_entries = entries + 15 * row0;
 
     int cnt[15];
 #pragma unroll
     for (int k = 0; k < 15; k++) cnt[k] = 0;
-    for (int hb = 0; hb < cnt_row; hb += 32) {
-        const int h = hb + lane;
-        long long j = (h < cnt_row) ? table_get(T, row0 + h) : -1;
-        const bool valid = j >= 0 && j < no;
-        if (!__any_sync(0xffffffffu, valid)) continue;
-        float rx = 0.f, ry = 0.f, rz = 0.f;
-        if (valid) { rx = others[3 * j] - cx; ry = others[3 * j + 1] - cy; rz = others[3 * j + 2] - cz; }
+
+    if constexpr (NB > 0) {
+        float w[NB][15];
+        unsigned jv[NB];
 #pragma unroll
-        for (int k = 0; k < 15; k++) {
-            const float w = valid ? influence_w(rx, ry, rz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext) : 0.f;
-            cnt[k] += __popc(__ballot_sync(0xffffffffu, w > 0.f));
-        }
-    }
-    int run[16];
-    int total = 0;
+        for (int b = 0; b < NB; b++) {
+            const int h = b * 32 + lane;
+            long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
+            const bool valid = j >= 0 && j < no;
+            jv[b] = (unsigned)j;
+            float rx = 0.f, ry = 0.f, rz = 0.f;
+            const bool any = __any_sync(0xffffffffu, valid);
+            if (valid) { rx = others[3 * j] - cx; ry = others[3 * j + 1] - cy; rz = others[3 * j + 2] - cz; }
 #pragma unroll
-    for (int k = 0; k < 15; k++) { run[k] = total; total += cnt[k]; }
-    run[15] = total;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(counter, (unsigned long long)total);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    bool ok = true;
-    if (total > 65535 || base + (unsigned long long)total > (unsigned long long)capacity || base > 0x7fffffffULL) {
-        if (lane == 0) atomicOr(err, 1);
-        ok = false;
-    }
-    if (lane == 0) ebase[i] = ok ? (int)base : 0;
-    if (lane < 16) koff[(size_t)i * KOFF + lane] = ok ? (unsigned short)run[lane] : (unsigned short)0;
-    if (!ok || total == 0) return;
-    for (int hb = 0; hb < cnt_row; hb += 32) {
-        const int h = hb + lane;
-        long long j = (h < cnt_row) ? table_get(T, row0 + h) : -1;
-        const bool valid = j >= 0 && j < no;
-        if (!__any_sync(0xffffffffu, valid)) continue;
-        float rx = 0.f, ry = 0.f, rz = 0.f;
-        if (valid) { rx = others[3 * j] - cx; ry = others[3 * j + 1] - cy; rz = others[3 * j + 2] - cz; }
-#pragma unroll
-        for (int k = 0; k < 15; k++) {
-            const float w = valid ? influence_w(rx, ry, rz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext) : 0.f;
-            const unsigned m = __ballot_sync(0xffffffffu, w > 0.f);
-            if (w > 0.f) {
-                int2 e;
-                e.x = (int)((unsigned)j | ((unsigned)k << K_SHIFT));
-                e.y = __float_as_int(w);
-                entries[base + run[k] + __popc(m & lt_mask)] = e;
+            for (int k = 0; k < 15; k++) {
+                w[b][k] = (any && valid) ? influence_w(rx, ry, rz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext) : 0.f;
+                if (any) cnt[k] += __popc(__ballot_sync(0xffffffffu, w[b][k] > 0.f));
             }
-            run[k] += __popc(m);
+        }
+        int run[16];
+        int total = 0;
+#pragma unroll
+        for (int k = 0; k < 15; k++) { run[k] = total; total += cnt[k]; }
+        run[15] = total;
+        {
+            int mine = 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) mine = (lane == k) ? run[k] : mine;
+            if (lane < 16) koff[(size_t)i * KOFF + lane] = (unsigned short)mine;
+        }
+        if (total == 0) return;
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+#pragma unroll
+            for (int k = 0; k < 15; k++) {
+                const unsigned m = __ballot_sync(0xffffffffu, w[b][k] > 0.f);
+                if (w[b][k] > 0.f) {
+                    int2 e;
+                    e.x = (int)(jv[b] | ((unsigned)k << K_SHIFT));
+                    e.y = __float_as_int(w[b][k]);
+                    my_entries[run[k] + __popc(m & lt_mask)] = e;
+                }
+                run[k] += __popc(m);
+            }
+        }
+    } else {
+        for (int hb = 0; hb < cnt_row; hb += 32) {
+            const int h = hb + lane;
+            long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
+            const bool valid = j >= 0 && j < no;
+            if (!__any_sync(0xffffffffu, valid)) continue;
+            float rx = 0.f, ry = 0.f, rz = 0.f;
+            if (valid) { rx = others[3 * j] - cx; ry = others[3 * j + 1] - cy; rz = others[3 * j + 2] - cz; }
+#pragma unroll
+            for (int k = 0; k < 15; k++) {
+                const float w = valid ? influence_w(rx, ry, rz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext) : 0.f;
+                cnt[k] += __popc(__ballot_sync(0xffffffffu, w > 0.f));
+            }
+        }
+        int run[16];
+        int total = 0;
+#pragma unroll
+        for (int k = 0; k < 15; k++) { run[k] = total; total += cnt[k]; }
+        run[15] = total;
+        {
+            int mine = 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) mine = (lane == k) ? run[k] : mine;
+            if (lane < 16) koff[(size_t)i * KOFF + lane] = (unsigned short)mine;
+        }
+        if (total == 0) return;
+        for (int hb = 0; hb < cnt_row; hb += 32) {
+            const int h = hb + lane;
+            long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
+            const bool valid = j >= 0 && j < no;
+            if (!__any_sync(0xffffffffu, valid)) continue;
+            float rx = 0.f, ry = 0.f, rz = 0.f;
+            if (valid) { rx = others[3 * j] - cx; ry = others[3 * j + 1] - cy; rz = others[3 * j + 2] - cz; }
+#pragma unroll
+            for (int k = 0; k < 15; k++) {
+                const float w = valid ? influence_w(rx, ry, rz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext) : 0.f;
+                const unsigned m = __ballot_sync(0xffffffffu, w > 0.f);
+                if (w > 0.f) {
+                    int2 e;
+                    e.x = (int)((unsigned)j | ((unsigned)k << K_SHIFT));
+                    e.y = __float_as_int(w);
+                    my_entries[run[k] + __popc(m & lt_mask)] = e;
+                }
+                run[k] += __popc(m);
+            }
         }
     }
 }
@@ -240,9 +292,8 @@ __global__ void __launch_bounds__(256) kp_pack_w_kernel(const float* __restrict_
         const long long img = t / ((long long)NB * CK);
         const int r = (int)(t % ((long long)NB * CK));
         const int chunk = (int)(img / n_nblk), nblk = (int)(img % n_nblk);
-        const int word = r;                    // float index inside the image
-        const int j = word / (NB * 4);         // 16-byte K chunk
-        const int rem = word % (NB * 4);
+        const int j = r / (NB * 4);          // 16-byte K chunk
+        const int rem = r % (NB * 4);
         const int n8 = rem / 32, in8 = rem % 32;
         const int n = n8 * 8 + in8 / 4, e = in8 % 4;
         const int col = chunk * CK + j * 4 + e;
@@ -266,9 +317,6 @@ __global__ void __launch_bounds__(256) kp_pad_cols_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------- A-tile assembly (shared by fwd, dW)
-// Warp `warp` owns tile rows [warp*16, warp*16+16). For chunk `chunk` it zeroes them, walks the entry lists of its 16
-// points restricted to the chunk's kernel points, gathers float4 feature rows (U loads in flight per lane) and
-// accumulates w * x into the rows, then rounds the rows to TF32.
 // Where the 16 bytes (4 consecutive reduction columns 4*lane..4*lane+3) of tile row p live in shared memory.
 struct LayoutKMajor {  // forward: UMMA K-major, no swizzle (see A_SBO / A_LBO above)
     static __device__ __forceinline__ int off(int p, int lane) { return lane * A_LBO + (p >> 3) * A_SBO + (p & 7) * 16; }
@@ -286,40 +334,44 @@ struct LayoutMNMajor {
     }
 };
 
-template <int U, class LAY>
+// Warp `warp` owns tile rows [warp*RPW, warp*RPW + RPW). For chunk `chunk` it zeroes them, walks the entry lists of
+// its points restricted to the chunk's kernel points (flattened across the points, 32 entries per batch), gathers
+// float4 feature rows with U loads in flight per lane and accumulates w * x into the rows, then rounds them to TF32.
+template <int U, class LAY, int RPW>
 __device__ __forceinline__ void assemble_rows(unsigned char* sA, int warp, int lane, int chunk, int cin_p, int K,
-                                              const int* s_ebase, const unsigned short* s_koff,
+                                              const int* s_row0, const unsigned short* s_koff,
                                               const int2* __restrict__ entries, const float* __restrict__ x) {
     const int col0 = chunk * CK;
     const int kfirst = col0 / cin_p;
     const int klast = min(K - 1, (col0 + CK - 1) / cin_p);
     const int my_col = col0 + 4 * lane;
     const int k_l = my_col / cin_p, c_l = my_col % cin_p;
-    const int p0 = warp * 16;
+    const int p0 = warp * RPW;
 #pragma unroll
-    for (int r = 0; r < 16; r++)
+    for (int r = 0; r < RPW; r++)
         *reinterpret_cast<float4*>(sA + LAY::off(p0 + r, lane)) = make_float4(0.f, 0.f, 0.f, 0.f);
-    int start = 0, cnt = 0;
-    if (lane < 16 && kfirst < K) {
+    long long start = 0;
+    int cnt = 0;
+    if (lane < RPW && kfirst < K) {
         const unsigned short* ko = s_koff + (p0 + lane) * KOFF;
-        start = s_ebase[p0 + lane] + ko[kfirst];
+        start = 15LL * s_row0[p0 + lane] + ko[kfirst];
         cnt = (int)ko[klast + 1] - (int)ko[kfirst];
     }
     int incl = cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
+    for (int o = 1; o < RPW; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
-    const int E = __shfl_sync(0xffffffffu, incl, 31);
+    const int E = __shfl_sync(0xffffffffu, incl, RPW - 1);
     const int excl = incl - cnt;
+    const float* xc = x + c_l;
     for (int b0 = 0; b0 < E; b0 += 32) {
         const int e = b0 + lane;
         int pt = 0;
 #pragma unroll
-        for (int t = 0; t < 16; t++) pt += (__shfl_sync(0xffffffffu, incl, t) <= e) ? 1 : 0;
-        pt = min(pt, 15);
-        const int pstart = __shfl_sync(0xffffffffu, start, pt);
+        for (int t = 0; t < RPW - 1; t++) pt += (__shfl_sync(0xffffffffu, incl, t) <= e) ? 1 : 0;
+        const long long pstart = __shfl_sync(0xffffffffu, start, pt);
         const int pexcl = __shfl_sync(0xffffffffu, excl, pt);
         int2 rec = make_int2(0, 0);
         if (e < E) rec = entries[pstart + (e - pexcl)];
@@ -327,22 +379,22 @@ __device__ __forceinline__ void assemble_rows(unsigned char* sA, int warp, int l
         for (int g = 0; g < nb; g += U) {
             float4 xv[U];
             float wv[U];
-            int pv[U];
+            int ov[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int ee = min(g + u, 31);
                 const unsigned jk = (unsigned)__shfl_sync(0xffffffffu, rec.x, ee);
                 const float w = __int_as_float(__shfl_sync(0xffffffffu, rec.y, ee));
-                pv[u] = __shfl_sync(0xffffffffu, pt, ee);
+                ov[u] = LAY::off(p0 + __shfl_sync(0xffffffffu, pt, ee), lane);  // (row, lane) are coupled by the swizzle
                 const bool mine = (g + u < nb) && ((int)(jk >> K_SHIFT) == k_l);
                 wv[u] = mine ? w : 0.f;
                 xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (mine) xv[u] = __ldg(reinterpret_cast<const float4*>(x + (size_t)(jk & J_MASK) * cin_p + c_l));
+                if (mine) xv[u] = __ldg(reinterpret_cast<const float4*>(xc + (size_t)(jk & J_MASK) * cin_p));
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 if (wv[u] != 0.f) {
-                    float4* a = reinterpret_cast<float4*>(sA + LAY::off(p0 + pv[u], lane));
+                    float4* a = reinterpret_cast<float4*>(sA + ov[u]);
                     float4 v = *a;
                     v.x = fmaf(wv[u], xv[u].x, v.x); v.y = fmaf(wv[u], xv[u].y, v.y);
                     v.z = fmaf(wv[u], xv[u].z, v.z); v.w = fmaf(wv[u], xv[u].w, v.w);
@@ -352,11 +404,26 @@ __device__ __forceinline__ void assemble_rows(unsigned char* sA, int warp, int l
         }
     }
 #pragma unroll
-    for (int r = 0; r < 16; r++) {
+    for (int r = 0; r < RPW; r++) {
         float4* a = reinterpret_cast<float4*>(sA + LAY::off(p0 + r, lane));
         float4 v = *a;
         v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
         *a = v;
+    }
+}
+
+// stage the entry-list headers of one tile: row0 (first table column of the centre) and koff
+template <int FWD_THREADS>
+__device__ __forceinline__ void stage_headers(int tile_base, int n, int H, const int* __restrict__ rowptr,
+                                              const unsigned short* __restrict__ koff, int* s_row0,
+                                              unsigned short* s_koff) {
+    for (int t = threadIdx.x; t < TILE_M; t += FWD_THREADS) {
+        const int i = tile_base + t;
+        s_row0[t] = (i < n) ? (rowptr ? rowptr[i] : i * H) : 0;
+    }
+    for (int t = threadIdx.x; t < TILE_M * KOFF; t += FWD_THREADS) {
+        const int i = tile_base + t / KOFF;
+        s_koff[t] = (i < n) ? koff[(size_t)i * KOFF + (t % KOFF)] : (unsigned short)0;
     }
 }
 
@@ -365,29 +432,36 @@ struct FwdParams {
     int nq;              // centre points (rows of out)
     const float* x;      // [n_other, cin_p] features gathered through the entry lists
     int cin_p, K;
-    const int* ebase;
+    const int* rowptr;   // CSR row pointers of the centres' table, or null for a padded table of width H
+    int H;
     const unsigned short* koff;
     const int2* entries;
     const float* images; // packed weights [n_chunks][n_nblk][NB*CK]
     int NB, n_nblk, n_chunks;
-    float* out;          // [nq, cout]
+    int ksplit;          // CTAs along the reduction (blockIdx.y); > 1 => partial sums are added atomically into out
+    float* out;          // [nq, cout] (pre-zeroed when ksplit > 1)
     int cout;
     uint32_t tmem_cols;
 };
 
-__global__ void __launch_bounds__(FWD_THREADS) kp_fwd_kernel(FwdParams P) {
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) kp_fwd_kernel(FwdParams P) {
+    constexpr int FWD_THREADS = NW * 32, RPW = TILE_M / NW, NWARPS = NW;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;
     unsigned char* sB = smem + A_BYTES;
     const int b_bytes = P.NB * CK * 4;
     unsigned short* s_koff = reinterpret_cast<unsigned short*>(sB + b_bytes);
-    int* s_ebase = reinterpret_cast<int*>(s_koff + TILE_M * KOFF);
-    uint64_t* bar_b = reinterpret_cast<uint64_t*>(s_ebase + TILE_M);
+    int* s_row0 = reinterpret_cast<int*>(s_koff + TILE_M * KOFF);
+    uint64_t* bar_b = reinterpret_cast<uint64_t*>(s_row0 + TILE_M);
     uint64_t* bar_mma = bar_b + 1;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_mma + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_base = blockIdx.x * TILE_M;
+    const int cps = (P.n_chunks + P.ksplit - 1) / P.ksplit;
+    const int c0 = blockIdx.y * cps, c1 = min(P.n_chunks, c0 + cps);
+    if (c0 >= c1) return;
 
     if (tid == 0) {
         mbar_init(bar_b, 1);
@@ -396,14 +470,7 @@ __global__ void __launch_bounds__(FWD_THREADS) kp_fwd_kernel(FwdParams P) {
     }
     __syncwarp();
     if (warp == 0) tmem_alloc(s_tmem, P.tmem_cols);
-    for (int t = tid; t < TILE_M; t += FWD_THREADS) {
-        const int i = tile_base + t;
-        s_ebase[t] = (i < P.nq) ? P.ebase[i] : 0;
-    }
-    for (int t = tid; t < TILE_M * KOFF; t += FWD_THREADS) {
-        const int i = tile_base + t / KOFF;
-        s_koff[t] = (i < P.nq) ? P.koff[(size_t)i * KOFF + (t % KOFF)] : (unsigned short)0;
-    }
+    stage_headers<FWD_THREADS>(tile_base, P.nq, P.H, P.rowptr, P.koff, s_row0, s_koff);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -413,7 +480,7 @@ __global__ void __launch_bounds__(FWD_THREADS) kp_fwd_kernel(FwdParams P) {
     const uint32_t b_lbo = (uint32_t)P.NB * 16u;
 
     int step = 0;  // one MMA group (chunk, nblk) per step; bar_b / bar_mma complete once per step
-    for (int chunk = 0; chunk < P.n_chunks; chunk++) {
+    for (int chunk = c0; chunk < c1; chunk++) {
         for (int nblk = 0; nblk < P.n_nblk; nblk++, step++) {
             if (step > 0) mbar_wait(bar_mma, (uint32_t)((step - 1) & 1));  // previous MMAs done: A and B reusable
             if (tid == 0) {
@@ -421,7 +488,7 @@ __global__ void __launch_bounds__(FWD_THREADS) kp_fwd_kernel(FwdParams P) {
                 bulk_g2s(sB, P.images + ((size_t)chunk * P.n_nblk + nblk) * (size_t)P.NB * CK, (uint32_t)b_bytes, bar_b);
             }
             if (nblk == 0) {
-                assemble_rows<8, LayoutKMajor>(sA, warp, lane, chunk, P.cin_p, P.K, s_ebase, s_koff, P.entries, P.x);
+                assemble_rows<8, LayoutKMajor, RPW>(sA, warp, lane, chunk, P.cin_p, P.K, s_row0, s_koff, P.entries, P.x);
                 fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
             }
             __syncthreads();
@@ -432,7 +499,7 @@ __global__ void __launch_bounds__(FWD_THREADS) kp_fwd_kernel(FwdParams P) {
                 for (int kk = 0; kk < CK / 8; kk++) {  // K = 8 per tf32 MMA = two 16-byte K chunks
                     const uint64_t ad = make_desc(a_addr + kk * 2 * A_LBO, A_LBO, A_SBO);
                     const uint64_t bd = make_desc(b_addr + kk * 2 * b_lbo, b_lbo, B_SBO);
-                    umma_tf32(tmem + (uint32_t)(nblk * P.NB), ad, bd, idesc, (chunk > 0 || kk > 0) ? 1u : 0u);
+                    umma_tf32(tmem + (uint32_t)(nblk * P.NB), ad, bd, idesc, (chunk > c0 || kk > 0) ? 1u : 0u);
                 }
                 umma_commit(bar_mma);
             }
@@ -441,22 +508,29 @@ __global__ void __launch_bounds__(FWD_THREADS) kp_fwd_kernel(FwdParams P) {
     mbar_wait(bar_mma, (uint32_t)((step - 1) & 1));
     tc_fence_after();
 
-    // epilogue: warp w reads TMEM lanes 32*(w%4).., column blocks of 16 interleaved between the two warpgroups
+    // epilogue: warp w reads TMEM lanes 32*(w%4).., column blocks of 16 dealt round-robin over the 4 warps of a quadrant
     const int row = tile_base + 32 * (warp & 3) + lane;
     const int n_cb = (P.n_nblk * P.NB) / 16;
-    for (int cb = warp >> 2; cb < n_cb; cb += 2) {
+    const bool vec = (P.cout & 3) == 0;
+    for (int cb = warp >> 2; cb < n_cb; cb += NWARPS / 4) {
         float v[16];
         tmem_ld16(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cb * 16), v);
         if (row < P.nq) {
             float* o = P.out + (size_t)row * P.cout + cb * 16;
-            if ((P.cout & 3) == 0) {
 #pragma unroll
-                for (int t = 0; t < 16; t += 4)
-                    if (cb * 16 + t < P.cout) *reinterpret_cast<float4*>(o + t) = make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]);
-            } else {
+            for (int t = 0; t < 16; t += 4) {
+                if (vec && cb * 16 + t < P.cout) {
+                    const float4 f = make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]);
+                    if (P.ksplit > 1) atomicAdd(reinterpret_cast<float4*>(o + t), f);
+                    else *reinterpret_cast<float4*>(o + t) = f;
+                } else if (!vec) {
 #pragma unroll
-                for (int t = 0; t < 16; t++)
-                    if (cb * 16 + t < P.cout) o[t] = v[t];
+                    for (int u = 0; u < 4; u++)
+                        if (cb * 16 + t + u < P.cout) {
+                            if (P.ksplit > 1) atomicAdd(o + t + u, v[t + u]);
+                            else o[t + u] = v[t + u];
+                        }
+                }
             }
         }
     }
@@ -473,8 +547,7 @@ __host__ __device__ constexpr int dw_b_bytes(int NB) { return ((NB + 31) / 32) *
 struct DwParams {
     int nq;
     const float* x;      // [ns, cin_p]
-    int cin, cin_p, K;
-    const int* ebase;
+    int cin, cin_p, K, H;
     const unsigned short* koff;
     const int2* entries;
     const float* dout;   // [nq, cout]
@@ -484,14 +557,16 @@ struct DwParams {
     uint32_t tmem_cols;
 };
 
-__global__ void __launch_bounds__(FWD_THREADS) kp_dw_kernel(DwParams P) {
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) kp_dw_kernel(DwParams P) {
+    constexpr int FWD_THREADS = NW * 32, RPW = TILE_M / NW, NWARPS = NW;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;                       // 4 * MN_LBO = 64 KiB, 1024-aligned (swizzle uses address bits)
     unsigned char* sB = smem + 4 * MN_LBO;
     const int b_bytes = dw_b_bytes(P.NB);
     unsigned short* s_koff = reinterpret_cast<unsigned short*>(sB + b_bytes);
-    int* s_ebase = reinterpret_cast<int*>(s_koff + TILE_M * KOFF);
-    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(s_ebase + TILE_M);
+    int* s_row0 = reinterpret_cast<int*>(s_koff + TILE_M * KOFF);
+    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(s_row0 + TILE_M);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_mma + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -515,17 +590,10 @@ __global__ void __launch_bounds__(FWD_THREADS) kp_dw_kernel(DwParams P) {
     for (int tile = split; tile < P.n_tiles; tile += P.n_splits, step++) {
         const int tile_base = tile * TILE_M;
         if (step > 0) mbar_wait(bar_mma, (uint32_t)((step - 1) & 1));
-        for (int t = tid; t < TILE_M; t += FWD_THREADS) {
-            const int i = tile_base + t;
-            s_ebase[t] = (i < P.nq) ? P.ebase[i] : 0;
-        }
-        for (int t = tid; t < TILE_M * KOFF; t += FWD_THREADS) {
-            const int i = tile_base + t / KOFF;
-            s_koff[t] = (i < P.nq) ? P.koff[(size_t)i * KOFF + (t % KOFF)] : (unsigned short)0;
-        }
+        stage_headers<FWD_THREADS>(tile_base, P.nq, P.H, nullptr, P.koff, s_row0, s_koff);
         // dOut tile -> B (TF32), warp per point row, lane per group of 4 outputs
-        for (int r = 0; r < 16; r++) {
-            const int p = warp * 16 + r;
+        for (int r = 0; r < RPW; r++) {
+            const int p = warp * RPW + r;
             const int i = tile_base + p;
             for (int n4 = lane; n4 < P.NB / 4; n4 += 32) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -545,8 +613,8 @@ __global__ void __launch_bounds__(FWD_THREADS) kp_dw_kernel(DwParams P) {
                 *reinterpret_cast<float4*>(sB + LayoutMNMajor::off(p, n4)) = v;
             }
         }
-        __syncthreads();  // s_ebase / s_koff ready
-        assemble_rows<8, LayoutMNMajor>(sA, warp, lane, chunk, P.cin_p, P.K, s_ebase, s_koff, P.entries, P.x);
+        __syncthreads();  // headers ready
+        assemble_rows<8, LayoutMNMajor, RPW>(sA, warp, lane, chunk, P.cin_p, P.K, s_row0, s_koff, P.entries, P.x);
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
@@ -570,14 +638,22 @@ __global__ void __launch_bounds__(FWD_THREADS) kp_dw_kernel(DwParams P) {
     const int col = chunk * CK + r;
     const int k = col / P.cin_p, c = col % P.cin_p;
     const bool row_ok = k < P.K && c < P.cin;
-    for (int cb = warp >> 2; cb < P.NB / 16; cb += 2) {
+    const bool vec = (P.cout & 3) == 0;
+    for (int cb = warp >> 2; cb < P.NB / 16; cb += NWARPS / 4) {
         float v[16];
         tmem_ld16(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cb * 16), v);
         if (row_ok) {
             float* o = P.dw + ((size_t)k * P.cin + c) * P.cout + n0 + cb * 16;
 #pragma unroll
-            for (int t = 0; t < 16; t++)
-                if (n0 + cb * 16 + t < P.cout) atomicAdd(o + t, v[t]);
+            for (int t = 0; t < 16; t += 4) {
+                if (vec && n0 + cb * 16 + t < P.cout) {
+                    atomicAdd(reinterpret_cast<float4*>(o + t), make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]));
+                } else if (!vec) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (n0 + cb * 16 + t + u < P.cout) atomicAdd(o + t + u, v[t + u]);
+                }
+            }
         }
     }
     tc_fence_before();
@@ -605,48 +681,49 @@ __global__ void __launch_bounds__(256) kp_tr_fill_kernel(const IdxT* __restrict_
     if (j >= 0 && j < ns) col[rowptr[j] + atomicAdd(&cursor[j], 1)] = (int)(t / H);
 }
 
-// each row's centre list sorted ascending so that the dX sums run in a fixed order (rows are short)
-__global__ void __launch_bounds__(256) kp_tr_sort_kernel(const int* __restrict__ rowptr, int ns, int* __restrict__ col) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+// each row's centre list put in ascending order (rank by counting, one warp per row; the entries of a row are
+// distinct), so that the dX sums run in a fixed order whatever order the atomics above filled the row in
+__global__ void __launch_bounds__(256) kp_tr_sort_kernel(const int* __restrict__ rowptr, int ns,
+                                                        const int* __restrict__ col, int* __restrict__ col_sorted,
+                                                        int* __restrict__ rowptr_last, const int* __restrict__ total) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j == 0 && lane == 0) *rowptr_last = *total;  // rowptr[ns]
     if (j >= ns) return;
-    const int a = rowptr[j], b = rowptr[j + 1];
-    for (int u = a + 1; u < b; u++) {
-        const int v = col[u];
-        int t = u - 1;
-        while (t >= a && col[t] > v) { col[t + 1] = col[t]; t--; }
-        col[t + 1] = v;
+    const int a = rowptr[j];
+    const int b = (j + 1 < ns) ? rowptr[j + 1] : *total;
+    for (int e = a + lane; e < b; e += 32) {
+        const int v = col[e];
+        int rank = 0;
+        for (int u = a; u < b; u++) rank += (col[u] < v) ? 1 : 0;
+        col_sorted[a + rank] = v;
     }
 }
 
-__global__ void kp_set_last_kernel(int* rowptr, int n, const int* total) { rowptr[n] = *total; }
-
 // ---------------------------------------------------------------------------------------------------------- host side
-static long long entry_capacity(long long n_pairs) {
-    long long cap = n_pairs * 15;
-    const long long limit = 1LL << 29;  // 4 GiB of entries
-    if (cap > limit) cap = n_pairs * 4 > limit ? limit : n_pairs * 4;
-    return cap > 0 ? cap : 1;
-}
-
 struct Lists {
-    int* ebase;
     unsigned short* koff;
     int2* entries;
 };
 
 static int build_lists(Scratch& S, const float* centres, int nc, const float* others, int no, const Table& T,
-                       long long n_pairs, const float* kp, int K, float kp_sign, float extent, int* d_err, Lists* L,
+                       long long n_pairs, int max_row, const float* kp, int K, float kp_sign, float extent, Lists* L,
                        cudaStream_t stream) {
-    const long long cap = entry_capacity(n_pairs);
-    L->ebase = S.alloc<int>(nc);
+    if (n_pairs * 15 >= (1LL << 31)) return fail(KP_ERR_UNSUPPORTED, "kpconv: neighbour table too large (Nq*H*15 >= 2^31)");
     L->koff = S.alloc<unsigned short>((size_t)nc * KOFF);
-    L->entries = S.alloc<int2>((size_t)cap);
-    unsigned long long* counter = S.alloc<unsigned long long>(1);
+    L->entries = S.alloc<int2>((size_t)(n_pairs > 0 ? n_pairs : 1) * 15);
     if (S.status != KP_OK) return S.status;
-    KP_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
     ProfileScope ps("kp_influence", stream);
-    kp_influence_kernel<<<ceil_div(nc, 4), 128, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, 1.f / extent,
-                                                            L->ebase, L->koff, L->entries, cap, counter, d_err);
+    const int grid = ceil_div(nc, 8);
+    const float inv_ext = 1.f / extent;
+    if (max_row > 0 && max_row <= 32)
+        kp_influence_kernel<1><<<grid, 256, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, inv_ext, L->koff, L->entries);
+    else if (max_row > 0 && max_row <= 64)
+        kp_influence_kernel<2><<<grid, 256, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, inv_ext, L->koff, L->entries);
+    else if (max_row > 0 && max_row <= 96)
+        kp_influence_kernel<3><<<grid, 256, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, inv_ext, L->koff, L->entries);
+    else
+        kp_influence_kernel<0><<<grid, 256, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, inv_ext, L->koff, L->entries);
     KP_CHECK_LAUNCH();
     return KP_OK;
 }
@@ -654,15 +731,16 @@ static int build_lists(Scratch& S, const float* centres, int nc, const float* ot
 static int pad4(int c) { return (c + 3) & ~3; }
 
 // out[nc, cout] = sum over entry lists of w * x[j, :] contracted with W (strides sk, sc, sn over (k, c_in, n_out))
-static int run_forward(const char* tag, Scratch& S, int nc, const float* x, int n_x_rows, int cin, const Lists& L, const float* W,
-                       long long sk, long long sc, long long sn, int cout, int K, float* out, cudaStream_t stream) {
+static int run_forward(const char* tag, Scratch& S, int nc, const int* rowptr, int H, const float* x, int n_x_rows, int cin,
+                       const Lists& L, const float* W, long long sk, long long sc, long long sn, int cout, int K,
+                       float* out, cudaStream_t stream) {
     const int cin_p = pad4(cin);
     const float* xg = x;
     if (cin_p != cin) {
         float* xp = S.alloc<float>((size_t)n_x_rows * cin_p);
         if (S.status != KP_OK) return S.status;
-        kp_pad_cols_kernel<<<ceil_div((long long)n_x_rows * cin_p, 256) < 2048 ? ceil_div((long long)n_x_rows * cin_p, 256) : 2048,
-                             256, 0, stream>>>(x, n_x_rows, cin, cin_p, xp);
+        const long long tot = (long long)n_x_rows * cin_p;
+        kp_pad_cols_kernel<<<ceil_div(tot, 256) < 2048 ? ceil_div(tot, 256) : 2048, 256, 0, stream>>>(x, n_x_rows, cin, cin_p, xp);
         KP_CHECK_LAUNCH();
         xg = xp;
     }
@@ -682,17 +760,31 @@ static int run_forward(const char* tag, Scratch& S, int nc, const float* x, int 
     }
     FwdParams P;
     P.nq = nc; P.x = xg; P.cin_p = cin_p; P.K = K;
-    P.ebase = L.ebase; P.koff = L.koff; P.entries = L.entries;
+    P.rowptr = rowptr; P.H = H;
+    P.koff = L.koff; P.entries = L.entries;
     P.images = images; P.NB = NB; P.n_nblk = n_nblk; P.n_chunks = n_chunks;
     P.out = out; P.cout = cout;
+    // split the reduction across CTAs when the tiles alone cannot fill the 148 SMs (two CTAs each)
+    const int n_tiles = ceil_div(nc, TILE_M);
+    int ksplit = ceil_div(2 * 148, n_tiles);
+    if (ksplit > n_chunks) ksplit = n_chunks;
+    if (ksplit > 16) ksplit = 16;
+    if (ksplit < 1) ksplit = 1;
+    ksplit = ceil_div(n_chunks, ceil_div(n_chunks, ksplit));  // no empty splits
+    P.ksplit = ksplit;
+    if (ksplit > 1) KP_CUDA(cudaMemsetAsync(out, 0, (size_t)nc * cout * sizeof(float), stream));
     uint32_t cols = 32;
     while ((int)cols < n_nblk * NB) cols <<= 1;
     P.tmem_cols = cols;
     const size_t smem = (size_t)A_BYTES + (size_t)NB * CK * 4 + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
-    KP_CUDA(cudaFuncSetAttribute(kp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
+    if (smem <= (size_t)SMEM_TWO_CTAS) {
+        KP_CUDA(cudaFuncSetAttribute(kp_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ProfileScope ps(tag, stream);
-        kp_fwd_kernel<<<ceil_div(nc, TILE_M), FWD_THREADS, smem, stream>>>(P);
+        kp_fwd_kernel<8><<<dim3(n_tiles, ksplit), 256, smem, stream>>>(P);
+    } else {
+        KP_CUDA(cudaFuncSetAttribute(kp_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ProfileScope ps(tag, stream);
+        kp_fwd_kernel<16><<<dim3(n_tiles, ksplit), 512, smem, stream>>>(P);
     }
     KP_CHECK_LAUNCH();
     return KP_OK;
@@ -702,19 +794,9 @@ static int check_args(int nq, int ns, int H, int idx_stride, int cin, int cout, 
     if (nq < 0 || ns < 0 || H < 0 || idx_stride < H || cin <= 0 || cout <= 0) return fail(KP_ERR_ARG, "kpconv: bad sizes");
     if (K <= 0 || K > 15) return fail(KP_ERR_UNSUPPORTED, "kpconv: kernel_size must be 1..15");
     if (!(extent > 0.f)) return fail(KP_ERR_ARG, "kpconv: KP_extent must be positive");
+    if (H > 4096) return fail(KP_ERR_UNSUPPORTED, "kpconv: more than 4096 neighbour columns");
     if ((long long)ns >= (1LL << K_SHIFT) || (long long)nq >= (1LL << K_SHIFT))
         return fail(KP_ERR_UNSUPPORTED, "kpconv: more than 2^27 points in one call");
-    return KP_OK;
-}
-
-static int check_err_flag(int* d_err, cudaStream_t stream, bool sync_now) {
-    // The entry-list capacity is an exact upper bound for every realistic shape (15 entries per neighbour);
-    // only the capped case can overflow, and that one is checked synchronously.
-    if (!sync_now) return KP_OK;
-    int h = 0;
-    KP_CUDA(cudaMemcpyAsync(&h, d_err, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    KP_CUDA(cudaStreamSynchronize(stream));
-    if (h) return fail(KP_ERR_UNSUPPORTED, "kpconv: influence entry list overflow");
     return KP_OK;
 }
 
@@ -729,18 +811,12 @@ int kpconv_forward_device(const float* q, int nq, const float* s, int ns, const 
         return KP_OK;
     }
     Scratch S(stream);
-    int* d_err = S.alloc<int>(1);
-    if (S.status != KP_OK) return S.status;
-    KP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), stream));
     Table T;
     T.idx = idx; T.rowptr = nullptr; T.H = H; T.stride = idx_stride; T.is_i64 = idx_is_i64;
     Lists L;
-    const long long n_pairs = (long long)nq * H;
-    rc = build_lists(S, q, nq, s, ns, T, n_pairs, kp, K, 1.f, extent, d_err, &L, stream);
+    rc = build_lists(S, q, nq, s, ns, T, (long long)nq * H, H, kp, K, 1.f, extent, &L, stream);
     if (rc != KP_OK) return rc;
-    rc = run_forward("kp_fwd", S, nq, x, ns, cin, L, w, (long long)cin * cout, cout, 1, cout, K, out, stream);
-    if (rc != KP_OK) return rc;
-    return check_err_flag(d_err, stream, entry_capacity(n_pairs) < n_pairs * 15);
+    return run_forward("kp_fwd", S, nq, nullptr, H, x, ns, cin, L, w, (long long)cin * cout, cout, 1, cout, K, out, stream);
 }
 
 int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
@@ -749,12 +825,11 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
     int rc = check_args(nq, ns, H, idx_stride, cin, cout, K, extent);
     if (rc != KP_OK) return rc;
     KP_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * cin * cout * sizeof(float), stream));
-    if (ns > 0) KP_CUDA(cudaMemsetAsync(dx, 0, (size_t)ns * cin * sizeof(float), stream));
-    if (nq == 0 || ns == 0 || H == 0) return KP_OK;
+    if (nq == 0 || ns == 0 || H == 0) {
+        if (ns > 0) KP_CUDA(cudaMemsetAsync(dx, 0, (size_t)ns * cin * sizeof(float), stream));
+        return KP_OK;
+    }
     Scratch S(stream);
-    int* d_err = S.alloc<int>(1);
-    if (S.status != KP_OK) return S.status;
-    KP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), stream));
     const long long n_pairs = (long long)nq * H;
 
     // ---- dW: entry lists centred on the queries (same as forward)
@@ -762,7 +837,7 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
         Table T;
         T.idx = idx; T.rowptr = nullptr; T.H = H; T.stride = idx_stride; T.is_i64 = idx_is_i64;
         Lists L;
-        rc = build_lists(S, q, nq, s, ns, T, n_pairs, kp, K, 1.f, extent, d_err, &L, stream);
+        rc = build_lists(S, q, nq, s, ns, T, n_pairs, H, kp, K, 1.f, extent, &L, stream);
         if (rc != KP_OK) return rc;
         const int cin_p = pad4(cin);
         const float* xg = x;
@@ -776,8 +851,8 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
         }
         const int cout_p = (cout + 15) & ~15;
         DwParams P;
-        P.nq = nq; P.x = xg; P.cin = cin; P.cin_p = cin_p; P.K = K;
-        P.ebase = L.ebase; P.koff = L.koff; P.entries = L.entries;
+        P.nq = nq; P.x = xg; P.cin = cin; P.cin_p = cin_p; P.K = K; P.H = H;
+        P.koff = L.koff; P.entries = L.entries;
         P.dout = dout; P.cout = cout;
         P.NB = cout_p < 256 ? cout_p : 256;
         const int n_slices = ceil_div(cout_p, P.NB);
@@ -792,10 +867,14 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
         while ((int)cols < P.NB) cols <<= 1;
         P.tmem_cols = cols;
         const size_t smem = (size_t)4 * MN_LBO + (size_t)dw_b_bytes(P.NB) + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
-        KP_CUDA(cudaFuncSetAttribute(kp_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        {
+        if (smem <= (size_t)SMEM_TWO_CTAS) {
+            KP_CUDA(cudaFuncSetAttribute(kp_dw_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ProfileScope ps("kp_dw", stream);
-            kp_dw_kernel<<<dim3(n_chunks, splits, n_slices), FWD_THREADS, smem, stream>>>(P);
+            kp_dw_kernel<8><<<dim3(n_chunks, splits, n_slices), 256, smem, stream>>>(P);
+        } else {
+            KP_CUDA(cudaFuncSetAttribute(kp_dw_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ProfileScope ps("kp_dw", stream);
+            kp_dw_kernel<16><<<dim3(n_chunks, splits, n_slices), 512, smem, stream>>>(P);
         }
         KP_CHECK_LAUNCH();
     }
@@ -808,34 +887,33 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
         int* total = S.alloc<int>(1);
         int* scan_tmp = S.alloc<int>(scan_tmp_ints(ns));
         int* col = S.alloc<int>((size_t)n_pairs);
+        int* col_sorted = S.alloc<int>((size_t)n_pairs);
         if (S.status != KP_OK) return S.status;
+        ProfileScope* pst = new ProfileScope("kp_transpose", stream);
         KP_CUDA(cudaMemsetAsync(deg, 0, (size_t)(ns + 1) * sizeof(int), stream));
         KP_CUDA(cudaMemsetAsync(cursor, 0, (size_t)ns * sizeof(int), stream));
         const int grid = ceil_div(n_pairs, 256);
-        ProfileScope* pst = new ProfileScope("kp_transpose", stream);
         if (idx_is_i64) kp_tr_count_kernel<long long><<<grid, 256, 0, stream>>>((const long long*)idx, nq, H, idx_stride, ns, deg);
         else kp_tr_count_kernel<int><<<grid, 256, 0, stream>>>((const int*)idx, nq, H, idx_stride, ns, deg);
         KP_CHECK_LAUNCH();
         rc = exclusive_scan(deg, rowptr, ns, total, scan_tmp, stream);
         if (rc != KP_OK) return rc;
-        kp_set_last_kernel<<<1, 1, 0, stream>>>(rowptr, ns, total);
-        KP_CHECK_LAUNCH();
         if (idx_is_i64) kp_tr_fill_kernel<long long><<<grid, 256, 0, stream>>>((const long long*)idx, nq, H, idx_stride, ns, rowptr, cursor, col);
         else kp_tr_fill_kernel<int><<<grid, 256, 0, stream>>>((const int*)idx, nq, H, idx_stride, ns, rowptr, cursor, col);
         KP_CHECK_LAUNCH();
-        kp_tr_sort_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(rowptr, ns, col);
+        kp_tr_sort_kernel<<<ceil_div(ns, 8), 256, 0, stream>>>(rowptr, ns, col, col_sorted, rowptr + ns, total);
         delete pst;
         KP_CHECK_LAUNCH();
         Table T;
-        T.idx = col; T.rowptr = rowptr; T.H = 0; T.stride = 0; T.is_i64 = 0;
+        T.idx = col_sorted; T.rowptr = rowptr; T.H = 0; T.stride = 0; T.is_i64 = 0;
         Lists L;
-        rc = build_lists(S, s, ns, q, nq, T, n_pairs, kp, K, -1.f, extent, d_err, &L, stream);
+        rc = build_lists(S, s, ns, q, nq, T, n_pairs, 0, kp, K, -1.f, extent, &L, stream);
         if (rc != KP_OK) return rc;
         // W'[k][c' = o][n' = c] = W[k][c][o]
-        rc = run_forward("kp_fwd_dx", S, ns, dout, nq, cout, L, w, (long long)cin * cout, 1, cout, cin, K, dx, stream);
+        rc = run_forward("kp_fwd_dx", S, ns, rowptr, 0, dout, nq, cout, L, w, (long long)cin * cout, 1, cout, cin, K, dx, stream);
         if (rc != KP_OK) return rc;
     }
-    return check_err_flag(d_err, stream, entry_capacity(n_pairs) < n_pairs * 15);
+    return KP_OK;
 }
 
 }  // namespace kp
