@@ -7,7 +7,8 @@
 
 namespace kp {
 int batch_query_device(const float* q, int nq, const float* s, int ns, const int* qb_host, const int* sb_host, int nb,
-                       float radius, void* out, int out_is_i64, int cap, int* hmax_host, cudaStream_t stream);
+                       float radius, void* out, int out_is_i64, int cap, int* hmax_host, int* d_result,
+                       cudaStream_t stream);
 int grid_subsample_device(const float* pts, int n, const int* lens_host, int nb, const float* feats, int fdim,
                           const int* classes, int ldim, float dl, int max_p, int order_mode, const float* rot_host,
                           float* out_pts, int* out_lens_host, float* out_feats, int* out_classes, int* m_host,
@@ -58,7 +59,15 @@ int kp_batch_query_dev(const float* queries, int nq, const float* supports, int 
                        const int* s_batches, int nb, float radius, void* out, int out_is_i64, int cap, int* hmax,
                        void* stream) {
     return batch_query_device(queries, nq, supports, ns, q_batches, s_batches, nb, radius, out, out_is_i64, cap, hmax,
-                              (cudaStream_t)stream);
+                              nullptr, (cudaStream_t)stream);
+}
+
+int kp_batch_query_dev_async(const float* queries, int nq, const float* supports, int ns, const int* q_batches,
+                             const int* s_batches, int nb, float radius, void* out, int out_is_i64, int cap,
+                             int* d_result, void* stream) {
+    if (!d_result) return fail(KP_ERR_ARG, "batch_query_async: d_result is required");
+    return batch_query_device(queries, nq, supports, ns, q_batches, s_batches, nb, radius, out, out_is_i64, cap, nullptr,
+                              d_result, (cudaStream_t)stream);
 }
 
 int kp_batch_query_host(const float* queries, int nq, const float* supports, int ns, const int* q_batches,
@@ -75,7 +84,7 @@ int kp_batch_query_host(const float* queries, int nq, const float* supports, int
     while (true) {
         if ((rc = dout.alloc((size_t)nq * cap * sizeof(int)))) return rc;
         rc = batch_query_device((const float*)dq.p, nq, (const float*)ds.p, ns, q_batches, s_batches, nb, radius, dout.p,
-                                0, cap, hmax, 0);
+                                0, cap, hmax, nullptr, 0);
         if (rc != KP_OK) return rc;
         if (*hmax <= cap) break;
         cap = *hmax;  // rare: a row was wider than the first guess, redo with the exact width

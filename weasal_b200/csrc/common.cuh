@@ -50,34 +50,53 @@ struct ProfileScope {
     }
 };
 
-// ---- stream-ordered scratch memory --------------------------------------------------------------------------------
-// Temporaries come from the device's default stream-ordered pool (cudaMallocAsync); the pool's release threshold
-// is raised once so that steady-state calls never hit the OS allocator.
-int pool_init_once();
+// ---- scratch memory ----------------------------------------------------------------------------------------------------
+// Every entry point carves its temporaries out of a per-(thread, stream) arena that persists across calls: calls on
+// one stream execute in order, so the next call may reuse the bytes of the previous one without any allocator
+// traffic (a training step makes ~400 temporaries). The arena grows by adding blocks; at the start of a later call
+// the blocks are merged into one (after a stream sync) so steady state is a single bump pointer.
+struct ArenaBlock { char* base; size_t cap; };
+struct Arena {
+    ArenaBlock blocks[16];
+    int nblocks = 0;
+    int cur = 0;
+    size_t off = 0;
+};
+Arena* arena_for(cudaStream_t stream);
+int arena_begin(Arena* a, cudaStream_t stream);
+void* arena_alloc(Arena* a, size_t bytes);
 
 struct Scratch {
     cudaStream_t stream;
-    void* ptrs[48];
-    int n = 0;
+    Arena* arena;
     int status = KP_OK;
-    explicit Scratch(cudaStream_t s) : stream(s) { status = pool_init_once(); }
+    explicit Scratch(cudaStream_t s) : stream(s) {
+        arena = arena_for(s);
+        status = arena_begin(arena, s);
+    }
     template <typename T>
     T* alloc(size_t count) {
         if (status != KP_OK) return nullptr;
-        void* p = nullptr;
-        size_t bytes = (count ? count : 1) * sizeof(T);
-        cudaError_t e = cudaMallocAsync(&p, bytes, stream);
-        if (e != cudaSuccess || n >= 48) {
-            status = fail(KP_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+        void* p = arena_alloc(arena, (count ? count : 1) * sizeof(T));
+        if (!p) {
+            status = fail(KP_ERR_CUDA, "scratch arena: cudaMalloc failed");
             return nullptr;
         }
-        ptrs[n++] = p;
         return reinterpret_cast<T*>(p);
     }
-    ~Scratch() {
-        for (int i = 0; i < n; i++) cudaFreeAsync(ptrs[i], stream);
-    }
 };
+
+// small host arrays (batch offsets, grid rotations) travel to the device as a kernel argument: no pageable
+// host->device copy, which costs ~25 us of host time each
+constexpr int SMALL_WORDS = 252;
+struct SmallBlob {
+    int n;
+    int w[SMALL_WORDS];
+};
+int upload_small(const void* host, size_t bytes, void* d_dst, cudaStream_t stream);
+inline int upload_offsets(const int* host_offsets, int n_plus_1, int* d_dst, cudaStream_t stream) {
+    return upload_small(host_offsets, (size_t)n_plus_1 * sizeof(int), d_dst, stream);
+}
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline int num_bits(unsigned long long v) {  // bits needed to represent values in [0, v]

@@ -454,8 +454,8 @@ int grid_subsample_device(const float* pts, int n, const int* lens_host, int nb,
     int* d_seg_start = S.alloc<int>(n + 1);
     if (S.status != KP_OK) return S.status;
 
-    KP_CUDA(cudaMemcpyAsync(d_offs, offs.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
-    if (rot_host) KP_CUDA(cudaMemcpyAsync(d_rot, rot_host, (size_t)nb * 9 * sizeof(float), cudaMemcpyHostToDevice, stream));
+    { int rc0 = upload_offsets(offs.data(), nb + 1, d_offs, stream); if (rc0 != KP_OK) return rc0; }
+    if (rot_host) { int rc0 = upload_small(rot_host, (size_t)nb * 9 * sizeof(float), d_rot, stream); if (rc0 != KP_OK) return rc0; }
     KP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), stream));
 
     GsParams P;
@@ -498,7 +498,7 @@ int grid_subsample_device(const float* pts, int n, const int* lens_host, int nb,
         long long* d_soff = S.alloc<long long>(nb);
         d_pos_local = S.alloc<int>(n);
         if (S.status != KP_OK) return S.status;
-        KP_CUDA(cudaMemcpyAsync(d_soff, soff.data(), nb * sizeof(long long), cudaMemcpyHostToDevice, stream));
+        { int rc0 = upload_small(soff.data(), nb * sizeof(long long), d_soff, stream); if (rc0 != KP_OK) return rc0; }
         ProfileScope pso("gs_order", stream);
         gs_order_kernel<<<nb, ORD_THREADS, 0, stream>>>(d_seq_key, d_seq_start, sched, d_scratch, d_soff, d_offs,
                                                        d_pos_local);

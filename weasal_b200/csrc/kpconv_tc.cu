@@ -186,11 +186,12 @@ __global__ void __launch_bounds__(256) kp_influence_kernel(const float* __restri
 #pragma unroll
     for (int k = 0; k < 15; k++) cnt[k] = 0;
 
-    if constexpr (NB > 0) {
-        float w[NB][15];
-        unsigned jv[NB];
+    if (NB > 0 && cnt_row <= NB * 32) {
+        constexpr int NBR = NB > 0 ? NB : 1;
+        float w[NBR][15];
+        unsigned jv[NBR];
 #pragma unroll
-        for (int b = 0; b < NB; b++) {
+        for (int b = 0; b < NBR; b++) {
             const int h = b * 32 + lane;
             long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
             const bool valid = j >= 0 && j < no;
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(256) kp_influence_kernel(const float* __restri
         }
         if (total == 0) return;
 #pragma unroll
-        for (int b = 0; b < NB; b++) {
+        for (int b = 0; b < NBR; b++) {
 #pragma unroll
             for (int k = 0; k < 15; k++) {
                 const unsigned m = __ballot_sync(0xffffffffu, w[b][k] > 0.f);
@@ -722,6 +723,8 @@ static int build_lists(Scratch& S, const float* centres, int nc, const float* ot
         kp_influence_kernel<2><<<grid, 256, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, inv_ext, L->koff, L->entries);
     else if (max_row > 0 && max_row <= 96)
         kp_influence_kernel<3><<<grid, 256, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, inv_ext, L->koff, L->entries);
+    else if (max_row == 0)  // CSR rows of unknown length: rows up to 64 entries take the single-evaluation path
+        kp_influence_kernel<2><<<grid, 256, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, inv_ext, L->koff, L->entries);
     else
         kp_influence_kernel<0><<<grid, 256, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, inv_ext, L->koff, L->entries);
     KP_CHECK_LAUNCH();

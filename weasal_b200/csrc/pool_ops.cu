@@ -7,27 +7,39 @@
 
 namespace kp {
 
-template <typename IdxT>
+// lanes stride the channels; the neighbour loop is outermost so each index is read once per row, and a lane keeps the
+// running maxima of its (up to CPL) channels in registers. C > 32*CPL falls back to repeating the sweep per block of
+// 32*CPL channels.
+template <typename IdxT, int CPL>
 __global__ void __launch_bounds__(256) max_pool_fwd_kernel(const float* __restrict__ x, int ns, int C,
                                                           const IdxT* __restrict__ idx, int nq, int H, int stride,
                                                           float* __restrict__ out, int* __restrict__ arg) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= nq) return;
-    for (int c0 = 0; c0 < C; c0 += 32) {
-        const int c = c0 + lane;
-        float best = 0.f;
-        int bj = -1;
-        bool first = true;
+    const IdxT* row = idx + (size_t)i * stride;
+    for (int cb = 0; cb < C; cb += 32 * CPL) {
+        float best[CPL];
+        int bj[CPL];
+#pragma unroll
+        for (int u = 0; u < CPL; u++) { best[u] = 0.f; bj[u] = -1; }
         for (int h = 0; h < H; h++) {
-            const long long j = (long long)idx[(size_t)i * stride + h];
+            const long long j = (long long)row[h];
             const bool real = j >= 0 && j < ns;
-            const float v = (real && c < C) ? x[(size_t)j * C + c] : 0.f;
-            if (first || v > best) { best = v; bj = real ? (int)j : -1; first = false; }
+#pragma unroll
+            for (int u = 0; u < CPL; u++) {
+                const int c = cb + u * 32 + lane;
+                const float v = (real && c < C) ? __ldg(x + (size_t)j * C + c) : 0.f;
+                if (h == 0 || v > best[u]) { best[u] = v; bj[u] = real ? (int)j : -1; }
+            }
         }
-        if (c < C) {
-            out[(size_t)i * C + c] = best;
-            arg[(size_t)i * C + c] = bj;
+#pragma unroll
+        for (int u = 0; u < CPL; u++) {
+            const int c = cb + u * 32 + lane;
+            if (c < C) {
+                out[(size_t)i * C + c] = best[u];
+                arg[(size_t)i * C + c] = bj[u];
+            }
         }
     }
 }
@@ -59,8 +71,13 @@ __global__ void __launch_bounds__(256) closest_pool_kernel(const float* __restri
 int max_pool_fwd_device(const float* x, int ns, int C, const void* idx, int is_i64, int nq, int H, int stride,
                         float* out, int* arg, cudaStream_t stream) {
     if (nq == 0 || C == 0) return KP_OK;
-    if (is_i64) max_pool_fwd_kernel<long long><<<ceil_div(nq, 8), 256, 0, stream>>>(x, ns, C, (const long long*)idx, nq, H, stride, out, arg);
-    else max_pool_fwd_kernel<int><<<ceil_div(nq, 8), 256, 0, stream>>>(x, ns, C, (const int*)idx, nq, H, stride, out, arg);
+    if (C <= 64) {
+        if (is_i64) max_pool_fwd_kernel<long long, 2><<<ceil_div(nq, 8), 256, 0, stream>>>(x, ns, C, (const long long*)idx, nq, H, stride, out, arg);
+        else max_pool_fwd_kernel<int, 2><<<ceil_div(nq, 8), 256, 0, stream>>>(x, ns, C, (const int*)idx, nq, H, stride, out, arg);
+    } else {
+        if (is_i64) max_pool_fwd_kernel<long long, 8><<<ceil_div(nq, 8), 256, 0, stream>>>(x, ns, C, (const long long*)idx, nq, H, stride, out, arg);
+        else max_pool_fwd_kernel<int, 8><<<ceil_div(nq, 8), 256, 0, stream>>>(x, ns, C, (const int*)idx, nq, H, stride, out, arg);
+    }
     KP_CHECK_LAUNCH();
     return KP_OK;
 }

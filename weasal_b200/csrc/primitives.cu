@@ -48,16 +48,77 @@ int profile_read(char* buf, int buflen) {
     return (int)out.size();
 }
 
-int pool_init_once() {
-    static thread_local int done_dev = -1;
+namespace {
+struct ArenaKey { cudaStream_t stream; int device; Arena arena; };
+thread_local std::vector<ArenaKey*> g_arenas;
+}  // namespace
+
+Arena* arena_for(cudaStream_t stream) {
     int dev = 0;
-    KP_CUDA(cudaGetDevice(&dev));
-    if (done_dev == dev) return KP_OK;
-    cudaMemPool_t pool;
-    KP_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-    unsigned long long thr = ~0ULL;
-    KP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-    done_dev = dev;
+    cudaGetDevice(&dev);
+    for (auto* k : g_arenas)
+        if (k->stream == stream && k->device == dev) return &k->arena;
+    auto* k = new ArenaKey{stream, dev, Arena()};
+    g_arenas.push_back(k);
+    return &k->arena;
+}
+
+int arena_begin(Arena* a, cudaStream_t stream) {
+    if (a->nblocks > 1) {  // merge the blocks a previous call had to add
+        size_t total = 0;
+        for (int i = 0; i < a->nblocks; i++) total += a->blocks[i].cap;
+        KP_CUDA(cudaStreamSynchronize(stream));
+        for (int i = 0; i < a->nblocks; i++) cudaFree(a->blocks[i].base);
+        a->nblocks = 0;
+        void* p = nullptr;
+        KP_CUDA(cudaMalloc(&p, total));
+        a->blocks[0] = {(char*)p, total};
+        a->nblocks = 1;
+    }
+    a->cur = 0;
+    a->off = 0;
+    return KP_OK;
+}
+
+void* arena_alloc(Arena* a, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    while (a->cur < a->nblocks) {
+        ArenaBlock& b = a->blocks[a->cur];
+        if (a->off + bytes <= b.cap) {
+            void* p = b.base + a->off;
+            a->off += bytes;
+            return p;
+        }
+        a->cur++;
+        a->off = 0;
+    }
+    if (a->nblocks >= 16) return nullptr;
+    size_t prev = a->nblocks ? a->blocks[a->nblocks - 1].cap : 0;
+    size_t cap = bytes > 2 * prev ? bytes : 2 * prev;
+    if (cap < ((size_t)32 << 20)) cap = (size_t)32 << 20;
+    void* p = nullptr;
+    if (cudaMalloc(&p, cap) != cudaSuccess) return nullptr;
+    a->blocks[a->nblocks] = {(char*)p, cap};
+    a->cur = a->nblocks++;
+    a->off = bytes;
+    return p;
+}
+
+__global__ void write_small_kernel(SmallBlob b, int* dst) {
+    for (int i = threadIdx.x; i < b.n; i += blockDim.x) dst[i] = b.w[i];
+}
+
+int upload_small(const void* host, size_t bytes, void* d_dst, cudaStream_t stream) {
+    if (bytes == 0) return KP_OK;
+    if ((bytes & 3) == 0 && bytes <= SMALL_WORDS * sizeof(int)) {
+        SmallBlob b;
+        b.n = (int)(bytes / 4);
+        memcpy(b.w, host, bytes);
+        write_small_kernel<<<1, 128, 0, stream>>>(b, (int*)d_dst);
+        KP_CHECK_LAUNCH();
+    } else {
+        KP_CUDA(cudaMemcpyAsync(d_dst, host, bytes, cudaMemcpyHostToDevice, stream));
+    }
     return KP_OK;
 }
 

@@ -234,8 +234,12 @@ __global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32) rs_search_kernel(
 // ---------------------------------------------------------------------------------------------------------- host side
 // q, s, out are device pointers; qb_host / sb_host are host batch lengths. out is [nq, cap] (int32 or int64).
 // *hmax_host receives the true maximum neighbour count (may exceed cap: rows then hold their cap closest).
+// d_result (optional): device int[2] that receives {max neighbour count, error bits}. When given, the call does NOT
+// synchronise and *hmax_host is left untouched: the caller reads d_result later (the pyramid builder reads the
+// results of all its searches with one copy). Error bits: 1 = grid too large, 2 = more than 1024 neighbours.
 int batch_query_device(const float* q, int nq, const float* s, int ns, const int* qb_host, const int* sb_host, int nb,
-                       float radius, void* out, int out_is_i64, int cap, int* hmax_host, cudaStream_t stream) {
+                       float radius, void* out, int out_is_i64, int cap, int* hmax_host, int* d_result,
+                       cudaStream_t stream) {
     if (nq < 0 || ns < 0 || nb <= 0 || cap < 0 || !(radius > 0.f)) return fail(KP_ERR_ARG, "batch_query: bad sizes / radius");
     if (nb > 1023) return fail(KP_ERR_UNSUPPORTED, "batch_query: more than 1023 batch elements");
     std::vector<int> qoff(nb + 1, 0), soff(nb + 1, 0);
@@ -245,8 +249,11 @@ int batch_query_device(const float* q, int nq, const float* s, int ns, const int
         soff[b + 1] = soff[b] + sb_host[b];
     }
     if (qoff[nb] != nq || soff[nb] != ns) return fail(KP_ERR_ARG, "batch_query: batch lengths do not sum to N");
-    *hmax_host = 0;
-    if (nq == 0) return KP_OK;
+    if (hmax_host) *hmax_host = 0;
+    if (nq == 0) {
+        if (d_result) KP_CUDA(cudaMemsetAsync(d_result, 0, 2 * sizeof(int), stream));
+        return KP_OK;
+    }
 
     Scratch S(stream);
     int* d_qoff = S.alloc<int>(nb + 1);
@@ -262,12 +269,12 @@ int batch_query_device(const float* q, int nq, const float* s, int ns, const int
     int* d_sslot = S.alloc<int>(ns);
     int* d_srank = S.alloc<int>(ns);
     float4* d_sorted = S.alloc<float4>(ns);
-    int* d_hmax = S.alloc<int>(2);
+    int* d_hmax = d_result ? d_result : S.alloc<int>(2);
     if (S.status != KP_OK) return S.status;
     int* d_err = d_hmax + 1;
 
-    KP_CUDA(cudaMemcpyAsync(d_qoff, qoff.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
-    KP_CUDA(cudaMemcpyAsync(d_soff, soff.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    { int rc0 = upload_offsets(qoff.data(), nb + 1, d_qoff, stream); if (rc0 != KP_OK) return rc0; }
+    { int rc0 = upload_offsets(soff.data(), nb + 1, d_soff, stream); if (rc0 != KP_OK) return rc0; }
     KP_CUDA(cudaMemsetAsync(d_hmax, 0, 2 * sizeof(int), stream));
 
     ProfileScope* ps = new ProfileScope("rs_build", stream);
@@ -310,6 +317,7 @@ int batch_query_device(const float* q, int nq, const float* s, int ns, const int
     delete ps2;
     KP_CHECK_LAUNCH();
 
+    if (d_result) return KP_OK;
     int h[2] = {0, 0};
     KP_CUDA(cudaMemcpyAsync(h, d_hmax, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     KP_CUDA(cudaStreamSynchronize(stream));

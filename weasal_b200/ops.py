@@ -60,6 +60,50 @@ def batch_query(queries, supports, q_batches, s_batches, radius, limit=None, dty
     return out[:, :width]
 
 
+class PendingSearches:
+    """Radius searches issued without a host sync (kp_batch_query_dev_async). ``resolve()`` reads all their
+    {Hmax, error} results with one device->host copy, re-runs the rare search whose rows outgrew its buffer, and
+    returns the column-sliced index matrices in issue order."""
+
+    def __init__(self, device, capacity=64):
+        self.results = torch.zeros((capacity, 2), dtype=torch.int32, device=device)
+        self.items = []
+
+    def add(self, queries, supports, q_batches, s_batches, radius, limit=None, dtype=torch.int64, cap_hint=80):
+        _need_cuda(queries, supports)
+        q, s = _f32c(queries), _f32c(supports)
+        qb, sb = _lens(q_batches), _lens(s_batches)
+        nq, ns = q.shape[0], s.shape[0]
+        cap = int(limit) if limit is not None else int(cap_hint)
+        out = torch.empty((nq, max(cap, 1)), dtype=dtype, device=q.device)
+        slot = len(self.items)
+        if slot >= self.results.shape[0]:
+            raise RuntimeError("PendingSearches: capacity exceeded")
+        rc = _lib.lib().kp_batch_query_dev_async(q.data_ptr(), nq, s.data_ptr(), ns, qb.ctypes.data, sb.ctypes.data,
+                                                 len(qb), float(radius), out.data_ptr(),
+                                                 1 if dtype == torch.int64 else 0, cap,
+                                                 self.results[slot].data_ptr(), _stream())
+        _lib.check(rc, "batch_query")
+        self.items.append((out, cap, limit, (q, s, qb, sb, radius, dtype)))
+        return slot
+
+    def resolve(self):
+        res = self.results[:max(len(self.items), 1)].cpu().numpy()  # the one synchronisation
+        outs = []
+        for slot, (out, cap, limit, args) in enumerate(self.items):
+            hmax, err = int(res[slot, 0]), int(res[slot, 1])
+            if err & 1:
+                raise RuntimeError("batch_query: cloud extent / radius exceeds 2^18 cells per axis")
+            if err & 2:
+                raise RuntimeError("batch_query: more than 1024 neighbours for one query")
+            if limit is None and hmax > cap:
+                q, s, qb, sb, radius, dtype = args
+                outs.append(batch_query(q, s, qb, sb, radius, dtype=dtype, cap_hint=hmax))
+            else:
+                outs.append(out[:, :min(hmax, cap)])
+        return outs
+
+
 # -------------------------------------------------------------------------------------------------- grid subsampling
 def grid_subsample(points, batches, features=None, classes=None, sampleDl=0.1, max_p=0, order="reference", rot=None):
     """GPU ``batch_grid_subsampling`` core (datasets/common.py:77-182 minus the numpy rotation, which ``rot`` folds

@@ -78,6 +78,8 @@ def segmentation_inputs(stacked_points, stacked_features, labels, stack_lengths,
     layer_blocks = []
     in_points, in_neighbors, in_pools, in_upsamples, in_lengths = [], [], [], [], []
     empty_idx = lambda: torch.zeros((0, 1), dtype=index_dtype, device=dev)
+    # every search is issued without a host sync; their widths are read back together at the end
+    pending = ops.PendingSearches(dev)
 
     for block in config.architecture:
         if not ('pool' in block or 'strided' in block or 'global' in block or 'upsample' in block):
@@ -89,7 +91,7 @@ def segmentation_inputs(stacked_points, stacked_features, labels, stack_lengths,
                 r = r_normal * config.deform_radius / config.conv_radius
             else:
                 r = r_normal
-            conv_i = batch_neighbors(pts, pts, lens, lens, r, limit=lim(layer), dtype=index_dtype)
+            conv_i = pending.add(pts, pts, lens, lens, r, limit=lim(layer), dtype=index_dtype)
         else:
             conv_i = empty_idx()
         if 'pool' in block or 'strided' in block:
@@ -100,9 +102,9 @@ def segmentation_inputs(stacked_points, stacked_features, labels, stack_lengths,
                 r = r_normal * config.deform_radius / config.conv_radius
             else:
                 r = r_normal
-            pool_i = batch_neighbors(pool_p, pts, pool_b, lens, r, limit=lim(layer), dtype=index_dtype)
-            up_i = batch_neighbors(pts, pool_p, lens, pool_b, 2 * r, limit=lim(layer + 1) if limits is not None and
-                                   layer + 1 < len(limits) else None, dtype=index_dtype)
+            pool_i = pending.add(pool_p, pts, pool_b, lens, r, limit=lim(layer), dtype=index_dtype)
+            up_i = pending.add(pts, pool_p, lens, pool_b, 2 * r, limit=lim(layer + 1) if limits is not None and
+                               layer + 1 < len(limits) else None, dtype=index_dtype)
         else:
             pool_i = empty_idx()
             pool_p = torch.zeros((0, 3), dtype=torch.float32, device=dev)
@@ -118,6 +120,12 @@ def segmentation_inputs(stacked_points, stacked_features, labels, stack_lengths,
         layer_blocks = []
         if 'global' in block or 'upsample' in block:
             break
+
+    found = pending.resolve()
+    for lst in (in_neighbors, in_pools, in_upsamples):
+        for i, v in enumerate(lst):
+            if isinstance(v, int):
+                lst[i] = found[v]
 
     feats = to_dev(stacked_features, torch.float32) if stacked_features is not None else None
     labs = to_dev(labels) if labels is not None else None
