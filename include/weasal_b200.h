@@ -64,7 +64,8 @@ int kp_batch_query_dev(const float* queries, int nq, const float* supports, int 
                        void* stream);
 
 /* Same search without the host synchronisation: d_result is a DEVICE int[2] that receives {true maximum neighbour
- * count, error bits (1 = extent/radius above 2^18 cells per axis, 2 = more than 1024 neighbours for one query)}.
+ * count, error bits (1 = extent/radius above 2^18 cells per axis, 2 = more than 1024 neighbours for one query,
+ * 4 = a query had more than 256 neighbours: repeat the search with kp_batch_query_dev, which escalates itself)}.
  * The device pyramid builder issues all searches of a batch this way and reads the results back with one copy. */
 int kp_batch_query_dev_async(const float* queries, int nq, const float* supports, int ns, const int* q_batches,
                              const int* s_batches, int nb, float radius, void* out, int out_is_i64, int cap,

@@ -404,3 +404,27 @@ def test_pooling_ops_match_reference_formulation(torch_cuda):
         assert torch.allclose(x1.grad, x2.grad, rtol=0, atol=1e-5)
     y = ops.max_pool(x, idx.to(torch.int32))
     assert torch.equal(y, ref_max(x))
+
+
+def test_batch_query_more_than_256_neighbours_escalates(torch_cuda):
+    """Rows beyond the fast kernel's 256-hit staging: the call repeats itself with the 1024-hit variant; beyond 1024
+    the library reports KP_ERR_TOO_DENSE instead of returning truncated rows."""
+    torch = torch_cuda
+    from weasal_b200 import ops, radius_neighbors as rn
+    rng = np.random.default_rng(4)
+    s = rng.uniform(0, 1, (900, 3)).astype(np.float32)
+    L = np.array([900], np.int32)
+    got = rn.batch_query(s, s, L, L, radius=0.7)
+    assert got.shape[1] > 256
+    assert np.array_equal(got, oracle.batch_neighbors(s, s, L, L, 0.7))
+    # the same through the deferred (no-sync) path used by the pyramid builder
+    d = torch.from_numpy(s).cuda()
+    pend = ops.PendingSearches(d.device)
+    pend.add(d, d, L, L, 0.7, dtype=torch.int32)
+    pend.add(d, d, L, L, 0.1, dtype=torch.int32)
+    a, b = pend.resolve()
+    assert np.array_equal(a.cpu().numpy(), got)
+    assert np.array_equal(b.cpu().numpy(), oracle.batch_neighbors(s, s, L, L, 0.1))
+    big = rng.uniform(0, 1, (3000, 3)).astype(np.float32)
+    with pytest.raises(RuntimeError, match="1024 neighbours"):
+        rn.batch_query(big, big, np.array([3000], np.int32), np.array([3000], np.int32), radius=0.9)

@@ -160,19 +160,78 @@ __device__ __forceinline__ float influence_w(float rx, float ry, float rz, float
 // entries per table column is the exact worst case, so the list never overflows and needs no allocator. Inside the
 // slot the entries are packed, grouped by kernel point (koff[i][k] = first entry of kernel point k, koff[i][15] =
 // count), each group in table-column order.
-// One warp per centre, lanes = neighbours. NB > 0: the row fits NB batches of 32 and every weight is evaluated once
-// (kept in registers between counting and writing); NB == 0: any row length, two evaluation passes.
-template <int NB>
-__global__ void __launch_bounds__(256) kp_influence_kernel(const float* __restrict__ centres, int nc,
-                                                          const float* __restrict__ others, int no, Table T,
-                                                          const float* __restrict__ kp, int K, float kp_sign,
-                                                          float inv_ext, unsigned short* __restrict__ koff,
-                                                          int2* __restrict__ entries) {
+constexpr int INF_WARPS = 8;
+constexpr int INF_MAX_ROW = 128;  // real neighbours staged per centre in shared memory (longer rows: two-pass path)
+
+// any row length: lanes = neighbours, one pass to count per kernel point, one to write
+__device__ __forceinline__ void influence_long_row(const float* __restrict__ others, int no, const Table& T, size_t pos0,
+                                               int cnt_row, float cx, float cy, float cz, const float* s_kp,
+                                               float inv_ext, unsigned short* __restrict__ koff_row,
+                                               int2* __restrict__ my_entries, int lane) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int cnt[15];
+#pragma unroll
+    for (int k = 0; k < 15; k++) cnt[k] = 0;
+    for (int hb = 0; hb < cnt_row; hb += 32) {
+        const int h = hb + lane;
+        long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
+        const bool valid = j >= 0 && j < no;
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        float rx = 0.f, ry = 0.f, rz = 0.f;
+        if (valid) { rx = others[3 * j] - cx; ry = others[3 * j + 1] - cy; rz = others[3 * j + 2] - cz; }
+#pragma unroll
+        for (int k = 0; k < 15; k++) {
+            const float w = valid ? influence_w(rx, ry, rz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext) : 0.f;
+            cnt[k] += __popc(__ballot_sync(0xffffffffu, w > 0.f));
+        }
+    }
+    int run[16];
+    int total = 0;
+#pragma unroll
+    for (int k = 0; k < 15; k++) { run[k] = total; total += cnt[k]; }
+    run[15] = total;
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) mine = (lane == k) ? run[k] : mine;
+    if (lane < 16) koff_row[lane] = (unsigned short)mine;
+    if (total == 0) return;
+    for (int hb = 0; hb < cnt_row; hb += 32) {
+        const int h = hb + lane;
+        long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
+        const bool valid = j >= 0 && j < no;
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        float rx = 0.f, ry = 0.f, rz = 0.f;
+        if (valid) { rx = others[3 * j] - cx; ry = others[3 * j + 1] - cy; rz = others[3 * j + 2] - cz; }
+#pragma unroll
+        for (int k = 0; k < 15; k++) {
+            const float w = valid ? influence_w(rx, ry, rz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext) : 0.f;
+            const unsigned m = __ballot_sync(0xffffffffu, w > 0.f);
+            if (w > 0.f) {
+                int2 e;
+                e.x = (int)((unsigned)j | ((unsigned)k << K_SHIFT));
+                e.y = __float_as_int(w);
+                my_entries[run[k] + __popc(m & lt_mask)] = e;
+            }
+            run[k] += __popc(m);
+        }
+    }
+}
+
+// One warp per centre. The real neighbours of the row are compacted into shared memory (shadow entries dropped), then
+// the warp sweeps the (kernel point, neighbour) pairs in kernel-point-major order, 32 pairs per step, one influence
+// evaluation per lane: ballot-compacting the non-zero weights in that order yields the list already grouped by kernel
+// point and ordered by table column, in a single pass.
+__global__ void __launch_bounds__(INF_WARPS * 32) kp_influence_kernel(const float* __restrict__ centres, int nc,
+                                                                     const float* __restrict__ others, int no, Table T,
+                                                                     const float* __restrict__ kp, int K, float kp_sign,
+                                                                     float inv_ext, unsigned short* __restrict__ koff,
+                                                                     int2* __restrict__ entries) {
     __shared__ float s_kp[16 * 3];
+    __shared__ float4 s_nb[INF_WARPS][INF_MAX_ROW];
     if (threadIdx.x < 48) s_kp[threadIdx.x] = (threadIdx.x < 3 * K) ? kp_sign * kp[threadIdx.x] : 1e30f;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * INF_WARPS + warp;
     if (i >= nc) return;
     const unsigned lt_mask = (1u << lane) - 1u;
     const float cx = centres[3 * (size_t)i], cy = centres[3 * (size_t)i + 1], cz = centres[3 * (size_t)i + 2];
@@ -181,103 +240,71 @@ __global__ void __launch_bounds__(256) kp_influence_kernel(const float* __restri
     if (T.rowptr) { row0 = (size_t)T.rowptr[i]; pos0 = row0; cnt_row = T.rowptr[i + 1] - T.rowptr[i]; }
     else { row0 = (size_t)i * T.H; pos0 = (size_t)i * T.stride; cnt_row = T.H; }
     int2* my_entries = entries + 15 * row0;
-
-    int cnt[15];
-#pragma unroll
-    for (int k = 0; k < 15; k++) cnt[k] = 0;
-
-    if (NB > 0 && cnt_row <= NB * 32) {
-        constexpr int NBR = NB > 0 ? NB : 1;
-        float w[NBR][15];
-        unsigned jv[NBR];
-#pragma unroll
-        for (int b = 0; b < NBR; b++) {
-            const int h = b * 32 + lane;
-            long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
-            const bool valid = j >= 0 && j < no;
-            jv[b] = (unsigned)j;
-            float rx = 0.f, ry = 0.f, rz = 0.f;
-            const bool any = __any_sync(0xffffffffu, valid);
-            if (valid) { rx = others[3 * j] - cx; ry = others[3 * j + 1] - cy; rz = others[3 * j + 2] - cz; }
-#pragma unroll
-            for (int k = 0; k < 15; k++) {
-                w[b][k] = (any && valid) ? influence_w(rx, ry, rz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext) : 0.f;
-                if (any) cnt[k] += __popc(__ballot_sync(0xffffffffu, w[b][k] > 0.f));
-            }
-        }
-        int run[16];
-        int total = 0;
-#pragma unroll
-        for (int k = 0; k < 15; k++) { run[k] = total; total += cnt[k]; }
-        run[15] = total;
-        {
-            int mine = 0;
-#pragma unroll
-            for (int k = 0; k < 16; k++) mine = (lane == k) ? run[k] : mine;
-            if (lane < 16) koff[(size_t)i * KOFF + lane] = (unsigned short)mine;
-        }
-        if (total == 0) return;
-#pragma unroll
-        for (int b = 0; b < NBR; b++) {
-#pragma unroll
-            for (int k = 0; k < 15; k++) {
-                const unsigned m = __ballot_sync(0xffffffffu, w[b][k] > 0.f);
-                if (w[b][k] > 0.f) {
-                    int2 e;
-                    e.x = (int)(jv[b] | ((unsigned)k << K_SHIFT));
-                    e.y = __float_as_int(w[b][k]);
-                    my_entries[run[k] + __popc(m & lt_mask)] = e;
-                }
-                run[k] += __popc(m);
-            }
-        }
-    } else {
-        for (int hb = 0; hb < cnt_row; hb += 32) {
-            const int h = hb + lane;
-            long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
-            const bool valid = j >= 0 && j < no;
-            if (!__any_sync(0xffffffffu, valid)) continue;
-            float rx = 0.f, ry = 0.f, rz = 0.f;
-            if (valid) { rx = others[3 * j] - cx; ry = others[3 * j + 1] - cy; rz = others[3 * j + 2] - cz; }
-#pragma unroll
-            for (int k = 0; k < 15; k++) {
-                const float w = valid ? influence_w(rx, ry, rz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext) : 0.f;
-                cnt[k] += __popc(__ballot_sync(0xffffffffu, w > 0.f));
-            }
-        }
-        int run[16];
-        int total = 0;
-#pragma unroll
-        for (int k = 0; k < 15; k++) { run[k] = total; total += cnt[k]; }
-        run[15] = total;
-        {
-            int mine = 0;
-#pragma unroll
-            for (int k = 0; k < 16; k++) mine = (lane == k) ? run[k] : mine;
-            if (lane < 16) koff[(size_t)i * KOFF + lane] = (unsigned short)mine;
-        }
-        if (total == 0) return;
-        for (int hb = 0; hb < cnt_row; hb += 32) {
-            const int h = hb + lane;
-            long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
-            const bool valid = j >= 0 && j < no;
-            if (!__any_sync(0xffffffffu, valid)) continue;
-            float rx = 0.f, ry = 0.f, rz = 0.f;
-            if (valid) { rx = others[3 * j] - cx; ry = others[3 * j + 1] - cy; rz = others[3 * j + 2] - cz; }
-#pragma unroll
-            for (int k = 0; k < 15; k++) {
-                const float w = valid ? influence_w(rx, ry, rz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext) : 0.f;
-                const unsigned m = __ballot_sync(0xffffffffu, w > 0.f);
-                if (w > 0.f) {
-                    int2 e;
-                    e.x = (int)((unsigned)j | ((unsigned)k << K_SHIFT));
-                    e.y = __float_as_int(w);
-                    my_entries[run[k] + __popc(m & lt_mask)] = e;
-                }
-                run[k] += __popc(m);
-            }
-        }
+    unsigned short* koff_row = koff + (size_t)i * KOFF;
+    if (cnt_row > INF_MAX_ROW) return;  // kp_influence_long_kernel takes these rows
+    float4* nb = s_nb[warp];
+    int hn = 0;
+    for (int hb = 0; hb < cnt_row; hb += 32) {
+        const int h = hb + lane;
+        long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
+        const bool valid = j >= 0 && j < no;
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        if (valid)
+            nb[hn + __popc(m & lt_mask)] = make_float4(others[3 * j] - cx, others[3 * j + 1] - cy, others[3 * j + 2] - cz,
+                                                       __int_as_float((int)j));
+        hn += __popc(m);
     }
+    __syncwarp();
+    const int npairs = K * hn;
+    const int my_first = min(lane * hn, npairs);  // first pair of kernel point `lane` (lanes 0..15)
+    int myoff = 0, run = 0;
+    int k = hn > 0 ? lane / hn : 0;
+    int h = hn > 0 ? lane % hn : 0;
+    int base = 0;
+    for (; base < npairs; base += 32) {
+        const bool valid = base + lane < npairs;
+        float w = 0.f;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+            v = nb[h];
+            w = influence_w(v.x, v.y, v.z, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, w > 0.f);
+        if (w > 0.f) {
+            int2 e;
+            e.x = (int)((unsigned)__float_as_int(v.w) | ((unsigned)k << K_SHIFT));
+            e.y = __float_as_int(w);
+            my_entries[run + __popc(m & lt_mask)] = e;
+        }
+        if (my_first >= base && my_first < base + 32) myoff = run + __popc(m & ((1u << (my_first - base)) - 1u));
+        run += __popc(m);
+        h += 32;
+        while (h >= hn && hn > 0) { h -= hn; k++; }
+    }
+    if (my_first >= base) myoff = run;  // kernel points that start at or after the end of the sweep
+    if (lane < 16) koff_row[lane] = (unsigned short)myoff;
+}
+
+// rows longer than INF_MAX_ROW (only possible for very dense tables); every other warp exits at once
+__global__ void __launch_bounds__(INF_WARPS * 32) kp_influence_long_kernel(const float* __restrict__ centres, int nc,
+                                                                          const float* __restrict__ others, int no,
+                                                                          Table T, const float* __restrict__ kp, int K,
+                                                                          float kp_sign, float inv_ext,
+                                                                          unsigned short* __restrict__ koff,
+                                                                          int2* __restrict__ entries) {
+    __shared__ float s_kp[16 * 3];
+    if (threadIdx.x < 48) s_kp[threadIdx.x] = (threadIdx.x < 3 * K) ? kp_sign * kp[threadIdx.x] : 1e30f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * INF_WARPS + (threadIdx.x >> 5);
+    if (i >= nc) return;
+    size_t row0, pos0;
+    int cnt_row;
+    if (T.rowptr) { row0 = (size_t)T.rowptr[i]; pos0 = row0; cnt_row = T.rowptr[i + 1] - T.rowptr[i]; }
+    else { row0 = (size_t)i * T.H; pos0 = (size_t)i * T.stride; cnt_row = T.H; }
+    if (cnt_row <= INF_MAX_ROW) return;
+    influence_long_row(others, no, T, pos0, cnt_row, centres[3 * (size_t)i], centres[3 * (size_t)i + 1],
+                       centres[3 * (size_t)i + 2], s_kp, inv_ext, koff + (size_t)i * KOFF, entries + 15 * row0, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------- weight pack
@@ -715,18 +742,14 @@ static int build_lists(Scratch& S, const float* centres, int nc, const float* ot
     L->entries = S.alloc<int2>((size_t)(n_pairs > 0 ? n_pairs : 1) * 15);
     if (S.status != KP_OK) return S.status;
     ProfileScope ps("kp_influence", stream);
-    const int grid = ceil_div(nc, 8);
-    const float inv_ext = 1.f / extent;
-    if (max_row > 0 && max_row <= 32)
-        kp_influence_kernel<1><<<grid, 256, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, inv_ext, L->koff, L->entries);
-    else if (max_row > 0 && max_row <= 64)
-        kp_influence_kernel<2><<<grid, 256, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, inv_ext, L->koff, L->entries);
-    else if (max_row > 0 && max_row <= 96)
-        kp_influence_kernel<3><<<grid, 256, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, inv_ext, L->koff, L->entries);
-    else if (max_row == 0)  // CSR rows of unknown length: rows up to 64 entries take the single-evaluation path
-        kp_influence_kernel<2><<<grid, 256, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, inv_ext, L->koff, L->entries);
-    else
-        kp_influence_kernel<0><<<grid, 256, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, inv_ext, L->koff, L->entries);
+    kp_influence_kernel<<<ceil_div(nc, INF_WARPS), INF_WARPS * 32, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign,
+                                                                             1.f / extent, L->koff, L->entries);
+    if (max_row == 0 || max_row > INF_MAX_ROW) {  // CSR rows of unknown length, or a padded table wider than the staging
+        KP_CHECK_LAUNCH();
+        kp_influence_long_kernel<<<ceil_div(nc, INF_WARPS), INF_WARPS * 32, 0, stream>>>(centres, nc, others, no, T, kp, K,
+                                                                                      kp_sign, 1.f / extent, L->koff,
+                                                                                      L->entries);
+    }
     KP_CHECK_LAUNCH();
     return KP_OK;
 }

@@ -22,8 +22,11 @@
 namespace kp {
 
 constexpr unsigned long long CELL_EMPTY = ~0ULL;
-constexpr int RS_WARPS_PER_CTA = 4;
-constexpr int RS_MAX_HITS = 1024;  // hits staged per query (8 KB of shared memory per warp)
+// hits staged per query in shared memory: the fast variant keeps 256 (2 KB per warp, 16 warps per CTA, four CTAs per
+// SM); a query with more neighbours than that raises RS_ERR_RETRY and the call is repeated with the 1024-hit variant
+constexpr int RS_HITS_SMALL = 256, RS_WARPS_SMALL = 16;
+constexpr int RS_HITS_BIG = 1024, RS_WARPS_BIG = 4;
+constexpr int RS_ERR_GRID = 1, RS_ERR_DENSE = 2, RS_ERR_RETRY = 4;
 
 struct GridPlan {   // written by the plan kernel, read by the others
     float inv_cell;
@@ -90,7 +93,7 @@ __global__ void rs_plan_kernel(const unsigned* __restrict__ bbox, int nb, float 
     const float slack = 0.0009765625f + vmax * 9.5367431640625e-07f;
     const float cell = radius * (1.f + slack);
     plan->inv_cell = 1.f / cell;
-    if (!(vmax < 260000.f)) atomicOr(err, 1);  // 18 bits per axis in the cell key
+    if (!(vmax < 260000.f)) atomicOr(err, 1);  // RS_ERR_GRID: 18 bits per axis in the cell key
 }
 
 __device__ __forceinline__ int cell_coord(float p, float origin, float inv_cell) {
@@ -146,17 +149,17 @@ __global__ void __launch_bounds__(256) rs_fill_kernel(const float* __restrict__ 
     sorted[tstart[sslot[i]] + srank[i]] = v;
 }
 
-template <typename OutT>
-__global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32) rs_search_kernel(
+template <typename OutT, int HITS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) rs_search_kernel(
     SearchParams P, const unsigned* __restrict__ bbox, const GridPlan* __restrict__ plan,
     const unsigned long long* __restrict__ tkeys, const int* __restrict__ tcount, const int* __restrict__ tstart,
     int tmask, const float4* __restrict__ sorted, OutT* __restrict__ out, int cap, int* __restrict__ hmax,
     int* __restrict__ err) {
-    __shared__ float s_d2[RS_WARPS_PER_CTA][RS_MAX_HITS];
-    __shared__ int s_idx[RS_WARPS_PER_CTA][RS_MAX_HITS];
+    __shared__ float s_d2[WARPS][HITS];
+    __shared__ int s_idx[WARPS][HITS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int qi = blockIdx.x * RS_WARPS_PER_CTA + warp;
+    const int qi = blockIdx.x * WARPS + warp;
     if (qi >= P.nq) return;
     float* hd = s_d2[warp];
     int* hi = s_idx[warp];
@@ -184,35 +187,47 @@ __global__ void __launch_bounds__(RS_WARPS_PER_CTA * 32) rs_search_kernel(
                 }
             }
         }
-        unsigned cells = __ballot_sync(0xffffffffu, c_cnt > 0);
-        while (cells) {
-            const int l = __ffs(cells) - 1;
-            cells &= cells - 1;
-            const int st = __shfl_sync(0xffffffffu, c_start, l);
-            const int cn = __shfl_sync(0xffffffffu, c_cnt, l);
-            for (int base = 0; base < cn; base += 32) {
-                const int c = base + lane;
-                bool hit = false;
-                float d2 = 0.f;
-                int sj = 0;
-                if (c < cn) {
-                    const float4 sp = sorted[st + c];
-                    d2 = sq_dist_ref(qx, qy, qz, sp.x, sp.y, sp.z);
-                    sj = __float_as_int(sp.w);
-                    hit = d2 < P.r2;
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (hit) {
-                    const int pos = count + __popc(m & lt_mask);
-                    if (pos < RS_MAX_HITS) { hd[pos] = d2; hi[pos] = sj; }
-                }
-                count += __popc(m);
+        // the candidates of all cells form one flat list (prefix sums over the lanes); the warp sweeps it 32 at a
+        // time, so the loads of different cells are in flight together
+        int incl = c_cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - c_cnt;
+        for (int base = 0; base < total; base += 32) {
+            const int c = base + lane;
+            int l = 0;  // first lane whose inclusive prefix exceeds c
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const int t = __shfl_sync(0xffffffffu, incl, l + step - 1);
+                if (t <= c) l += step;
             }
+            l = min(l, 31);
+            const int st = __shfl_sync(0xffffffffu, c_start, l);
+            const int ex = __shfl_sync(0xffffffffu, excl, l);
+            bool hit = false;
+            float d2 = 0.f;
+            int sj = 0;
+            if (c < total) {
+                const float4 sp = sorted[st + (c - ex)];
+                d2 = sq_dist_ref(qx, qy, qz, sp.x, sp.y, sp.z);
+                sj = __float_as_int(sp.w);
+                hit = d2 < P.r2;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                const int pos = count + __popc(m & lt_mask);
+                if (pos < HITS) { hd[pos] = d2; hi[pos] = sj; }
+            }
+            count += __popc(m);
         }
     }
-    if (count > RS_MAX_HITS) {
-        if (lane == 0) atomicOr(err, 2);
-        count = RS_MAX_HITS;
+    if (count > HITS) {
+        if (lane == 0) atomicOr(err, HITS == RS_HITS_BIG ? RS_ERR_DENSE : RS_ERR_RETRY);
+        count = HITS;
     }
     if (lane == 0 && count > *(volatile int*)hmax) atomicMax(hmax, count);
     __syncwarp();
@@ -306,23 +321,43 @@ int batch_query_device(const float* q, int nq, const float* s, int ns, const int
     SearchParams P;
     P.q = q; P.nq = nq; P.s = s; P.ns = ns; P.q_off = d_qoff; P.s_off = d_soff; P.nb = nb;
     P.r2 = radius * radius;  // neighbors.cpp:226, f32
-    const int grid = ceil_div(nq, RS_WARPS_PER_CTA);
-    ProfileScope* ps2 = new ProfileScope("rs_search", stream);
-    if (out_is_i64)
-        rs_search_kernel<long long><<<grid, RS_WARPS_PER_CTA * 32, 0, stream>>>(
-            P, d_bbox, d_plan, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (long long*)out, cap, d_hmax, d_err);
-    else
-        rs_search_kernel<int><<<grid, RS_WARPS_PER_CTA * 32, 0, stream>>>(
-            P, d_bbox, d_plan, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (int*)out, cap, d_hmax, d_err);
-    delete ps2;
+    auto launch = [&](bool big) -> int {
+        ProfileScope ps2("rs_search", stream);
+        if (!big) {
+            const int grid = ceil_div(nq, RS_WARPS_SMALL);
+            if (out_is_i64)
+                rs_search_kernel<long long, RS_HITS_SMALL, RS_WARPS_SMALL><<<grid, RS_WARPS_SMALL * 32, 0, stream>>>(
+                    P, d_bbox, d_plan, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (long long*)out, cap, d_hmax, d_err);
+            else
+                rs_search_kernel<int, RS_HITS_SMALL, RS_WARPS_SMALL><<<grid, RS_WARPS_SMALL * 32, 0, stream>>>(
+                    P, d_bbox, d_plan, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (int*)out, cap, d_hmax, d_err);
+        } else {
+            const int grid = ceil_div(nq, RS_WARPS_BIG);
+            if (out_is_i64)
+                rs_search_kernel<long long, RS_HITS_BIG, RS_WARPS_BIG><<<grid, RS_WARPS_BIG * 32, 0, stream>>>(
+                    P, d_bbox, d_plan, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (long long*)out, cap, d_hmax, d_err);
+            else
+                rs_search_kernel<int, RS_HITS_BIG, RS_WARPS_BIG><<<grid, RS_WARPS_BIG * 32, 0, stream>>>(
+                    P, d_bbox, d_plan, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (int*)out, cap, d_hmax, d_err);
+        }
+        return KP_OK;
+    };
+    launch(false);
     KP_CHECK_LAUNCH();
 
     if (d_result) return KP_OK;
     int h[2] = {0, 0};
     KP_CUDA(cudaMemcpyAsync(h, d_hmax, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     KP_CUDA(cudaStreamSynchronize(stream));
-    if (h[1] & 1) return fail(KP_ERR_UNSUPPORTED, "batch_query: cloud extent / radius exceeds 2^18 cells per axis");
-    if (h[1] & 2) return fail(KP_ERR_TOO_DENSE, "batch_query: more than 1024 neighbours for one query");
+    if (h[1] & RS_ERR_RETRY) {  // a query outgrew the 256-hit staging: repeat with the 1024-hit variant
+        KP_CUDA(cudaMemsetAsync(d_hmax, 0, 2 * sizeof(int), stream));
+        launch(true);
+        KP_CHECK_LAUNCH();
+        KP_CUDA(cudaMemcpyAsync(h, d_hmax, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        KP_CUDA(cudaStreamSynchronize(stream));
+    }
+    if (h[1] & RS_ERR_GRID) return fail(KP_ERR_UNSUPPORTED, "batch_query: cloud extent / radius exceeds 2^18 cells per axis");
+    if (h[1] & RS_ERR_DENSE) return fail(KP_ERR_TOO_DENSE, "batch_query: more than 1024 neighbours for one query");
     *hmax_host = h[0];
     return KP_OK;
 }

@@ -96,9 +96,10 @@ class PendingSearches:
                 raise RuntimeError("batch_query: cloud extent / radius exceeds 2^18 cells per axis")
             if err & 2:
                 raise RuntimeError("batch_query: more than 1024 neighbours for one query")
-            if limit is None and hmax > cap:
+            if (err & 4) or (limit is None and hmax > cap):
+                # rare: a row outgrew the buffer (or the kernel's 256-hit staging): redo this one synchronously
                 q, s, qb, sb, radius, dtype = args
-                outs.append(batch_query(q, s, qb, sb, radius, dtype=dtype, cap_hint=hmax))
+                outs.append(batch_query(q, s, qb, sb, radius, limit=limit, dtype=dtype, cap_hint=max(hmax, cap)))
             else:
                 outs.append(out[:, :min(hmax, cap)])
         return outs
