@@ -171,14 +171,15 @@ def run_ours(args):
     pin_batches = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items() if k != "lengths"} for b in batches]
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
 
-    def step(inp, lens):
+    def step(inp, lens, allreduce=True):
         li = pyramid.segmentation_inputs(inp["points"], inp["features"], inp["labels"], lens, view, device=dev)
         batch = pyramid.DeviceBatch(li)
         logits = net(batch)
         loss = F.cross_entropy(logits, batch.labels)
         opt.zero_grad(set_to_none=True)
         loss.backward()
-        reducer.step()
+        if allreduce:
+            reducer.step()
         torch.nn.utils.clip_grad_value_(net.parameters(), 100.0)
         opt.step()
         return loss, batch
@@ -239,7 +240,8 @@ def run_ours(args):
         shapes, sbytes = None, 0
         for it in range(psteps):
             flush.zero_()
-            _, batch = step(dev_batches[it % N_BATCHES], batches[it % N_BATCHES]["lengths"])
+            # rank 0 only: no collective inside this leg
+            _, batch = step(dev_batches[it % N_BATCHES], batches[it % N_BATCHES]["lengths"], allreduce=False)
             if it == 0:
                 shapes = conv_shapes(batch, net)
                 sbytes = search_bytes(batch)
@@ -300,7 +302,7 @@ def run_ours(args):
             "clocks": clk, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
             "grad_allreduce_bytes": reducer.bytes() if world > 1 else 0,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -393,10 +395,22 @@ def run_reference(args, budget_s=150.0, as_leg=False):
                        "points_per_step": pts / K, "spheres_per_step": bn},
             "cpu_baseline": leg, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) was sent to stderr."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # libraries that print to stdout (e.g. the NCCL version banner) must not break the one-line contract
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
