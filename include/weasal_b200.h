@@ -115,6 +115,20 @@ int kp_kpconv_backward_dev(const float* q_pts, int nq, const float* s_pts, int n
                            int cout, const float* kernel_points, int K, float KP_extent, const float* d_out,
                            float* d_x, float* d_weights, void* stream);
 
+/* Training variant: the forward pass leaves its influence entry lists (which depend only on the geometry and the kernel
+ * points) in two caller-owned device buffers of the sizes kp_kpconv_lists_bytes reports, and the backward pass of the
+ * same call reuses them instead of rebuilding them. Results are identical to the plain pair above. */
+void kp_kpconv_lists_bytes(int nq, int H, long long* koff_bytes, long long* entries_bytes);
+int kp_kpconv_forward_keep_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                               int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,
+                               int cout, const float* kernel_points, int K, float KP_extent, float* out,
+                               void* lists_koff, void* lists_entries, void* stream);
+int kp_kpconv_backward_kept_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                                int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,
+                                int cout, const float* kernel_points, int K, float KP_extent, const float* d_out,
+                                float* d_x, float* d_weights, const void* lists_koff, const void* lists_entries,
+                                void* stream);
+
 /* fp32 CUDA-core pieces (bring-up / cross-check of the tensor-core path; not the product path):
  *   wf [nq, K*cin] = kernel-point-weighted neighbour features; dx [ns,cin] += adjoint scatter of dwf [nq,K*cin]. */
 int kp_kpconv_wf_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds, int idx_is_i64,

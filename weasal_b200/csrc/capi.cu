@@ -19,12 +19,14 @@ int kpconv_wf_device(const float* q, int nq, const float* s, int ns, const void*
 int kpconv_dx_atomic_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
                             int idx_stride, const float* dwf, int cin, const float* kp, int K, float extent, float* dx,
                             cudaStream_t stream);
+void kpconv_lists_bytes(int nq, int H, long long* koff_bytes, long long* entries_bytes);
 int kpconv_forward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
                           int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
-                          float extent, float* out, cudaStream_t stream);
+                          float extent, float* out, void* lists_koff, void* lists_entries, cudaStream_t stream);
 int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
                            int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
-                           float extent, const float* dout, float* dx, float* dw, cudaStream_t stream);
+                           float extent, const float* dout, float* dx, float* dw, const void* lists_koff,
+                           const void* lists_entries, cudaStream_t stream);
 int profile_read(char* buf, int buflen);
 int max_pool_fwd_device(const float* x, int ns, int C, const void* idx, int is_i64, int nq, int H, int stride,
                         float* out, int* arg, cudaStream_t stream);
@@ -161,7 +163,29 @@ int kp_kpconv_forward_dev(const float* q_pts, int nq, const float* s_pts, int ns
                           int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,
                           int cout, const float* kernel_points, int K, float KP_extent, float* out, void* stream) {
     return kpconv_forward_device(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, weights, cout,
-                                 kernel_points, K, KP_extent, out, (cudaStream_t)stream);
+                                 kernel_points, K, KP_extent, out, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+void kp_kpconv_lists_bytes(int nq, int H, long long* koff_bytes, long long* entries_bytes) {
+    kpconv_lists_bytes(nq, H, koff_bytes, entries_bytes);
+}
+
+int kp_kpconv_forward_keep_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                               int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,
+                               int cout, const float* kernel_points, int K, float KP_extent, float* out,
+                               void* lists_koff, void* lists_entries, void* stream) {
+    return kpconv_forward_device(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, weights, cout,
+                                 kernel_points, K, KP_extent, out, lists_koff, lists_entries, (cudaStream_t)stream);
+}
+
+int kp_kpconv_backward_kept_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                                int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,
+                                int cout, const float* kernel_points, int K, float KP_extent, const float* d_out,
+                                float* d_x, float* d_weights, const void* lists_koff, const void* lists_entries,
+                                void* stream) {
+    return kpconv_backward_device(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, weights, cout,
+                                  kernel_points, K, KP_extent, d_out, d_x, d_weights, lists_koff, lists_entries,
+                                  (cudaStream_t)stream);
 }
 
 int kp_kpconv_backward_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
@@ -169,7 +193,8 @@ int kp_kpconv_backward_dev(const float* q_pts, int nq, const float* s_pts, int n
                            int cout, const float* kernel_points, int K, float KP_extent, const float* d_out,
                            float* d_x, float* d_weights, void* stream) {
     return kpconv_backward_device(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, weights, cout,
-                                  kernel_points, K, KP_extent, d_out, d_x, d_weights, (cudaStream_t)stream);
+                                  kernel_points, K, KP_extent, d_out, d_x, d_weights, nullptr, nullptr,
+                                  (cudaStream_t)stream);
 }
 
 int kp_max_pool_forward_dev(const float* x, int ns, int channels, const void* inds, int idx_is_i64, int nq, int H,

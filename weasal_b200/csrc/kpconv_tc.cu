@@ -736,10 +736,10 @@ struct Lists {
 
 static int build_lists(Scratch& S, const float* centres, int nc, const float* others, int no, const Table& T,
                        long long n_pairs, int max_row, const float* kp, int K, float kp_sign, float extent, Lists* L,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, void* ext_koff = nullptr, void* ext_entries = nullptr) {
     if (n_pairs * 15 >= (1LL << 31)) return fail(KP_ERR_UNSUPPORTED, "kpconv: neighbour table too large (Nq*H*15 >= 2^31)");
-    L->koff = S.alloc<unsigned short>((size_t)nc * KOFF);
-    L->entries = S.alloc<int2>((size_t)(n_pairs > 0 ? n_pairs : 1) * 15);
+    L->koff = ext_koff ? (unsigned short*)ext_koff : S.alloc<unsigned short>((size_t)nc * KOFF);
+    L->entries = ext_entries ? (int2*)ext_entries : S.alloc<int2>((size_t)(n_pairs > 0 ? n_pairs : 1) * 15);
     if (S.status != KP_OK) return S.status;
     ProfileScope ps("kp_influence", stream);
     kp_influence_kernel<<<ceil_div(nc, INF_WARPS), INF_WARPS * 32, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign,
@@ -826,9 +826,16 @@ static int check_args(int nq, int ns, int H, int idx_stride, int cin, int cout, 
     return KP_OK;
 }
 
+// lists_koff / lists_entries (optional, caller-owned device buffers of kpconv_lists_bytes): the forward pass leaves
+// the influence entry lists there so that backward can reuse them instead of rebuilding them.
+void kpconv_lists_bytes(int nq, int H, long long* koff_bytes, long long* entries_bytes) {
+    *koff_bytes = (long long)(nq > 0 ? nq : 1) * KOFF * 2;
+    *entries_bytes = (long long)(nq > 0 ? nq : 1) * (H > 0 ? H : 1) * 15 * 8;
+}
+
 int kpconv_forward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
                           int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
-                          float extent, float* out, cudaStream_t stream) {
+                          float extent, float* out, void* lists_koff, void* lists_entries, cudaStream_t stream) {
     int rc = check_args(nq, ns, H, idx_stride, cin, cout, K, extent);
     if (rc != KP_OK) return rc;
     if (nq == 0) return KP_OK;
@@ -840,14 +847,15 @@ int kpconv_forward_device(const float* q, int nq, const float* s, int ns, const 
     Table T;
     T.idx = idx; T.rowptr = nullptr; T.H = H; T.stride = idx_stride; T.is_i64 = idx_is_i64;
     Lists L;
-    rc = build_lists(S, q, nq, s, ns, T, (long long)nq * H, H, kp, K, 1.f, extent, &L, stream);
+    rc = build_lists(S, q, nq, s, ns, T, (long long)nq * H, H, kp, K, 1.f, extent, &L, stream, lists_koff, lists_entries);
     if (rc != KP_OK) return rc;
     return run_forward("kp_fwd", S, nq, nullptr, H, x, ns, cin, L, w, (long long)cin * cout, cout, 1, cout, K, out, stream);
 }
 
 int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
                            int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
-                           float extent, const float* dout, float* dx, float* dw, cudaStream_t stream) {
+                           float extent, const float* dout, float* dx, float* dw, const void* lists_koff,
+                           const void* lists_entries, cudaStream_t stream) {
     int rc = check_args(nq, ns, H, idx_stride, cin, cout, K, extent);
     if (rc != KP_OK) return rc;
     KP_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * cin * cout * sizeof(float), stream));
@@ -863,8 +871,13 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
         Table T;
         T.idx = idx; T.rowptr = nullptr; T.H = H; T.stride = idx_stride; T.is_i64 = idx_is_i64;
         Lists L;
-        rc = build_lists(S, q, nq, s, ns, T, n_pairs, H, kp, K, 1.f, extent, &L, stream);
-        if (rc != KP_OK) return rc;
+        if (lists_koff && lists_entries) {  // left behind by the forward pass
+            L.koff = (unsigned short*)lists_koff;
+            L.entries = (int2*)lists_entries;
+        } else {
+            rc = build_lists(S, q, nq, s, ns, T, n_pairs, H, kp, K, 1.f, extent, &L, stream);
+            if (rc != KP_OK) return rc;
+        }
         const int cin_p = pad4(cin);
         const float* xg = x;
         if (cin_p != cin) {

@@ -170,6 +170,7 @@ class KPConvFunction(torch.autograd.Function):
         K, cin, cout = w.shape
         nq, ns = q.shape[0], s.shape[0]
         L = _lib.lib()
+        lists = None
         if kpconv_impl() == "simt":  # fp32 cross-check path (CUDA-core gather + library GEMM), not the product path
             wf = torch.empty((nq, K * cin), dtype=torch.float32, device=q.device)
             _lib.check(L.kp_kpconv_wf_dev(q.data_ptr(), nq, s.data_ptr(), ns, idx.data_ptr(), i64, H, stride,
@@ -178,9 +179,23 @@ class KPConvFunction(torch.autograd.Function):
             out = wf @ w.reshape(K * cin, cout)
         else:
             out = torch.empty((nq, cout), dtype=torch.float32, device=q.device)
-            _lib.check(L.kp_kpconv_forward_dev(q.data_ptr(), nq, s.data_ptr(), ns, idx.data_ptr(), i64, H, stride,
-                                               xx.data_ptr(), cin, w.data_ptr(), cout, kp.data_ptr(), K,
-                                               float(KP_extent), out.data_ptr(), _stream()), "kpconv_forward")
+            need_grad = ctx.needs_input_grad[3] or ctx.needs_input_grad[4]
+            if need_grad and nq > 0 and ns > 0 and H > 0:
+                # keep the influence entry lists for the backward pass (they depend on geometry only)
+                kb, eb = C.c_longlong(0), C.c_longlong(0)
+                L.kp_kpconv_lists_bytes(nq, H, C.byref(kb), C.byref(eb))
+                lk = torch.empty(kb.value, dtype=torch.uint8, device=q.device)
+                le = torch.empty(eb.value, dtype=torch.uint8, device=q.device)
+                _lib.check(L.kp_kpconv_forward_keep_dev(q.data_ptr(), nq, s.data_ptr(), ns, idx.data_ptr(), i64, H,
+                                                        stride, xx.data_ptr(), cin, w.data_ptr(), cout, kp.data_ptr(),
+                                                        K, float(KP_extent), out.data_ptr(), lk.data_ptr(),
+                                                        le.data_ptr(), _stream()), "kpconv_forward")
+                lists = (lk, le)
+            else:
+                _lib.check(L.kp_kpconv_forward_dev(q.data_ptr(), nq, s.data_ptr(), ns, idx.data_ptr(), i64, H, stride,
+                                                   xx.data_ptr(), cin, w.data_ptr(), cout, kp.data_ptr(), K,
+                                                   float(KP_extent), out.data_ptr(), _stream()), "kpconv_forward")
+        ctx.lists = lists
         ctx.save_for_backward(q, s, idx, xx, w, kp)
         ctx.meta = (i64, H, stride, float(KP_extent))
         return out
@@ -207,9 +222,12 @@ class KPConvFunction(torch.autograd.Function):
         else:
             dx = torch.empty((ns, cin), dtype=torch.float32, device=q.device)
             dw = torch.empty((K, cin, cout), dtype=torch.float32, device=q.device)
-            _lib.check(L.kp_kpconv_backward_dev(q.data_ptr(), nq, s.data_ptr(), ns, idx.data_ptr(), i64, H, stride,
-                                                xx.data_ptr(), cin, w.data_ptr(), cout, kp.data_ptr(), K, ext,
-                                                do.data_ptr(), dx.data_ptr(), dw.data_ptr(), _stream()),
+            lk, le = ctx.lists if ctx.lists is not None else (None, None)
+            _lib.check(L.kp_kpconv_backward_kept_dev(q.data_ptr(), nq, s.data_ptr(), ns, idx.data_ptr(), i64, H, stride,
+                                                     xx.data_ptr(), cin, w.data_ptr(), cout, kp.data_ptr(), K, ext,
+                                                     do.data_ptr(), dx.data_ptr(), dw.data_ptr(),
+                                                     lk.data_ptr() if lk is not None else None,
+                                                     le.data_ptr() if le is not None else None, _stream()),
                        "kpconv_backward")
         return None, None, None, dx, dw, None, None
 
