@@ -28,11 +28,6 @@ constexpr int RS_HITS_SMALL = 256, RS_WARPS_SMALL = 16;
 constexpr int RS_HITS_BIG = 1024, RS_WARPS_BIG = 4;
 constexpr int RS_ERR_GRID = 1, RS_ERR_DENSE = 2, RS_ERR_RETRY = 4;
 
-struct GridPlan {   // written by the plan kernel, read by the others
-    float inv_cell;
-    float pad0, pad1, pad2;
-};
-
 struct SearchParams {
     const float* q; int nq;
     const float* s; int ns;
@@ -40,9 +35,14 @@ struct SearchParams {
     float r2;
 };
 
-__global__ void rs_bbox_init_kernel(unsigned* bbox, int nb) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+// one launch resets everything a search needs: hash table, bounding boxes, result slots, the cell-storage cursor
+__global__ void __launch_bounds__(256) rs_init_kernel(unsigned long long* tkeys, int* tcount, int tsize, unsigned* bbox,
+                                                     int nb, int* result2, int* cursor) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < tsize) { tkeys[i] = CELL_EMPTY; tcount[i] = 0; }
     if (i < nb * 6) bbox[i] = ((i % 6) < 3) ? 0xffffffffu : 0u;
+    if (i < 2) result2[i] = 0;
+    if (i == 0) *cursor = 0;
 }
 
 __global__ void __launch_bounds__(256) rs_bbox_kernel(const float* __restrict__ s, int ns,
@@ -78,22 +78,26 @@ __global__ void __launch_bounds__(256) rs_bbox_kernel(const float* __restrict__ 
 
 // Cell edge = radius * (1 + slack). The slack covers the f32 rounding of (p - origin) * inv_cell, which grows with
 // the cell coordinate: |error| <= ~4 * Vmax * 2^-24 cells, so slack = 2^-10 + Vmax * 2^-20 keeps every true
-// neighbour within +-1 cell on each axis.
-__global__ void rs_plan_kernel(const unsigned* __restrict__ bbox, int nb, float radius, GridPlan* plan,
-                               int* __restrict__ err) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    float ext = 0.f;
-    for (int b = 0; b < nb; b++)
-        for (int a = 0; a < 3; a++) {
-            const unsigned lo = bbox[b * 6 + a], hi = bbox[b * 6 + 3 + a];
-            if (lo == 0xffffffffu) continue;  // empty batch element
-            ext = fmaxf(ext, ord2f(hi) - ord2f(lo));
-        }
-    const float vmax = ext / radius + 2.f;
-    const float slack = 0.0009765625f + vmax * 9.5367431640625e-07f;
-    const float cell = radius * (1.f + slack);
-    plan->inv_cell = 1.f / cell;
-    if (!(vmax < 260000.f)) atomicOr(err, 1);  // RS_ERR_GRID: 18 bits per axis in the cell key
+// neighbour within +-1 cell on each axis. Every CTA derives the same value from the bounding boxes (thread 0, then
+// broadcast through shared memory); returns false when the grid would not fit 18 bits per axis.
+__device__ __forceinline__ float block_inv_cell(const unsigned* __restrict__ bbox, int nb, float radius, float* s_slot,
+                                                bool* fits) {
+    if (threadIdx.x == 0) {
+        float ext = 0.f;
+        for (int b = 0; b < nb; b++)
+            for (int a = 0; a < 3; a++) {
+                const unsigned lo = bbox[b * 6 + a], hi = bbox[b * 6 + 3 + a];
+                if (lo == 0xffffffffu) continue;  // empty batch element
+                ext = fmaxf(ext, ord2f(hi) - ord2f(lo));
+            }
+        const float vmax = ext / radius + 2.f;
+        const float slack = 0.0009765625f + vmax * 9.5367431640625e-07f;
+        s_slot[0] = 1.f / (radius * (1.f + slack));
+        s_slot[1] = (vmax < 260000.f) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    if (fits) *fits = s_slot[1] != 0.f;
+    return s_slot[0];
 }
 
 __device__ __forceinline__ int cell_coord(float p, float origin, float inv_cell) {
@@ -107,22 +111,17 @@ __device__ __forceinline__ unsigned long long cell_key(int b, int cx, int cy, in
            (unsigned long long)cx;
 }
 
-__global__ void rs_table_init_kernel(unsigned long long* tkeys, int* tcount, int tsize) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < tsize) { tkeys[i] = CELL_EMPTY; tcount[i] = 0; }
-}
-
 __global__ void __launch_bounds__(256) rs_insert_kernel(const float* __restrict__ s, int ns,
                                                        const int* __restrict__ s_off, int nb,
-                                                       const unsigned* __restrict__ bbox,
-                                                       const GridPlan* __restrict__ plan,
+                                                       const unsigned* __restrict__ bbox, float radius,
                                                        unsigned long long* __restrict__ tkeys,
                                                        int* __restrict__ tcount, int tmask, int* __restrict__ sslot,
                                                        int* __restrict__ srank) {
+    __shared__ float s_plan[2];
+    const float inv = block_inv_cell(bbox, nb, radius, s_plan, nullptr);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ns) return;
     const int b = batch_of(s_off, nb, i);
-    const float inv = plan->inv_cell;
     const int cx = cell_coord(s[3 * (size_t)i], ord2f(bbox[b * 6 + 0]), inv);
     const int cy = cell_coord(s[3 * (size_t)i + 1], ord2f(bbox[b * 6 + 1]), inv);
     const int cz = cell_coord(s[3 * (size_t)i + 2], ord2f(bbox[b * 6 + 2]), inv);
@@ -138,6 +137,16 @@ __global__ void __launch_bounds__(256) rs_insert_kernel(const float* __restrict_
     srank[i] = atomicAdd(&tcount[slot], 1);
 }
 
+// every occupied cell claims a contiguous range of the cell-sorted support array (the order of the ranges does not
+// matter: rows are sorted by (d2, index) at the end)
+__global__ void __launch_bounds__(256) rs_assign_kernel(const int* __restrict__ tcount, int* __restrict__ tstart,
+                                                       int tsize, int* __restrict__ cursor) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= tsize) return;
+    const int c = tcount[i];
+    if (c > 0) tstart[i] = atomicAdd(cursor, c);
+}
+
 __global__ void __launch_bounds__(256) rs_fill_kernel(const float* __restrict__ s, int ns,
                                                      const int* __restrict__ sslot, const int* __restrict__ srank,
                                                      const int* __restrict__ tstart, float4* __restrict__ sorted) {
@@ -151,12 +160,16 @@ __global__ void __launch_bounds__(256) rs_fill_kernel(const float* __restrict__ 
 
 template <typename OutT, int HITS, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) rs_search_kernel(
-    SearchParams P, const unsigned* __restrict__ bbox, const GridPlan* __restrict__ plan,
+    SearchParams P, const unsigned* __restrict__ bbox, float radius,
     const unsigned long long* __restrict__ tkeys, const int* __restrict__ tcount, const int* __restrict__ tstart,
     int tmask, const float4* __restrict__ sorted, OutT* __restrict__ out, int cap, int* __restrict__ hmax,
     int* __restrict__ err) {
     __shared__ float s_d2[WARPS][HITS];
     __shared__ int s_idx[WARPS][HITS];
+    __shared__ float s_plan[2];
+    bool fits;
+    const float inv = block_inv_cell(bbox, P.nb, radius, s_plan, &fits);
+    if (!fits && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, RS_ERR_GRID);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int qi = blockIdx.x * WARPS + warp;
@@ -168,7 +181,6 @@ __global__ void __launch_bounds__(WARPS * 32) rs_search_kernel(
     const int b = batch_of(P.q_off, P.nb, qi);
     int count = 0;
     if (P.s_off[b + 1] > P.s_off[b]) {
-        const float inv = plan->inv_cell;
         const int cx = cell_coord(qx, ord2f(bbox[b * 6 + 0]), inv);
         const int cy = cell_coord(qy, ord2f(bbox[b * 6 + 1]), inv);
         const int cz = cell_coord(qz, ord2f(bbox[b * 6 + 2]), inv);
@@ -271,50 +283,42 @@ int batch_query_device(const float* q, int nq, const float* s, int ns, const int
     }
 
     Scratch S(stream);
-    int* d_qoff = S.alloc<int>(nb + 1);
-    int* d_soff = S.alloc<int>(nb + 1);
+    int* d_qoff = S.alloc<int>(2 * (nb + 1));
+    int* d_soff = d_qoff + (nb + 1);
     unsigned* d_bbox = S.alloc<unsigned>((size_t)nb * 6);
-    GridPlan* d_plan = S.alloc<GridPlan>(1);
     int tsize = 1024;
     while (tsize < 2 * ns) tsize <<= 1;
     unsigned long long* d_tkeys = S.alloc<unsigned long long>(tsize);
     int* d_tcount = S.alloc<int>(tsize);
     int* d_tstart = S.alloc<int>(tsize);
-    int* d_scan_tmp = S.alloc<int>(scan_tmp_ints(tsize));
     int* d_sslot = S.alloc<int>(ns);
     int* d_srank = S.alloc<int>(ns);
     float4* d_sorted = S.alloc<float4>(ns);
+    int* d_cursor = S.alloc<int>(1);
     int* d_hmax = d_result ? d_result : S.alloc<int>(2);
     if (S.status != KP_OK) return S.status;
     int* d_err = d_hmax + 1;
 
-    { int rc0 = upload_offsets(qoff.data(), nb + 1, d_qoff, stream); if (rc0 != KP_OK) return rc0; }
-    { int rc0 = upload_offsets(soff.data(), nb + 1, d_soff, stream); if (rc0 != KP_OK) return rc0; }
-    KP_CUDA(cudaMemsetAsync(d_hmax, 0, 2 * sizeof(int), stream));
-
+    {
+        std::vector<int> both(qoff);
+        both.insert(both.end(), soff.begin(), soff.end());
+        int rc0 = upload_offsets(both.data(), 2 * (nb + 1), d_qoff, stream);
+        if (rc0 != KP_OK) return rc0;
+    }
     ProfileScope* ps = new ProfileScope("rs_build", stream);
+    rs_init_kernel<<<ceil_div(tsize > nb * 6 ? tsize : nb * 6, 256), 256, 0, stream>>>(d_tkeys, d_tcount, tsize, d_bbox, nb,
+                                                                                    d_hmax, d_cursor);
+    KP_CHECK_LAUNCH();
     if (ns > 0) {
-        rs_bbox_init_kernel<<<ceil_div(nb * 6, 256), 256, 0, stream>>>(d_bbox, nb);
-        KP_CHECK_LAUNCH();
         rs_bbox_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(s, ns, d_soff, nb, d_bbox);
         KP_CHECK_LAUNCH();
-        rs_plan_kernel<<<1, 32, 0, stream>>>(d_bbox, nb, radius, d_plan, d_err);
-        KP_CHECK_LAUNCH();
-        rs_table_init_kernel<<<ceil_div(tsize, 256), 256, 0, stream>>>(d_tkeys, d_tcount, tsize);
-        KP_CHECK_LAUNCH();
-        rs_insert_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(s, ns, d_soff, nb, d_bbox, d_plan, d_tkeys, d_tcount,
+        rs_insert_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(s, ns, d_soff, nb, d_bbox, radius, d_tkeys, d_tcount,
                                                               tsize - 1, d_sslot, d_srank);
         KP_CHECK_LAUNCH();
-        int rc = exclusive_scan(d_tcount, d_tstart, tsize, nullptr, d_scan_tmp, stream);
-        if (rc != KP_OK) return rc;
+        rs_assign_kernel<<<ceil_div(tsize, 256), 256, 0, stream>>>(d_tcount, d_tstart, tsize, d_cursor);
+        KP_CHECK_LAUNCH();
         rs_fill_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(s, ns, d_sslot, d_srank, d_tstart, d_sorted);
         KP_CHECK_LAUNCH();
-    } else {
-        rs_table_init_kernel<<<ceil_div(tsize, 256), 256, 0, stream>>>(d_tkeys, d_tcount, tsize);
-        KP_CHECK_LAUNCH();
-        rs_bbox_init_kernel<<<ceil_div(nb * 6, 256), 256, 0, stream>>>(d_bbox, nb);
-        KP_CHECK_LAUNCH();
-        KP_CUDA(cudaMemsetAsync(d_plan, 0, sizeof(GridPlan), stream));
     }
 
     delete ps;
@@ -327,18 +331,18 @@ int batch_query_device(const float* q, int nq, const float* s, int ns, const int
             const int grid = ceil_div(nq, RS_WARPS_SMALL);
             if (out_is_i64)
                 rs_search_kernel<long long, RS_HITS_SMALL, RS_WARPS_SMALL><<<grid, RS_WARPS_SMALL * 32, 0, stream>>>(
-                    P, d_bbox, d_plan, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (long long*)out, cap, d_hmax, d_err);
+                    P, d_bbox, radius, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (long long*)out, cap, d_hmax, d_err);
             else
                 rs_search_kernel<int, RS_HITS_SMALL, RS_WARPS_SMALL><<<grid, RS_WARPS_SMALL * 32, 0, stream>>>(
-                    P, d_bbox, d_plan, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (int*)out, cap, d_hmax, d_err);
+                    P, d_bbox, radius, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (int*)out, cap, d_hmax, d_err);
         } else {
             const int grid = ceil_div(nq, RS_WARPS_BIG);
             if (out_is_i64)
                 rs_search_kernel<long long, RS_HITS_BIG, RS_WARPS_BIG><<<grid, RS_WARPS_BIG * 32, 0, stream>>>(
-                    P, d_bbox, d_plan, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (long long*)out, cap, d_hmax, d_err);
+                    P, d_bbox, radius, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (long long*)out, cap, d_hmax, d_err);
             else
                 rs_search_kernel<int, RS_HITS_BIG, RS_WARPS_BIG><<<grid, RS_WARPS_BIG * 32, 0, stream>>>(
-                    P, d_bbox, d_plan, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (int*)out, cap, d_hmax, d_err);
+                    P, d_bbox, radius, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (int*)out, cap, d_hmax, d_err);
         }
         return KP_OK;
     };
