@@ -273,8 +273,18 @@ def run_ours(args):
         if cand:
             dom = max(cand, key=lambda t: kernels[t]["ms_per_step"])
             a = kernels[dom]["achieved_gbs"]
+            # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/traffic.json,
+            # written by tools/ncu_summarise.py); null when no capture of it has been committed
+            traffic = None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                kname = {"kp_fwd": "kp_fwd_kernel", "kp_fwd_dx": "kp_fwd_kernel", "kp_dw": "kp_dw_kernel",
+                         "rs_search": "rs_search_kernel"}[dom]
+                traffic = tj[kname]["dram_bytes_per_launch"]
+            except Exception:
+                pass
             roof = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
-                    "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                    "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                     "bytes_per_launch": alg_bytes[dom] / max(kernels[dom]["launches_per_step"], 1),
                     "launch_ms": kernels[dom]["ms_per_step"] / max(kernels[dom]["launches_per_step"], 1)}
 
