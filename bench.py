@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -204,6 +204,8 @@ def run_ours(args):
                 loss, _ = step(dev_batches[b], batches[b]["lengths"])
             e1.record()
             e1.synchronize()
+            if os.environ.get("WEASAL_DEBUG") and rank == 0:
+                print(f"[bench] {'e2e' if e2e else 'dev'} step {it}: {e0.elapsed_time(e1):.2f} ms", file=sys.stderr)
             if it >= n_warm:
                 total_ms += e0.elapsed_time(e1)
                 pts += batches[b]["points"].shape[0]

@@ -53,8 +53,8 @@ struct ProfileScope {
 // ---- scratch memory ----------------------------------------------------------------------------------------------------
 // Every entry point carves its temporaries out of a per-(thread, stream) arena that persists across calls: calls on
 // one stream execute in order, so the next call may reuse the bytes of the previous one without any allocator
-// traffic (a training step makes ~400 temporaries). The arena grows by adding blocks; at the start of a later call
-// the blocks are merged into one (after a stream sync) so steady state is a single bump pointer.
+// traffic (a training step makes ~400 temporaries). The arena grows by adding geometrically larger blocks (first one
+// 128 MB) and never returns memory, so steady state is a bump pointer over one or two blocks.
 struct ArenaBlock { char* base; size_t cap; };
 struct Arena {
     ArenaBlock blocks[16];

@@ -394,6 +394,7 @@ __device__ __forceinline__ void assemble_rows(unsigned char* sA, int warp, int l
     const int E = __shfl_sync(0xffffffffu, incl, RPW - 1);
     const int excl = incl - cnt;
     const float* xc = x + c_l;
+    const int kc = klast - kfirst + 1;  // kernel points in this chunk (lanes with equal k_l form a group)
     for (int b0 = 0; b0 < E; b0 += 32) {
         const int e = b0 + lane;
         int pt = 0;
@@ -402,22 +403,37 @@ __device__ __forceinline__ void assemble_rows(unsigned char* sA, int warp, int l
         const long long pstart = __shfl_sync(0xffffffffu, start, pt);
         const int pexcl = __shfl_sync(0xffffffffu, excl, pt);
         int2 rec = make_int2(0, 0);
-        if (e < E) rec = entries[pstart + (e - pexcl)];
-        const int nb = min(32, E - b0);
-        for (int g = 0; g < nb; g += U) {
+        int ek = -1;
+        if (e < E) {
+            rec = entries[pstart + (e - pexcl)];
+            ek = (int)((unsigned)rec.x >> K_SHIFT);
+            rec.x = (int)(((unsigned)rec.x & J_MASK) | ((unsigned)pt << K_SHIFT));  // the kernel point is implied by the
+        }                                                                          // consuming lane group: carry the row
+        // Each lane group (lanes sharing a kernel point) walks ITS entries of the batch; groups advance together, so
+        // one step serves up to kc entries.
+        unsigned mymask = 0;
+        for (int g = 0; g < kc; g++) {
+            const unsigned m = __ballot_sync(0xffffffffu, ek == kfirst + g);
+            if (k_l == kfirst + g) mymask = m;
+        }
+        int steps = __popc(mymask);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
+        for (int g = 0; g < steps; g += U) {
             float4 xv[U];
             float wv[U];
             int ov[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const int ee = min(g + u, 31);
-                const unsigned jk = (unsigned)__shfl_sync(0xffffffffu, rec.x, ee);
+                const bool have = mymask != 0u;
+                const int ee = have ? (__ffs(mymask) - 1) : 0;
+                mymask &= mymask - 1u;
+                const unsigned jp = (unsigned)__shfl_sync(0xffffffffu, rec.x, ee);
                 const float w = __int_as_float(__shfl_sync(0xffffffffu, rec.y, ee));
-                ov[u] = LAY::off(p0 + __shfl_sync(0xffffffffu, pt, ee), lane);  // (row, lane) are coupled by the swizzle
-                const bool mine = (g + u < nb) && ((int)(jk >> K_SHIFT) == k_l);
-                wv[u] = mine ? w : 0.f;
+                ov[u] = LAY::off(p0 + (int)(jp >> K_SHIFT), lane);  // (row, lane) are coupled by the swizzle
+                wv[u] = have ? w : 0.f;
                 xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (mine) xv[u] = __ldg(reinterpret_cast<const float4*>(xc + (size_t)(jk & J_MASK) * cin_p));
+                if (have) xv[u] = __ldg(reinterpret_cast<const float4*>(xc + (size_t)(jp & J_MASK) * cin_p));
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
@@ -440,7 +456,8 @@ __device__ __forceinline__ void assemble_rows(unsigned char* sA, int warp, int l
     }
 }
 
-// stage the entry-list headers of one tile: row0 (first table column of the centre) and koff
+// stage the entry-list headers of one tile: row0 (first table column of the centre) and koff (32 bytes per centre,
+// moved as two 16-byte words)
 template <int FWD_THREADS>
 __device__ __forceinline__ void stage_headers(int tile_base, int n, int H, const int* __restrict__ rowptr,
                                               const unsigned short* __restrict__ koff, int* s_row0,
@@ -449,9 +466,11 @@ __device__ __forceinline__ void stage_headers(int tile_base, int n, int H, const
         const int i = tile_base + t;
         s_row0[t] = (i < n) ? (rowptr ? rowptr[i] : i * H) : 0;
     }
-    for (int t = threadIdx.x; t < TILE_M * KOFF; t += FWD_THREADS) {
-        const int i = tile_base + t / KOFF;
-        s_koff[t] = (i < n) ? koff[(size_t)i * KOFF + (t % KOFF)] : (unsigned short)0;
+    const uint4* src = reinterpret_cast<const uint4*>(koff);
+    uint4* dst = reinterpret_cast<uint4*>(s_koff);
+    for (int t = threadIdx.x; t < TILE_M * 2; t += FWD_THREADS) {
+        const int i = tile_base + (t >> 1);
+        dst[t] = (i < n) ? __ldg(src + (size_t)i * 2 + (t & 1)) : make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
