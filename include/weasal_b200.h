@@ -117,7 +117,12 @@ int kp_kpconv_backward_dev(const float* q_pts, int nq, const float* s_pts, int n
 
 /* Training variant: the forward pass leaves its influence entry lists (which depend only on the geometry and the kernel
  * points) in two caller-owned device buffers of the sizes kp_kpconv_lists_bytes reports, and the backward pass of the
- * same call reuses them instead of rebuilding them. Results are identical to the plain pair above. */
+ * same call reuses them instead of rebuilding them. Backward also accepts the transposed neighbour table
+ * (kp_transpose_table_dev: CSR over the supports, rowptr int32 [ns+1], col int32 [nq*H]), which depends on the index
+ * matrix only and can therefore be shared by every KPConv that uses that matrix; NULL = build it internally.
+ * Results are identical to the plain pair above. */
+int kp_transpose_table_dev(const void* neighb_inds, int idx_is_i64, int nq, int H, int idx_stride, int ns,
+                           int* rowptr, int* col, void* stream);
 void kp_kpconv_lists_bytes(int nq, int H, long long* koff_bytes, long long* entries_bytes);
 int kp_kpconv_forward_keep_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
                                int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,
@@ -127,7 +132,7 @@ int kp_kpconv_backward_kept_dev(const float* q_pts, int nq, const float* s_pts, 
                                 int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,
                                 int cout, const float* kernel_points, int K, float KP_extent, const float* d_out,
                                 float* d_x, float* d_weights, const void* lists_koff, const void* lists_entries,
-                                void* stream);
+                                const int* t_rowptr, const int* t_col, void* stream);
 
 /* fp32 CUDA-core pieces (bring-up / cross-check of the tensor-core path; not the product path):
  *   wf [nq, K*cin] = kernel-point-weighted neighbour features; dx [ns,cin] += adjoint scatter of dwf [nq,K*cin]. */

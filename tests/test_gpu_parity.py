@@ -428,3 +428,32 @@ def test_batch_query_more_than_256_neighbours_escalates(torch_cuda):
     big = rng.uniform(0, 1, (3000, 3)).astype(np.float32)
     with pytest.raises(RuntimeError, match="1024 neighbours"):
         rn.batch_query(big, big, np.array([3000], np.int32), np.array([3000], np.int32), radius=0.9)
+
+
+@pytest.mark.parametrize("K,radius,cin,cout", [(15, 0.8, 8, 16), (9, 0.45, 12, 20), (1, 0.45, 16, 8)])
+def test_kpconv_long_rows_and_fewer_kernel_points(K, radius, cin, cout, torch_cuda):
+    """Rows wider than the 128-neighbour shared-memory staging of the influence kernel (the two-pass path, also taken by
+    the transposed table) and kernel sizes below 15."""
+    torch = torch_cuda
+    rng = np.random.default_rng(K)
+    n = 400
+    s = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    L = np.array([n], np.int32)
+    idx = oracle.batch_neighbors(s, s, L, L, radius)
+    if radius > 0.7:
+        assert idx.shape[1] > 128
+    a = dict(q_pts=s, s_pts=s, idx=idx, x=rng.normal(size=(n, cin)).astype(np.float32),
+             weights=(rng.normal(size=(K, cin, cout)) / np.sqrt(cin)).astype(np.float32),
+             kernel_points=(rng.normal(size=(K, 3)) * 0.3).astype(np.float32), extent=np.float32(0.3),
+             d_out=rng.normal(size=(n, cout)).astype(np.float32))
+    out, dx, dw = _run_kpconv(torch, a, torch.int64)
+    o_out = oracle.kpconv_forward(s, s, idx, a["x"], a["weights"], a["kernel_points"], 0.3)
+    o_dx, o_dw = oracle.kpconv_backward(s, s, idx, a["x"], a["weights"], a["kernel_points"], 0.3, a["d_out"])
+    assert rel_max(out, o_out) < KP_TOL and rel_max(dx, o_dx) < KP_TOL and rel_max(dw, o_dw) < KP_TOL
+
+
+def test_batch_query_no_supports_at_all(torch_cuda):
+    from weasal_b200 import radius_neighbors as rn
+    q = np.random.default_rng(0).uniform(0, 1, (10, 3)).astype(np.float32)
+    with pytest.raises(RuntimeError, match="^Error$"):
+        rn.batch_query(q, np.zeros((0, 3), np.float32), [10], [0], radius=0.5)

@@ -21,7 +21,7 @@ KP_OK, KP_ERR_CUDA, KP_ERR_ARG, KP_ERR_CAPACITY, KP_ERR_TOO_DENSE, KP_ERR_EMPTY,
 SYMBOLS = ["kp_last_error", "kp_version", "kp_launch_count", "kp_free_host", "kp_batch_query_host",
            "kp_batch_query_dev", "kp_batch_query_dev_async", "kp_grid_subsample_host", "kp_grid_subsample_dev", "kp_kpconv_forward_dev",
            "kp_kpconv_backward_dev", "kp_kpconv_lists_bytes", "kp_kpconv_forward_keep_dev",
-           "kp_kpconv_backward_kept_dev", "kp_kpconv_wf_dev", "kp_kpconv_dx_atomic_dev", "kp_profile_enable",
+           "kp_kpconv_backward_kept_dev", "kp_transpose_table_dev", "kp_kpconv_wf_dev", "kp_kpconv_dx_atomic_dev", "kp_profile_enable",
            "kp_profile_read", "kp_max_pool_forward_dev", "kp_max_pool_backward_dev", "kp_closest_pool_dev"]
 
 
@@ -52,7 +52,9 @@ def lib():
     L.kp_kpconv_lists_bytes.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.kp_kpconv_lists_bytes.restype = None
     L.kp_kpconv_forward_keep_dev.argtypes = conv_common + [vp, C.c_int, vp, C.c_int, C.c_float, vp, vp, vp, vp]
-    L.kp_kpconv_backward_kept_dev.argtypes = conv_common + [vp, C.c_int, vp, C.c_int, C.c_float, vp, vp, vp, vp, vp, vp]
+    L.kp_kpconv_backward_kept_dev.argtypes = conv_common + [vp, C.c_int, vp, C.c_int, C.c_float, vp, vp, vp, vp, vp, vp,
+                                                            vp, vp]
+    L.kp_transpose_table_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.kp_kpconv_wf_dev.argtypes = conv_common + [vp, C.c_int, C.c_float, vp, vp]
     L.kp_kpconv_dx_atomic_dev.argtypes = conv_common + [vp, C.c_int, C.c_float, vp, vp]
     L.kp_profile_enable.argtypes = [C.c_int]

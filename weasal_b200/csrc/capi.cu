@@ -26,7 +26,9 @@ int kpconv_forward_device(const float* q, int nq, const float* s, int ns, const 
 int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
                            int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
                            float extent, const float* dout, float* dx, float* dw, const void* lists_koff,
-                           const void* lists_entries, cudaStream_t stream);
+                           const void* lists_entries, const int* t_rowptr, const int* t_col, cudaStream_t stream);
+int transpose_table_entry(const void* idx, int idx_is_i64, int nq, int H, int idx_stride, int ns, int* rowptr,
+                          int* col_sorted, cudaStream_t stream);
 int profile_read(char* buf, int buflen);
 int max_pool_fwd_device(const float* x, int ns, int C, const void* idx, int is_i64, int nq, int H, int stride,
                         float* out, int* arg, cudaStream_t stream);
@@ -182,10 +184,15 @@ int kp_kpconv_backward_kept_dev(const float* q_pts, int nq, const float* s_pts, 
                                 int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,
                                 int cout, const float* kernel_points, int K, float KP_extent, const float* d_out,
                                 float* d_x, float* d_weights, const void* lists_koff, const void* lists_entries,
-                                void* stream) {
+                                const int* t_rowptr, const int* t_col, void* stream) {
     return kpconv_backward_device(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, weights, cout,
                                   kernel_points, K, KP_extent, d_out, d_x, d_weights, lists_koff, lists_entries,
-                                  (cudaStream_t)stream);
+                                  t_rowptr, t_col, (cudaStream_t)stream);
+}
+
+int kp_transpose_table_dev(const void* neighb_inds, int idx_is_i64, int nq, int H, int idx_stride, int ns,
+                           int* rowptr, int* col, void* stream) {
+    return transpose_table_entry(neighb_inds, idx_is_i64, nq, H, idx_stride, ns, rowptr, col, (cudaStream_t)stream);
 }
 
 int kp_kpconv_backward_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
@@ -193,7 +200,7 @@ int kp_kpconv_backward_dev(const float* q_pts, int nq, const float* s_pts, int n
                            int cout, const float* kernel_points, int K, float KP_extent, const float* d_out,
                            float* d_x, float* d_weights, void* stream) {
     return kpconv_backward_device(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, weights, cout,
-                                  kernel_points, K, KP_extent, d_out, d_x, d_weights, nullptr, nullptr,
+                                  kernel_points, K, KP_extent, d_out, d_x, d_weights, nullptr, nullptr, nullptr, nullptr,
                                   (cudaStream_t)stream);
 }
 

@@ -871,10 +871,45 @@ int kpconv_forward_device(const float* q, int nq, const float* s, int ns, const 
     return run_forward("kp_fwd", S, nq, nullptr, H, x, ns, cin, L, w, (long long)cin * cout, cout, 1, cout, K, out, stream);
 }
 
+// Transposed neighbour table (CSR over the supports): row j lists, in ascending order, the centres i whose row contains
+// j. Depends on the index matrix only, so callers may build it once per table and hand it to every backward pass that
+// uses the table. rowptr has ns + 1 entries, col has nq * H.
+int transpose_table_device(Scratch& S, const void* idx, int idx_is_i64, int nq, int H, int idx_stride, int ns,
+                           int* rowptr, int* col_sorted, cudaStream_t stream) {
+    const long long n_pairs = (long long)nq * H;
+    int* deg = S.alloc<int>((size_t)2 * ns + 1);  // degrees, then the fill cursors
+    int* cursor = deg + ns;
+    int* total = S.alloc<int>(1);
+    int* scan_tmp = S.alloc<int>(scan_tmp_ints(ns));
+    int* col = S.alloc<int>((size_t)(n_pairs > 0 ? n_pairs : 1));
+    if (S.status != KP_OK) return S.status;
+    ProfileScope pst("kp_transpose", stream);
+    KP_CUDA(cudaMemsetAsync(deg, 0, ((size_t)2 * ns + 1) * sizeof(int), stream));
+    const int grid = ceil_div(n_pairs > 0 ? n_pairs : 1, 256);
+    if (idx_is_i64) kp_tr_count_kernel<long long><<<grid, 256, 0, stream>>>((const long long*)idx, nq, H, idx_stride, ns, deg);
+    else kp_tr_count_kernel<int><<<grid, 256, 0, stream>>>((const int*)idx, nq, H, idx_stride, ns, deg);
+    KP_CHECK_LAUNCH();
+    int rc = exclusive_scan(deg, rowptr, ns, total, scan_tmp, stream);
+    if (rc != KP_OK) return rc;
+    if (idx_is_i64) kp_tr_fill_kernel<long long><<<grid, 256, 0, stream>>>((const long long*)idx, nq, H, idx_stride, ns, rowptr, cursor, col);
+    else kp_tr_fill_kernel<int><<<grid, 256, 0, stream>>>((const int*)idx, nq, H, idx_stride, ns, rowptr, cursor, col);
+    KP_CHECK_LAUNCH();
+    kp_tr_sort_kernel<<<ceil_div(ns, 8), 256, 0, stream>>>(rowptr, ns, col, col_sorted, rowptr + ns, total);
+    KP_CHECK_LAUNCH();
+    return KP_OK;
+}
+
+int transpose_table_entry(const void* idx, int idx_is_i64, int nq, int H, int idx_stride, int ns, int* rowptr,
+                          int* col_sorted, cudaStream_t stream) {
+    if (nq < 0 || ns <= 0 || H < 0 || idx_stride < H) return fail(KP_ERR_ARG, "transpose_table: bad sizes");
+    Scratch S(stream);
+    return transpose_table_device(S, idx, idx_is_i64, nq, H, idx_stride, ns, rowptr, col_sorted, stream);
+}
+
 int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
                            int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
                            float extent, const float* dout, float* dx, float* dw, const void* lists_koff,
-                           const void* lists_entries, cudaStream_t stream) {
+                           const void* lists_entries, const int* t_rowptr, const int* t_col, cudaStream_t stream) {
     int rc = check_args(nq, ns, H, idx_stride, cin, cout, K, extent);
     if (rc != KP_OK) return rc;
     KP_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * cin * cout * sizeof(float), stream));
@@ -939,29 +974,17 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
 
     // ---- dX: the forward kernel on the transposed table, with W^T and -kp
     {
-        int* deg = S.alloc<int>(ns + 1);
-        int* rowptr = S.alloc<int>(ns + 1);
-        int* cursor = S.alloc<int>(ns);
-        int* total = S.alloc<int>(1);
-        int* scan_tmp = S.alloc<int>(scan_tmp_ints(ns));
-        int* col = S.alloc<int>((size_t)n_pairs);
-        int* col_sorted = S.alloc<int>((size_t)n_pairs);
-        if (S.status != KP_OK) return S.status;
-        ProfileScope* pst = new ProfileScope("kp_transpose", stream);
-        KP_CUDA(cudaMemsetAsync(deg, 0, (size_t)(ns + 1) * sizeof(int), stream));
-        KP_CUDA(cudaMemsetAsync(cursor, 0, (size_t)ns * sizeof(int), stream));
-        const int grid = ceil_div(n_pairs, 256);
-        if (idx_is_i64) kp_tr_count_kernel<long long><<<grid, 256, 0, stream>>>((const long long*)idx, nq, H, idx_stride, ns, deg);
-        else kp_tr_count_kernel<int><<<grid, 256, 0, stream>>>((const int*)idx, nq, H, idx_stride, ns, deg);
-        KP_CHECK_LAUNCH();
-        rc = exclusive_scan(deg, rowptr, ns, total, scan_tmp, stream);
-        if (rc != KP_OK) return rc;
-        if (idx_is_i64) kp_tr_fill_kernel<long long><<<grid, 256, 0, stream>>>((const long long*)idx, nq, H, idx_stride, ns, rowptr, cursor, col);
-        else kp_tr_fill_kernel<int><<<grid, 256, 0, stream>>>((const int*)idx, nq, H, idx_stride, ns, rowptr, cursor, col);
-        KP_CHECK_LAUNCH();
-        kp_tr_sort_kernel<<<ceil_div(ns, 8), 256, 0, stream>>>(rowptr, ns, col, col_sorted, rowptr + ns, total);
-        delete pst;
-        KP_CHECK_LAUNCH();
+        const int* rowptr = t_rowptr;
+        const int* col_sorted = t_col;
+        if (!rowptr || !col_sorted) {
+            int* rp = S.alloc<int>(ns + 1);
+            int* cs = S.alloc<int>((size_t)n_pairs);
+            if (S.status != KP_OK) return S.status;
+            rc = transpose_table_device(S, idx, idx_is_i64, nq, H, idx_stride, ns, rp, cs, stream);
+            if (rc != KP_OK) return rc;
+            rowptr = rp;
+            col_sorted = cs;
+        }
         Table T;
         T.idx = col_sorted; T.rowptr = rowptr; T.H = 0; T.stride = 0; T.is_i64 = 0;
         Lists L;

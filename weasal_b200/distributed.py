@@ -16,41 +16,29 @@ import torch.distributed as dist
 
 
 class GradAllReducer:
-    """Flat-buffer gradient averaging. Parameters without a gradient (the reference's BatchNorm layers are
-    identities on 2-D features and never receive one) contribute zeros and stay ``grad=None``."""
+    """Flat-buffer gradient averaging: one concatenation, ONE all-reduce, one fused copy back per step.
+    Parameters without a gradient (the reference's BatchNorm layers are identities on 2-D features and never receive
+    one) are skipped and stay ``grad=None``; every rank runs the same network, so every rank
+    skips the same ones."""
 
     def __init__(self, params, group=None):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
-        n = sum(p.numel() for p in self.params)
-        ref = self.params[0]
-        self.flat = torch.zeros(n, dtype=torch.float32, device=ref.device)
-        self.views = []
-        o = 0
-        for p in self.params:
-            self.views.append(self.flat[o:o + p.numel()].view_as(p))
-            o += p.numel()
 
     def bytes(self):
-        return self.flat.numel() * 4
+        return sum(p.numel() for p in self.params) * 4
 
     @torch.no_grad()
     def step(self):
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return
-        had = []
-        for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                v.zero_()
-                had.append(False)
-            else:
-                v.copy_(p.grad)
-                had.append(True)
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        self.flat.div_(dist.get_world_size(self.group))
-        for p, v, h in zip(self.params, self.views, had):
-            if h:
-                p.grad.copy_(v)
+        grads = [p.grad for p in self.params if p.grad is not None]
+        if not grads:
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        flat.div_(dist.get_world_size(self.group))
+        torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)])
 
 
 def shard_indices(n_items, rank, world_size):

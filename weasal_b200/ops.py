@@ -196,6 +196,7 @@ class KPConvFunction(torch.autograd.Function):
                                                    xx.data_ptr(), cin, w.data_ptr(), cout, kp.data_ptr(), K,
                                                    float(KP_extent), out.data_ptr(), _stream()), "kpconv_forward")
         ctx.lists = lists
+        ctx.idx_obj = neighb_inds  # the caller's tensor object: the transposed table is cached on it (see backward)
         ctx.save_for_backward(q, s, idx, xx, w, kp)
         ctx.meta = (i64, H, stride, float(KP_extent))
         return out
@@ -223,11 +224,25 @@ class KPConvFunction(torch.autograd.Function):
             dx = torch.empty((ns, cin), dtype=torch.float32, device=q.device)
             dw = torch.empty((K, cin, cout), dtype=torch.float32, device=q.device)
             lk, le = ctx.lists if ctx.lists is not None else (None, None)
+            # The transposed neighbour table depends on the index matrix only: build it once per matrix and let every
+            # KPConv that shares the matrix (the two blocks of a layer) reuse it.
+            tr = getattr(ctx.idx_obj, "_kp_transposed", None)
+            if tr is None or tr[2] != (idx.data_ptr(), nq, H, stride, ns):
+                rowptr = torch.empty(ns + 1, dtype=torch.int32, device=q.device)
+                col = torch.empty(max(nq * H, 1), dtype=torch.int32, device=q.device)
+                _lib.check(L.kp_transpose_table_dev(idx.data_ptr(), i64, nq, H, stride, ns, rowptr.data_ptr(),
+                                                    col.data_ptr(), _stream()), "transpose_table")
+                tr = (rowptr, col, (idx.data_ptr(), nq, H, stride, ns))
+                try:
+                    ctx.idx_obj._kp_transposed = tr
+                except Exception:
+                    pass
             _lib.check(L.kp_kpconv_backward_kept_dev(q.data_ptr(), nq, s.data_ptr(), ns, idx.data_ptr(), i64, H, stride,
                                                      xx.data_ptr(), cin, w.data_ptr(), cout, kp.data_ptr(), K, ext,
                                                      do.data_ptr(), dx.data_ptr(), dw.data_ptr(),
                                                      lk.data_ptr() if lk is not None else None,
-                                                     le.data_ptr() if le is not None else None, _stream()),
+                                                     le.data_ptr() if le is not None else None, tr[0].data_ptr(),
+                                                     tr[1].data_ptr(), _stream()),
                        "kpconv_backward")
         return None, None, None, dx, dw, None, None
 
