@@ -149,7 +149,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     from weasal_b200 import _lib, grid_subsampling, pyramid
-    from weasal_b200.blocks import KPConv
+    from weasal_b200.kpconv import KPConv
     from weasal_b200.distributed import GradAllReducer
     from weasal_b200.net import CfgView, KPFCNNHarness, net_config
     import ctypes as C

@@ -64,7 +64,7 @@ def test_shims_validate_like_the_reference_wrappers():
 
 
 def test_kpconv_module_contract():
-    from weasal_b200.blocks import KPConv
+    from weasal_b200.kpconv import KPConv
     np.random.seed(0)
     torch.manual_seed(0)
     m = KPConv(15, 3, 16, 32, 0.24, 0.6)

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 from weasal_b200 import grid_subsampling, pyramid  # noqa: E402
-from weasal_b200.blocks import KPConv  # noqa: E402
+from weasal_b200.kpconv import KPConv  # noqa: E402
 from weasal_b200.net import CfgView, KPFCNNHarness, net_config  # noqa: E402
 
 cfg_name = sys.argv[1] if len(sys.argv) > 1 else "vaihingen_pl"

@@ -2,7 +2,7 @@
 
   radius_neighbors / grid_subsampling   numpy drop-ins for the reference's two C++ extension modules
   ops                                   device-tensor entry points (radius search, grid subsampling, KPConv fwd/bwd)
-  blocks.KPConv                         drop-in nn.Module for models.blocks.KPConv
+  kpconv.KPConv                         drop-in nn.Module for models.blocks.KPConv
   pyramid                               device-side segmentation_inputs (neighbors / pools / upsamples per layer)
   dropin.install()                      registers all of the above under the reference's module names
 All arithmetic runs in libweasal_b200.so (hand-written CUDA, C-ABI in include/weasal_b200.h); there is no CPU path.

@@ -3,7 +3,7 @@
 After :func:`install`, the unchanged WeaSAL sources resolve
   * ``cpp_wrappers.cpp_neighbors.radius_neighbors``     -> :mod:`weasal_b200.radius_neighbors`
   * ``cpp_wrappers.cpp_subsampling.grid_subsampling``   -> :mod:`weasal_b200.grid_subsampling`
-  * ``models.blocks.KPConv``                            -> :class:`weasal_b200.blocks.KPConv` (when ``models.blocks`` is
+  * ``models.blocks.KPConv``                            -> :class:`weasal_b200.kpconv.KPConv` (when ``models.blocks`` is
     importable; call before ``models.architectures`` does ``from models.blocks import *``).
 """
 import sys
@@ -27,6 +27,6 @@ def install(patch_kpconv=True):
             import models.blocks as ref_blocks
         except Exception:
             return False
-        from .blocks import KPConv
+        from .kpconv import KPConv
         ref_blocks.KPConv = KPConv
     return True
