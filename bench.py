@@ -185,8 +185,11 @@ def run_ours(args):
         return loss, batch
 
     def timed(n_warm, n_steps, e2e):
+        import gc
         pts = 0
         total_ms = 0.0
+        gc.collect()
+        gc.disable()  # the step is host-launch bound: a generational GC pause inside a step shows up as a 10 % outlier
         for it in range(n_warm + n_steps):
             b = it % N_BATCHES
             if it == n_warm:
@@ -209,6 +212,7 @@ def run_ours(args):
             if it >= n_warm:
                 total_ms += e0.elapsed_time(e1)
                 pts += batches[b]["points"].shape[0]
+        gc.enable()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

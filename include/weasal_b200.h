@@ -71,6 +71,18 @@ int kp_batch_query_dev_async(const float* queries, int nq, const float* supports
                              const int* s_batches, int nb, float radius, void* out, int out_is_i64, int cap,
                              int* d_result, void* stream);
 
+/* Split form of the search, for callers that query the same supports at the same radius more than once (in the
+ * pyramid of datasets/common.py:505-534 the grid over layer l+1 at radius 2r serves the upsample search of layer l
+ * and the conv and pool searches of layer l+1). `grid` is a caller-owned DEVICE buffer of kp_search_grid_bytes(ns, nb)
+ * bytes; build once, query any number of times with the same (ns, nb, radius). Query semantics are those of
+ * kp_batch_query_dev (hmax != NULL: synchronising) / kp_batch_query_dev_async (d_result != NULL: not synchronising). */
+long long kp_search_grid_bytes(int ns, int nb);
+int kp_search_grid_build_dev(const float* supports, int ns, const int* s_batches, int nb, float radius, void* grid,
+                             void* stream);
+int kp_search_grid_query_dev(const void* grid, int ns, int nb, float radius, const float* queries, int nq,
+                             const int* q_batches, void* out, int out_is_i64, int cap, int* hmax, int* d_result,
+                             void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Grid subsampling.
  * Replaces: cpp_wrappers/cpp_subsampling/wrapper.cpp:62-333 `subsample_batch(points, batches, features, classes,

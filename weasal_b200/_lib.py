@@ -19,7 +19,8 @@ KP_OK, KP_ERR_CUDA, KP_ERR_ARG, KP_ERR_CAPACITY, KP_ERR_TOO_DENSE, KP_ERR_EMPTY,
 
 # every symbol include/weasal_b200.h declares (tests check the library exports all of them)
 SYMBOLS = ["kp_last_error", "kp_version", "kp_launch_count", "kp_free_host", "kp_batch_query_host",
-           "kp_batch_query_dev", "kp_batch_query_dev_async", "kp_grid_subsample_host", "kp_grid_subsample_dev", "kp_kpconv_forward_dev",
+           "kp_batch_query_dev", "kp_batch_query_dev_async", "kp_search_grid_bytes", "kp_search_grid_build_dev",
+           "kp_search_grid_query_dev", "kp_grid_subsample_host", "kp_grid_subsample_dev", "kp_kpconv_forward_dev",
            "kp_kpconv_backward_dev", "kp_kpconv_lists_bytes", "kp_kpconv_forward_keep_dev",
            "kp_kpconv_backward_kept_dev", "kp_transpose_table_dev", "kp_kpconv_wf_dev", "kp_kpconv_dx_atomic_dev", "kp_profile_enable",
            "kp_profile_read", "kp_max_pool_forward_dev", "kp_max_pool_backward_dev", "kp_closest_pool_dev"]
@@ -40,6 +41,11 @@ def lib():
     L.kp_batch_query_dev.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_float, vp, C.c_int, C.c_int,
                                      c_i32p, vp]
     L.kp_batch_query_dev_async.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_float, vp, C.c_int, C.c_int,
+                                           vp, vp]
+    L.kp_search_grid_bytes.argtypes = [C.c_int, C.c_int]
+    L.kp_search_grid_bytes.restype = C.c_longlong
+    L.kp_search_grid_build_dev.argtypes = [vp, C.c_int, vp, C.c_int, C.c_float, vp, vp]
+    L.kp_search_grid_query_dev.argtypes = [vp, C.c_int, C.c_int, C.c_float, vp, C.c_int, vp, vp, C.c_int, C.c_int, c_i32p,
                                            vp, vp]
     L.kp_grid_subsample_host.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_float, C.c_int,
                                          C.c_int, vp, C.POINTER(c_f32p), vp, C.POINTER(c_f32p), C.POINTER(c_i32p),

@@ -9,6 +9,10 @@ namespace kp {
 int batch_query_device(const float* q, int nq, const float* s, int ns, const int* qb_host, const int* sb_host, int nb,
                        float radius, void* out, int out_is_i64, int cap, int* hmax_host, int* d_result,
                        cudaStream_t stream);
+size_t grid_bytes(int ns, int nb);
+int grid_build_device(const float* s, int ns, const int* sb_host, int nb, float radius, void* grid_buf, cudaStream_t stream);
+int grid_query_device(const void* grid_buf, int ns, int nb, float radius, const float* q, int nq, const int* qb_host,
+                      void* out, int out_is_i64, int cap, int* hmax_host, int* d_result, cudaStream_t stream);
 int grid_subsample_device(const float* pts, int n, const int* lens_host, int nb, const float* feats, int fdim,
                           const int* classes, int ldim, float dl, int max_p, int order_mode, const float* rot_host,
                           float* out_pts, int* out_lens_host, float* out_feats, int* out_classes, int* m_host,
@@ -100,6 +104,21 @@ int kp_batch_query_host(const float* queries, int nq, const float* supports, int
     KP_CUDA(cudaMemcpy2D(*out, (size_t)(*hmax) * sizeof(int), dout.p, (size_t)cap * sizeof(int),
                          (size_t)(*hmax) * sizeof(int), nq, cudaMemcpyDeviceToHost));
     return KP_OK;
+}
+
+long long kp_search_grid_bytes(int ns, int nb) { return (long long)grid_bytes(ns, nb); }
+
+int kp_search_grid_build_dev(const float* supports, int ns, const int* s_batches, int nb, float radius, void* grid,
+                             void* stream) {
+    return grid_build_device(supports, ns, s_batches, nb, radius, grid, (cudaStream_t)stream);
+}
+
+int kp_search_grid_query_dev(const void* grid, int ns, int nb, float radius, const float* queries, int nq,
+                             const int* q_batches, void* out, int out_is_i64, int cap, int* hmax, int* d_result,
+                             void* stream) {
+    if (!hmax && !d_result) return fail(KP_ERR_ARG, "search_grid_query: hmax or d_result is required");
+    return grid_query_device(grid, ns, nb, radius, queries, nq, q_batches, out, out_is_i64, cap, hmax, d_result,
+                             (cudaStream_t)stream);
 }
 
 int kp_grid_subsample_dev(const float* points, int n, const int* batches, int nb, const float* features, int fdim,

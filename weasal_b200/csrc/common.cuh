@@ -61,6 +61,7 @@ struct Arena {
     int nblocks = 0;
     int cur = 0;
     size_t off = 0;
+    int hold = 0;  // > 0: nested entry points append to the arena instead of restarting it
 };
 Arena* arena_for(cudaStream_t stream);
 int arena_begin(Arena* a, cudaStream_t stream);
@@ -72,7 +73,7 @@ struct Scratch {
     int status = KP_OK;
     explicit Scratch(cudaStream_t s) : stream(s) {
         arena = arena_for(s);
-        status = arena_begin(arena, s);
+        if (arena->hold == 0) status = arena_begin(arena, s);  // a held arena keeps its contents (see ArenaHold)
     }
     template <typename T>
     T* alloc(size_t count) {
@@ -84,6 +85,13 @@ struct Scratch {
         }
         return reinterpret_cast<T*>(p);
     }
+};
+
+// While alive, entry points called from inside another entry point keep what the outer one allocated.
+struct ArenaHold {
+    Arena* a;
+    explicit ArenaHold(Scratch& s) : a(s.arena) { a->hold++; }
+    ~ArenaHold() { a->hold--; }
 };
 
 // small host arrays (batch offsets, grid rotations) travel to the device as a kernel argument: no pageable

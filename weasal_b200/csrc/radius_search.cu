@@ -259,96 +259,141 @@ __global__ void __launch_bounds__(WARPS * 32) rs_search_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------------------- host side
-// q, s, out are device pointers; qb_host / sb_host are host batch lengths. out is [nq, cap] (int32 or int64).
-// *hmax_host receives the true maximum neighbour count (may exceed cap: rows then hold their cap closest).
-// d_result (optional): device int[2] that receives {max neighbour count, error bits}. When given, the call does NOT
-// synchronise and *hmax_host is left untouched: the caller reads d_result later (the pyramid builder reads the
-// results of all its searches with one copy). Error bits: 1 = grid too large, 2 = more than 1024 neighbours.
-int batch_query_device(const float* q, int nq, const float* s, int ns, const int* qb_host, const int* sb_host, int nb,
-                       float radius, void* out, int out_is_i64, int cap, int* hmax_host, int* d_result,
-                       cudaStream_t stream) {
-    if (nq < 0 || ns < 0 || nb <= 0 || cap < 0 || !(radius > 0.f)) return fail(KP_ERR_ARG, "batch_query: bad sizes / radius");
-    if (nb > 1023) return fail(KP_ERR_UNSUPPORTED, "batch_query: more than 1023 batch elements");
-    std::vector<int> qoff(nb + 1, 0), soff(nb + 1, 0);
+// A search grid lives in ONE caller-owned device buffer (grid_bytes) so that it can outlive the call that built it: in
+// the pyramid the grid over layer l+1 at radius 2r serves the upsample search of layer l and the conv and pool
+// searches of layer l+1 (datasets/common.py:505, 531, 534), i.e. 5 builds per batch instead of 13.
+struct GridView {
+    int ns, nb, tsize;
+    float radius;
+    unsigned long long* tkeys;
+    int *tcount, *tstart, *s_off, *cursor;
+    unsigned* bbox;
+    float4* sorted;
+};
+
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+static int grid_tsize(int ns) {
+    int tsize = 1024;
+    while (tsize < 2 * ns) tsize <<= 1;
+    return tsize;
+}
+
+size_t grid_bytes(int ns, int nb) {
+    const size_t t = (size_t)grid_tsize(ns);
+    return align256(t * 8) + 2 * align256(t * 4) + align256((size_t)(nb + 1) * 4) + align256(4) + align256((size_t)nb * 24) +
+           align256((size_t)(ns > 0 ? ns : 1) * 16);
+}
+
+static GridView grid_view(void* buf, int ns, int nb, float radius) {
+    GridView g;
+    g.ns = ns; g.nb = nb; g.radius = radius; g.tsize = grid_tsize(ns);
+    char* p = (char*)buf;
+    g.tkeys = (unsigned long long*)p; p += align256((size_t)g.tsize * 8);
+    g.tcount = (int*)p; p += align256((size_t)g.tsize * 4);
+    g.tstart = (int*)p; p += align256((size_t)g.tsize * 4);
+    g.s_off = (int*)p; p += align256((size_t)(nb + 1) * 4);
+    g.cursor = (int*)p; p += align256(4);
+    g.bbox = (unsigned*)p; p += align256((size_t)nb * 24);
+    g.sorted = (float4*)p;
+    return g;
+}
+
+static int check_batches(const int* b_host, int nb, int n, std::vector<int>& off) {
+    off.assign(nb + 1, 0);
     for (int b = 0; b < nb; b++) {
-        if (qb_host[b] < 0 || sb_host[b] < 0) return fail(KP_ERR_ARG, "batch_query: negative batch length");
-        qoff[b + 1] = qoff[b] + qb_host[b];
-        soff[b + 1] = soff[b] + sb_host[b];
+        if (b_host[b] < 0) return fail(KP_ERR_ARG, "batch_query: negative batch length");
+        off[b + 1] = off[b] + b_host[b];
     }
-    if (qoff[nb] != nq || soff[nb] != ns) return fail(KP_ERR_ARG, "batch_query: batch lengths do not sum to N");
+    if (off[nb] != n) return fail(KP_ERR_ARG, "batch_query: batch lengths do not sum to N");
+    return KP_OK;
+}
+
+// supports -> grid (5 launches): init, bounding boxes, hash insert + per-cell counts, cell ranges, cell-sorted copy
+int grid_build_device(const float* s, int ns, const int* sb_host, int nb, float radius, void* grid_buf,
+                      cudaStream_t stream) {
+    if (ns < 0 || nb <= 0 || !(radius > 0.f)) return fail(KP_ERR_ARG, "batch_query: bad sizes / radius");
+    if (nb > 1023) return fail(KP_ERR_UNSUPPORTED, "batch_query: more than 1023 batch elements");
+    std::vector<int> soff;
+    int rc = check_batches(sb_host, nb, ns, soff);
+    if (rc != KP_OK) return rc;
+    GridView g = grid_view(grid_buf, ns, nb, radius);
+    Scratch S(stream);
+    int* d_sslot = S.alloc<int>(ns);
+    int* d_srank = S.alloc<int>(ns);
+    int* d_dummy = S.alloc<int>(2);
+    if (S.status != KP_OK) return S.status;
+    rc = upload_offsets(soff.data(), nb + 1, g.s_off, stream);
+    if (rc != KP_OK) return rc;
+    ProfileScope ps("rs_build", stream);
+    rs_init_kernel<<<ceil_div(g.tsize > nb * 6 ? g.tsize : nb * 6, 256), 256, 0, stream>>>(g.tkeys, g.tcount, g.tsize, g.bbox,
+                                                                                        nb, d_dummy, g.cursor);
+    KP_CHECK_LAUNCH();
+    if (ns > 0) {
+        rs_bbox_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(s, ns, g.s_off, nb, g.bbox);
+        KP_CHECK_LAUNCH();
+        rs_insert_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(s, ns, g.s_off, nb, g.bbox, radius, g.tkeys, g.tcount,
+                                                              g.tsize - 1, d_sslot, d_srank);
+        KP_CHECK_LAUNCH();
+        rs_assign_kernel<<<ceil_div(g.tsize, 256), 256, 0, stream>>>(g.tcount, g.tstart, g.tsize, g.cursor);
+        KP_CHECK_LAUNCH();
+        rs_fill_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(s, ns, d_sslot, d_srank, g.tstart, g.sorted);
+        KP_CHECK_LAUNCH();
+    }
+    return KP_OK;
+}
+
+// queries against a built grid. out is [nq, cap] (int32 or int64); rows keep their cap closest neighbours.
+// d_result != null: device int[2] receives {true max count, error bits}, no host sync. Otherwise the call synchronises,
+// escalates to the 1024-hit kernel if needed and stores the true max count in *hmax_host.
+int grid_query_device(const void* grid_buf, int ns, int nb, float radius, const float* q, int nq, const int* qb_host,
+                      void* out, int out_is_i64, int cap, int* hmax_host, int* d_result, cudaStream_t stream) {
+    if (nq < 0 || cap < 0) return fail(KP_ERR_ARG, "batch_query: bad sizes");
+    std::vector<int> qoff;
+    int rc = check_batches(qb_host, nb, nq, qoff);
+    if (rc != KP_OK) return rc;
     if (hmax_host) *hmax_host = 0;
     if (nq == 0) {
         if (d_result) KP_CUDA(cudaMemsetAsync(d_result, 0, 2 * sizeof(int), stream));
         return KP_OK;
     }
-
+    GridView g = grid_view(const_cast<void*>(grid_buf), ns, nb, radius);
     Scratch S(stream);
-    int* d_qoff = S.alloc<int>(2 * (nb + 1));
-    int* d_soff = d_qoff + (nb + 1);
-    unsigned* d_bbox = S.alloc<unsigned>((size_t)nb * 6);
-    int tsize = 1024;
-    while (tsize < 2 * ns) tsize <<= 1;
-    unsigned long long* d_tkeys = S.alloc<unsigned long long>(tsize);
-    int* d_tcount = S.alloc<int>(tsize);
-    int* d_tstart = S.alloc<int>(tsize);
-    int* d_sslot = S.alloc<int>(ns);
-    int* d_srank = S.alloc<int>(ns);
-    float4* d_sorted = S.alloc<float4>(ns);
-    int* d_cursor = S.alloc<int>(1);
+    int* d_qoff = S.alloc<int>(nb + 1 + 2);
     int* d_hmax = d_result ? d_result : S.alloc<int>(2);
     if (S.status != KP_OK) return S.status;
     int* d_err = d_hmax + 1;
-
-    {
-        std::vector<int> both(qoff);
-        both.insert(both.end(), soff.begin(), soff.end());
-        int rc0 = upload_offsets(both.data(), 2 * (nb + 1), d_qoff, stream);
-        if (rc0 != KP_OK) return rc0;
+    {   // offsets and the zeroed result slots travel in one kernel-argument upload when the slots are ours
+        std::vector<int> blob(qoff);
+        rc = upload_offsets(blob.data(), nb + 1, d_qoff, stream);
+        if (rc != KP_OK) return rc;
+        KP_CUDA(cudaMemsetAsync(d_hmax, 0, 2 * sizeof(int), stream));
     }
-    ProfileScope* ps = new ProfileScope("rs_build", stream);
-    rs_init_kernel<<<ceil_div(tsize > nb * 6 ? tsize : nb * 6, 256), 256, 0, stream>>>(d_tkeys, d_tcount, tsize, d_bbox, nb,
-                                                                                    d_hmax, d_cursor);
-    KP_CHECK_LAUNCH();
-    if (ns > 0) {
-        rs_bbox_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(s, ns, d_soff, nb, d_bbox);
-        KP_CHECK_LAUNCH();
-        rs_insert_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(s, ns, d_soff, nb, d_bbox, radius, d_tkeys, d_tcount,
-                                                              tsize - 1, d_sslot, d_srank);
-        KP_CHECK_LAUNCH();
-        rs_assign_kernel<<<ceil_div(tsize, 256), 256, 0, stream>>>(d_tcount, d_tstart, tsize, d_cursor);
-        KP_CHECK_LAUNCH();
-        rs_fill_kernel<<<ceil_div(ns, 256), 256, 0, stream>>>(s, ns, d_sslot, d_srank, d_tstart, d_sorted);
-        KP_CHECK_LAUNCH();
-    }
-
-    delete ps;
     SearchParams P;
-    P.q = q; P.nq = nq; P.s = s; P.ns = ns; P.q_off = d_qoff; P.s_off = d_soff; P.nb = nb;
+    P.q = q; P.nq = nq; P.s = nullptr; P.ns = ns; P.q_off = d_qoff; P.s_off = g.s_off; P.nb = nb;
     P.r2 = radius * radius;  // neighbors.cpp:226, f32
-    auto launch = [&](bool big) -> int {
+    auto launch = [&](bool big) {
         ProfileScope ps2("rs_search", stream);
         if (!big) {
             const int grid = ceil_div(nq, RS_WARPS_SMALL);
             if (out_is_i64)
                 rs_search_kernel<long long, RS_HITS_SMALL, RS_WARPS_SMALL><<<grid, RS_WARPS_SMALL * 32, 0, stream>>>(
-                    P, d_bbox, radius, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (long long*)out, cap, d_hmax, d_err);
+                    P, g.bbox, radius, g.tkeys, g.tcount, g.tstart, g.tsize - 1, g.sorted, (long long*)out, cap, d_hmax, d_err);
             else
                 rs_search_kernel<int, RS_HITS_SMALL, RS_WARPS_SMALL><<<grid, RS_WARPS_SMALL * 32, 0, stream>>>(
-                    P, d_bbox, radius, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (int*)out, cap, d_hmax, d_err);
+                    P, g.bbox, radius, g.tkeys, g.tcount, g.tstart, g.tsize - 1, g.sorted, (int*)out, cap, d_hmax, d_err);
         } else {
             const int grid = ceil_div(nq, RS_WARPS_BIG);
             if (out_is_i64)
                 rs_search_kernel<long long, RS_HITS_BIG, RS_WARPS_BIG><<<grid, RS_WARPS_BIG * 32, 0, stream>>>(
-                    P, d_bbox, radius, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (long long*)out, cap, d_hmax, d_err);
+                    P, g.bbox, radius, g.tkeys, g.tcount, g.tstart, g.tsize - 1, g.sorted, (long long*)out, cap, d_hmax, d_err);
             else
                 rs_search_kernel<int, RS_HITS_BIG, RS_WARPS_BIG><<<grid, RS_WARPS_BIG * 32, 0, stream>>>(
-                    P, d_bbox, radius, d_tkeys, d_tcount, d_tstart, tsize - 1, d_sorted, (int*)out, cap, d_hmax, d_err);
+                    P, g.bbox, radius, g.tkeys, g.tcount, g.tstart, g.tsize - 1, g.sorted, (int*)out, cap, d_hmax, d_err);
         }
-        return KP_OK;
     };
     launch(false);
     KP_CHECK_LAUNCH();
-
     if (d_result) return KP_OK;
     int h[2] = {0, 0};
     KP_CUDA(cudaMemcpyAsync(h, d_hmax, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -364,6 +409,25 @@ int batch_query_device(const float* q, int nq, const float* s, int ns, const int
     if (h[1] & RS_ERR_DENSE) return fail(KP_ERR_TOO_DENSE, "batch_query: more than 1024 neighbours for one query");
     *hmax_host = h[0];
     return KP_OK;
+}
+
+// one-shot search: the grid lives in this call's scratch
+int batch_query_device(const float* q, int nq, const float* s, int ns, const int* qb_host, const int* sb_host, int nb,
+                       float radius, void* out, int out_is_i64, int cap, int* hmax_host, int* d_result,
+                       cudaStream_t stream) {
+    if (nq < 0 || ns < 0 || nb <= 0 || cap < 0 || !(radius > 0.f)) return fail(KP_ERR_ARG, "batch_query: bad sizes / radius");
+    void* buf = nullptr;
+    {
+        // the grid must survive the Scratch objects of the two calls below, which share this thread's arena: take it
+        // from the arena first and let the nested calls allocate after it
+        Scratch S(stream);
+        buf = S.alloc<char>(grid_bytes(ns, nb));
+        if (S.status != KP_OK) return S.status;
+        ArenaHold hold(S);
+        int rc = grid_build_device(s, ns, sb_host, nb, radius, buf, stream);
+        if (rc != KP_OK) return rc;
+        return grid_query_device(buf, ns, nb, radius, q, nq, qb_host, out, out_is_i64, cap, hmax_host, d_result, stream);
+    }
 }
 
 }  // namespace kp

@@ -60,6 +60,21 @@ def batch_query(queries, supports, q_batches, s_batches, radius, limit=None, dty
     return out[:, :width]
 
 
+class SearchGrid:
+    """Hash grid over a set of supports at one radius (kp_search_grid_build_dev), reusable by several searches."""
+
+    def __init__(self, supports, s_batches, radius):
+        _need_cuda(supports)
+        self.s = _f32c(supports)
+        self.sb = _lens(s_batches)
+        self.radius = float(radius)
+        L = _lib.lib()
+        self.buf = torch.empty(int(L.kp_search_grid_bytes(self.s.shape[0], len(self.sb))), dtype=torch.uint8,
+                               device=self.s.device)
+        _lib.check(L.kp_search_grid_build_dev(self.s.data_ptr(), self.s.shape[0], self.sb.ctypes.data, len(self.sb),
+                                              self.radius, self.buf.data_ptr(), _stream()), "search_grid_build")
+
+
 class PendingSearches:
     """Radius searches issued without a host sync (kp_batch_query_dev_async). ``resolve()`` reads all their
     {Hmax, error} results with one device->host copy, re-runs the rare search whose rows outgrew its buffer, and
@@ -69,7 +84,9 @@ class PendingSearches:
         self.results = torch.zeros((capacity, 2), dtype=torch.int32, device=device)
         self.items = []
 
-    def add(self, queries, supports, q_batches, s_batches, radius, limit=None, dtype=torch.int64, cap_hint=80):
+    def add(self, queries, supports, q_batches, s_batches, radius, limit=None, dtype=torch.int64, cap_hint=80,
+            grid=None):
+        """``grid``: a :class:`SearchGrid` built over ``supports`` at ``radius`` (skips the grid build)."""
         _need_cuda(queries, supports)
         q, s = _f32c(queries), _f32c(supports)
         qb, sb = _lens(q_batches), _lens(s_batches)
@@ -79,10 +96,15 @@ class PendingSearches:
         slot = len(self.items)
         if slot >= self.results.shape[0]:
             raise RuntimeError("PendingSearches: capacity exceeded")
-        rc = _lib.lib().kp_batch_query_dev_async(q.data_ptr(), nq, s.data_ptr(), ns, qb.ctypes.data, sb.ctypes.data,
-                                                 len(qb), float(radius), out.data_ptr(),
-                                                 1 if dtype == torch.int64 else 0, cap,
-                                                 self.results[slot].data_ptr(), _stream())
+        if grid is not None:
+            rc = _lib.lib().kp_search_grid_query_dev(grid.buf.data_ptr(), ns, len(sb), grid.radius, q.data_ptr(), nq,
+                                                     qb.ctypes.data, out.data_ptr(), 1 if dtype == torch.int64 else 0,
+                                                     cap, None, self.results[slot].data_ptr(), _stream())
+        else:
+            rc = _lib.lib().kp_batch_query_dev_async(q.data_ptr(), nq, s.data_ptr(), ns, qb.ctypes.data, sb.ctypes.data,
+                                                     len(qb), float(radius), out.data_ptr(),
+                                                     1 if dtype == torch.int64 else 0, cap,
+                                                     self.results[slot].data_ptr(), _stream())
         _lib.check(rc, "batch_query")
         self.items.append((out, cap, limit, (q, s, qb, sb, radius, dtype)))
         return slot

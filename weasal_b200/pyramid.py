@@ -80,6 +80,15 @@ def segmentation_inputs(stacked_points, stacked_features, labels, stack_lengths,
     empty_idx = lambda: torch.zeros((0, 1), dtype=index_dtype, device=dev)
     # every search is issued without a host sync; their widths are read back together at the end
     pending = ops.PendingSearches(dev)
+    # one hash grid per (point set, radius): the grid over layer l+1 at radius 2r serves the upsample search of layer l
+    # and the conv and pool searches of layer l+1
+    grids = {}
+
+    def grid_of(p, b, r):
+        key = (p.data_ptr(), p.shape[0], float(r))
+        if key not in grids:
+            grids[key] = ops.SearchGrid(p, b, r)
+        return grids[key]
 
     for block in config.architecture:
         if not ('pool' in block or 'strided' in block or 'global' in block or 'upsample' in block):
@@ -91,7 +100,7 @@ def segmentation_inputs(stacked_points, stacked_features, labels, stack_lengths,
                 r = r_normal * config.deform_radius / config.conv_radius
             else:
                 r = r_normal
-            conv_i = pending.add(pts, pts, lens, lens, r, limit=lim(layer), dtype=index_dtype)
+            conv_i = pending.add(pts, pts, lens, lens, r, limit=lim(layer), dtype=index_dtype, grid=grid_of(pts, lens, r))
         else:
             conv_i = empty_idx()
         if 'pool' in block or 'strided' in block:
@@ -102,9 +111,10 @@ def segmentation_inputs(stacked_points, stacked_features, labels, stack_lengths,
                 r = r_normal * config.deform_radius / config.conv_radius
             else:
                 r = r_normal
-            pool_i = pending.add(pool_p, pts, pool_b, lens, r, limit=lim(layer), dtype=index_dtype)
+            pool_i = pending.add(pool_p, pts, pool_b, lens, r, limit=lim(layer), dtype=index_dtype,
+                                 grid=grid_of(pts, lens, r))
             up_i = pending.add(pts, pool_p, lens, pool_b, 2 * r, limit=lim(layer + 1) if limits is not None and
-                               layer + 1 < len(limits) else None, dtype=index_dtype)
+                               layer + 1 < len(limits) else None, dtype=index_dtype, grid=grid_of(pool_p, pool_b, 2 * r))
         else:
             pool_i = empty_idx()
             pool_p = torch.zeros((0, 3), dtype=torch.float32, device=dev)
