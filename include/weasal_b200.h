@@ -130,7 +130,8 @@ int kp_kpconv_backward_dev(const float* q_pts, int nq, const float* s_pts, int n
 /* Training variant: the forward pass leaves its influence entry lists (which depend only on the geometry and the kernel
  * points) in two caller-owned device buffers of the sizes kp_kpconv_lists_bytes reports, and the backward pass of the
  * same call reuses them instead of rebuilding them. Backward also accepts the transposed neighbour table
- * (kp_transpose_table_dev: CSR over the supports, rowptr int32 [ns+1], col int32 [nq*H]), which depends on the index
+ * (kp_transpose_table_dev: CSR over the supports, rowptr int32 [ns+2] = ns+1 row pointers followed by the longest
+ * row's length, col int32 [nq*H]), which depends on the index
  * matrix only and can therefore be shared by every KPConv that uses that matrix; NULL = build it internally.
  * Results are identical to the plain pair above. */
 int kp_transpose_table_dev(const void* neighb_inds, int idx_is_i64, int nq, int H, int idx_stride, int ns,

@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) kp_influence_long_kernel(const
                                                                           float kp_sign, float inv_ext,
                                                                           unsigned short* __restrict__ koff,
                                                                           int2* __restrict__ entries) {
+    if (T.rowptr && T.rowptr[nc + 1] <= INF_MAX_ROW) return;  // CSR tables record their longest row after the pointers
     __shared__ float s_kp[16 * 3];
     if (threadIdx.x < 48) s_kp[threadIdx.x] = (threadIdx.x < 3 * K) ? kp_sign * kp[threadIdx.x] : 1e30f;
     __syncthreads();
@@ -739,6 +740,7 @@ __global__ void __launch_bounds__(256) kp_tr_sort_kernel(const int* __restrict__
     if (j >= ns) return;
     const int a = rowptr[j];
     const int b = (j + 1 < ns) ? rowptr[j + 1] : *total;
+    if (lane == 0 && b - a > *(volatile int*)(rowptr_last + 1)) atomicMax(rowptr_last + 1, b - a);  // rowptr[ns+1]: longest row
     for (int e = a + lane; e < b; e += 32) {
         const int v = col[e];
         int rank = 0;
@@ -873,7 +875,7 @@ int kpconv_forward_device(const float* q, int nq, const float* s, int ns, const 
 
 // Transposed neighbour table (CSR over the supports): row j lists, in ascending order, the centres i whose row contains
 // j. Depends on the index matrix only, so callers may build it once per table and hand it to every backward pass that
-// uses the table. rowptr has ns + 1 entries, col has nq * H.
+// uses the table. rowptr has ns + 2 entries (ns + 1 row pointers, then the longest row's length), col has nq * H.
 int transpose_table_device(Scratch& S, const void* idx, int idx_is_i64, int nq, int H, int idx_stride, int ns,
                            int* rowptr, int* col_sorted, cudaStream_t stream) {
     const long long n_pairs = (long long)nq * H;
@@ -885,6 +887,7 @@ int transpose_table_device(Scratch& S, const void* idx, int idx_is_i64, int nq, 
     if (S.status != KP_OK) return S.status;
     ProfileScope pst("kp_transpose", stream);
     KP_CUDA(cudaMemsetAsync(deg, 0, ((size_t)2 * ns + 1) * sizeof(int), stream));
+    KP_CUDA(cudaMemsetAsync(rowptr + ns + 1, 0, sizeof(int), stream));
     const int grid = ceil_div(n_pairs > 0 ? n_pairs : 1, 256);
     if (idx_is_i64) kp_tr_count_kernel<long long><<<grid, 256, 0, stream>>>((const long long*)idx, nq, H, idx_stride, ns, deg);
     else kp_tr_count_kernel<int><<<grid, 256, 0, stream>>>((const int*)idx, nq, H, idx_stride, ns, deg);
@@ -977,7 +980,7 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
         const int* rowptr = t_rowptr;
         const int* col_sorted = t_col;
         if (!rowptr || !col_sorted) {
-            int* rp = S.alloc<int>(ns + 1);
+            int* rp = S.alloc<int>(ns + 2);
             int* cs = S.alloc<int>((size_t)n_pairs);
             if (S.status != KP_OK) return S.status;
             rc = transpose_table_device(S, idx, idx_is_i64, nq, H, idx_stride, ns, rp, cs, stream);

@@ -250,7 +250,7 @@ class KPConvFunction(torch.autograd.Function):
             # KPConv that shares the matrix (the two blocks of a layer) reuse it.
             tr = getattr(ctx.idx_obj, "_kp_transposed", None)
             if tr is None or tr[2] != (idx.data_ptr(), nq, H, stride, ns):
-                rowptr = torch.empty(ns + 1, dtype=torch.int32, device=q.device)
+                rowptr = torch.empty(ns + 2, dtype=torch.int32, device=q.device)
                 col = torch.empty(max(nq * H, 1), dtype=torch.int32, device=q.device)
                 _lib.check(L.kp_transpose_table_dev(idx.data_ptr(), i64, nq, H, stride, ns, rowptr.data_ptr(),
                                                     col.data_ptr(), _stream()), "transpose_table")
