@@ -206,13 +206,21 @@ __global__ void __launch_bounds__(ORD_THREADS) gs_order_kernel(const unsigned lo
     int* nxt = cur + cap;
     int* mem = nxt + cap;
     int* wsum = mem + cap;
-    int* bfirst = wsum + cap;
+    int* bkt = wsum + cap;   // bucket of every element of the current generation (one modulo per element)
+    int* bfirst = bkt + cap;
     // bucket arrays sized for the last generation this element can reach
     long long pcap = sched.bkt[0];
     for (int i = 0; i < sched.n; i++) if (sched.elt[i] < cap || i == 0) pcap = sched.bkt[i];
     int* bcnt = bfirst + pcap;
     int* bbase = bcnt + pcap;
     const int tid = threadIdx.x;
+    // keys below 2^32 (any realistic voxel grid) take the 32-bit modulo, several times cheaper than the 64-bit one
+    __shared__ int s_wide;
+    if (tid == 0) s_wide = 0;
+    __syncthreads();
+    for (int t = tid; t < m; t += ORD_THREADS) if (keys[t] >> 32) s_wide = 1;
+    __syncthreads();
+    const bool wide = s_wide != 0;
 
     for (int g = 0; g < sched.n; g++) {
         const int e0 = (int)sched.elt[g];
@@ -224,7 +232,9 @@ __global__ void __launch_bounds__(ORD_THREADS) gs_order_kernel(const unsigned lo
         for (int j = tid; j < (int)Pn; j += ORD_THREADS) { bfirst[j] = INT_MAX; bcnt[j] = 0; }
         __syncthreads();
         for (int t = tid; t < ns; t += ORD_THREADS) {
-            const int bk = (int)(keys[ord_elem(cur, len0, e0, t)] % Pn);
+            const unsigned long long key = keys[ord_elem(cur, len0, e0, t)];
+            const int bk = wide ? (int)(key % Pn) : (int)((unsigned)key % (unsigned)Pn);
+            bkt[t] = bk;
             atomicMin(&bfirst[bk], t);
             atomicAdd(&bcnt[bk], 1);
         }
@@ -234,7 +244,7 @@ __global__ void __launch_bounds__(ORD_THREADS) gs_order_kernel(const unsigned lo
         const int lo = min(tid * chunk, ns), hi = min(lo + chunk, ns);
         int local = 0;
         for (int t = lo; t < hi; t++) {
-            const int bk = (int)(keys[ord_elem(cur, len0, e0, t)] % Pn);
+            const int bk = bkt[t];
             const int w = (bfirst[bk] == t) ? bcnt[bk] : 0;
             wsum[t] = w;
             local += w;
@@ -244,21 +254,18 @@ __global__ void __launch_bounds__(ORD_THREADS) gs_order_kernel(const unsigned lo
         for (int t = lo; t < hi; t++) {
             const int w = wsum[t];
             excl += w;
-            if (w) {
-                const int bk = (int)(keys[ord_elem(cur, len0, e0, t)] % Pn);
-                bbase[bk] = total - excl;  // nodes in buckets first touched after this one
-            }
+            if (w) bbase[bkt[t]] = total - excl;  // nodes in buckets first touched after this one
         }
         __syncthreads();
         for (int j = tid; j < (int)Pn; j += ORD_THREADS) bfirst[j] = 0;  // reuse as fill cursor
         __syncthreads();
         for (int t = tid; t < ns; t += ORD_THREADS) {
-            const int bk = (int)(keys[ord_elem(cur, len0, e0, t)] % Pn);
+            const int bk = bkt[t];
             mem[bbase[bk] + atomicAdd(&bfirst[bk], 1)] = t;
         }
         __syncthreads();
         for (int t = tid; t < ns; t += ORD_THREADS) {
-            const int bk = (int)(keys[ord_elem(cur, len0, e0, t)] % Pn);
+            const int bk = bkt[t];
             const int r0 = bbase[bk], c = bcnt[bk];
             int later = 0;
             for (int u = 0; u < c; u++) later += (mem[r0 + u] > t) ? 1 : 0;
@@ -491,7 +498,7 @@ int grid_subsample_device(const float* pts, int n, const int* lens_host, int nb,
             soff[b] = tot;
             long long pcap = sched.bkt[0];
             for (int i = 0; i < sched.n; i++) if (sched.elt[i] < lens_host[b] || i == 0) pcap = sched.bkt[i];
-            tot += 4LL * lens_host[b] + 3LL * pcap + 8;
+            tot += 5LL * lens_host[b] + 3LL * pcap + 8;
         }
         if (tot > 0x7fffffffLL * 2) return fail(KP_ERR_UNSUPPORTED, "grid_subsample: cloud too large for reference-order scratch");
         int* d_scratch = S.alloc<int>((size_t)tot);
