@@ -457,3 +457,4 @@ def test_batch_query_no_supports_at_all(torch_cuda):
     q = np.random.default_rng(0).uniform(0, 1, (10, 3)).astype(np.float32)
     with pytest.raises(RuntimeError, match="^Error$"):
         rn.batch_query(q, np.zeros((0, 3), np.float32), [10], [0], radius=0.5)
+

@@ -109,11 +109,14 @@ class PendingSearches:
         self.items.append((out, cap, limit, (q, s, qb, sb, radius, dtype)))
         return slot
 
-    def resolve(self):
-        res = self.results[:max(len(self.items), 1)].cpu().numpy()  # the one synchronisation
+    def resolve(self, start=0):
+        """Index matrices of the searches issued since slot ``start``."""
+        if len(self.items) <= start:
+            return []
+        res = self.results[start:len(self.items)].cpu().numpy()  # the one synchronisation
         outs = []
-        for slot, (out, cap, limit, args) in enumerate(self.items):
-            hmax, err = int(res[slot, 0]), int(res[slot, 1])
+        for k, (out, cap, limit, args) in enumerate(self.items[start:]):
+            hmax, err = int(res[k, 0]), int(res[k, 1])
             if err & 1:
                 raise RuntimeError("batch_query: cloud extent / radius exceeds 2^18 cells per axis")
             if err & 2:

@@ -56,90 +56,127 @@ def batch_grid_subsampling(points, batches_len, sampleDl=0.1, max_p=0, random_gr
     return s_points, s_len
 
 
+class PyramidBuilder:
+    """The walk over ``config.architecture`` of datasets/common.py:461-577, one pyramid layer per :meth:`step`.
+
+    Every radius search is issued without a host sync (``ops.PendingSearches``); grids are shared between the searches
+    that use the same supports and radius. ``resolve()`` reads the widths of the searches issued so far with one
+    device->host copy and swaps the placeholders for the column-sliced index matrices.
+    """
+
+    def __init__(self, stacked_points, stack_lengths, config, neighborhood_limits=None, random_grid_orient=True,
+                 order="reference", index_dtype=torch.int64, device="cuda"):
+        self.dev = torch.device(device)
+        self.cfg, self.order, self.dtype, self.orient = config, order, index_dtype, random_grid_orient
+        t = stacked_points if torch.is_tensor(stacked_points) else torch.from_numpy(np.ascontiguousarray(stacked_points))
+        self.pts = t.to(self.dev, non_blocking=True).to(torch.float32)
+        self.lens = np.ascontiguousarray(stack_lengths.cpu().numpy() if torch.is_tensor(stack_lengths)
+                                         else stack_lengths, dtype=np.int32)
+        self.limits = list(neighborhood_limits) if neighborhood_limits is not None and len(neighborhood_limits) else None
+        self.r_normal = config.first_subsampling_dl * config.conv_radius
+        self.points, self.neighbors, self.pools, self.upsamples, self.lengths = [], [], [], [], []
+        self.pending = ops.PendingSearches(self.dev)
+        self.resolved = 0
+        self.grids = {}
+        self.blocks = list(config.architecture)
+        self.pos = 0
+        self.done = False
+        # number of layers = pooling / strided blocks before the first 'global' / 'upsample' block, plus one
+        self.n_layers = 0
+        for b in self.blocks:
+            if 'pool' in b or 'strided' in b or 'global' in b or 'upsample' in b:
+                self.n_layers += 1
+                if 'global' in b or 'upsample' in b:
+                    break
+
+    def _lim(self, layer):
+        return int(self.limits[layer]) if self.limits is not None and layer < len(self.limits) else None
+
+    def _grid(self, p, b, r):
+        key = (p.data_ptr(), p.shape[0], float(r))
+        if key not in self.grids:
+            self.grids[key] = ops.SearchGrid(p, b, r)
+        return self.grids[key]
+
+    def _empty(self):
+        return torch.zeros((0, 1), dtype=self.dtype, device=self.dev)
+
+    def step(self):
+        """Issue the work of the next layer (conv search, subsampling, pool and upsample searches)."""
+        if self.done:
+            return False
+        cfg, layer_blocks = self.cfg, []
+        while self.pos < len(self.blocks):
+            block = self.blocks[self.pos]
+            self.pos += 1
+            if not ('pool' in block or 'strided' in block or 'global' in block or 'upsample' in block):
+                layer_blocks.append(block)
+                continue
+            layer, pts, lens, r_normal = len(self.points), self.pts, self.lens, self.r_normal
+            if layer_blocks:
+                deform = any('deformable' in b for b in layer_blocks)
+                r = r_normal * cfg.deform_radius / cfg.conv_radius if deform else r_normal
+                conv_i = self.pending.add(pts, pts, lens, lens, r, limit=self._lim(layer), dtype=self.dtype,
+                                          grid=self._grid(pts, lens, r))
+            else:
+                conv_i = self._empty()
+            if 'pool' in block or 'strided' in block:
+                dl = 2 * r_normal / cfg.conv_radius
+                pool_p, pool_b = batch_grid_subsampling(pts, lens, sampleDl=dl, random_grid_orient=self.orient,
+                                                        order=self.order)
+                r = r_normal * cfg.deform_radius / cfg.conv_radius if 'deformable' in block else r_normal
+                pool_i = self.pending.add(pool_p, pts, pool_b, lens, r, limit=self._lim(layer), dtype=self.dtype,
+                                          grid=self._grid(pts, lens, r))
+                up_i = self.pending.add(pts, pool_p, lens, pool_b, 2 * r, limit=self._lim(layer + 1), dtype=self.dtype,
+                                        grid=self._grid(pool_p, pool_b, 2 * r))
+            else:
+                pool_i, up_i = self._empty(), self._empty()
+                pool_p = torch.zeros((0, 3), dtype=torch.float32, device=self.dev)
+                pool_b = np.zeros((0,), np.int32)
+            self.points.append(pts)
+            self.neighbors.append(conv_i)
+            self.pools.append(pool_i)
+            self.upsamples.append(up_i)
+            self.lengths.append(torch.from_numpy(lens.copy()).to(self.dev, non_blocking=True))
+            self.pts, self.lens = pool_p, pool_b
+            self.r_normal *= 2
+            if 'global' in block or 'upsample' in block:
+                self.done = True
+            return True
+        self.done = True
+        return False
+
+    def resolve(self):
+        found = self.pending.resolve(start=self.resolved)
+        for lst in (self.neighbors, self.pools, self.upsamples):
+            for i, v in enumerate(lst):
+                if isinstance(v, int):
+                    lst[i] = found[v - self.resolved]
+        self.resolved += len(found)
+        for key in [k for k in self.grids if k[0] != self.pts.data_ptr()]:
+            del self.grids[key]  # only the grid over the newest layer can be needed again
+
+
 def segmentation_inputs(stacked_points, stacked_features, labels, stack_lengths, config, neighborhood_limits=None,
                         random_grid_orient=True, order="reference", index_dtype=torch.int64, device="cuda"):
-    """Same walk over ``config.architecture`` as datasets/common.py:461-577; every array is a device tensor."""
+    """Device counterpart of datasets/common.py:461-577: the flat list ``points*L + neighbors*L + pools*L +
+    upsamples*L + lengths*L + [features, labels]`` of device tensors. All searches of the batch are issued before the
+    single synchronisation that reads their widths back."""
     dev = torch.device(device)
+    pb = PyramidBuilder(stacked_points, stack_lengths, config, neighborhood_limits, random_grid_orient, order,
+                        index_dtype, dev)
+    while pb.step():
+        pass
+    pb.resolve()
 
     def to_dev(a, dtype=None):
         t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
         t = t.to(dev, non_blocking=True)
         return t.to(dtype) if dtype is not None else t
 
-    pts = to_dev(stacked_points, torch.float32)
-    lens = np.ascontiguousarray(stack_lengths.cpu().numpy() if torch.is_tensor(stack_lengths) else stack_lengths,
-                                dtype=np.int32)
-    limits = list(neighborhood_limits) if neighborhood_limits is not None and len(neighborhood_limits) > 0 else None
-
-    def lim(layer):
-        return int(limits[layer]) if limits is not None else None
-
-    r_normal = config.first_subsampling_dl * config.conv_radius
-    layer_blocks = []
-    in_points, in_neighbors, in_pools, in_upsamples, in_lengths = [], [], [], [], []
-    empty_idx = lambda: torch.zeros((0, 1), dtype=index_dtype, device=dev)
-    # every search is issued without a host sync; their widths are read back together at the end
-    pending = ops.PendingSearches(dev)
-    # one hash grid per (point set, radius): the grid over layer l+1 at radius 2r serves the upsample search of layer l
-    # and the conv and pool searches of layer l+1
-    grids = {}
-
-    def grid_of(p, b, r):
-        key = (p.data_ptr(), p.shape[0], float(r))
-        if key not in grids:
-            grids[key] = ops.SearchGrid(p, b, r)
-        return grids[key]
-
-    for block in config.architecture:
-        if not ('pool' in block or 'strided' in block or 'global' in block or 'upsample' in block):
-            layer_blocks.append(block)
-            continue
-        layer = len(in_points)
-        if layer_blocks:
-            if any('deformable' in b for b in layer_blocks):
-                r = r_normal * config.deform_radius / config.conv_radius
-            else:
-                r = r_normal
-            conv_i = pending.add(pts, pts, lens, lens, r, limit=lim(layer), dtype=index_dtype, grid=grid_of(pts, lens, r))
-        else:
-            conv_i = empty_idx()
-        if 'pool' in block or 'strided' in block:
-            dl = 2 * r_normal / config.conv_radius
-            pool_p, pool_b = batch_grid_subsampling(pts, lens, sampleDl=dl, random_grid_orient=random_grid_orient,
-                                                    order=order)
-            if 'deformable' in block:
-                r = r_normal * config.deform_radius / config.conv_radius
-            else:
-                r = r_normal
-            pool_i = pending.add(pool_p, pts, pool_b, lens, r, limit=lim(layer), dtype=index_dtype,
-                                 grid=grid_of(pts, lens, r))
-            up_i = pending.add(pts, pool_p, lens, pool_b, 2 * r, limit=lim(layer + 1) if limits is not None and
-                               layer + 1 < len(limits) else None, dtype=index_dtype, grid=grid_of(pool_p, pool_b, 2 * r))
-        else:
-            pool_i = empty_idx()
-            pool_p = torch.zeros((0, 3), dtype=torch.float32, device=dev)
-            pool_b = np.zeros((0,), np.int32)
-            up_i = empty_idx()
-        in_points.append(pts)
-        in_neighbors.append(conv_i)
-        in_pools.append(pool_i)
-        in_upsamples.append(up_i)
-        in_lengths.append(torch.from_numpy(lens.copy()).to(dev, non_blocking=True))
-        pts, lens = pool_p, pool_b
-        r_normal *= 2
-        layer_blocks = []
-        if 'global' in block or 'upsample' in block:
-            break
-
-    found = pending.resolve()
-    for lst in (in_neighbors, in_pools, in_upsamples):
-        for i, v in enumerate(lst):
-            if isinstance(v, int):
-                lst[i] = found[v]
-
     feats = to_dev(stacked_features, torch.float32) if stacked_features is not None else None
     labs = to_dev(labels) if labels is not None else None
-    return in_points + in_neighbors + in_pools + in_upsamples + in_lengths + [feats, labs]
+    return pb.points + pb.neighbors + pb.pools + pb.upsamples + pb.lengths + [feats, labs]
 
 
 class DeviceBatch:
