@@ -56,10 +56,11 @@ def build_batches(cfg_name, seed, n_batches, subsample_fn):
 # ---------------------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     """SM clock and throttle reasons sampled through NVML from a background thread while the benchmark runs (an
-    `nvidia-smi -lms` loop at a useful rate measurably slows a launch-bound step down, in-process NVML reads do not)."""
+    `nvidia-smi -lms` loop at a useful rate slows a launch-bound step down by up to 2x; NVML reads also take driver
+    locks, so they are spaced 100 ms apart)."""
     BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, gpu_index, period_s=0.05):
+    def __init__(self, gpu_index, period_s=0.1):
         self.idx, self.period, self.rows, self.stop_flag, self.thread, self.h = gpu_index, period_s, [], False, None, None
         try:
             import pynvml

@@ -101,9 +101,11 @@ struct SmallBlob {
     int n;
     int w[SMALL_WORDS];
 };
-int upload_small(const void* host, size_t bytes, void* d_dst, cudaStream_t stream);
-inline int upload_offsets(const int* host_offsets, int n_plus_1, int* d_dst, cudaStream_t stream) {
-    return upload_small(host_offsets, (size_t)n_plus_1 * sizeof(int), d_dst, stream);
+// (the same launch can zero up to a few ints elsewhere: result slots, error flags)
+int upload_small(const void* host, size_t bytes, void* d_dst, cudaStream_t stream, int* zero_dst = nullptr, int zero_n = 0);
+inline int upload_offsets(const int* host_offsets, int n_plus_1, int* d_dst, cudaStream_t stream, int* zero_dst = nullptr,
+                          int zero_n = 0) {
+    return upload_small(host_offsets, (size_t)n_plus_1 * sizeof(int), d_dst, stream, zero_dst, zero_n);
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -81,11 +81,6 @@ __device__ __forceinline__ void load_point(const GsParams& P, int i, int b, floa
     if (P.rot) rotate_fwd(P.rot + 9 * b, x, y, z);
 }
 
-__global__ void gs_bbox_init_kernel(unsigned* bbox, int nb) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nb * 6) bbox[i] = ((i % 6) < 3) ? 0xffffffffu : 0u;
-}
-
 __global__ void __launch_bounds__(256) gs_bbox_kernel(GsParams P, unsigned* __restrict__ bbox) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool ok = i < P.n;
@@ -130,9 +125,12 @@ __device__ __forceinline__ unsigned long long voxel_key(const GsParams& P, const
     return ix + NX * iy + NX * NY * iz;
 }
 
-__global__ void gs_table_init_kernel(unsigned long long* tkeys, int* tfirst, int tsize) {
+// one launch resets the hash table, the bounding boxes and the error flag
+__global__ void gs_init_kernel(unsigned long long* tkeys, int* tfirst, int tsize, unsigned* bbox, int nb, int* err) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < tsize) { tkeys[i] = HT_EMPTY; tfirst[i] = INT_MAX; }
+    if (i < nb * 6) bbox[i] = ((i % 6) < 3) ? 0xffffffffu : 0u;
+    if (i == 0) *err = 0;
 }
 
 __global__ void __launch_bounds__(256) gs_insert_kernel(GsParams P, const unsigned* __restrict__ bbox,
@@ -463,7 +461,6 @@ int grid_subsample_device(const float* pts, int n, const int* lens_host, int nb,
 
     { int rc0 = upload_offsets(offs.data(), nb + 1, d_offs, stream); if (rc0 != KP_OK) return rc0; }
     if (rot_host) { int rc0 = upload_small(rot_host, (size_t)nb * 9 * sizeof(float), d_rot, stream); if (rc0 != KP_OK) return rc0; }
-    KP_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), stream));
 
     GsParams P;
     P.pts = pts; P.n = n; P.nb = nb; P.offsets = d_offs; P.rot = d_rot; P.dl = dl;
@@ -471,11 +468,10 @@ int grid_subsample_device(const float* pts, int n, const int* lens_host, int nb,
     const int nblk = ceil_div(n, 256);
 
     ProfileScope* ps = new ProfileScope("gs_hash", stream);
-    gs_bbox_init_kernel<<<ceil_div(nb * 6, 256), 256, 0, stream>>>(d_bbox, nb);
+    gs_init_kernel<<<ceil_div(tsize > nb * 6 ? tsize : nb * 6, 256), 256, 0, stream>>>(d_tkeys, d_tfirst, tsize, d_bbox, nb,
+                                                                                    d_err);
     KP_CHECK_LAUNCH();
     gs_bbox_kernel<<<nblk, 256, 0, stream>>>(P, d_bbox);
-    KP_CHECK_LAUNCH();
-    gs_table_init_kernel<<<ceil_div(tsize, 256), 256, 0, stream>>>(d_tkeys, d_tfirst, tsize);
     KP_CHECK_LAUNCH();
     gs_insert_kernel<<<nblk, 256, 0, stream>>>(P, d_bbox, d_tkeys, d_tfirst, tsize - 1, d_pkey, d_pslot, d_err);
     KP_CHECK_LAUNCH();

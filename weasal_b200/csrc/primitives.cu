@@ -98,20 +98,22 @@ void* arena_alloc(Arena* a, size_t bytes) {
     return p;
 }
 
-__global__ void write_small_kernel(SmallBlob b, int* dst) {
+__global__ void write_small_kernel(SmallBlob b, int* dst, int* zero_dst, int zero_n) {
     for (int i = threadIdx.x; i < b.n; i += blockDim.x) dst[i] = b.w[i];
+    for (int i = threadIdx.x; i < zero_n; i += blockDim.x) zero_dst[i] = 0;
 }
 
-int upload_small(const void* host, size_t bytes, void* d_dst, cudaStream_t stream) {
-    if (bytes == 0) return KP_OK;
+int upload_small(const void* host, size_t bytes, void* d_dst, cudaStream_t stream, int* zero_dst, int zero_n) {
+    if (bytes == 0 && zero_n == 0) return KP_OK;
     if ((bytes & 3) == 0 && bytes <= SMALL_WORDS * sizeof(int)) {
         SmallBlob b;
         b.n = (int)(bytes / 4);
         memcpy(b.w, host, bytes);
-        write_small_kernel<<<1, 128, 0, stream>>>(b, (int*)d_dst);
+        write_small_kernel<<<1, 128, 0, stream>>>(b, (int*)d_dst, zero_dst, zero_n);
         KP_CHECK_LAUNCH();
     } else {
         KP_CUDA(cudaMemcpyAsync(d_dst, host, bytes, cudaMemcpyHostToDevice, stream));
+        if (zero_n) KP_CUDA(cudaMemsetAsync(zero_dst, 0, (size_t)zero_n * sizeof(int), stream));
     }
     return KP_OK;
 }
@@ -146,6 +148,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const int* __r
     }
 }
 
+// single CTA, out of place: the whole scan in one launch for arrays up to 64k entries (launch-bound regime)
+__global__ void __launch_bounds__(SCAN_THREADS) scan_small_kernel(const int* __restrict__ in, int* __restrict__ out, int m,
+                                                                 int* __restrict__ total_out) {
+    __shared__ int s_warp[33];
+    const int chunk = (m + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int lo = min((int)threadIdx.x * chunk, m), hi = min(lo + chunk, m);
+    int sum = 0;
+    for (int i = lo; i < hi; i++) sum += in[i];
+    int total;
+    int excl = block_exclusive_scan(sum, s_warp, &total);
+    for (int i = lo; i < hi; i++) {
+        const int v = in[i];
+        out[i] = excl;
+        excl += v;
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = total;
+}
+
 // single CTA: exclusive scan of m values in place (m <= 1024 * chunk)
 __global__ void __launch_bounds__(SCAN_THREADS) scan_single_kernel(int* __restrict__ data, int m,
                                                                   int* __restrict__ total_out) {
@@ -178,6 +198,11 @@ size_t scan_tmp_ints(int n) { return (size_t)ceil_div(n > 0 ? n : 1, SCAN_TILE) 
 int exclusive_scan(const int* d_in, int* d_out, int n, int* d_total, int* tmp, cudaStream_t stream) {
     if (n <= 0) {
         if (d_total) KP_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int), stream));
+        return KP_OK;
+    }
+    if (n <= 65536 && d_in != d_out) {
+        scan_small_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_in, d_out, n, d_total);
+        KP_CHECK_LAUNCH();
         return KP_OK;
     }
     const int nblk = ceil_div(n, SCAN_TILE);

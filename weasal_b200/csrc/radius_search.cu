@@ -364,10 +364,8 @@ int grid_query_device(const void* grid_buf, int ns, int nb, float radius, const 
     if (S.status != KP_OK) return S.status;
     int* d_err = d_hmax + 1;
     {   // offsets and the zeroed result slots travel in one kernel-argument upload when the slots are ours
-        std::vector<int> blob(qoff);
-        rc = upload_offsets(blob.data(), nb + 1, d_qoff, stream);
+        rc = upload_offsets(qoff.data(), nb + 1, d_qoff, stream, d_hmax, 2);
         if (rc != KP_OK) return rc;
-        KP_CUDA(cudaMemsetAsync(d_hmax, 0, 2 * sizeof(int), stream));
     }
     SearchParams P;
     P.q = q; P.nq = nq; P.s = nullptr; P.ns = ns; P.q_off = d_qoff; P.s_off = g.s_off; P.nb = nb;
