@@ -55,13 +55,14 @@ def build_batches(cfg_name, seed, n_batches, subsample_fn):
 
 # ---------------------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """SM clock and throttle reasons sampled through NVML from a background thread while the benchmark runs (an
-    `nvidia-smi -lms` loop at a useful rate slows a launch-bound step down by up to 2x; NVML reads also take driver
-    locks, so they are spaced 100 ms apart)."""
+    """SM clock and throttle reasons read through NVML from the benchmark thread itself, a few times inside the timed
+    region while kernels are in flight. (A background `nvidia-smi -lms` loop slowed the launch-bound step down by up
+    to 2x and a polling NVML thread by 10-30 %: both contend with kernel launches for driver locks / the GIL; a
+    handful of in-line reads cost well under 1 %.)"""
     BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, gpu_index, period_s=0.1):
-        self.idx, self.period, self.rows, self.stop_flag, self.thread, self.h = gpu_index, period_s, [], False, None, None
+    def __init__(self, gpu_index):
+        self.rows, self.h, self.max_mhz = [], None, None
         try:
             import pynvml
             self.nv = pynvml
@@ -73,30 +74,23 @@ class ClockSampler:
         except Exception:
             self.h = None
 
-    def _run(self):
+    def sample(self):
+        if self.h is None:
+            return
         nv = self.nv
-        while not self.stop_flag:
+        try:
+            sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
             try:
-                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                try:
-                    why = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    why = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.rows.append((float(sm), int(why)))
+                why = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:
-                pass
-            time.sleep(self.period)
+                why = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.rows.append((float(sm), int(why)))
+        except Exception:
+            pass
 
-    def start(self):
-        if self.h is not None:
-            self.thread = threading.Thread(target=self._run, daemon=True)
-            self.thread.start()
-
-    def stop(self):
+    def summary(self):
         if self.h is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
-        self.stop_flag = True
-        self.thread.join(timeout=2)
         sm = [r[0] for r in self.rows]
         reasons = sorted({n for r in self.rows for n, b in self.BITS.items() if r[1] & b})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
@@ -200,7 +194,7 @@ def run_ours(args):
         opt.step()
         return loss, batch
 
-    def timed(n_warm, n_steps, e2e):
+    def timed(n_warm, n_steps, e2e, clocks=None):
         import gc
         pts = 0
         total_ms = 0.0
@@ -222,6 +216,8 @@ def run_ours(args):
             else:
                 loss, _ = step(dev_batches[b], batches[b]["lengths"])
             e1.record()
+            if clocks is not None and it >= n_warm and (it - n_warm) % max(n_steps // 8, 1) == 0:
+                clocks.sample()  # the step's kernels are still in flight here: a reading under load
             e1.synchronize()
             if os.environ.get("WEASAL_DEBUG") and rank == 0:
                 print(f"[bench] {'e2e' if e2e else 'dev'} step {it}: {e0.elapsed_time(e1):.2f} ms", file=sys.stderr)
@@ -244,14 +240,12 @@ def run_ours(args):
     L = _lib.lib()
     clocks = ClockSampler(local)
     launches0 = _lib.launch_count()
-    if rank == 0:
-        clocks.start()  # sampled from the warm-up on: the timed region alone (~0.2 s) would give two or three samples
     timed(W, 0, False)
     launches0 = _lib.launch_count()
-    ms, pts = timed(0, K, False)
+    ms, pts = timed(0, K, False, clocks if rank == 0 else None)
     gpu_launches = _lib.launch_count() - launches0
-    clk = clocks.stop() if rank == 0 else None
-    e2e_ms, e2e_pts = timed(W, K, True)
+    e2e_ms, e2e_pts = timed(W, K, True, clocks if rank == 0 else None)
+    clk = clocks.summary() if rank == 0 else None
 
     # per-kernel device times (CUDA events on the launching stream, recorded inside the library)
     roof, kernels = None, {}

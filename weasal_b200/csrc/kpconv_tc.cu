@@ -26,6 +26,7 @@
 //                  K = points) against the dOut tile, accumulated in TMEM across a CTA's point tiles, then added to dW.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 namespace kp {
@@ -818,6 +819,11 @@ static int run_forward(const char* tag, Scratch& S, int nc, const int* rowptr, i
     if (ksplit > 16) ksplit = 16;
     if (ksplit < 1) ksplit = 1;
     ksplit = ceil_div(n_chunks, ceil_div(n_chunks, ksplit));  // no empty splits
+    // Split partial sums meet in `out` through float atomics, so their order (the last bits of the result) varies from
+    // run to run. WEASAL_KPCONV_DETERMINISTIC=1 keeps one CTA per tile: bit-reproducible forward / dX, slower on the
+    // deep layers.
+    static const bool deterministic = getenv("WEASAL_KPCONV_DETERMINISTIC") && atoi(getenv("WEASAL_KPCONV_DETERMINISTIC")) != 0;
+    if (deterministic) ksplit = 1;
     P.ksplit = ksplit;
     if (ksplit > 1) KP_CUDA(cudaMemsetAsync(out, 0, (size_t)nc * cout * sizeof(float), stream));
     uint32_t cols = 32;
