@@ -181,9 +181,9 @@ def run_ours(args):
     pin_batches = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items() if k != "lengths"} for b in batches]
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
 
-    def step(inp, lens, allreduce=True):
-        li = pyramid.segmentation_inputs(inp["points"], inp["features"], inp["labels"], lens, view, device=dev)
-        batch = pyramid.DeviceBatch(li)
+    prefetch = pyramid.PyramidPrefetcher(view, dev)
+
+    def net_step(batch, allreduce=True):
         logits = net(batch)
         loss = F.cross_entropy(logits, batch.labels)
         opt.zero_grad(set_to_none=True)
@@ -192,42 +192,56 @@ def run_ours(args):
             reducer.step()
         torch.nn.utils.clip_grad_value_(net.parameters(), 100.0)
         opt.step()
-        return loss, batch
+        return loss
+
+    def run_steps(first, n, e2e, allreduce=True, clocks=None, keep=None):
+        """n steps over batches first, first+1, ...: the pyramid of step t+1 is built on the prefetcher's side stream
+        (one native call, the counterpart of the reference's DataLoader workers) while step t trains. The pipeline
+        starts and ends empty, so exactly n pyramids and n training steps happen inside the call."""
+        src = pin_batches if e2e else dev_batches  # e2e: the worker copies the batch from pinned host memory
+
+        def submit(it):
+            b = it % N_BATCHES
+            prefetch.submit(src[b]["points"], src[b]["features"], src[b]["labels"], batches[b]["lengths"])
+
+        pts = 0
+        ahead = os.environ.get("WEASAL_BENCH_PREFETCH", "1") != "0"  # 0: build each pyramid when its step starts (A/B)
+        if n > 0 and ahead:
+            submit(first)
+        for it in range(first, first + n):
+            flush.zero_()  # evict L2 between steps (256 MB > 126 MB L2)
+            if not ahead:
+                submit(it)
+            batch = prefetch.get()
+            if ahead and it + 1 < first + n:
+                submit(it + 1)
+            loss = net_step(batch, allreduce)
+            if e2e:
+                loss_host = loss.item()  # device -> host read of the step's result
+            if clocks is not None and (it - first) % max(n // 8, 1) == 0:
+                clocks.sample()  # the step's kernels are still in flight here: a reading under load
+            if keep is not None:
+                keep.append(batch)
+            pts += batches[it % N_BATCHES]["points"].shape[0]
+        return pts
 
     def timed(n_warm, n_steps, e2e, clocks=None):
         import gc
-        pts = 0
-        total_ms = 0.0
         gc.collect()
         gc.disable()  # the step is host-launch bound: a generational GC pause inside a step shows up as a 10 % outlier
-        for it in range(n_warm + n_steps):
-            b = it % N_BATCHES
-            if it == n_warm:
-                if world > 1:
-                    dist.barrier()
-                torch.cuda.synchronize()
-            flush.zero_()  # evict L2 between steps (256 MB > 126 MB L2); outside the timed events
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            if e2e:
-                inp = {k: v.to(dev, non_blocking=True) for k, v in pin_batches[b].items()}
-                loss, _ = step(inp, batches[b]["lengths"])
-                loss_host = loss.item()  # device -> host read of the step's result
-            else:
-                loss, _ = step(dev_batches[b], batches[b]["lengths"])
-            e1.record()
-            if clocks is not None and it >= n_warm and (it - n_warm) % max(n_steps // 8, 1) == 0:
-                clocks.sample()  # the step's kernels are still in flight here: a reading under load
-            e1.synchronize()
-            if os.environ.get("WEASAL_DEBUG") and rank == 0:
-                print(f"[bench] {'e2e' if e2e else 'dev'} step {it}: {e0.elapsed_time(e1):.2f} ms", file=sys.stderr)
-            if it >= n_warm:
-                total_ms += e0.elapsed_time(e1)
-                pts += batches[b]["points"].shape[0]
-        gc.enable()
+        run_steps(0, n_warm, e2e)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pts = run_steps(n_warm, n_steps, e2e, clocks=clocks)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        gc.enable()
+        total_ms = e0.elapsed_time(e1) if n_steps > 0 else 0.0
         t = torch.tensor([total_ms, float(pts)], dtype=torch.float64, device=dev)
         if world > 1:
             tmax = t.clone()
@@ -253,13 +267,11 @@ def run_ours(args):
         L.kp_profile_enable(1)
         psteps = min(K, 8)
         shapes, sbytes = None, 0
-        for it in range(psteps):
-            flush.zero_()
-            # rank 0 only: no collective inside this leg
-            _, batch = step(dev_batches[it % N_BATCHES], batches[it % N_BATCHES]["lengths"], allreduce=False)
-            if it == 0:
-                shapes = conv_shapes(batch, net)
-                sbytes = search_bytes(batch)
+        kept = []
+        run_steps(0, psteps, False, allreduce=False, keep=kept)  # rank 0 only: no collective inside this leg
+        shapes = conv_shapes(kept[0], net)
+        sbytes = search_bytes(kept[0])
+        del kept
         torch.cuda.synchronize()
         L.kp_profile_enable(0)
         buf = C.create_string_buffer(1 << 16)
@@ -318,7 +330,8 @@ def run_ours(args):
                                    f"synthetic ALS spheres of radius {cfg['in_radius']} m per step",
                        "points_per_step_per_gpu": n0, "global_points_per_step": n0 * world,
                        "first_subsampling_dl": cfg["dl"], "layers": 5, "kpconv_per_forward": 10,
-                       "parallelism": f"dp{world}", "l2": "flushed between steps (256 MB write)",
+                       "parallelism": f"dp{world}", "l2": "flushed between steps (256 MB write, inside the timed region)",
+                       "pyramid": "built one step ahead on a side stream by one native call (kp_pyramid_build_dev)",
                        "random_grid_orient": True, "neighborhood_limits": None,
                        "harness_linear_precision": "tf32"},
             "e2e": {"value": e2e_pts / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -328,6 +341,7 @@ def run_ours(args):
             "grad_allreduce_bytes": reducer.bytes() if world > 1 else 0,
         }
         emit(line)
+    prefetch.close()
     if world > 1:
         dist.destroy_process_group()
 

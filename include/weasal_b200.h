@@ -110,6 +110,32 @@ int kp_grid_subsample_dev(const float* points, int n, const int* batches, int nb
                           void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Pyramid builder: the whole per-layer walk of one batch in one call.
+ * Replaces: datasets/common.py:461-577 `PointCloudDataset.segmentation_inputs` (the loop over config.architecture):
+ *           per layer l the conv search (common.py:505), `batch_grid_subsampling` to layer l+1 incl. its random grid
+ *           orientation (common.py:521, 89-135), the pool search (:531), the upsample search at twice the radius (:534)
+ *           and the `big_neighborhood_filter` column crop (:336-346, 544-547).
+ * points0 [n0,3] is a DEVICE pointer; every other input array is a HOST array:
+ *   lengths0 [nb]; conv_radius / pool_radius / up_radius / sample_dl [n_layers] (conv_radius[l] == 0: no conv search at
+ *   layer l; pool / upsample / sample_dl entries of the last layer are ignored); rot [n_layers-1][nb][3][3] f32 grid
+ *   orientations or NULL; limits [n_layers] neighbourhood limits or NULL (0 = unlimited).
+ * Outputs are carved from the caller's DEVICE `slab` (slab_bytes); offsets [5*n_layers] receives byte offsets into it:
+ *   [0,L) points of layer l ([n,3] f32; layer 0 = -1, the caller's points0), [L,2L) conv matrices [n_l, stride],
+ *   [2L,3L) pool matrices [n_{l+1}, stride], [3L,4L) upsample matrices [n_l, stride], [4L,5L) batch lengths (int32
+ *   [nb]); -1 = absent. n_out [L], lengths_out [L*nb], widths [3*L] (true maximum neighbour counts, conv / pool /
+ *   upsample blocks of L) and strides [3*L] (row strides = limit, or cap when unlimited) are HOST arrays. Index
+ *   matrices are int64 (idx_is_i64) or int32, rows sorted by (d2, index) and padded with the support count.
+ * Returns KP_ERR_CAPACITY with *need_bytes (slab too small) or *need_cap (an unlimited search found rows wider than
+ * cap) set to what a repeat call needs. Synchronises the stream; issues no Python-visible work, so it can run from a
+ * prefetch thread on a side stream while another thread launches the network.
+ */
+int kp_pyramid_build_dev(const float* points0, int n0, const int* lengths0, int nb, int n_layers,
+                         const float* conv_radius, const float* pool_radius, const float* up_radius,
+                         const float* sample_dl, const float* rot, const int* limits, int order, int idx_is_i64, int cap,
+                         void* slab, long long slab_bytes, long long* offsets, int* n_out, int* lengths_out, int* widths,
+                         int* strides, long long* need_bytes, int* need_cap, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * KPConv (rigid, 'linear' influence, 'sum' aggregation), forward and backward.
  * Replaces: models/blocks.py:238-374 `KPConv.forward(q_pts, s_pts, neighb_inds, x)` and the autograd backward of
  *           that expression (gradients w.r.t. x and weights only; blocks.py:235-236).
@@ -146,6 +172,16 @@ int kp_kpconv_backward_kept_dev(const float* q_pts, int nq, const float* s_pts, 
                                 int cout, const float* kernel_points, int K, float KP_extent, const float* d_out,
                                 float* d_x, float* d_weights, const void* lists_koff, const void* lists_entries,
                                 const int* t_rowptr, const int* t_col, void* stream);
+
+/* Backward for a SYMMETRIC neighbour table: queries == supports (pts [n,3]) and no row lost a neighbour to a crop, as
+ * for the conv matrices `neighbors[l]` of datasets/common.py:505 when no neighbourhood limit bites. Then j is in row i
+ * exactly when i is in row j (the f32 squared distance is exactly symmetric), the table is its own transpose and the
+ * dX pass needs no transposed copy. The caller asserts the symmetry; results equal kp_kpconv_backward_dev's.
+ * lists_koff / lists_entries: the forward pass's lists (kp_kpconv_forward_keep_dev) or NULL. */
+int kp_kpconv_backward_sym_dev(const float* pts, int n, const void* neighb_inds, int idx_is_i64, int H, int idx_stride,
+                               const float* x, int cin, const float* weights, int cout, const float* kernel_points,
+                               int K, float KP_extent, const float* d_out, float* d_x, float* d_weights,
+                               const void* lists_koff, const void* lists_entries, void* stream);
 
 /* fp32 CUDA-core pieces (bring-up / cross-check of the tensor-core path; not the product path):
  *   wf [nq, K*cin] = kernel-point-weighted neighbour features; dx [ns,cin] += adjoint scatter of dwf [nq,K*cin]. */

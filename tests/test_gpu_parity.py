@@ -303,8 +303,9 @@ def test_kpconv_all_shadow_rows_and_linearity(torch_cuda):
 
 
 # ----------------------------------------------------------------------------------------------------------- pyramid
-def test_pyramid_matches_reference_segmentation_inputs(torch_cuda):
-    """Whole device pyramid against the reference's segmentation_inputs (golden, random grid orientation included):
+@pytest.mark.parametrize("native", [True, False])
+def test_pyramid_matches_reference_segmentation_inputs(native, torch_cuda):
+    """Whole device pyramid (one native call, or driven per operator from Python) against the reference's segmentation_inputs (golden, random grid orientation included):
     points bit-exact; index matrices identical where the reference's order is defined, i.e. up to permutations
     inside groups of exactly equal d2 (nanoflann's unstable std::sort)."""
     torch = torch_cuda
@@ -320,7 +321,8 @@ def test_pyramid_matches_reference_segmentation_inputs(torch_cuda):
                         'nearest_upsample', 'unary']
 
     np.random.seed(int(g["seed"]))
-    li = pyramid.segmentation_inputs(g["in_pts"], None, None, g["in_lens"], Cfg(), neighborhood_limits=list(g["limits"]))
+    li = pyramid.segmentation_inputs(g["in_pts"], None, None, g["in_lens"], Cfg(), neighborhood_limits=list(g["limits"]),
+                                     native=native)
     L = int(g["L"])
     assert (len(li) - 2) // 5 == L
     for l in range(L):
@@ -335,6 +337,97 @@ def test_pyramid_matches_reference_segmentation_inputs(torch_cuda):
                 assert (np.sort(got, 1) == np.sort(ref, 1)).mean() > 0.999
                 frac_rows_equal = (got == ref).all(1).mean()
                 assert frac_rows_equal > 0.995, f"{nm}{l}: {frac_rows_equal}"
+
+
+def _vaihingen_cfg():
+    from weasal_b200.net import CfgView, net_config
+    return CfgView(net_config("vaihingen_pl"))
+
+
+def test_native_pyramid_equals_operator_driver_and_prefetcher(torch_cuda):
+    """kp_pyramid_build_dev (one call), the per-operator Python driver and the prefetch thread produce identical
+    batches (same kernels underneath): every tensor bit-equal, at BASELINE size, random grid orientation on."""
+    torch = torch_cuda
+    from weasal_b200 import pyramid
+    cfg = _vaihingen_cfg()
+    b = make_batch("vaihingen_pl", seed=3)
+    feats = np.ones((len(b["points"]), 4), np.float32)
+    labels = np.zeros(len(b["points"]), np.int64)
+    np.random.seed(11)
+    ref = pyramid.segmentation_inputs(b["points"], feats, labels, b["lengths"], cfg, native=False)
+    np.random.seed(11)
+    nat = pyramid.segmentation_inputs(b["points"], feats, labels, b["lengths"], cfg, native=True)
+    pf = pyramid.PyramidPrefetcher(cfg, "cuda")
+    np.random.seed(11)
+    pf.submit(torch.from_numpy(b["points"]).pin_memory(), torch.from_numpy(feats).pin_memory(),
+              torch.from_numpy(labels).pin_memory(), b["lengths"])
+    pf.submit(b["points"], feats, labels, b["lengths"])  # a second one in flight, different orientations
+    got = pf.get()
+    second = pf.get()
+    pf.close()
+    pre = got.points + got.neighbors + got.pools + got.upsamples + got.lengths + [got.features, got.labels]
+    assert len(ref) == len(nat) == len(pre)
+    for k, (a, c, d) in enumerate(zip(ref, nat, pre)):
+        assert a.shape == c.shape == d.shape and a.dtype == c.dtype == d.dtype, f"entry {k}"
+        assert torch.equal(a, c), f"native entry {k}"
+        assert torch.equal(a, d), f"prefetched entry {k}"
+    assert second.points[0].shape == got.points[0].shape
+    assert not torch.equal(second.points[1][:100], got.points[1][:100])  # new orientations were drawn
+    # conv matrices are marked as their own transpose; check the claim itself on one layer
+    for l in range(len(got.neighbors)):
+        assert getattr(nat[len(got.points) + l], "_kp_symmetric", False)
+    nb = got.neighbors[2].cpu().numpy()
+    n = nb.shape[0]
+    src = np.repeat(np.arange(n), nb.shape[1])
+    ok = nb.ravel() < n
+    fwd = set(zip(src[ok].tolist(), nb.ravel()[ok].tolist()))
+    assert all((j, i) in fwd for i, j in list(fwd)[:20000])
+
+
+def test_native_pyramid_grows_cap_and_slab(torch_cuda):
+    """A first call with a neighbour capacity / slab that is too small reports what it needs and the wrapper repeats."""
+    torch = torch_cuda
+    from weasal_b200 import pyramid
+    cfg = _vaihingen_cfg()
+    b = make_batch("vaihingen_pl", seed=4, batch_num=2, in_radius=10.0)
+    P = torch.from_numpy(b["points"]).cuda()
+    np.random.seed(5)
+    want = pyramid.build_native(P, b["lengths"], cfg)
+    pyramid._SLAB_HINT.clear()
+    np.random.seed(5)
+    got = pyramid.build_native(P, b["lengths"], cfg, cap=7)
+    for a, c in zip(sum(want[:5], []), sum(got[:5], [])):
+        assert torch.equal(a, c)
+    pyramid._SLAB_HINT[(5, 8, 80)] = 40.0  # far too small a slab
+    np.random.seed(5)
+    got = pyramid.build_native(P, b["lengths"], cfg)
+    for a, c in zip(sum(want[:5], []), sum(got[:5], [])):
+        assert torch.equal(a, c)
+
+
+def test_kpconv_backward_symmetric_table_shortcut(torch_cuda):
+    """Backward through a conv matrix marked `_kp_symmetric` (its own transpose) equals the general path that builds
+    the transposed CSR table."""
+    torch = torch_cuda
+    from weasal_b200 import ops
+    b = make_batch("vaihingen_pl", seed=6, batch_num=2, in_radius=8.0)
+    P = torch.from_numpy(b["points"]).cuda()
+    idx = ops.batch_query(P, P, b["lengths"], b["lengths"], 0.6)
+    rng = np.random.default_rng(0)
+    cin, cout = 16, 32
+    w0 = torch.from_numpy((rng.normal(size=(15, cin, cout)) / 4).astype(np.float32)).cuda()
+    kp = torch.from_numpy((rng.normal(size=(15, 3)) * 0.25).astype(np.float32)).cuda()
+    x0 = torch.from_numpy(rng.normal(size=(len(b["points"]), cin)).astype(np.float32)).cuda()
+    do = torch.from_numpy(rng.normal(size=(len(b["points"]), cout)).astype(np.float32)).cuda()
+    res = []
+    for sym in (False, True):
+        ii = idx.clone()
+        if sym:
+            ii._kp_symmetric = True
+        x, w = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+        ops.kpconv(P, P, ii, x, w, kp, 0.24).backward(do)
+        res.append((x.grad.cpu().numpy(), w.grad.cpu().numpy()))
+    assert rel_max(res[1][0], res[0][0]) < 1e-5 and rel_max(res[1][1], res[0][1]) < 1e-5
 
 
 def test_full_size_vaihingen_batch_properties(torch_cuda):

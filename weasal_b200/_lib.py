@@ -23,7 +23,8 @@ SYMBOLS = ["kp_last_error", "kp_version", "kp_launch_count", "kp_free_host", "kp
            "kp_search_grid_query_dev", "kp_grid_subsample_host", "kp_grid_subsample_dev", "kp_kpconv_forward_dev",
            "kp_kpconv_backward_dev", "kp_kpconv_lists_bytes", "kp_kpconv_forward_keep_dev",
            "kp_kpconv_backward_kept_dev", "kp_transpose_table_dev", "kp_kpconv_wf_dev", "kp_kpconv_dx_atomic_dev", "kp_profile_enable",
-           "kp_profile_read", "kp_max_pool_forward_dev", "kp_max_pool_backward_dev", "kp_closest_pool_dev"]
+           "kp_profile_read", "kp_max_pool_forward_dev", "kp_max_pool_backward_dev", "kp_closest_pool_dev",
+           "kp_pyramid_build_dev", "kp_kpconv_backward_sym_dev"]
 
 
 def lib():
@@ -68,6 +69,10 @@ def lib():
     L.kp_max_pool_forward_dev.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.kp_max_pool_backward_dev.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]
     L.kp_closest_pool_dev.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.kp_kpconv_backward_sym_dev.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp,
+                                             C.c_int, C.c_float, vp, vp, vp, vp, vp, vp]
+    L.kp_pyramid_build_dev.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int,
+                                       vp, C.c_longlong, vp, vp, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

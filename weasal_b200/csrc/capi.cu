@@ -30,10 +30,16 @@ int kpconv_forward_device(const float* q, int nq, const float* s, int ns, const 
 int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
                            int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
                            float extent, const float* dout, float* dx, float* dw, const void* lists_koff,
-                           const void* lists_entries, const int* t_rowptr, const int* t_col, cudaStream_t stream);
+                           const void* lists_entries, const int* t_rowptr, const int* t_col, int table_symmetric,
+                           cudaStream_t stream);
 int transpose_table_entry(const void* idx, int idx_is_i64, int nq, int H, int idx_stride, int ns, int* rowptr,
                           int* col_sorted, cudaStream_t stream);
 int profile_read(char* buf, int buflen);
+int pyramid_build_device(const float* pts0, int n0, const int* lens0, int nb, int L, const float* conv_r,
+                         const float* pool_r, const float* up_r, const float* dl, const float* rot, const int* limits,
+                         int order, int idx_is_i64, int cap, void* slab, long long slab_bytes, long long* offs, int* n_out,
+                         int* lens_out, int* widths, int* strides, long long* need_bytes, int* need_cap,
+                         cudaStream_t stream);
 int max_pool_fwd_device(const float* x, int ns, int C, const void* idx, int is_i64, int nq, int H, int stride,
                         float* out, int* arg, cudaStream_t stream);
 int max_pool_bwd_device(const float* dout, const int* arg, int nq, int C, float* dx, int ns, cudaStream_t stream);
@@ -206,7 +212,16 @@ int kp_kpconv_backward_kept_dev(const float* q_pts, int nq, const float* s_pts, 
                                 const int* t_rowptr, const int* t_col, void* stream) {
     return kpconv_backward_device(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, weights, cout,
                                   kernel_points, K, KP_extent, d_out, d_x, d_weights, lists_koff, lists_entries,
-                                  t_rowptr, t_col, (cudaStream_t)stream);
+                                  t_rowptr, t_col, 0, (cudaStream_t)stream);
+}
+
+int kp_kpconv_backward_sym_dev(const float* pts, int n, const void* neighb_inds, int idx_is_i64, int H, int idx_stride,
+                               const float* x, int cin, const float* weights, int cout, const float* kernel_points,
+                               int K, float KP_extent, const float* d_out, float* d_x, float* d_weights,
+                               const void* lists_koff, const void* lists_entries, void* stream) {
+    return kpconv_backward_device(pts, n, pts, n, neighb_inds, idx_is_i64, H, idx_stride, x, cin, weights, cout,
+                                  kernel_points, K, KP_extent, d_out, d_x, d_weights, lists_koff, lists_entries, nullptr,
+                                  nullptr, 1, (cudaStream_t)stream);
 }
 
 int kp_transpose_table_dev(const void* neighb_inds, int idx_is_i64, int nq, int H, int idx_stride, int ns,
@@ -220,7 +235,17 @@ int kp_kpconv_backward_dev(const float* q_pts, int nq, const float* s_pts, int n
                            float* d_x, float* d_weights, void* stream) {
     return kpconv_backward_device(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, weights, cout,
                                   kernel_points, K, KP_extent, d_out, d_x, d_weights, nullptr, nullptr, nullptr, nullptr,
-                                  (cudaStream_t)stream);
+                                  0, (cudaStream_t)stream);
+}
+
+int kp_pyramid_build_dev(const float* points0, int n0, const int* lengths0, int nb, int n_layers,
+                         const float* conv_radius, const float* pool_radius, const float* up_radius,
+                         const float* sample_dl, const float* rot, const int* limits, int order, int idx_is_i64, int cap,
+                         void* slab, long long slab_bytes, long long* offsets, int* n_out, int* lengths_out, int* widths,
+                         int* strides, long long* need_bytes, int* need_cap, void* stream) {
+    return pyramid_build_device(points0, n0, lengths0, nb, n_layers, conv_radius, pool_radius, up_radius, sample_dl, rot,
+                                limits, order, idx_is_i64, cap, slab, slab_bytes, offsets, n_out, lengths_out, widths,
+                                strides, need_bytes, need_cap, (cudaStream_t)stream);
 }
 
 int kp_max_pool_forward_dev(const float* x, int ns, int channels, const void* inds, int idx_is_i64, int nq, int H,

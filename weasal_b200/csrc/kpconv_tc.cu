@@ -918,9 +918,11 @@ int transpose_table_entry(const void* idx, int idx_is_i64, int nq, int H, int id
 int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
                            int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
                            float extent, const float* dout, float* dx, float* dw, const void* lists_koff,
-                           const void* lists_entries, const int* t_rowptr, const int* t_col, cudaStream_t stream) {
+                           const void* lists_entries, const int* t_rowptr, const int* t_col, int table_symmetric,
+                           cudaStream_t stream) {
     int rc = check_args(nq, ns, H, idx_stride, cin, cout, K, extent);
     if (rc != KP_OK) return rc;
+    if (table_symmetric && nq != ns) return fail(KP_ERR_ARG, "kpconv: a symmetric table needs nq == ns");
     KP_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * cin * cout * sizeof(float), stream));
     if (nq == 0 || ns == 0 || H == 0) {
         if (ns > 0) KP_CUDA(cudaMemsetAsync(dx, 0, (size_t)ns * cin * sizeof(float), stream));
@@ -982,7 +984,17 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
     }
 
     // ---- dX: the forward kernel on the transposed table, with W^T and -kp
-    {
+    if (table_symmetric) {
+        // queries == supports and no row was cropped: j is in row i exactly when i is in row j (the f32 distance is
+        // exactly symmetric), so the table is its own transpose and no CSR copy is needed
+        Table T;
+        T.idx = idx; T.rowptr = nullptr; T.H = H; T.stride = idx_stride; T.is_i64 = idx_is_i64;
+        Lists L;
+        rc = build_lists(S, s, ns, q, nq, T, n_pairs, H, kp, K, -1.f, extent, &L, stream);
+        if (rc != KP_OK) return rc;
+        rc = run_forward("kp_fwd_dx", S, ns, nullptr, H, dout, nq, cout, L, w, (long long)cin * cout, 1, cout, cin, K, dx, stream);
+        if (rc != KP_OK) return rc;
+    } else {
         const int* rowptr = t_rowptr;
         const int* col_sorted = t_col;
         if (!rowptr || !col_sorted) {

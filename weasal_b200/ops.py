@@ -249,6 +249,15 @@ class KPConvFunction(torch.autograd.Function):
             dx = torch.empty((ns, cin), dtype=torch.float32, device=q.device)
             dw = torch.empty((K, cin, cout), dtype=torch.float32, device=q.device)
             lk, le = ctx.lists if ctx.lists is not None else (None, None)
+            if getattr(ctx.idx_obj, "_kp_symmetric", False) and q.data_ptr() == s.data_ptr() and nq == ns:
+                # the pyramid builder marked this conv matrix as its own transpose (queries == supports, no crop)
+                _lib.check(L.kp_kpconv_backward_sym_dev(q.data_ptr(), nq, idx.data_ptr(), i64, H, stride, xx.data_ptr(),
+                                                        cin, w.data_ptr(), cout, kp.data_ptr(), K, ext, do.data_ptr(),
+                                                        dx.data_ptr(), dw.data_ptr(),
+                                                        lk.data_ptr() if lk is not None else None,
+                                                        le.data_ptr() if le is not None else None, _stream()),
+                           "kpconv_backward")
+                return None, None, None, dx, dw, None, None
             # The transposed neighbour table depends on the index matrix only: build it once per matrix and let every
             # KPConv that shares the matrix (the two blocks of a layer) reuse it.
             tr = getattr(ctx.idx_obj, "_kp_transposed", None)

@@ -157,12 +157,149 @@ class PyramidBuilder:
             del self.grids[key]  # only the grid over the newest layer can be needed again
 
 
+def layer_plan(config):
+    """Per-layer radii of the walk over ``config.architecture`` (datasets/common.py:468-567): conv search radius
+    (0 = the layer has no conv block), pool search radius, upsample radius (2r) and the subsampling cell ``dl`` towards
+    the next layer; float64 lists of length L."""
+    r_normal = config.first_subsampling_dl * config.conv_radius
+    conv_r, pool_r, up_r, dls = [], [], [], []
+    layer_blocks = []
+    for block in config.architecture:
+        if not ('pool' in block or 'strided' in block or 'global' in block or 'upsample' in block):
+            layer_blocks.append(block)
+            continue
+        if layer_blocks:
+            deform = any('deformable' in b for b in layer_blocks)
+            conv_r.append(r_normal * config.deform_radius / config.conv_radius if deform else r_normal)
+        else:
+            conv_r.append(0.0)
+        if 'pool' in block or 'strided' in block:
+            dls.append(2 * r_normal / config.conv_radius)
+            pool_r.append(r_normal * config.deform_radius / config.conv_radius if 'deformable' in block else r_normal)
+            up_r.append(2 * r_normal)
+        else:
+            dls.append(0.0)
+            pool_r.append(0.0)
+            up_r.append(0.0)
+        r_normal *= 2
+        layer_blocks = []
+        if 'global' in block or 'upsample' in block:
+            break
+    return conv_r, pool_r, up_r, dls
+
+
+_SLAB_HINT = {}  # (n_layers, index bytes) -> slab bytes per input point that sufficed last time
+
+
+def draw_grid_rotations(config, nb, random_grid_orient=True):
+    """All grid orientations of one batch, drawn layer by layer in the reference's order (common.py:98-105 runs inside
+    each batch_grid_subsampling call): float32 [pooled layers, nb, 3, 3], or None."""
+    if not random_grid_orient:
+        return None
+    dls = layer_plan(config)[3]
+    rots = [random_grid_rotations(nb) for d in dls if d > 0]
+    return np.ascontiguousarray(np.stack(rots), dtype=np.float32) if rots else None
+
+
+def build_native(points, stack_lengths, config, neighborhood_limits=None, random_grid_orient=True, order="reference",
+                 index_dtype=torch.int64, cap=80, stream=None, rot=None):
+    """The whole pyramid of one batch through ONE native call (kp_pyramid_build_dev): no Python between the ~150
+    launches, the GIL released for its duration. ``points`` is a CUDA float32 [N,3] tensor. Returns the lists
+    (points, neighbors, pools, upsamples, lengths) and the slab tensor all of them but ``points[0]`` are views of.
+    ``stream``: the CUDA stream to run on (default: torch's current stream); the call returns after synchronising it.
+    ``rot``: grid orientations from :func:`draw_grid_rotations` (default: drawn here)."""
+    import ctypes as C
+    from . import _lib
+    if not points.is_cuda:
+        raise RuntimeError("weasal_b200: tensors must be CUDA tensors (there is no CPU fallback)")
+    dev = points.device
+    pts = points.contiguous() if points.dtype == torch.float32 else points.float().contiguous()
+    lens = np.ascontiguousarray(stack_lengths.cpu().numpy() if torch.is_tensor(stack_lengths) else stack_lengths,
+                                dtype=np.int32).reshape(-1)
+    nb, n0 = len(lens), pts.shape[0]
+    conv_r, pool_r, up_r, dls = layer_plan(config)
+    L = len(conv_r)
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    conv_r, pool_r, up_r, dls = f32(conv_r), f32(pool_r), f32(up_r), f32(dls)
+    if rot is None:  # (a prefetching caller draws them itself, in submission order)
+        rot = draw_grid_rotations(config, nb, random_grid_orient)
+    limits = None
+    if neighborhood_limits is not None and len(neighborhood_limits):
+        limits = np.zeros(L, np.int32)
+        limits[:min(L, len(neighborhood_limits))] = np.asarray(neighborhood_limits, np.int64)[:L]
+    i64 = index_dtype == torch.int64
+    isz = 8 if i64 else 4
+    offs = np.zeros(5 * L, np.int64)
+    n_out, lens_out = np.zeros(L, np.int32), np.zeros(L * nb, np.int32)
+    widths, strides = np.zeros(3 * L, np.int32), np.zeros(3 * L, np.int32)
+    need_bytes, need_cap = C.c_longlong(0), C.c_int(0)
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    per_point = _SLAB_HINT.get((L, isz, cap), 2.6 * (2.2 * cap * isz + 12))
+    slab_bytes = int(per_point * n0) + (1 << 16)
+    lib = _lib.lib()
+    while True:
+        with torch.cuda.stream(st):
+            slab = torch.empty(slab_bytes, dtype=torch.uint8, device=dev)
+        rc = lib.kp_pyramid_build_dev(pts.data_ptr(), n0, lens.ctypes.data, nb, L, conv_r.ctypes.data, pool_r.ctypes.data,
+                                      up_r.ctypes.data, dls.ctypes.data, rot.ctypes.data if rot is not None else None,
+                                      limits.ctypes.data if limits is not None else None,
+                                      1 if order == "reference" else 0, 1 if i64 else 0, int(cap), slab.data_ptr(),
+                                      slab_bytes, offs.ctypes.data, n_out.ctypes.data, lens_out.ctypes.data,
+                                      widths.ctypes.data, strides.ctypes.data, C.byref(need_bytes), C.byref(need_cap),
+                                      C.c_void_p(st.cuda_stream))
+        if rc == _lib.KP_ERR_CAPACITY:
+            if need_cap.value > cap:
+                cap = need_cap.value
+                slab_bytes = int(slab_bytes * (cap / max(strides.max(), 1)) * 1.1)
+            if need_bytes.value > slab_bytes:
+                slab_bytes = int(need_bytes.value)
+            continue
+        _lib.check(rc, "pyramid_build")
+        break
+    _SLAB_HINT[(L, isz, cap)] = 1.15 * need_bytes.value / n0
+
+    def view(off, rows, cols, dtype, esz):
+        return slab[off:off + rows * cols * esz].view(dtype).view(rows, cols)
+
+    empty_idx = lambda: torch.zeros((0, 1), dtype=index_dtype, device=dev)
+    P, Nn, Po, Up, Le = [], [], [], [], []
+    for l in range(L):
+        n = int(n_out[l])
+        P.append(pts if l == 0 else view(int(offs[l]), n, 3, torch.float32, 4))
+        for kind, lst in ((0, Nn), (1, Po), (2, Up)):
+            o, w, sd = int(offs[(1 + kind) * L + l]), int(widths[kind * L + l]), int(strides[kind * L + l])
+            if o < 0:
+                lst.append(empty_idx())
+            else:
+                rows = int(n_out[l + 1]) if kind == 1 else n
+                lst.append(view(o, rows, sd, index_dtype, isz)[:, :min(w, sd)])
+        Le.append(slab[int(offs[4 * L + l]):int(offs[4 * L + l]) + 4 * nb].view(torch.int32))
+    # conv matrices of a layer searched against itself without a crop are symmetric (j in row i <=> i in row j, the
+    # f32 distance is exactly symmetric): KPConv's backward can use the matrix itself as its transposed table
+    for l in range(L):
+        if Nn[l].shape[0] and int(widths[l]) <= int(strides[l]):
+            Nn[l]._kp_symmetric = True
+    return P, Nn, Po, Up, Le, slab
+
+
 def segmentation_inputs(stacked_points, stacked_features, labels, stack_lengths, config, neighborhood_limits=None,
-                        random_grid_orient=True, order="reference", index_dtype=torch.int64, device="cuda"):
+                        random_grid_orient=True, order="reference", index_dtype=torch.int64, device="cuda",
+                        native=True):
     """Device counterpart of datasets/common.py:461-577: the flat list ``points*L + neighbors*L + pools*L +
-    upsamples*L + lengths*L + [features, labels]`` of device tensors. All searches of the batch are issued before the
-    single synchronisation that reads their widths back."""
+    upsamples*L + lengths*L + [features, labels]`` of device tensors. ``native`` (default) walks the layers inside
+    one C call (kp_pyramid_build_dev); ``native=False`` drives the per-operator entry points from Python, issuing all
+    searches of the batch before the single synchronisation that reads their widths back. Same kernels, same results."""
     dev = torch.device(device)
+    if native:
+        def to_dev0(a, dtype=None):
+            t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+            t = t.to(dev, non_blocking=True)
+            return t.to(dtype) if dtype is not None else t
+        P, Nn, Po, Up, Le, _ = build_native(to_dev0(stacked_points, torch.float32), stack_lengths, config,
+                                         neighborhood_limits, random_grid_orient, order, index_dtype)
+        feats = to_dev0(stacked_features, torch.float32) if stacked_features is not None else None
+        labs = to_dev0(labels) if labels is not None else None
+        return P + Nn + Po + Up + Le + [feats, labs]
     pb = PyramidBuilder(stacked_points, stack_lengths, config, neighborhood_limits, random_grid_orient, order,
                         index_dtype, dev)
     while pb.step():
@@ -177,6 +314,75 @@ def segmentation_inputs(stacked_points, stacked_features, labels, stack_lengths,
     feats = to_dev(stacked_features, torch.float32) if stacked_features is not None else None
     labs = to_dev(labels) if labels is not None else None
     return pb.points + pb.neighbors + pb.pools + pb.upsamples + pb.lengths + [feats, labs]
+
+
+class PyramidPrefetcher:
+    """Builds the pyramids of upcoming batches on a side stream from a worker thread while the caller trains on the
+    current one — the counterpart of the reference's DataLoader workers (train_*.py: ``num_workers=input_threads``),
+    which run ``segmentation_inputs`` ahead of the training loop. The worker spends its time inside ONE native call
+    (kp_pyramid_build_dev, GIL released), so it does not compete with the training thread for the interpreter.
+
+        pf.submit(points, features, labels, lengths)   # host (pinned) or device tensors / numpy arrays
+        batch = pf.get()                               # DeviceBatch, complete on the device
+
+    Grid orientations are drawn from ``np.random`` at submit time, in submission order."""
+
+    def __init__(self, config, device="cuda", neighborhood_limits=None, random_grid_orient=True, order="reference",
+                 index_dtype=torch.int64):
+        import queue
+        import threading
+        self.dev = torch.device(device)
+        if self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.cfg, self.limits, self.orient, self.order, self.dtype = config, neighborhood_limits, random_grid_orient, order, index_dtype
+        self.side = torch.cuda.Stream(self.dev)
+        self.q_in, self.q_out = queue.Queue(), queue.Queue()
+        self.thread = threading.Thread(target=self._run, name="weasal-pyramid", daemon=True)
+        self.thread.start()
+
+    def submit(self, points, features, labels, lengths, extras=None):
+        lens = np.ascontiguousarray(lengths.cpu().numpy() if torch.is_tensor(lengths) else lengths, dtype=np.int32).reshape(-1)
+        rot = draw_grid_rotations(self.cfg, len(lens), self.orient)
+        self.q_in.put((points, features, labels, lens, rot, extras))
+
+    def _run(self):
+        torch.cuda.set_device(self.dev)
+        while True:
+            item = self.q_in.get()
+            if item is None:
+                return
+            try:
+                points, features, labels, lens, rot, extras = item
+
+                def to_dev(a, dtype=None):
+                    if a is None:
+                        return None
+                    t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+                    t = t.to(self.dev, non_blocking=True)
+                    return t.to(dtype) if dtype is not None and t.dtype != dtype else t
+
+                with torch.cuda.stream(self.side):
+                    pts, feats, labs = to_dev(points, torch.float32), to_dev(features, torch.float32), to_dev(labels)
+                    P, Nn, Po, Up, Le, slab = build_native(pts, lens, self.cfg, self.limits, self.orient, self.order,
+                                                           self.dtype, stream=self.side, rot=rot)
+                    self.side.synchronize()
+                self.q_out.put((DeviceBatch(P + Nn + Po + Up + Le + [feats, labs], extras), (slab, pts, feats, labs)))
+            except BaseException as e:  # surfaced by get()
+                self.q_out.put((e, None))
+
+    def get(self):
+        batch, owned = self.q_out.get()
+        if owned is None:
+            raise batch
+        cur = torch.cuda.current_stream(self.dev)
+        for t in owned:  # allocated on the side stream, consumed on the caller's: tell the caching allocator
+            if t is not None and t.is_cuda:
+                t.record_stream(cur)
+        return batch
+
+    def close(self):
+        self.q_in.put(None)
+        self.thread.join(timeout=10)
 
 
 class DeviceBatch:
