@@ -98,15 +98,23 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------- algorithmic
+def layer_rows(batch):
+    """real (unpadded) points per layer"""
+    if getattr(batch, "build", None) is not None:
+        return [int(n) for n in batch.build.n_out]
+    return [p.shape[0] for p in batch.points]
+
+
 def conv_shapes(batch, net):
-    """(Nq, Ns, H, Cin, Cout) of every KPConv call in one forward, from the built pyramid."""
+    """(Nq, Ns, H, Cin, Cout) of every KPConv call in one forward, from the built pyramid (real rows, stored widths)."""
     out = []
+    rows = layer_rows(batch)
     for blk in net.encoder:
         l = blk.layer
         if blk.strided:
-            nq, ns, H = batch.points[l + 1].shape[0], batch.points[l].shape[0], batch.pools[l].shape[1]
+            nq, ns, H = rows[l + 1], rows[l], batch.pools[l].shape[1]
         else:
-            nq, ns, H = batch.points[l].shape[0], batch.points[l].shape[0], batch.neighbors[l].shape[1]
+            nq, ns, H = rows[l], rows[l], batch.neighbors[l].shape[1]
         out.append((nq, ns, H, blk.conv.in_channels, blk.conv.out_channels))
     return out
 
@@ -128,12 +136,13 @@ def search_bytes(batch, idx_bytes=8):
     """12*Nq + 12*Ns + 8*B + idx_bytes*Nq*Hmax per call, summed over the pyramid's 13 searches."""
     tot = 0
     L = len(batch.points)
+    rows = layer_rows(batch)
     for l in range(L):
-        n = batch.points[l].shape[0]
+        n = rows[l]
         B = batch.lengths[l].shape[0]
         tot += 24 * n + 8 * B + idx_bytes * n * batch.neighbors[l].shape[1]
         if l + 1 < L:
-            m = batch.points[l + 1].shape[0]
+            m = rows[l + 1]
             tot += 12 * (n + m) + 8 * B + idx_bytes * m * batch.pools[l].shape[1]
             tot += 12 * (n + m) + 8 * B + idx_bytes * n * batch.upsamples[l].shape[1]
     return tot
@@ -181,20 +190,26 @@ def run_ours(args):
     pin_batches = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items() if k != "lengths"} for b in batches]
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
 
-    prefetch = pyramid.PyramidPrefetcher(view, dev)
+    from weasal_b200.engine import GraphedTrainStep, calibrate_static_caps
+    # Static shapes + one CUDA graph per step (weasal_b200/engine.py). Capacities come from a calibration pass over
+    # the batches, like the reference's sampler calibration (batch_limit / neighborhood_limits): rows padded to a
+    # per-layer capacity, neighbourhood limits chosen so that no row is cropped (results equal the unlimited pyramid).
+    use_graph = os.environ.get("WEASAL_BENCH_GRAPH", "1") != "0"
+    n_cap = limits = None
+    if use_graph:
+        n_cap, limits = calibrate_static_caps(view, [b["points"] for b in dev_batches], [b["lengths"] for b in batches])
+    prefetch = pyramid.PyramidPrefetcher(view, dev, neighborhood_limits=limits, n_cap=n_cap)
+    trainer = GraphedTrainStep(net, opt, F.cross_entropy, reducer=reducer if world > 1 else None, clip_value=100.0)
+    eager = GraphedTrainStep(net, opt, F.cross_entropy, reducer=None, clip_value=100.0)  # profile leg: no collective
+    if use_graph:  # capture before the prefetch pipeline runs (nothing else issues CUDA work meanwhile)
+        prefetch.submit(dev_batches[0]["points"], dev_batches[0]["features"], dev_batches[0]["labels"], batches[0]["lengths"])
+        trainer.prepare(prefetch.get())
+        torch.cuda.synchronize()
 
     def net_step(batch, allreduce=True):
-        logits = net(batch)
-        loss = F.cross_entropy(logits, batch.labels)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        if allreduce:
-            reducer.step()
-        torch.nn.utils.clip_grad_value_(net.parameters(), 100.0)
-        opt.step()
-        return loss
+        return trainer.step(batch) if allreduce else eager._body(batch)
 
-    def run_steps(first, n, e2e, allreduce=True, clocks=None, keep=None):
+    def run_steps(first, n, e2e, allreduce=True, clocks=None, on_batch=None):
         """n steps over batches first, first+1, ...: the pyramid of step t+1 is built on the prefetcher's side stream
         (one native call, the counterpart of the reference's DataLoader workers) while step t trains. The pipeline
         starts and ends empty, so exactly n pyramids and n training steps happen inside the call."""
@@ -215,13 +230,18 @@ def run_ours(args):
             batch = prefetch.get()
             if ahead and it + 1 < first + n:
                 submit(it + 1)
+            t_l0 = time.perf_counter()
             loss = net_step(batch, allreduce)
+            if os.environ.get("WEASAL_DEBUG") and rank == 0:
+                print(f"[bench] {'e2e' if e2e else 'dev'} step {it}: build {prefetch.stats[-1][0] * 1e3:.2f} ms, get() waited "
+                      f"{prefetch.stats[-1][1] * 1e3:.2f} ms, net launches {(time.perf_counter() - t_l0) * 1e3:.2f} ms",
+                      file=sys.stderr)
             if e2e:
                 loss_host = loss.item()  # device -> host read of the step's result
             if clocks is not None and (it - first) % max(n // 8, 1) == 0:
                 clocks.sample()  # the step's kernels are still in flight here: a reading under load
-            if keep is not None:
-                keep.append(batch)
+            if on_batch is not None:
+                on_batch(batch)
             pts += batches[it % N_BATCHES]["points"].shape[0]
         return pts
 
@@ -256,8 +276,11 @@ def run_ours(args):
     launches0 = _lib.launch_count()
     timed(W, 0, False)
     launches0 = _lib.launch_count()
+    g0 = trainer.n_graphed
     ms, pts = timed(0, K, False, clocks if rank == 0 else None)
-    gpu_launches = _lib.launch_count() - launches0
+    # library kernels launched in the timed region: the pyramid's (counted live) + those inside the replayed graphs
+    gpu_launches = _lib.launch_count() - launches0 + (trainer.n_graphed - g0) * trainer.launches_per_replay
+    graphed_steps = trainer.n_graphed - g0
     e2e_ms, e2e_pts = timed(W, K, True, clocks if rank == 0 else None)
     clk = clocks.summary() if rank == 0 else None
 
@@ -267,11 +290,14 @@ def run_ours(args):
         L.kp_profile_enable(1)
         psteps = min(K, 8)
         shapes, sbytes = None, 0
-        kept = []
-        run_steps(0, psteps, False, allreduce=False, keep=kept)  # rank 0 only: no collective inside this leg
-        shapes = conv_shapes(kept[0], net)
-        sbytes = search_bytes(kept[0])
-        del kept
+        seen = []
+
+        def first_shapes(batch):
+            if not seen:
+                seen.append((conv_shapes(batch, net), search_bytes(batch)))
+
+        run_steps(0, psteps, False, allreduce=False, on_batch=first_shapes)  # rank 0 only: no collective in this leg
+        shapes, sbytes = seen[0]
         torch.cuda.synchronize()
         L.kp_profile_enable(0)
         buf = C.create_string_buffer(1 << 16)
@@ -332,7 +358,10 @@ def run_ours(args):
                        "first_subsampling_dl": cfg["dl"], "layers": 5, "kpconv_per_forward": 10,
                        "parallelism": f"dp{world}", "l2": "flushed between steps (256 MB write, inside the timed region)",
                        "pyramid": "built one step ahead on a side stream by one native call (kp_pyramid_build_dev)",
-                       "random_grid_orient": True, "neighborhood_limits": None,
+                       "random_grid_orient": True,
+                       "neighborhood_limits": limits if limits is None else f"calibrated, no row cropped: {limits}",
+                       "step": (f"one CUDA graph per step over static-shape batches (rows padded to {n_cap}); "
+                                f"{graphed_steps} of {K} timed steps graphed") if use_graph else "eager launches",
                        "harness_linear_precision": "tf32"},
             "e2e": {"value": e2e_pts / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / K},

@@ -119,7 +119,7 @@ int kp_grid_subsample_dev(const float* points, int n, const int* batches, int nb
  *   lengths0 [nb]; conv_radius / pool_radius / up_radius / sample_dl [n_layers] (conv_radius[l] == 0: no conv search at
  *   layer l; pool / upsample / sample_dl entries of the last layer are ignored); rot [n_layers-1][nb][3][3] f32 grid
  *   orientations or NULL; limits [n_layers] neighbourhood limits or NULL (0 = unlimited).
- * Outputs are carved from the caller's DEVICE `slab` (slab_bytes); offsets [5*n_layers] receives byte offsets into it:
+ * Outputs are carved from the caller's DEVICE `slab` (slab_bytes); offsets [5*n_layers + 2] receives byte offsets into it:
  *   [0,L) points of layer l ([n,3] f32; layer 0 = -1, the caller's points0), [L,2L) conv matrices [n_l, stride],
  *   [2L,3L) pool matrices [n_{l+1}, stride], [3L,4L) upsample matrices [n_l, stride], [4L,5L) batch lengths (int32
  *   [nb]); -1 = absent. n_out [L], lengths_out [L*nb], widths [3*L] (true maximum neighbour counts, conv / pool /
@@ -134,6 +134,23 @@ int kp_pyramid_build_dev(const float* points0, int n0, const int* lengths0, int 
                          const float* sample_dl, const float* rot, const int* limits, int order, int idx_is_i64, int cap,
                          void* slab, long long slab_bytes, long long* offsets, int* n_out, int* lengths_out, int* widths,
                          int* strides, long long* need_bytes, int* need_cap, void* stream);
+
+/* Static-shape variant for consumers that bind their inputs once (a captured CUDA graph of the training step): layer l
+ * always has n_cap[l] rows (HOST array [n_layers]). Points are padded with 1e6, index rows with the shadow value, which
+ * is the SUPPORT layer's n_cap (so that "index == row count of the support tensor" still marks a shadow, the convention
+ * of models/blocks.py:278/357), the optional layer-0 features [n0,fdim] f32 with 0 and labels [n0] int64 with
+ * label_pad (DEVICE pointers or NULL; they travel in the slab so the consumer copies one buffer). Layer 0's points
+ * live in the slab too (offsets[0] >= 0); offsets has 5*n_layers + 2 entries ([5L] features, [5L+1] labels). The slab
+ * layout depends on (n_cap, limits / cap, nb, fdim) alone. Padded query rows have no neighbours and nothing refers to
+ * a padded support row, so every operator of the path computes the same values on the real rows. A layer that outgrows
+ * its capacity returns KP_ERR_CAPACITY with *need_cap = -(layer + 1). */
+int kp_pyramid_build_static_dev(const float* points0, int n0, const int* lengths0, int nb, int n_layers,
+                                const float* conv_radius, const float* pool_radius, const float* up_radius,
+                                const float* sample_dl, const float* rot, const int* limits, int order, int idx_is_i64,
+                                int cap, const int* n_cap, const float* features, int fdim, const long long* labels,
+                                long long label_pad, void* slab, long long slab_bytes, long long* offsets, int* n_out,
+                                int* lengths_out, int* widths, int* strides, long long* need_bytes, int* need_cap,
+                                void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * KPConv (rigid, 'linear' influence, 'sum' aggregation), forward and backward.

@@ -216,3 +216,25 @@ def test_random_grid_rotations_replay_numpy_stream():
     v = np.array([[0.0, 0.0, 1.0]])
     Rz = axis_angle_rotations(v, np.array([np.pi / 2]))[0]
     assert np.allclose(Rz @ np.array([1.0, 0, 0]), [0, 1, 0], atol=1e-12)
+
+
+def test_layer_plan_and_rotation_draw_order_follow_the_reference_walk():
+    """Host logic of the native pyramid builder: per-layer radii of datasets/common.py:468-567 and the order in which
+    the grid orientations are drawn (one batch_grid_subsampling call per pooled layer, common.py:98-105)."""
+    from weasal_b200 import pyramid
+    from weasal_b200.net import CfgView, net_config
+    cfg = CfgView(net_config("vaihingen_pl"))
+    conv_r, pool_r, up_r, dls = pyramid.layer_plan(cfg)
+    assert len(conv_r) == 5
+    assert np.allclose(conv_r, [0.6, 1.2, 2.4, 4.8, 9.6]) and np.allclose(pool_r[:4], conv_r[:4]) and pool_r[4] == 0
+    assert np.allclose(up_r[:4], [1.2, 2.4, 4.8, 9.6]) and np.allclose(dls[:4], [0.48, 0.96, 1.92, 3.84]) and dls[4] == 0
+    assert np.float32(up_r[0]) == np.float32(conv_r[1])  # the upsample grid of layer l is the conv grid of layer l+1
+    np.random.seed(7)
+    R = pyramid.draw_grid_rotations(cfg, 3)
+    np.random.seed(7)
+    want = np.stack([pyramid.random_grid_rotations(3) for _ in range(4)])
+    assert R.shape == (4, 3, 3, 3) and R.dtype == np.float32 and np.array_equal(R, want)
+    assert pyramid.draw_grid_rotations(cfg, 3, random_grid_orient=False) is None
+    # no CPU path: the builder refuses host tensors
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pyramid.NativeBuild(torch.zeros(4, 3), [4], cfg)

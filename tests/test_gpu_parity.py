@@ -427,7 +427,8 @@ def test_kpconv_backward_symmetric_table_shortcut(torch_cuda):
         x, w = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
         ops.kpconv(P, P, ii, x, w, kp, 0.24).backward(do)
         res.append((x.grad.cpu().numpy(), w.grad.cpu().numpy()))
-    assert rel_max(res[1][0], res[0][0]) < 1e-5 and rel_max(res[1][1], res[0][1]) < 1e-5
+    # (the dX sums run in a different order and are rounded to TF32 before the contraction)
+    assert rel_max(res[1][0], res[0][0]) < 3e-4 and rel_max(res[1][1], res[0][1]) < 1e-5
 
 
 def test_full_size_vaihingen_batch_properties(torch_cuda):
@@ -551,3 +552,91 @@ def test_batch_query_no_supports_at_all(torch_cuda):
     with pytest.raises(RuntimeError, match="^Error$"):
         rn.batch_query(q, np.zeros((0, 3), np.float32), [10], [0], radius=0.5)
 
+
+
+# ------------------------------------------------------------------------------------------ static shapes + CUDA graph
+def test_graphed_static_step_matches_eager_dynamic_step(torch_cuda):
+    """The training step replayed from a CUDA graph over padded static-shape batches computes what the eager step
+    computes over the ordinary batches: same losses, same parameters after three SGD steps (dropout off)."""
+    torch = torch_cuda
+    import copy
+    import torch.nn.functional as F
+    from weasal_b200 import pyramid
+    from weasal_b200.engine import GraphedTrainStep, calibrate_static_caps
+    from weasal_b200.kpconv import KPConv
+    from weasal_b200.net import CfgView, KPFCNNHarness, net_config
+    ncfg = dict(net_config("vaihingen_pl"), dropout=0.0)
+    view = CfgView(ncfg)
+    data = [make_batch("vaihingen_pl", seed=s, batch_num=2, in_radius=9.0) for s in (1, 2, 3)]
+    dev = torch.device("cuda")
+    P = [torch.from_numpy(b["points"]).to(dev) for b in data]
+    Fe = [torch.from_numpy(b["features"]).to(dev) for b in data]
+    Lb = [torch.from_numpy(b["labels"] % 9).to(dev) for b in data]
+    n_cap, limits = calibrate_static_caps(view, P, [b["lengths"] for b in data])
+    np.random.seed(0)
+    torch.manual_seed(0)
+    net_a = KPFCNNHarness(ncfg, KPConv).to(dev)
+    net_b = copy.deepcopy(net_a)
+    losses = []
+    for net, caps in ((net_a, None), (net_b, n_cap)):
+        opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-3)
+        tr = GraphedTrainStep(net, opt, F.cross_entropy, clip_value=100.0)
+        pf = pyramid.PyramidPrefetcher(view, dev, neighborhood_limits=limits if caps else None, n_cap=caps,
+                                       random_grid_orient=False)
+        ls = []
+        for i in range(3):
+            pf.submit(P[i], Fe[i], Lb[i], data[i]["lengths"])
+            batch = pf.get()
+            assert (batch.static_slab is not None) == (caps is not None)
+            ls.append(float(tr.step(batch)))
+        pf.close()
+        assert (tr.n_graphed, tr.n_eager) == ((3, 0) if caps else (0, 3))
+        if caps:
+            assert tr.launches_per_replay > 50
+        losses.append(ls)
+    assert np.allclose(losses[0], losses[1], rtol=2e-3), losses
+    for (na, pa), (nb_, pb) in zip(net_a.named_parameters(), net_b.named_parameters()):
+        d = float((pa - pb).abs().max())
+        assert d <= 2e-3 * max(float(pa.abs().max()), 1e-3), (na, d)
+
+
+def test_static_pyramid_layout_and_overflow_fallback(torch_cuda):
+    """Static layout: real rows equal the ordinary pyramid, padded rows are all-shadow / 1e6 / ignore_index; a batch
+    that outgrows a capacity comes back in the ordinary layout."""
+    torch = torch_cuda
+    from weasal_b200 import pyramid
+    from weasal_b200.engine import calibrate_static_caps
+    cfg = _vaihingen_cfg()
+    b = make_batch("vaihingen_pl", seed=8, batch_num=2, in_radius=9.0)
+    dev = torch.device("cuda")
+    P, Fe, Lb = (torch.from_numpy(b[k]).to(dev) for k in ("points", "features", "labels"))
+    n_cap, limits = calibrate_static_caps(cfg, [P], [b["lengths"]])
+    want = pyramid.build_native(P, b["lengths"], cfg, random_grid_orient=False)
+    pf = pyramid.PyramidPrefetcher(cfg, dev, neighborhood_limits=limits, n_cap=n_cap, random_grid_orient=False)
+    pf.submit(P, Fe, Lb, b["lengths"])
+    got = pf.get()
+    assert got.static_slab is not None and got.no_crop
+    for l in range(len(want[0])):
+        n = want[0][l].shape[0]
+        assert got.points[l].shape[0] == n_cap[l]
+        assert torch.equal(got.points[l][:n], want[0][l]) and bool((got.points[l][n:] == 1e6).all())
+        for k, (mine, ref) in enumerate(((got.neighbors[l], want[1][l]), (got.pools[l], want[2][l]), (got.upsamples[l], want[3][l]))):
+            if ref.shape[0] == 0:
+                assert mine.shape[0] == 0
+                continue
+            rows, w = ref.shape
+            ns_ref = want[0][l + 1].shape[0] if k == 2 else n          # shadow value of the ordinary matrix
+            ns_cap = n_cap[l + 1] if k == 2 else n_cap[l]               # ... and of the static one
+            m = mine[:rows, :w]
+            assert torch.equal(torch.where(ref == ns_ref, torch.full_like(ref, ns_cap), ref), m)
+            assert bool((mine[:rows, w:] == ns_cap).all()) and bool((mine[rows:] == ns_cap).all())
+    assert torch.equal(got.features[:len(P)], Fe) and bool((got.features[len(P):] == 0).all())
+    assert torch.equal(got.labels[:len(P)], Lb) and bool((got.labels[len(P):] == -100).all())
+    pf.close()
+    small = [max(c // 2, 256) for c in n_cap]
+    pf = pyramid.PyramidPrefetcher(cfg, dev, neighborhood_limits=limits, n_cap=small, random_grid_orient=False)
+    pf.submit(P, Fe, Lb, b["lengths"])
+    got = pf.get()
+    pf.close()
+    assert got.static_slab is None and got.points[0].shape[0] == len(P)
+    assert torch.equal(got.neighbors[0], want[1][0][:, :got.neighbors[0].shape[1]])

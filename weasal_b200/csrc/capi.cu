@@ -39,6 +39,7 @@ int pyramid_build_device(const float* pts0, int n0, const int* lens0, int nb, in
                          const float* pool_r, const float* up_r, const float* dl, const float* rot, const int* limits,
                          int order, int idx_is_i64, int cap, void* slab, long long slab_bytes, long long* offs, int* n_out,
                          int* lens_out, int* widths, int* strides, long long* need_bytes, int* need_cap,
+                         const int* n_cap, const float* feats, int fdim, const long long* labels, long long label_pad,
                          cudaStream_t stream);
 int max_pool_fwd_device(const float* x, int ns, int C, const void* idx, int is_i64, int nq, int H, int stride,
                         float* out, int* arg, cudaStream_t stream);
@@ -245,7 +246,21 @@ int kp_pyramid_build_dev(const float* points0, int n0, const int* lengths0, int 
                          int* strides, long long* need_bytes, int* need_cap, void* stream) {
     return pyramid_build_device(points0, n0, lengths0, nb, n_layers, conv_radius, pool_radius, up_radius, sample_dl, rot,
                                 limits, order, idx_is_i64, cap, slab, slab_bytes, offsets, n_out, lengths_out, widths,
-                                strides, need_bytes, need_cap, (cudaStream_t)stream);
+                                strides, need_bytes, need_cap, nullptr, nullptr, 0, nullptr, 0, (cudaStream_t)stream);
+}
+
+int kp_pyramid_build_static_dev(const float* points0, int n0, const int* lengths0, int nb, int n_layers,
+                                const float* conv_radius, const float* pool_radius, const float* up_radius,
+                                const float* sample_dl, const float* rot, const int* limits, int order, int idx_is_i64,
+                                int cap, const int* n_cap, const float* features, int fdim, const long long* labels,
+                                long long label_pad, void* slab, long long slab_bytes, long long* offsets, int* n_out,
+                                int* lengths_out, int* widths, int* strides, long long* need_bytes, int* need_cap,
+                                void* stream) {
+    if (!n_cap) return fail(KP_ERR_ARG, "pyramid_build_static: n_cap is required");
+    return pyramid_build_device(points0, n0, lengths0, nb, n_layers, conv_radius, pool_radius, up_radius, sample_dl, rot,
+                                limits, order, idx_is_i64, cap, slab, slab_bytes, offsets, n_out, lengths_out, widths,
+                                strides, need_bytes, need_cap, n_cap, features, fdim, labels, label_pad,
+                                (cudaStream_t)stream);
 }
 
 int kp_max_pool_forward_dev(const float* x, int ns, int channels, const void* inds, int idx_is_i64, int nq, int H,

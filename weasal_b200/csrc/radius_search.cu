@@ -33,6 +33,8 @@ struct SearchParams {
     const float* s; int ns;
     const int* q_off; const int* s_off; int nb;
     float r2;
+    int shadow;    // padding value of the rows (the reference pads with ns, neighbors.cpp:324)
+    int nq_rows;   // rows of `out` (>= nq); rows [nq, nq_rows) are filled with `shadow` (static-shape batches)
 };
 
 // one launch resets everything a search needs: hash table, bounding boxes, result slots, the cell-storage cursor
@@ -173,7 +175,11 @@ __global__ void __launch_bounds__(WARPS * 32) rs_search_kernel(
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int qi = blockIdx.x * WARPS + warp;
-    if (qi >= P.nq) return;
+    if (qi >= P.nq) {
+        if (qi < P.nq_rows)
+            for (int h = lane; h < cap; h += 32) out[(size_t)qi * cap + h] = (OutT)P.shadow;
+        return;
+    }
     float* hd = s_d2[warp];
     int* hi = s_idx[warp];
 
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(WARPS * 32) rs_search_kernel(
         }
         if (rank < cap) row[rank] = (OutT)ii;
     }
-    for (int h = count + lane; h < cap; h += 32) row[h] = (OutT)P.ns;
+    for (int h = count + lane; h < cap; h += 32) row[h] = (OutT)P.shadow;
 }
 
 // ---------------------------------------------------------------------------------------------------------- host side
@@ -346,14 +352,25 @@ int grid_build_device(const float* s, int ns, const int* sb_host, int nb, float 
 // queries against a built grid. out is [nq, cap] (int32 or int64); rows keep their cap closest neighbours.
 // d_result != null: device int[2] receives {true max count, error bits}, no host sync. Otherwise the call synchronises,
 // escalates to the 1024-hit kernel if needed and stores the true max count in *hmax_host.
+int grid_query_device_ex(const void* grid_buf, int ns, int nb, float radius, const float* q, int nq, const int* qb_host,
+                         void* out, int out_is_i64, int cap, int* hmax_host, int* d_result, int shadow, int nq_rows,
+                         cudaStream_t stream);
 int grid_query_device(const void* grid_buf, int ns, int nb, float radius, const float* q, int nq, const int* qb_host,
                       void* out, int out_is_i64, int cap, int* hmax_host, int* d_result, cudaStream_t stream) {
-    if (nq < 0 || cap < 0) return fail(KP_ERR_ARG, "batch_query: bad sizes");
+    return grid_query_device_ex(grid_buf, ns, nb, radius, q, nq, qb_host, out, out_is_i64, cap, hmax_host, d_result, ns, nq,
+                                stream);
+}
+
+// shadow: the value rows are padded with; nq_rows >= nq: rows of `out` (the extra ones are filled with `shadow`)
+int grid_query_device_ex(const void* grid_buf, int ns, int nb, float radius, const float* q, int nq, const int* qb_host,
+                         void* out, int out_is_i64, int cap, int* hmax_host, int* d_result, int shadow, int nq_rows,
+                         cudaStream_t stream) {
+    if (nq < 0 || cap < 0 || nq_rows < nq) return fail(KP_ERR_ARG, "batch_query: bad sizes");
     std::vector<int> qoff;
     int rc = check_batches(qb_host, nb, nq, qoff);
     if (rc != KP_OK) return rc;
     if (hmax_host) *hmax_host = 0;
-    if (nq == 0) {
+    if (nq_rows == 0) {
         if (d_result) KP_CUDA(cudaMemsetAsync(d_result, 0, 2 * sizeof(int), stream));
         return KP_OK;
     }
@@ -370,10 +387,11 @@ int grid_query_device(const void* grid_buf, int ns, int nb, float radius, const 
     SearchParams P;
     P.q = q; P.nq = nq; P.s = nullptr; P.ns = ns; P.q_off = d_qoff; P.s_off = g.s_off; P.nb = nb;
     P.r2 = radius * radius;  // neighbors.cpp:226, f32
+    P.shadow = shadow; P.nq_rows = nq_rows;
     auto launch = [&](bool big) {
         ProfileScope ps2("rs_search", stream);
         if (!big) {
-            const int grid = ceil_div(nq, RS_WARPS_SMALL);
+            const int grid = ceil_div(nq_rows, RS_WARPS_SMALL);
             if (out_is_i64)
                 rs_search_kernel<long long, RS_HITS_SMALL, RS_WARPS_SMALL><<<grid, RS_WARPS_SMALL * 32, 0, stream>>>(
                     P, g.bbox, radius, g.tkeys, g.tcount, g.tstart, g.tsize - 1, g.sorted, (long long*)out, cap, d_hmax, d_err);
@@ -381,7 +399,7 @@ int grid_query_device(const void* grid_buf, int ns, int nb, float radius, const 
                 rs_search_kernel<int, RS_HITS_SMALL, RS_WARPS_SMALL><<<grid, RS_WARPS_SMALL * 32, 0, stream>>>(
                     P, g.bbox, radius, g.tkeys, g.tcount, g.tstart, g.tsize - 1, g.sorted, (int*)out, cap, d_hmax, d_err);
         } else {
-            const int grid = ceil_div(nq, RS_WARPS_BIG);
+            const int grid = ceil_div(nq_rows, RS_WARPS_BIG);
             if (out_is_i64)
                 rs_search_kernel<long long, RS_HITS_BIG, RS_WARPS_BIG><<<grid, RS_WARPS_BIG * 32, 0, stream>>>(
                     P, g.bbox, radius, g.tkeys, g.tcount, g.tstart, g.tsize - 1, g.sorted, (long long*)out, cap, d_hmax, d_err);

@@ -8,6 +8,8 @@ in the main process on the training stream and returns the same flat list
 (indices int64 as collated by the reference, common.py:551-553). :class:`DeviceBatch` exposes that list with the
 field names of ``<DS>CustomBatch`` (datasets/Vaihingen3D_PseudoLabel.py:1407-1481) so the unchanged networks consume it.
 """
+import time
+
 import numpy as np
 import torch
 
@@ -188,9 +190,6 @@ def layer_plan(config):
     return conv_r, pool_r, up_r, dls
 
 
-_SLAB_HINT = {}  # (n_layers, index bytes) -> slab bytes per input point that sufficed last time
-
-
 def draw_grid_rotations(config, nb, random_grid_orient=True):
     """All grid orientations of one batch, drawn layer by layer in the reference's order (common.py:98-105 runs inside
     each batch_grid_subsampling call): float32 [pooled layers, nb, 3, 3], or None."""
@@ -201,6 +200,160 @@ def draw_grid_rotations(config, nb, random_grid_orient=True):
     return np.ascontiguousarray(np.stack(rots), dtype=np.float32) if rots else None
 
 
+_SLAB_HINT = {}  # (n_layers, index bytes, cap) -> slab bytes per input point that sufficed last time
+
+
+class StaticCapacityExceeded(RuntimeError):
+    """A batch does not fit the static capacities (kp_pyramid_build_static_dev returned KP_ERR_CAPACITY)."""
+
+
+class NativeBuild:
+    """One kp_pyramid_build_dev call split into the three phases a prefetching caller runs on different threads:
+    ``__init__`` (argument arrays; caller thread), ``run`` (the native call, GIL released; worker thread) and
+    ``views`` (tensor views of the slab; consumer thread)."""
+
+    def __init__(self, points, stack_lengths, config, neighborhood_limits=None, random_grid_orient=True,
+                 order="reference", index_dtype=torch.int64, cap=80, rot=None, n_cap=None, features=None, labels=None,
+                 label_pad=-100):
+        """``n_cap`` (per-layer row capacities) selects the static-shape layout of kp_pyramid_build_static_dev;
+        ``features`` / ``labels`` (CUDA tensors) are then padded into the slab as well."""
+        if not points.is_cuda:
+            raise RuntimeError("weasal_b200: tensors must be CUDA tensors (there is no CPU fallback)")
+        self.dev = points.device
+        self.pts = points.contiguous() if points.dtype == torch.float32 else points.float().contiguous()
+        self.lens = np.ascontiguousarray(stack_lengths.cpu().numpy() if torch.is_tensor(stack_lengths) else stack_lengths,
+                                         dtype=np.int32).reshape(-1)
+        self.nb, self.n0 = len(self.lens), self.pts.shape[0]
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        self.conv_r, self.pool_r, self.up_r, self.dls = (f32(a) for a in layer_plan(config))
+        self.L = L = len(self.conv_r)
+        # (a prefetching caller draws the orientations itself, in submission order)
+        self.rot = rot if rot is not None else draw_grid_rotations(config, self.nb, random_grid_orient)
+        self.limits = None
+        if neighborhood_limits is not None and len(neighborhood_limits):
+            self.limits = np.zeros(L, np.int32)
+            self.limits[:min(L, len(neighborhood_limits))] = np.asarray(neighborhood_limits, np.int64)[:L]
+        self.order, self.dtype, self.cap = order, index_dtype, int(cap)
+        self.isz = 8 if index_dtype == torch.int64 else 4
+        self.offs = np.zeros(5 * L + 2, np.int64)
+        self.n_cap = np.ascontiguousarray(n_cap, dtype=np.int32) if n_cap is not None else None
+        self.feats = self.labs = None
+        self.label_pad = int(label_pad)
+        if self.n_cap is not None:
+            if len(self.n_cap) != L:
+                raise ValueError("n_cap needs one entry per layer")
+            if features is not None:
+                self.feats = features.contiguous() if features.dtype == torch.float32 else features.float().contiguous()
+            if labels is not None:
+                self.labs = labels.contiguous() if labels.dtype == torch.int64 else labels.long().contiguous()
+        self.n_out, self.lens_out = np.zeros(L, np.int32), np.zeros(L * self.nb, np.int32)
+        self.widths, self.strides = np.zeros(3 * L, np.int32), np.zeros(3 * L, np.int32)
+        self.need_bytes, self.need_cap = np.zeros(1, np.int64), np.zeros(1, np.int32)
+
+    def static_slab_bytes(self):
+        """Exact size of the static layout (256-byte aligned ranges in the builder's order)."""
+        al = lambda b: (int(b) + 255) & ~255
+        nc, isz, L = self.n_cap, self.isz, self.L
+        w = lambda l: int(self.limits[l]) if self.limits is not None and l < L and self.limits[l] > 0 else self.cap
+        tot = al(int(nc[0]) * 12)
+        if self.feats is not None:
+            tot += al(int(nc[0]) * self.feats.shape[1] * 4)
+        if self.labs is not None:
+            tot += al(int(nc[0]) * 8)
+        for l in range(L):
+            tot += al(self.nb * 4)
+            if self.conv_r[l] > 0:
+                tot += al(int(nc[l]) * w(l) * isz)
+            if l + 1 < L and self.dls[l] > 0:
+                tot += al(int(nc[l + 1]) * 12) + al(int(nc[l + 1]) * w(l) * isz) + al(int(nc[l]) * w(l + 1) * isz)
+        return tot + 256
+
+    def slab_bytes(self):
+        if self.n_cap is not None:
+            return self.static_slab_bytes()
+        per_point = _SLAB_HINT.get((self.L, self.isz, self.cap), 2.6 * (2.2 * self.cap * self.isz + 12))
+        return int(per_point * self.n0) + (1 << 16)
+
+    def run(self, slab, stream_handle):
+        """Returns True when done, False when it has to be repeated with a larger ``cap`` / slab (see slab_bytes)."""
+        from . import _lib
+        p = lambda a: a.ctypes.data if a is not None else None
+        if self.n_cap is not None:
+            rc = _lib.lib().kp_pyramid_build_static_dev(
+                self.pts.data_ptr(), self.n0, p(self.lens), self.nb, self.L, p(self.conv_r), p(self.pool_r),
+                p(self.up_r), p(self.dls), p(self.rot), p(self.limits), 1 if self.order == "reference" else 0,
+                1 if self.isz == 8 else 0, self.cap, p(self.n_cap),
+                self.feats.data_ptr() if self.feats is not None else None,
+                self.feats.shape[1] if self.feats is not None else 0,
+                self.labs.data_ptr() if self.labs is not None else None, self.label_pad, slab.data_ptr(), slab.numel(),
+                p(self.offs), p(self.n_out), p(self.lens_out), p(self.widths), p(self.strides), p(self.need_bytes),
+                p(self.need_cap), stream_handle)
+            if rc == _lib.KP_ERR_CAPACITY:
+                raise StaticCapacityExceeded(_lib.last_error())
+            _lib.check(rc, "pyramid_build_static")
+            return True
+        rc = _lib.lib().kp_pyramid_build_dev(
+            self.pts.data_ptr(), self.n0, p(self.lens), self.nb, self.L, p(self.conv_r), p(self.pool_r), p(self.up_r),
+            p(self.dls), p(self.rot), p(self.limits), 1 if self.order == "reference" else 0, 1 if self.isz == 8 else 0,
+            self.cap, slab.data_ptr(), slab.numel(), p(self.offs), p(self.n_out), p(self.lens_out), p(self.widths),
+            p(self.strides), p(self.need_bytes), p(self.need_cap), stream_handle)
+        if rc == _lib.KP_ERR_CAPACITY:
+            need = int(self.need_bytes[0])
+            if int(self.need_cap[0]) > self.cap:
+                need = max(need, int(slab.numel() * int(self.need_cap[0]) / max(int(self.strides.max()), 1) * 1.1))
+                self.cap = int(self.need_cap[0])
+            _SLAB_HINT[(self.L, self.isz, self.cap)] = 1.05 * max(need, slab.numel()) / self.n0
+            return False
+        _lib.check(rc, "pyramid_build")
+        _SLAB_HINT[(self.L, self.isz, self.cap)] = max(1.15 * int(self.need_bytes[0]) / self.n0,
+                                                       _SLAB_HINT.get((self.L, self.isz, self.cap), 0.0) * 0.98)
+        return True
+
+    def no_crop(self):
+        """True when no row of any matrix lost a neighbour to its width (limits / cap never bit)."""
+        return bool((self.widths <= self.strides).all())
+
+    def views(self, slab, mark_symmetric=None):
+        """Tensor views of a built slab. Static layout: rows = capacities and full-stride widths (shapes never change
+        from batch to batch); ``mark_symmetric`` overrides the per-batch no-crop test for the conv matrices."""
+        L, nb, isz, dev = self.L, self.nb, self.isz, self.dev
+        static = self.n_cap is not None
+
+        def view(off, rows, cols, dtype, esz):
+            return slab[off:off + rows * cols * esz].view(dtype).view(rows, cols)
+
+        rows_of = (lambda l: int(self.n_cap[l])) if static else (lambda l: int(self.n_out[l]))
+        P, Nn, Po, Up, Le = [], [], [], [], []
+        for l in range(L):
+            n = rows_of(l)
+            P.append(self.pts if (l == 0 and not static) else view(int(self.offs[l]), n, 3, torch.float32, 4))
+            for kind, lst in ((0, Nn), (1, Po), (2, Up)):
+                o, w, sd = int(self.offs[(1 + kind) * L + l]), int(self.widths[kind * L + l]), int(self.strides[kind * L + l])
+                if o < 0:
+                    lst.append(torch.zeros((0, 1), dtype=self.dtype, device=dev))
+                else:
+                    rows = rows_of(l + 1) if kind == 1 else n
+                    m = view(o, rows, sd, self.dtype, isz)
+                    lst.append(m if static else m[:, :min(w, sd)])
+            o = int(self.offs[4 * L + l])
+            Le.append(slab[o:o + 4 * nb].view(torch.int32))
+        # conv matrices of a layer searched against itself without a crop are symmetric (j in row i <=> i in row j, the
+        # f32 distance is exactly symmetric): KPConv's backward can use the matrix itself as its transposed table
+        for l in range(L):
+            sym = (int(self.widths[l]) <= int(self.strides[l])) if mark_symmetric is None else mark_symmetric
+            if Nn[l].shape[0] and sym:
+                Nn[l]._kp_symmetric = True
+        return P, Nn, Po, Up, Le
+
+    def static_extras(self, slab):
+        """(features [n_cap0, fdim], labels [n_cap0]) views of a static slab (None where not supplied)."""
+        n = int(self.n_cap[0])
+        fo, lo = int(self.offs[5 * self.L]), int(self.offs[5 * self.L + 1])
+        f = slab[fo:fo + n * self.feats.shape[1] * 4].view(torch.float32).view(n, self.feats.shape[1]) if fo >= 0 else None
+        lb = slab[lo:lo + n * 8].view(torch.int64) if lo >= 0 else None
+        return f, lb
+
+
 def build_native(points, stack_lengths, config, neighborhood_limits=None, random_grid_orient=True, order="reference",
                  index_dtype=torch.int64, cap=80, stream=None, rot=None):
     """The whole pyramid of one batch through ONE native call (kp_pyramid_build_dev): no Python between the ~150
@@ -209,77 +362,14 @@ def build_native(points, stack_lengths, config, neighborhood_limits=None, random
     ``stream``: the CUDA stream to run on (default: torch's current stream); the call returns after synchronising it.
     ``rot``: grid orientations from :func:`draw_grid_rotations` (default: drawn here)."""
     import ctypes as C
-    from . import _lib
-    if not points.is_cuda:
-        raise RuntimeError("weasal_b200: tensors must be CUDA tensors (there is no CPU fallback)")
-    dev = points.device
-    pts = points.contiguous() if points.dtype == torch.float32 else points.float().contiguous()
-    lens = np.ascontiguousarray(stack_lengths.cpu().numpy() if torch.is_tensor(stack_lengths) else stack_lengths,
-                                dtype=np.int32).reshape(-1)
-    nb, n0 = len(lens), pts.shape[0]
-    conv_r, pool_r, up_r, dls = layer_plan(config)
-    L = len(conv_r)
-    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
-    conv_r, pool_r, up_r, dls = f32(conv_r), f32(pool_r), f32(up_r), f32(dls)
-    if rot is None:  # (a prefetching caller draws them itself, in submission order)
-        rot = draw_grid_rotations(config, nb, random_grid_orient)
-    limits = None
-    if neighborhood_limits is not None and len(neighborhood_limits):
-        limits = np.zeros(L, np.int32)
-        limits[:min(L, len(neighborhood_limits))] = np.asarray(neighborhood_limits, np.int64)[:L]
-    i64 = index_dtype == torch.int64
-    isz = 8 if i64 else 4
-    offs = np.zeros(5 * L, np.int64)
-    n_out, lens_out = np.zeros(L, np.int32), np.zeros(L * nb, np.int32)
-    widths, strides = np.zeros(3 * L, np.int32), np.zeros(3 * L, np.int32)
-    need_bytes, need_cap = C.c_longlong(0), C.c_int(0)
-    st = stream if stream is not None else torch.cuda.current_stream(dev)
-    per_point = _SLAB_HINT.get((L, isz, cap), 2.6 * (2.2 * cap * isz + 12))
-    slab_bytes = int(per_point * n0) + (1 << 16)
-    lib = _lib.lib()
+    nbld = NativeBuild(points, stack_lengths, config, neighborhood_limits, random_grid_orient, order, index_dtype, cap, rot)
+    st = stream if stream is not None else torch.cuda.current_stream(nbld.dev)
     while True:
         with torch.cuda.stream(st):
-            slab = torch.empty(slab_bytes, dtype=torch.uint8, device=dev)
-        rc = lib.kp_pyramid_build_dev(pts.data_ptr(), n0, lens.ctypes.data, nb, L, conv_r.ctypes.data, pool_r.ctypes.data,
-                                      up_r.ctypes.data, dls.ctypes.data, rot.ctypes.data if rot is not None else None,
-                                      limits.ctypes.data if limits is not None else None,
-                                      1 if order == "reference" else 0, 1 if i64 else 0, int(cap), slab.data_ptr(),
-                                      slab_bytes, offs.ctypes.data, n_out.ctypes.data, lens_out.ctypes.data,
-                                      widths.ctypes.data, strides.ctypes.data, C.byref(need_bytes), C.byref(need_cap),
-                                      C.c_void_p(st.cuda_stream))
-        if rc == _lib.KP_ERR_CAPACITY:
-            if need_cap.value > cap:
-                cap = need_cap.value
-                slab_bytes = int(slab_bytes * (cap / max(strides.max(), 1)) * 1.1)
-            if need_bytes.value > slab_bytes:
-                slab_bytes = int(need_bytes.value)
-            continue
-        _lib.check(rc, "pyramid_build")
-        break
-    _SLAB_HINT[(L, isz, cap)] = 1.15 * need_bytes.value / n0
-
-    def view(off, rows, cols, dtype, esz):
-        return slab[off:off + rows * cols * esz].view(dtype).view(rows, cols)
-
-    empty_idx = lambda: torch.zeros((0, 1), dtype=index_dtype, device=dev)
-    P, Nn, Po, Up, Le = [], [], [], [], []
-    for l in range(L):
-        n = int(n_out[l])
-        P.append(pts if l == 0 else view(int(offs[l]), n, 3, torch.float32, 4))
-        for kind, lst in ((0, Nn), (1, Po), (2, Up)):
-            o, w, sd = int(offs[(1 + kind) * L + l]), int(widths[kind * L + l]), int(strides[kind * L + l])
-            if o < 0:
-                lst.append(empty_idx())
-            else:
-                rows = int(n_out[l + 1]) if kind == 1 else n
-                lst.append(view(o, rows, sd, index_dtype, isz)[:, :min(w, sd)])
-        Le.append(slab[int(offs[4 * L + l]):int(offs[4 * L + l]) + 4 * nb].view(torch.int32))
-    # conv matrices of a layer searched against itself without a crop are symmetric (j in row i <=> i in row j, the
-    # f32 distance is exactly symmetric): KPConv's backward can use the matrix itself as its transposed table
-    for l in range(L):
-        if Nn[l].shape[0] and int(widths[l]) <= int(strides[l]):
-            Nn[l]._kp_symmetric = True
-    return P, Nn, Po, Up, Le, slab
+            slab = torch.empty(nbld.slab_bytes(), dtype=torch.uint8, device=nbld.dev)
+        if nbld.run(slab, C.c_void_p(st.cuda_stream)):
+            break
+    return (*nbld.views(slab), slab)
 
 
 def segmentation_inputs(stacked_points, stacked_features, labels, stack_lengths, config, neighborhood_limits=None,
@@ -319,31 +409,66 @@ def segmentation_inputs(stacked_points, stacked_features, labels, stack_lengths,
 class PyramidPrefetcher:
     """Builds the pyramids of upcoming batches on a side stream from a worker thread while the caller trains on the
     current one — the counterpart of the reference's DataLoader workers (train_*.py: ``num_workers=input_threads``),
-    which run ``segmentation_inputs`` ahead of the training loop. The worker spends its time inside ONE native call
-    (kp_pyramid_build_dev, GIL released), so it does not compete with the training thread for the interpreter.
+    which run ``segmentation_inputs`` ahead of the training loop.
 
         pf.submit(points, features, labels, lengths)   # host (pinned) or device tensors / numpy arrays
         batch = pf.get()                               # DeviceBatch, complete on the device
 
+    The worker runs nothing but ONE native call per batch (kp_pyramid_build_dev, GIL released): argument arrays,
+    host->device copies and the output slab are prepared by ``submit`` and the tensor views by ``get``, both on the
+    caller's thread, so the two threads hardly ever compete for the interpreter. Output slabs live in a ring of
+    ``slots`` buffers; a slot is reused only after the consumer's stream has passed the step that read it.
     Grid orientations are drawn from ``np.random`` at submit time, in submission order."""
 
     def __init__(self, config, device="cuda", neighborhood_limits=None, random_grid_orient=True, order="reference",
-                 index_dtype=torch.int64):
+                 index_dtype=torch.int64, slots=3, n_cap=None):
+        """``n_cap``: per-layer row capacities -> batches come in the static layout of kp_pyramid_build_static_dev
+        (features and labels inside the slab; ``batch.static_slab`` set) for :class:`weasal_b200.engine.GraphedTrainStep`;
+        a batch that does not fit falls back to the ordinary layout."""
         import queue
+        import sys
         import threading
         self.dev = torch.device(device)
         if self.dev.index is None:
             self.dev = torch.device("cuda", torch.cuda.current_device())
         self.cfg, self.limits, self.orient, self.order, self.dtype = config, neighborhood_limits, random_grid_orient, order, index_dtype
+        self.n_cap = list(n_cap) if n_cap is not None else None
         self.side = torch.cuda.Stream(self.dev)
+        self.slabs = [None] * slots          # ring of output slabs (uint8 tensors allocated on the side stream)
+        self.free_ev = [None] * slots        # recorded on the consumer's stream when a slot's batch has been consumed
+        self.n_sub, self.last_slot = 0, None
+        self.stats = []  # per batch: (seconds the native call took in the worker, seconds get() waited for it)
         self.q_in, self.q_out = queue.Queue(), queue.Queue()
+        # the worker holds the GIL for microseconds per batch but must get it promptly when its call returns: with the
+        # default 5 ms switch interval every hand-over from the launch-bound training thread would stall that long
+        if sys.getswitchinterval() > 2e-4:
+            sys.setswitchinterval(2e-4)
         self.thread = threading.Thread(target=self._run, name="weasal-pyramid", daemon=True)
         self.thread.start()
 
     def submit(self, points, features, labels, lengths, extras=None):
+        import ctypes as C
         lens = np.ascontiguousarray(lengths.cpu().numpy() if torch.is_tensor(lengths) else lengths, dtype=np.int32).reshape(-1)
         rot = draw_grid_rotations(self.cfg, len(lens), self.orient)
-        self.q_in.put((points, features, labels, lens, rot, extras))
+
+        def to_dev(a, dtype=None):
+            if a is None:
+                return None
+            t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+            t = t.to(self.dev, non_blocking=True)
+            return t.to(dtype) if dtype is not None and t.dtype != dtype else t
+
+        slot = self.n_sub % len(self.slabs)
+        self.n_sub += 1
+        with torch.cuda.stream(self.side):
+            if self.free_ev[slot] is not None:
+                self.side.wait_event(self.free_ev[slot])  # the step that read this slot's previous batch has finished
+            pts, feats, labs = to_dev(points, torch.float32), to_dev(features, torch.float32), to_dev(labels)
+            nbld = NativeBuild(pts, lens, self.cfg, self.limits, self.orient, self.order, self.dtype, rot=rot,
+                               n_cap=self.n_cap, features=feats, labels=labs)
+            if self.slabs[slot] is None or self.slabs[slot].numel() < nbld.slab_bytes():
+                self.slabs[slot] = torch.empty(int(nbld.slab_bytes() * 1.25), dtype=torch.uint8, device=self.dev)
+        self.q_in.put((nbld, slot, (pts, feats, labs), extras, C.c_void_p(self.side.cuda_stream)))
 
     def _run(self):
         torch.cuda.set_device(self.dev)
@@ -352,32 +477,49 @@ class PyramidPrefetcher:
             if item is None:
                 return
             try:
-                points, features, labels, lens, rot, extras = item
-
-                def to_dev(a, dtype=None):
-                    if a is None:
-                        return None
-                    t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
-                    t = t.to(self.dev, non_blocking=True)
-                    return t.to(dtype) if dtype is not None and t.dtype != dtype else t
-
-                with torch.cuda.stream(self.side):
-                    pts, feats, labs = to_dev(points, torch.float32), to_dev(features, torch.float32), to_dev(labels)
-                    P, Nn, Po, Up, Le, slab = build_native(pts, lens, self.cfg, self.limits, self.orient, self.order,
-                                                           self.dtype, stream=self.side, rot=rot)
-                    self.side.synchronize()
-                self.q_out.put((DeviceBatch(P + Nn + Po + Up + Le + [feats, labs], extras), (slab, pts, feats, labs)))
+                nbld, slot, owned, extras, sh = item
+                t0 = time.perf_counter()
+                while True:
+                    try:
+                        if nbld.run(self.slabs[slot], sh):
+                            break
+                    except StaticCapacityExceeded:  # this batch goes out in the ordinary (dynamic) layout
+                        nbld = NativeBuild(nbld.pts, nbld.lens, self.cfg, self.limits, self.orient, self.order,
+                                           self.dtype, rot=nbld.rot)
+                    # rare: grow the slab / neighbour capacity and repeat
+                    if self.slabs[slot].numel() < nbld.slab_bytes():
+                        with torch.cuda.stream(self.side):
+                            self.slabs[slot] = torch.empty(int(nbld.slab_bytes() * 1.25), dtype=torch.uint8, device=self.dev)
+                nbld.build_s = time.perf_counter() - t0
+                self.q_out.put((nbld, slot, owned, extras))
             except BaseException as e:  # surfaced by get()
-                self.q_out.put((e, None))
+                self.q_out.put((e, None, None, None))
 
     def get(self):
-        batch, owned = self.q_out.get()
-        if owned is None:
-            raise batch
+        t0 = time.perf_counter()
+        nbld, slot, owned, extras = self.q_out.get()
+        if slot is None:
+            raise nbld
+        self.stats.append((nbld.build_s, time.perf_counter() - t0))
         cur = torch.cuda.current_stream(self.dev)
+        if self.last_slot is not None:  # everything the caller launched for the previous batch precedes this event
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.free_ev[self.last_slot] = ev
+        self.last_slot = slot
+        slab = self.slabs[slot]
         for t in owned:  # allocated on the side stream, consumed on the caller's: tell the caching allocator
             if t is not None and t.is_cuda:
                 t.record_stream(cur)
+        slab.record_stream(cur)
+        P, Nn, Po, Up, Le = nbld.views(slab)
+        feats, labs = owned[1], owned[2]
+        if nbld.n_cap is not None:
+            feats, labs = nbld.static_extras(slab)
+        batch = DeviceBatch(P + Nn + Po + Up + Le + [feats, labs], extras)
+        batch.build, batch.no_crop = nbld, nbld.no_crop()
+        batch.static_slab = slab[:nbld.static_slab_bytes()] if nbld.n_cap is not None else None
+        batch.n_points = int(nbld.n_out[0])
         return batch
 
     def close(self):
