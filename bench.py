@@ -194,12 +194,13 @@ def run_ours(args):
     # Static shapes + one CUDA graph per step (weasal_b200/engine.py). Capacities come from a calibration pass over
     # the batches, like the reference's sampler calibration (batch_limit / neighborhood_limits): rows padded to a
     # per-layer capacity, neighbourhood limits chosen so that no row is cropped (results equal the unlimited pyramid).
-    use_graph = os.environ.get("WEASAL_BENCH_GRAPH", "1") != "0"
+    use_graph = os.environ.get("WEASAL_BENCH_GRAPH", "1") != "0"  # "eager": static batches, eager launches (ncu lists)
     n_cap = limits = None
     if use_graph:
         n_cap, limits = calibrate_static_caps(view, [b["points"] for b in dev_batches], [b["lengths"] for b in batches])
     prefetch = pyramid.PyramidPrefetcher(view, dev, neighborhood_limits=limits, n_cap=n_cap)
-    trainer = GraphedTrainStep(net, opt, F.cross_entropy, reducer=reducer if world > 1 else None, clip_value=100.0)
+    trainer = GraphedTrainStep(net, opt, F.cross_entropy, reducer=reducer if world > 1 else None, clip_value=100.0,
+                               use_graph=os.environ.get("WEASAL_BENCH_GRAPH", "1") == "1")
     eager = GraphedTrainStep(net, opt, F.cross_entropy, reducer=None, clip_value=100.0)  # profile leg: no collective
     if use_graph:  # capture before the prefetch pipeline runs (nothing else issues CUDA work meanwhile)
         prefetch.submit(dev_batches[0]["points"], dev_batches[0]["features"], dev_batches[0]["labels"], batches[0]["lengths"])
@@ -277,7 +278,12 @@ def run_ours(args):
     timed(W, 0, False)
     launches0 = _lib.launch_count()
     g0 = trainer.n_graphed
+    prof_range = os.environ.get("WEASAL_BENCH_PROFILE_RANGE") == "1"  # ncu --profile-from-start off: the timed steps only
+    if prof_range:
+        torch.cuda.profiler.start()
     ms, pts = timed(0, K, False, clocks if rank == 0 else None)
+    if prof_range:
+        torch.cuda.profiler.stop()
     # library kernels launched in the timed region: the pyramid's (counted live) + those inside the replayed graphs
     gpu_launches = _lib.launch_count() - launches0 + (trainer.n_graphed - g0) * trainer.launches_per_replay
     graphed_steps = trainer.n_graphed - g0

@@ -210,6 +210,21 @@ int kp_kpconv_dx_atomic_dev(const float* q_pts, int nq, const float* s_pts, int 
                             const float* kernel_points, int K, float KP_extent, float* dx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Unary blocks next to KPConv: Linear (+ bias) + LeakyReLU as one tcgen05 kernel each way.
+ * Replaces: models/blocks.py:467-507 `UnaryBlock.forward` = `nn.Linear(in, out, bias=False)` -> `BatchNormBlock`
+ *           (blocks.py:430-465: the identity on 2-D features when use_bn, `x + bias` otherwise) -> `LeakyReLU(0.1)`,
+ *           and its autograd backward.
+ *   x [n,cin] f32, weight [cout,cin] f32 (nn.Linear layout), bias [cout] or NULL, y [n,cout];
+ *   y = leaky_relu(x weight^T + bias, negative_slope); negative_slope = 1 means no activation.
+ *   backward: g = d_y * (y > 0 ? 1 : negative_slope) with y the forward OUTPUT (NULL when there is no activation);
+ *   d_x [n,cin] = g weight (may be NULL), d_weight [cout,cin] = g^T x (overwritten). The bias gradient (column sums
+ *   of g) is left to the caller. TF32 operands rounded to nearest, fp32 accumulation, like the KPConv contraction. */
+int kp_linear_forward_dev(const float* x, int n, int cin, const float* weight, const float* bias, int cout,
+                          float negative_slope, float* y, void* stream);
+int kp_linear_backward_dev(const float* x, int n, int cin, const float* weight, int cout, const float* y,
+                           float negative_slope, const float* d_y, float* d_x, float* d_weight, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Pooling gathers next to KPConv (the callers' side of the path).
  * Replaces: models/blocks.py:93-112 `max_pool(x, inds)` (shadow row = zeros, so a shadow entry contributes 0 to the
  *           max) and models/blocks.py:77-90 `closest_pool(x, inds)` (first column only), plus their adjoints.

@@ -572,7 +572,7 @@ def test_graphed_static_step_matches_eager_dynamic_step(torch_cuda):
     P = [torch.from_numpy(b["points"]).to(dev) for b in data]
     Fe = [torch.from_numpy(b["features"]).to(dev) for b in data]
     Lb = [torch.from_numpy(b["labels"] % 9).to(dev) for b in data]
-    n_cap, limits = calibrate_static_caps(view, P, [b["lengths"] for b in data])
+    n_cap, limits = calibrate_static_caps(view, P, [b["lengths"] for b in data], random_grid_orient=False)
     np.random.seed(0)
     torch.manual_seed(0)
     net_a = KPFCNNHarness(ncfg, KPConv).to(dev)
@@ -610,7 +610,7 @@ def test_static_pyramid_layout_and_overflow_fallback(torch_cuda):
     b = make_batch("vaihingen_pl", seed=8, batch_num=2, in_radius=9.0)
     dev = torch.device("cuda")
     P, Fe, Lb = (torch.from_numpy(b[k]).to(dev) for k in ("points", "features", "labels"))
-    n_cap, limits = calibrate_static_caps(cfg, [P], [b["lengths"]])
+    n_cap, limits = calibrate_static_caps(cfg, [P], [b["lengths"]], random_grid_orient=False)
     want = pyramid.build_native(P, b["lengths"], cfg, random_grid_orient=False)
     pf = pyramid.PyramidPrefetcher(cfg, dev, neighborhood_limits=limits, n_cap=n_cap, random_grid_orient=False)
     pf.submit(P, Fe, Lb, b["lengths"])
@@ -640,3 +640,36 @@ def test_static_pyramid_layout_and_overflow_fallback(torch_cuda):
     pf.close()
     assert got.static_slab is None and got.points[0].shape[0] == len(P)
     assert torch.equal(got.neighbors[0], want[1][0][:, :got.neighbors[0].shape[1]])
+
+
+# ------------------------------------------------------------------------------------------------------ unary blocks
+@pytest.mark.parametrize("n,cin,cout,bias,slope", [(5000, 32, 16, False, 0.1), (3000, 64, 9, True, 1.0),
+                                                   (2000, 1536, 512, False, 0.1), (300, 512, 1024, False, 1.0),
+                                                   (777, 6, 10, True, 0.1), (40000, 16, 64, False, 1.0),
+                                                   (129, 64, 64, True, 0.1)])
+def test_linear_act_matches_fp32_reference(n, cin, cout, bias, slope, torch_cuda):
+    """Unary block kernel (Linear + bias + LeakyReLU, forward / dX / dW / db) against the plain PyTorch fp32 expression
+    (models/blocks.py:467-507 on 2-D features); TF32 operands, 1e-3 relative like the KPConv contraction."""
+    torch = torch_cuda
+    import torch.nn.functional as F
+    from weasal_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(n + cin)
+    x0 = torch.randn(n, cin, device="cuda", generator=g)
+    w0 = torch.randn(cout, cin, device="cuda", generator=g) / np.sqrt(cin)
+    b0 = torch.randn(cout, device="cuda", generator=g) if bias else None
+    dy = torch.randn(n, cout, device="cuda", generator=g)
+    outs = []
+    for ours in (False, True):
+        x, w = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+        b = b0.clone().requires_grad_(True) if bias else None
+        if ours:
+            y = ops.linear_act(x, w, b, slope)
+        else:
+            y = F.linear(x, w, b)
+            y = F.leaky_relu(y, slope) if slope != 1.0 else y
+        y.backward(dy)
+        outs.append([t.detach().cpu().numpy() for t in (y, x.grad, w.grad)] + ([b.grad.cpu().numpy()] if bias else []))
+    for name, a, r in zip(("y", "dx", "dw", "db"), outs[1], outs[0]):
+        assert a.shape == r.shape
+        assert rel_max(a, r) < KP_TOL and rel_l2(a, r) < KP_TOL, (name, rel_max(a, r), rel_l2(a, r))

@@ -35,6 +35,10 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
 int transpose_table_entry(const void* idx, int idx_is_i64, int nq, int H, int idx_stride, int ns, int* rowptr,
                           int* col_sorted, cudaStream_t stream);
 int profile_read(char* buf, int buflen);
+int linear_forward_device(const float* x, int n, int cin, const float* w, const float* bias, int cout, float slope,
+                          float* y, cudaStream_t stream);
+int linear_backward_device(const float* x, int n, int cin, const float* w, int cout, const float* y, float slope,
+                           const float* dy, float* dx, float* dw, cudaStream_t stream);
 int pyramid_build_device(const float* pts0, int n0, const int* lens0, int nb, int L, const float* conv_r,
                          const float* pool_r, const float* up_r, const float* dl, const float* rot, const int* limits,
                          int order, int idx_is_i64, int cap, void* slab, long long slab_bytes, long long* offs, int* n_out,
@@ -261,6 +265,15 @@ int kp_pyramid_build_static_dev(const float* points0, int n0, const int* lengths
                                 limits, order, idx_is_i64, cap, slab, slab_bytes, offsets, n_out, lengths_out, widths,
                                 strides, need_bytes, need_cap, n_cap, features, fdim, labels, label_pad,
                                 (cudaStream_t)stream);
+}
+
+int kp_linear_forward_dev(const float* x, int n, int cin, const float* weight, const float* bias, int cout,
+                          float negative_slope, float* y, void* stream) {
+    return linear_forward_device(x, n, cin, weight, bias, cout, negative_slope, y, (cudaStream_t)stream);
+}
+int kp_linear_backward_dev(const float* x, int n, int cin, const float* weight, int cout, const float* y,
+                           float negative_slope, const float* d_y, float* d_x, float* d_weight, void* stream) {
+    return linear_backward_device(x, n, cin, weight, cout, y, negative_slope, d_y, d_x, d_weight, (cudaStream_t)stream);
 }
 
 int kp_max_pool_forward_dev(const float* x, int ns, int channels, const void* inds, int idx_is_i64, int nq, int H,

@@ -27,6 +27,8 @@
 #include "common.cuh"
 
 #include <cstdlib>
+#include <map>
+#include <utility>
 #include <vector>
 
 namespace kp {
@@ -458,6 +460,41 @@ __device__ __forceinline__ void assemble_rows(unsigned char* sA, int warp, int l
     }
 }
 
+// Dense variant of the A tile (linear layers next to KPConv: the A operand is a plain row-major matrix): warp `warp`
+// copies its RPW rows of columns [chunk*CK, chunk*CK + CK) from a[n, ld], optionally scaled by the LeakyReLU derivative
+// taken from `mask` (same shape: factor 1 where mask > 0, `slope` elsewhere), rounded to TF32. All RPW loads of a lane are
+// independent and issued together.
+template <class LAY, int RPW>
+__device__ __forceinline__ void dense_rows(unsigned char* sA, int warp, int lane, int chunk, int tile_base, int n,
+                                           const float* __restrict__ a, int ld, const float* __restrict__ mask,
+                                           float slope) {
+    const int col = chunk * CK + 4 * lane;
+    const int p0 = warp * RPW;
+    float4 v[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; r++) {
+        const int i = tile_base + p0 + r;
+        v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n && col < ld) v[r] = __ldg(reinterpret_cast<const float4*>(a + (size_t)i * ld + col));
+    }
+    if (mask) {
+#pragma unroll
+        for (int r = 0; r < RPW; r++) {
+            const int i = tile_base + p0 + r;
+            if (i < n && col < ld) {
+                const float4 y = __ldg(reinterpret_cast<const float4*>(mask + (size_t)i * ld + col));
+                v[r].x *= y.x > 0.f ? 1.f : slope; v[r].y *= y.y > 0.f ? 1.f : slope;
+                v[r].z *= y.z > 0.f ? 1.f : slope; v[r].w *= y.w > 0.f ? 1.f : slope;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; r++) {
+        v[r].x = to_tf32(v[r].x); v[r].y = to_tf32(v[r].y); v[r].z = to_tf32(v[r].z); v[r].w = to_tf32(v[r].w);
+        *reinterpret_cast<float4*>(sA + LAY::off(p0 + r, lane)) = v[r];
+    }
+}
+
 // stage the entry-list headers of one tile: row0 (first table column of the centre) and koff (32 bytes per centre,
 // moved as two 16-byte words)
 template <int FWD_THREADS>
@@ -488,12 +525,18 @@ struct FwdParams {
     const float* images; // packed weights [n_chunks][n_nblk][NB*CK]
     int NB, n_nblk, n_chunks;
     int ksplit;          // CTAs along the reduction (blockIdx.y); > 1 => partial sums are added atomically into out
-    float* out;          // [nq, cout] (pre-zeroed when ksplit > 1)
-    int cout;
+    float* out;          // [nq, cout] with row stride ldo (pre-zeroed when ksplit > 1)
+    int cout, ldo;
     uint32_t tmem_cols;
+    // dense mode (template DENSE): A = x[nq, cin_p] itself, optionally times the LeakyReLU derivative read from mask
+    const float* mask;
+    float slope_in;
+    // epilogue (ksplit == 1 only): out = leaky(acc + bias, slope_out); bias may be null, slope_out = 1 disables
+    const float* bias;
+    float slope_out;
 };
 
-template <int NW>
+template <int NW, bool DENSE>
 __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) kp_fwd_kernel(FwdParams P) {
     constexpr int FWD_THREADS = NW * 32, RPW = TILE_M / NW, NWARPS = NW;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -519,7 +562,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) kp_fwd_kernel(FwdPar
     }
     __syncwarp();
     if (warp == 0) tmem_alloc(s_tmem, P.tmem_cols);
-    stage_headers<FWD_THREADS>(tile_base, P.nq, P.H, P.rowptr, P.koff, s_row0, s_koff);
+    if (!DENSE) stage_headers<FWD_THREADS>(tile_base, P.nq, P.H, P.rowptr, P.koff, s_row0, s_koff);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -537,7 +580,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) kp_fwd_kernel(FwdPar
                 bulk_g2s(sB, P.images + ((size_t)chunk * P.n_nblk + nblk) * (size_t)P.NB * CK, (uint32_t)b_bytes, bar_b);
             }
             if (nblk == 0) {
-                assemble_rows<8, LayoutKMajor, RPW>(sA, warp, lane, chunk, P.cin_p, P.K, s_row0, s_koff, P.entries, P.x);
+                if (DENSE) dense_rows<LayoutKMajor, RPW>(sA, warp, lane, chunk, tile_base, P.nq, P.x, P.cin_p, P.mask, P.slope_in);
+                else assemble_rows<8, LayoutKMajor, RPW>(sA, warp, lane, chunk, P.cin_p, P.K, s_row0, s_koff, P.entries, P.x);
                 fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
             }
             __syncthreads();
@@ -560,12 +604,21 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) kp_fwd_kernel(FwdPar
     // epilogue: warp w reads TMEM lanes 32*(w%4).., column blocks of 16 dealt round-robin over the 4 warps of a quadrant
     const int row = tile_base + 32 * (warp & 3) + lane;
     const int n_cb = (P.n_nblk * P.NB) / 16;
-    const bool vec = (P.cout & 3) == 0;
+    const bool vec = (P.cout & 3) == 0 && (P.ldo & 3) == 0;
+    const bool post = P.ksplit == 1 && (P.bias != nullptr || P.slope_out != 1.f);
     for (int cb = warp >> 2; cb < n_cb; cb += NWARPS / 4) {
         float v[16];
         tmem_ld16(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cb * 16), v);
+        if (post) {
+#pragma unroll
+            for (int t = 0; t < 16; t++) {
+                float a = v[t];
+                if (P.bias && cb * 16 + t < P.cout) a += __ldg(P.bias + cb * 16 + t);
+                v[t] = a > 0.f ? a : a * P.slope_out;
+            }
+        }
         if (row < P.nq) {
-            float* o = P.out + (size_t)row * P.cout + cb * 16;
+            float* o = P.out + (size_t)row * P.ldo + cb * 16;
 #pragma unroll
             for (int t = 0; t < 16; t += 4) {
                 if (vec && cb * 16 + t < P.cout) {
@@ -604,9 +657,12 @@ struct DwParams {
     int n_tiles, n_splits;
     float* dw;           // [K, cin, cout], pre-zeroed
     uint32_t tmem_cols;
+    // dense mode: A = x[nq, cin_p] itself (times the LeakyReLU derivative read from mask), see dense_rows
+    const float* mask;
+    float slope_in;
 };
 
-template <int NW>
+template <int NW, bool DENSE>
 __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) kp_dw_kernel(DwParams P) {
     constexpr int FWD_THREADS = NW * 32, RPW = TILE_M / NW, NWARPS = NW;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -639,7 +695,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) kp_dw_kernel(DwParam
     for (int tile = split; tile < P.n_tiles; tile += P.n_splits, step++) {
         const int tile_base = tile * TILE_M;
         if (step > 0) mbar_wait(bar_mma, (uint32_t)((step - 1) & 1));
-        stage_headers<FWD_THREADS>(tile_base, P.nq, P.H, nullptr, P.koff, s_row0, s_koff);
+        if (!DENSE) stage_headers<FWD_THREADS>(tile_base, P.nq, P.H, nullptr, P.koff, s_row0, s_koff);
         // dOut tile -> B (TF32), warp per point row, lane per group of 4 outputs
         for (int r = 0; r < RPW; r++) {
             const int p = warp * RPW + r;
@@ -663,7 +719,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) kp_dw_kernel(DwParam
             }
         }
         __syncthreads();  // headers ready
-        assemble_rows<8, LayoutMNMajor, RPW>(sA, warp, lane, chunk, P.cin_p, P.K, s_row0, s_koff, P.entries, P.x);
+        if (DENSE) dense_rows<LayoutMNMajor, RPW>(sA, warp, lane, chunk, tile_base, P.nq, P.x, P.cin_p, P.mask, P.slope_in);
+        else assemble_rows<8, LayoutMNMajor, RPW>(sA, warp, lane, chunk, P.cin_p, P.K, s_row0, s_koff, P.entries, P.x);
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
@@ -778,6 +835,19 @@ static int build_lists(Scratch& S, const float* centres, int nc, const float* ot
 
 static int pad4(int c) { return (c + 3) & ~3; }
 
+// opt-in dynamic shared memory: raise a kernel's limit only when a launch needs more than it already has
+template <typename KernelT>
+static cudaError_t set_smem(KernelT kernel, size_t bytes) {
+    static thread_local std::map<std::pair<const void*, int>, size_t> have;  // (kernel, device) -> current limit
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& h = have[{(const void*)kernel, dev}];
+    if (bytes <= h) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) h = bytes;
+    return e;
+}
+
 // out[nc, cout] = sum over entry lists of w * x[j, :] contracted with W (strides sk, sc, sn over (k, c_in, n_out))
 static int run_forward(const char* tag, Scratch& S, int nc, const int* rowptr, int H, const float* x, int n_x_rows, int cin,
                        const Lists& L, const float* W, long long sk, long long sc, long long sn, int cout, int K,
@@ -811,7 +881,8 @@ static int run_forward(const char* tag, Scratch& S, int nc, const int* rowptr, i
     P.rowptr = rowptr; P.H = H;
     P.koff = L.koff; P.entries = L.entries;
     P.images = images; P.NB = NB; P.n_nblk = n_nblk; P.n_chunks = n_chunks;
-    P.out = out; P.cout = cout;
+    P.out = out; P.cout = cout; P.ldo = cout;
+    P.mask = nullptr; P.slope_in = 1.f; P.bias = nullptr; P.slope_out = 1.f;
     // split the reduction across CTAs when the tiles alone cannot fill the 148 SMs (two CTAs each)
     const int n_tiles = ceil_div(nc, TILE_M);
     int ksplit = ceil_div(2 * 148, n_tiles);
@@ -831,13 +902,13 @@ static int run_forward(const char* tag, Scratch& S, int nc, const int* rowptr, i
     P.tmem_cols = cols;
     const size_t smem = (size_t)A_BYTES + (size_t)NB * CK * 4 + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
     if (smem <= (size_t)SMEM_TWO_CTAS) {
-        KP_CUDA(cudaFuncSetAttribute(kp_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KP_CUDA(set_smem(kp_fwd_kernel<8, false>, smem));
         ProfileScope ps(tag, stream);
-        kp_fwd_kernel<8><<<dim3(n_tiles, ksplit), 256, smem, stream>>>(P);
+        kp_fwd_kernel<8, false><<<dim3(n_tiles, ksplit), 256, smem, stream>>>(P);
     } else {
-        KP_CUDA(cudaFuncSetAttribute(kp_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KP_CUDA(set_smem(kp_fwd_kernel<16, false>, smem));
         ProfileScope ps(tag, stream);
-        kp_fwd_kernel<16><<<dim3(n_tiles, ksplit), 512, smem, stream>>>(P);
+        kp_fwd_kernel<16, false><<<dim3(n_tiles, ksplit), 512, smem, stream>>>(P);
     }
     KP_CHECK_LAUNCH();
     return KP_OK;
@@ -967,18 +1038,19 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
         if (splits > P.n_tiles) splits = P.n_tiles;
         P.n_splits = splits;
         P.dw = dw;
+        P.mask = nullptr; P.slope_in = 1.f;
         uint32_t cols = 32;
         while ((int)cols < P.NB) cols <<= 1;
         P.tmem_cols = cols;
         const size_t smem = (size_t)4 * MN_LBO + (size_t)dw_b_bytes(P.NB) + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
         if (smem <= (size_t)SMEM_TWO_CTAS) {
-            KP_CUDA(cudaFuncSetAttribute(kp_dw_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            KP_CUDA(set_smem(kp_dw_kernel<8, false>, smem));
             ProfileScope ps("kp_dw", stream);
-            kp_dw_kernel<8><<<dim3(n_chunks, splits, n_slices), 256, smem, stream>>>(P);
+            kp_dw_kernel<8, false><<<dim3(n_chunks, splits, n_slices), 256, smem, stream>>>(P);
         } else {
-            KP_CUDA(cudaFuncSetAttribute(kp_dw_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            KP_CUDA(set_smem(kp_dw_kernel<16, false>, smem));
             ProfileScope ps("kp_dw", stream);
-            kp_dw_kernel<16><<<dim3(n_chunks, splits, n_slices), 512, smem, stream>>>(P);
+            kp_dw_kernel<16, false><<<dim3(n_chunks, splits, n_slices), 512, smem, stream>>>(P);
         }
         KP_CHECK_LAUNCH();
     }
@@ -1015,6 +1087,166 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
         rc = run_forward("kp_fwd_dx", S, ns, rowptr, 0, dout, nq, cout, L, w, (long long)cin * cout, 1, cout, cin, K, dx, stream);
         if (rc != KP_OK) return rc;
     }
+    return KP_OK;
+}
+
+// ------------------------------------------------------------------------------------------ dense linear layers
+// The unary blocks around every KPConv (models/blocks.py:467-507 UnaryBlock: Linear without bias -> BatchNorm, which
+// is the identity on these 2-D features or a bias when use_bn is off, blocks.py:453-465 -> LeakyReLU(0.1)) run on the same
+// tcgen05 pipeline with a dense A tile: one kernel for y = leaky(x W^T + b), one for dx = (dy * leaky'(y)) W, one for
+// dW = (dy * leaky'(y))^T x. The library GEMMs they replace pick 9-18 CTAs for the weight gradients of the shallow
+// layers (a 40k-row reduction into a 16x32 matrix) and need separate activation / bias kernels.
+__global__ void __launch_bounds__(256) kp_bias_act_kernel(float* __restrict__ y, long long n, int cout, int ld,
+                                                         const float* __restrict__ bias, float slope) {
+    const long long total = n * cout;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / cout;
+        const int c = (int)(t % cout);
+        float a = y[r * ld + c] + (bias ? bias[c] : 0.f);
+        y[r * ld + c] = a > 0.f ? a : a * slope;
+    }
+}
+
+// out[n, cout] (row stride ldo) = leaky( (a ⊙ leaky'(mask))[n, acols] · B + bias ), B(c, o) = W[c*sc + o*sn]
+static int run_dense(const char* tag, Scratch& S, int n, const float* a, int acols, int acols_valid, const float* mask,
+                     float slope_in, const float* W, long long sc, long long sn, int cout, const float* bias,
+                     float slope_out, float* out, int ldo, cudaStream_t stream) {
+    const int n_tiles = ceil_div(n, TILE_M);
+    const int n_chunks = ceil_div(acols, CK);
+    for (int o0 = 0; o0 < cout; o0 += 512) {  // TMEM holds 512 accumulator columns
+        const int co = cout - o0 < 512 ? cout - o0 : 512;
+        const int cout_p = (co + 15) & ~15;
+        const int NB = cout_p < 256 ? cout_p : 256;
+        const int n_nblk = ceil_div(cout_p, NB);
+        float* images = S.alloc<float>((size_t)n_chunks * n_nblk * NB * CK);
+        if (S.status != KP_OK) return S.status;
+        {
+            const long long total = (long long)n_chunks * n_nblk * NB * CK;
+            const int grid = ceil_div(total, 256) < 4096 ? ceil_div(total, 256) : 4096;
+            ProfileScope ps("lin_pack_w", stream);
+            kp_pack_w_kernel<<<grid, 256, 0, stream>>>(W + (long long)o0 * sn, 1, acols_valid, acols, co, 0, sc, sn, NB, n_nblk,
+                                                       n_chunks, images);
+            KP_CHECK_LAUNCH();
+        }
+        FwdParams P;
+        P.nq = n; P.x = a; P.cin_p = acols; P.K = 1;
+        P.rowptr = nullptr; P.H = 0; P.koff = nullptr; P.entries = nullptr;
+        P.images = images; P.NB = NB; P.n_nblk = n_nblk; P.n_chunks = n_chunks;
+        P.out = out + o0; P.cout = co; P.ldo = ldo;
+        P.mask = mask; P.slope_in = slope_in;
+        P.bias = bias ? bias + o0 : nullptr; P.slope_out = slope_out;
+        int ksplit = ceil_div(2 * 148, n_tiles);
+        if (ksplit > n_chunks) ksplit = n_chunks;
+        if (ksplit > 16) ksplit = 16;
+        if (ksplit < 1) ksplit = 1;
+        ksplit = ceil_div(n_chunks, ceil_div(n_chunks, ksplit));
+        static const bool deterministic = getenv("WEASAL_KPCONV_DETERMINISTIC") && atoi(getenv("WEASAL_KPCONV_DETERMINISTIC")) != 0;
+        if (deterministic) ksplit = 1;
+        P.ksplit = ksplit;
+        if (ksplit > 1) KP_CUDA(cudaMemset2DAsync(out + o0, (size_t)ldo * 4, 0, (size_t)co * 4, n, stream));
+        uint32_t cols = 32;
+        while ((int)cols < n_nblk * NB) cols <<= 1;
+        P.tmem_cols = cols;
+        const size_t smem = (size_t)A_BYTES + (size_t)NB * CK * 4 + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
+        if (smem <= (size_t)SMEM_TWO_CTAS) {
+            KP_CUDA(set_smem(kp_fwd_kernel<8, true>, smem));
+            ProfileScope ps(tag, stream);
+            kp_fwd_kernel<8, true><<<dim3(n_tiles, ksplit), 256, smem, stream>>>(P);
+        } else {
+            KP_CUDA(set_smem(kp_fwd_kernel<16, true>, smem));
+            ProfileScope ps(tag, stream);
+            kp_fwd_kernel<16, true><<<dim3(n_tiles, ksplit), 512, smem, stream>>>(P);
+        }
+        KP_CHECK_LAUNCH();
+        if (ksplit > 1 && (bias || slope_out != 1.f)) {  // the split partial sums met through atomics: finish separately
+            const long long total = (long long)n * co;
+            const int grid = ceil_div(total, 256) < 2368 ? ceil_div(total, 256) : 2368;
+            kp_bias_act_kernel<<<grid, 256, 0, stream>>>(out + o0, n, co, ldo, P.bias, slope_out);
+            KP_CHECK_LAUNCH();
+        }
+    }
+    return KP_OK;
+}
+
+// rows padded to a multiple of 4 columns when needed (float4 loads of the dense A tile)
+static int padded_cols(Scratch& S, const float* src, int n, int c, const float** dst, int* c_p, cudaStream_t stream) {
+    *c_p = pad4(c);
+    *dst = src;
+    if (*c_p == c) return KP_OK;
+    float* p = S.alloc<float>((size_t)n * *c_p);
+    if (S.status != KP_OK) return S.status;
+    const long long tot = (long long)n * *c_p;
+    kp_pad_cols_kernel<<<ceil_div(tot, 256) < 2048 ? ceil_div(tot, 256) : 2048, 256, 0, stream>>>(src, n, c, *c_p, p);
+    KP_CHECK_LAUNCH();
+    *dst = p;
+    return KP_OK;
+}
+
+static int check_linear(int n, int cin, int cout, float slope) {
+    if (n < 0 || cin <= 0 || cout <= 0) return fail(KP_ERR_ARG, "linear: bad sizes");
+    if (!(slope == slope)) return fail(KP_ERR_ARG, "linear: bad slope");
+    return KP_OK;
+}
+
+// y[n, cout] = leaky(x[n, cin] · w[cout, cin]^T + bias, slope); bias may be null; slope = 1: no activation
+int linear_forward_device(const float* x, int n, int cin, const float* w, const float* bias, int cout, float slope,
+                          float* y, cudaStream_t stream) {
+    int rc = check_linear(n, cin, cout, slope);
+    if (rc != KP_OK || n == 0) return rc;
+    Scratch S(stream);
+    const float* xa;
+    int cin_p;
+    if ((rc = padded_cols(S, x, n, cin, &xa, &cin_p, stream)) != KP_OK) return rc;
+    return run_dense("lin_fwd", S, n, xa, cin_p, cin, nullptr, 1.f, w, 1, cin, cout, bias, slope, y, cout, stream);
+}
+
+// dx[n, cin] = g · w, dw[cout, cin] = g^T · x with g = dy ⊙ leaky'(y) (y = the forward OUTPUT, or null when the layer
+// has no activation); dx may be null. dw is overwritten.
+int linear_backward_device(const float* x, int n, int cin, const float* w, int cout, const float* y, float slope,
+                           const float* dy, float* dx, float* dw, cudaStream_t stream) {
+    int rc = check_linear(n, cin, cout, slope);
+    if (rc != KP_OK) return rc;
+    KP_CUDA(cudaMemsetAsync(dw, 0, (size_t)cin * cout * sizeof(float), stream));
+    if (n == 0) return KP_OK;
+    Scratch S(stream);
+    const float *ga, *ya = y;
+    int cout_p;
+    if ((rc = padded_cols(S, dy, n, cout, &ga, &cout_p, stream)) != KP_OK) return rc;
+    if (y && cout_p != cout && (rc = padded_cols(S, y, n, cout, &ya, &cout_p, stream)) != KP_OK) return rc;
+    if (dx) {
+        rc = run_dense("lin_dx", S, n, ga, cout_p, cout, ya, slope, w, cin, 1, cin, nullptr, 1.f, dx, cin, stream);
+        if (rc != KP_OK) return rc;
+    }
+    // dW[o, c] = sum_i g[i, o] x[i, c]: kp_dw with A = g (M = o), B tile = x rows (N = c)
+    DwParams P;
+    P.nq = n; P.x = ga; P.cin = cout; P.cin_p = cout_p; P.K = 1; P.H = 0;
+    P.koff = nullptr; P.entries = nullptr;
+    P.dout = x; P.cout = cin;
+    const int cin_p16 = (cin + 15) & ~15;
+    P.NB = cin_p16 < 256 ? cin_p16 : 256;
+    const int n_slices = ceil_div(cin_p16, P.NB);
+    const int n_chunks = ceil_div(cout_p, CK);
+    P.n_tiles = ceil_div(n, TILE_M);
+    int splits = (2 * 148) / (n_chunks * n_slices);
+    if (splits < 1) splits = 1;
+    if (splits > P.n_tiles) splits = P.n_tiles;
+    P.n_splits = splits;
+    P.dw = dw;
+    P.mask = ya; P.slope_in = slope;
+    uint32_t cols = 32;
+    while ((int)cols < P.NB) cols <<= 1;
+    P.tmem_cols = cols;
+    const size_t smem = (size_t)4 * MN_LBO + (size_t)dw_b_bytes(P.NB) + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
+    if (smem <= (size_t)SMEM_TWO_CTAS) {
+        KP_CUDA(set_smem(kp_dw_kernel<8, true>, smem));
+        ProfileScope ps("lin_dw", stream);
+        kp_dw_kernel<8, true><<<dim3(n_chunks, splits, n_slices), 256, smem, stream>>>(P);
+    } else {
+        KP_CUDA(set_smem(kp_dw_kernel<16, true>, smem));
+        ProfileScope ps("lin_dw", stream);
+        kp_dw_kernel<16, true><<<dim3(n_chunks, splits, n_slices), 512, smem, stream>>>(P);
+    }
+    KP_CHECK_LAUNCH();
     return KP_OK;
 }
 

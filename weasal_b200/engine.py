@@ -22,14 +22,14 @@ from . import _lib
 from .pyramid import DeviceBatch, NativeBuild
 
 
-def calibrate_static_caps(config, point_sets, length_sets, row_margin=1.03, row_quantum=256, width_margin=2):
+def calibrate_static_caps(config, point_sets, length_sets, row_margin=1.03, row_quantum=256, width_margin=3,
+                          random_grid_orient=True):
     """Capacities that fit every given batch without cropping: per-layer row capacities ``n_cap`` and neighbourhood
     limits ``limits`` (the reference's calibrated ``neighborhood_limits``, here chosen so that no row is cropped:
     results equal the unlimited pyramid). ``point_sets``: CUDA [N,3] tensors, ``length_sets``: their batch lengths."""
-    from .pyramid import build_native
     n_max = conv_w = pool_w = up_w = None
     for pts, lens in zip(point_sets, length_sets):
-        nb = NativeBuild(pts, lens, config, random_grid_orient=True)
+        nb = NativeBuild(pts, lens, config, random_grid_orient=random_grid_orient)
         while True:
             slab = torch.empty(nb.slab_bytes(), dtype=torch.uint8, device=pts.device)
             if nb.run(slab, torch.cuda.current_stream(pts.device).cuda_stream):
@@ -60,7 +60,8 @@ class GraphedTrainStep:
     ``loss_fn(logits, labels)``; ``net(batch)`` consumes a :class:`DeviceBatch`. The returned loss is a device scalar
     (the graph's static output for graphed steps)."""
 
-    def __init__(self, net, optimizer, loss_fn, reducer=None, clip_value=None, warmup=3):
+    def __init__(self, net, optimizer, loss_fn, reducer=None, clip_value=None, warmup=3, use_graph=True):
+        self.use_graph = use_graph  # False: every batch takes the eager step (profiling under ncu)
         self.net, self.opt, self.loss_fn, self.reducer, self.clip, self.warmup = net, optimizer, loss_fn, reducer, clip_value, warmup
         self.graph = None
         self.slab = None          # the graph's input: one static slab, every tensor of the batch is a view of it
@@ -80,7 +81,7 @@ class GraphedTrainStep:
         if self.clip is not None:
             torch.nn.utils.clip_grad_value_(self.net.parameters(), self.clip)
         self.opt.step()
-        return loss
+        return loss.detach()  # (a live loss would keep the autograd graph, and with it every activation, alive)
 
     def _static_batch(self, nbld):
         """Fresh views of the graph's slab (fresh tensor objects: per-tensor caches such as KPConv's transposed tables
@@ -126,7 +127,7 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
 
     def _fits(self, batch):
-        if getattr(batch, "static_slab", None) is None or not batch.no_crop:
+        if not self.use_graph or getattr(batch, "static_slab", None) is None or not batch.no_crop:
             return False
         if self.layout is None:
             return True

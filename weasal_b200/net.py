@@ -42,7 +42,10 @@ class Unary(nn.Module):
         self.relu = relu
 
     def forward(self, x):
-        x = self.mlp(x)
+        if x.is_cuda:  # Linear (+ bias) + LeakyReLU as one tcgen05 kernel (include/weasal_b200.h: kp_linear_*_dev)
+            from . import ops
+            return ops.linear_act(x, self.mlp.weight, self.bias, 0.1 if self.relu else 1.0)
+        x = self.mlp(x)  # CPU: the reference's own formulation (reference arm only)
         if self.bias is not None:
             x = x + self.bias
         return F.leaky_relu(x, 0.1) if self.relu else x

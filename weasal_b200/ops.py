@@ -350,3 +350,48 @@ def max_pool(x, inds):
 
 def closest_pool(x, inds):
     return ClosestPoolFunction.apply(x, inds)
+
+
+# ------------------------------------------------------------------------------------------------------ unary blocks
+class LinearActFunction(torch.autograd.Function):
+    """``leaky_relu(x @ weight.T + bias, slope)`` (models/blocks.py:467-507 UnaryBlock on 2-D features) as one tcgen05
+    kernel; backward = one kernel for dX and one for dW, the LeakyReLU derivative applied while loading dY."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, slope):
+        _need_cuda(x, weight, bias)
+        xx, w = _f32c(x), _f32c(weight)
+        b = _f32c(bias) if bias is not None else None
+        n, cin = xx.shape
+        cout = w.shape[0]
+        y = torch.empty((n, cout), dtype=torch.float32, device=xx.device)
+        _lib.check(_lib.lib().kp_linear_forward_dev(xx.data_ptr(), n, cin, w.data_ptr(), b.data_ptr() if b is not None else None,
+                                                    cout, float(slope), y.data_ptr(), _stream()), "linear_forward")
+        ctx.save_for_backward(xx, w, y)
+        ctx.slope, ctx.has_bias = float(slope), bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        xx, w, y = ctx.saved_tensors
+        n, cin = xx.shape
+        cout = w.shape[0]
+        g = _f32c(d_y)
+        act = ctx.slope != 1.0
+        db = None
+        if ctx.has_bias:  # head layers only: materialise g once, its column sums are the bias gradient
+            if act:
+                g = torch.where(y > 0, g, g * ctx.slope)
+                act = False
+            db = g.sum(0)
+        dx = torch.empty((n, cin), dtype=torch.float32, device=xx.device) if ctx.needs_input_grad[0] else None
+        dw = torch.empty((cout, cin), dtype=torch.float32, device=xx.device)
+        _lib.check(_lib.lib().kp_linear_backward_dev(xx.data_ptr(), n, cin, w.data_ptr(), cout,
+                                                     y.data_ptr() if act else None, ctx.slope if act else 1.0,
+                                                     g.data_ptr(), dx.data_ptr() if dx is not None else None,
+                                                     dw.data_ptr(), _stream()), "linear_backward")
+        return dx, dw, db, None
+
+
+def linear_act(x, weight, bias=None, negative_slope=1.0):
+    return LinearActFunction.apply(x, weight, bias, negative_slope)
