@@ -659,17 +659,20 @@ def test_linear_act_matches_fp32_reference(n, cin, cout, bias, slope, torch_cuda
     w0 = torch.randn(cout, cin, device="cuda", generator=g) / np.sqrt(cin)
     b0 = torch.randn(cout, device="cuda", generator=g) if bias else None
     dy = torch.randn(n, cout, device="cuda", generator=g)
-    outs = []
-    for ours in (False, True):
-        x, w = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
-        b = b0.clone().requires_grad_(True) if bias else None
-        if ours:
-            y = ops.linear_act(x, w, b, slope)
-        else:
-            y = F.linear(x, w, b)
-            y = F.leaky_relu(y, slope) if slope != 1.0 else y
-        y.backward(dy)
-        outs.append([t.detach().cpu().numpy() for t in (y, x.grad, w.grad)] + ([b.grad.cpu().numpy()] if bias else []))
-    for name, a, r in zip(("y", "dx", "dw", "db"), outs[1], outs[0]):
+    x, w = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+    b = b0.clone().requires_grad_(True) if bias else None
+    y = ops.linear_act(x, w, b, slope)
+    y.backward(dy)
+    pre = F.linear(x0, w0, b0)
+    y_ref = F.leaky_relu(pre, slope) if slope != 1.0 else pre
+    # the LeakyReLU derivative is taken where OUR output is positive: a TF32 forward and an fp32 forward disagree on the
+    # sign of the few outputs within rounding of zero, and each such flip would show as a 0.9 * dy difference
+    g = dy * torch.where(y.detach() > 0, 1.0, slope) if slope != 1.0 else dy
+    ref = [y_ref, g @ w0, g.t() @ x0] + ([g.sum(0)] if bias else [])
+    got = [y.detach(), x.grad, w.grad] + ([b.grad] if bias else [])
+    near_zero = (pre.abs() < 2e-3 * pre.abs().max())
+    assert float(((y.detach() > 0) != (pre > 0))[~near_zero].float().sum()) == 0  # signs agree away from zero
+    for name, a, r in zip(("y", "dx", "dw", "db"), got, ref):
+        a, r = a.cpu().numpy(), r.cpu().numpy()
         assert a.shape == r.shape
         assert rel_max(a, r) < KP_TOL and rel_l2(a, r) < KP_TOL, (name, rel_max(a, r), rel_l2(a, r))

@@ -696,26 +696,44 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) kp_dw_kernel(DwParam
         const int tile_base = tile * TILE_M;
         if (step > 0) mbar_wait(bar_mma, (uint32_t)((step - 1) & 1));
         if (!DENSE) stage_headers<FWD_THREADS>(tile_base, P.nq, P.H, nullptr, P.koff, s_row0, s_koff);
-        // dOut tile -> B (TF32), warp per point row, lane per group of 4 outputs
-        for (int r = 0; r < RPW; r++) {
-            const int p = warp * RPW + r;
-            const int i = tile_base + p;
-            for (int n4 = lane; n4 < P.NB / 4; n4 += 32) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int n = n0 + n4 * 4;
-                if (i < P.nq) {
-                    const float* src = P.dout + (size_t)i * P.cout + n;
-                    if ((P.cout & 3) == 0) {
-                        if (n < P.cout) v = __ldg(reinterpret_cast<const float4*>(src));
-                    } else {
-                        if (n < P.cout) v.x = src[0];
-                        if (n + 1 < P.cout) v.y = src[1];
-                        if (n + 2 < P.cout) v.z = src[2];
-                        if (n + 3 < P.cout) v.w = src[3];
+        // dOut tile -> B (TF32): the warp's RPW rows x NB/4 float4 items are dealt round-robin to the lanes, eight loads
+        // in flight per lane (a row-at-a-time loop costs RPW dependent global-memory round trips per tile)
+        {
+            const int nv = P.NB >> 2;
+            const int items = RPW * nv;
+            const bool vec4 = (P.cout & 3) == 0;
+            for (int base = 0; base < items; base += 32 * 8) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int t = base + u * 32 + lane;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (t < items) {
+                        const int r = t / nv, n4 = t - r * nv;
+                        const int i = tile_base + warp * RPW + r;
+                        const int n = n0 + n4 * 4;
+                        if (i < P.nq && n < P.cout) {
+                            const float* src = P.dout + (size_t)i * P.cout + n;
+                            if (vec4) v[u] = __ldg(reinterpret_cast<const float4*>(src));
+                            else {
+                                v[u].x = src[0];
+                                if (n + 1 < P.cout) v[u].y = src[1];
+                                if (n + 2 < P.cout) v[u].z = src[2];
+                                if (n + 3 < P.cout) v[u].w = src[3];
+                            }
+                        }
                     }
                 }
-                v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-                *reinterpret_cast<float4*>(sB + LayoutMNMajor::off(p, n4)) = v;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int t = base + u * 32 + lane;
+                    if (t < items) {
+                        const int r = t / nv, n4 = t - r * nv;
+                        float4 w = v[u];
+                        w.x = to_tf32(w.x); w.y = to_tf32(w.y); w.z = to_tf32(w.z); w.w = to_tf32(w.w);
+                        *reinterpret_cast<float4*>(sB + LayoutMNMajor::off(warp * RPW + r, n4)) = w;
+                    }
+                }
             }
         }
         __syncthreads();  // headers ready

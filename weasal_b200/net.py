@@ -14,6 +14,11 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+import os
+
+UNARY_FUSED_MAX_CHANNELS = int(os.environ.get("WEASAL_UNARY_MAX_C", "64"))
+
+
 def max_pool(x, inds):
     """blocks.py:93-112: shadow row is zeros, so shadow entries contribute 0 to the max."""
     if x.is_cuda:
@@ -42,7 +47,10 @@ class Unary(nn.Module):
         self.relu = relu
 
     def forward(self, x):
-        if x.is_cuda:  # Linear (+ bias) + LeakyReLU as one tcgen05 kernel (include/weasal_b200.h: kp_linear_*_dev)
+        # Narrow layers (the shallow, many-row ones): Linear (+ bias) + LeakyReLU as one tcgen05 kernel each way
+        # (kp_linear_*_dev). Wide layers are plain large GEMMs, where the library GEMM is the faster tool (measured:
+        # tools/bench_linear.py, profiles/).
+        if x.is_cuda and max(self.mlp.in_features, self.mlp.out_features) <= UNARY_FUSED_MAX_CHANNELS:
             from . import ops
             return ops.linear_act(x, self.mlp.weight, self.bias, 0.1 if self.relu else 1.0)
         x = self.mlp(x)  # CPU: the reference's own formulation (reference arm only)
