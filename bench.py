@@ -229,10 +229,10 @@ def run_ours(args):
             if not ahead:
                 submit(it)
             batch = prefetch.get()
-            if ahead and it + 1 < first + n:
-                submit(it + 1)
             t_l0 = time.perf_counter()
             loss = net_step(batch, allreduce)
+            if ahead and it + 1 < first + n:
+                submit(it + 1)  # after this step's launch: the GPU starts on step t while the host prepares batch t+1
             if os.environ.get("WEASAL_DEBUG") and rank == 0:
                 print(f"[bench] {'e2e' if e2e else 'dev'} step {it}: build {prefetch.stats[-1][0] * 1e3:.2f} ms, get() waited "
                       f"{prefetch.stats[-1][1] * 1e3:.2f} ms, net launches {(time.perf_counter() - t_l0) * 1e3:.2f} ms",

@@ -433,7 +433,9 @@ class PyramidPrefetcher:
             self.dev = torch.device("cuda", torch.cuda.current_device())
         self.cfg, self.limits, self.orient, self.order, self.dtype = config, neighborhood_limits, random_grid_orient, order, index_dtype
         self.n_cap = list(n_cap) if n_cap is not None else None
-        self.side = torch.cuda.Stream(self.dev)
+        # high priority: the pyramid's ~150 small kernels slot in between the training stream's big ones instead of
+        # queueing behind them (a build took 4.2 ms instead of 2.0 ms when the training stream ran ahead)
+        self.side = torch.cuda.Stream(self.dev, priority=-1)
         self.slabs = [None] * slots          # ring of output slabs (uint8 tensors allocated on the side stream)
         self.free_ev = [None] * slots        # recorded on the consumer's stream when a slot's batch has been consumed
         self.n_sub, self.last_slot = 0, None
