@@ -494,6 +494,9 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if os.environ.get("WEASAL_BENCH_WATCHDOG"):  # debugging aid: dump every thread's stack and exit after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["WEASAL_BENCH_WATCHDOG"]), exit=True)
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return  # under torchrun only rank 0 runs the CPU reference

@@ -69,19 +69,27 @@ class GraphedTrainStep:
         self.loss = None
         self.launches_per_replay = 0   # library kernels inside one replay (bench.py's gpu_launches)
         self.n_graphed = self.n_eager = 0
+        self.tail_in_graph = True
 
     # ------------------------------------------------------------------------------------------------------ the step
-    def _body(self, batch):
+    def _head(self, batch):
         logits = self.net(batch)
         loss = self.loss_fn(logits, batch.labels)
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
+        return loss.detach()  # (a live loss would keep the autograd graph, and with it every activation, alive)
+
+    def _tail(self):
         if self.reducer is not None:
             self.reducer.step()
         if self.clip is not None:
             torch.nn.utils.clip_grad_value_(self.net.parameters(), self.clip)
         self.opt.step()
-        return loss.detach()  # (a live loss would keep the autograd graph, and with it every activation, alive)
+
+    def _body(self, batch):
+        loss = self._head(batch)
+        self._tail()
+        return loss
 
     def _static_batch(self, nbld):
         """Fresh views of the graph's slab (fresh tensor objects: per-tensor caches such as KPConv's transposed tables
@@ -109,8 +117,11 @@ class GraphedTrainStep:
         self.opt.zero_grad(set_to_none=True)
         g = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
+        # With a gradient all-reduce the graph ends after backward and the collective + clip + optimizer (a handful
+        # of multi-tensor launches) stay eager: the collective keeps its place in the process group's own stream order.
+        self.tail_in_graph = self.reducer is None
         with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
-            self.loss = self._body(self._static_batch(nbld))
+            self.loss = self._body(self._static_batch(nbld)) if self.tail_in_graph else self._head(self._static_batch(nbld))
         self.launches_per_replay = _lib.launch_count() - n0
         self.graph = g
         # the warm-up steps must not count as training: parameters back to their values, momentum buffers that did
@@ -148,5 +159,7 @@ class GraphedTrainStep:
             self._capture(batch)
         self.slab.copy_(batch.static_slab, non_blocking=True)
         self.graph.replay()
+        if not self.tail_in_graph:
+            self._tail()
         self.n_graphed += 1
         return self.loss
