@@ -22,13 +22,13 @@ from . import _lib
 from .pyramid import DeviceBatch, NativeBuild
 
 
-def calibrate_static_caps(config, point_sets, length_sets, row_margin=1.03, row_quantum=256, width_margin=3,
-                          random_grid_orient=True):
+def calibrate_static_caps(config, point_sets, length_sets, row_margin=1.05, row_quantum=256, width_margin=0.12,
+                          random_grid_orient=True, passes=2):
     """Capacities that fit every given batch without cropping: per-layer row capacities ``n_cap`` and neighbourhood
     limits ``limits`` (the reference's calibrated ``neighborhood_limits``, here chosen so that no row is cropped:
     results equal the unlimited pyramid). ``point_sets``: CUDA [N,3] tensors, ``length_sets``: their batch lengths."""
     n_max = conv_w = pool_w = up_w = None
-    for pts, lens in zip(point_sets, length_sets):
+    for pts, lens in list(zip(point_sets, length_sets)) * (passes if random_grid_orient else 1):
         nb = NativeBuild(pts, lens, config, random_grid_orient=random_grid_orient)
         while True:
             slab = torch.empty(nb.slab_bytes(), dtype=torch.uint8, device=pts.device)
@@ -46,7 +46,7 @@ def calibrate_static_caps(config, point_sets, length_sets, row_margin=1.03, row_
     limits = []
     for l in range(L):
         need = max(int(conv_w[l]), int(pool_w[l]), int(up_w[l - 1]) if l > 0 else 0)
-        limits.append(need + width_margin)
+        limits.append(need + max(4, int(np.ceil(need * width_margin))))
     return n_cap, limits
 
 
