@@ -144,9 +144,20 @@ __global__ void __launch_bounds__(256) rs_insert_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) rs_assign_kernel(const int* __restrict__ tcount, int* __restrict__ tstart,
                                                        int tsize, int* __restrict__ cursor) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= tsize) return;
-    const int c = tcount[i];
-    if (c > 0) tstart[i] = atomicAdd(cursor, c);
+    const int c = (i < tsize) ? tcount[i] : 0;
+    // one atomic per warp instead of one per occupied cell (tens of thousands of atomics on a single address serialise)
+    const int lane = threadIdx.x & 31;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(cursor, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (c > 0) tstart[i] = base + incl - c;
 }
 
 __global__ void __launch_bounds__(256) rs_fill_kernel(const float* __restrict__ s, int ns,
