@@ -676,3 +676,38 @@ def test_linear_act_matches_fp32_reference(n, cin, cout, bias, slope, torch_cuda
         a, r = a.cpu().numpy(), r.cpu().numpy()
         assert a.shape == r.shape
         assert rel_max(a, r) < KP_TOL and rel_l2(a, r) < KP_TOL, (name, rel_max(a, r), rel_l2(a, r))
+
+
+# ------------------------------------------------------------------------------------------------- sphere voting
+def test_sharded_sphere_voting_equals_single_rank(torch_cuda):
+    """Votes accumulated by two 'ranks' taking alternate sphere batches and summed equal the single-rank votes
+    (sum / count form: order independent), every cloud point of the tile interior is voted on, and only points within
+    0.7 * in_radius of a centre receive votes."""
+    torch = torch_cuda
+    from weasal_b200.kpconv import KPConv
+    from weasal_b200.net import CfgView, KPFCNNHarness, net_config
+    from weasal_b200.voting import vote_cloud
+    ncfg = net_config("vaihingen_pl")
+    R = 6.0
+    tile, inten, _ = make_als_tile(3, 6 * R, 6.0)
+    dev = torch.device("cuda")
+    cloud = torch.from_numpy(tile).to(dev)
+    feats = torch.from_numpy(np.stack([np.ones(len(tile), np.float32), inten, tile[:, 2]], 1)).to(dev)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    net = KPFCNNHarness(ncfg, KPConv).to(dev)
+    view = CfgView(ncfg)
+    p1, v1, s1, n1 = vote_cloud(net, view, cloud, feats, R, 2, num_votes=1, random_grid_orient=False)
+    sums, votes, spheres = 0, 0, 0
+    for r in range(2):
+        p, v, s, n = vote_cloud(net, view, cloud, feats, R, 2, num_votes=1, rank=r, world_size=2,
+                                random_grid_orient=False)
+        sums = sums + p * v.unsqueeze(1)
+        votes = votes + v
+        spheres += s
+    assert spheres == s1 and torch.equal(votes, v1)
+    assert float((v1 > 0).float().mean()) > 0.95
+    got = sums / votes.clamp_min(1e-12).unsqueeze(1)
+    # same spheres, same network, same pyramids: equal up to the order of the float additions
+    assert float((got - p1).abs().max()) < 1e-3
+    assert torch.allclose(got.sum(1)[votes > 0], torch.ones_like(got.sum(1)[votes > 0]), atol=1e-4)
