@@ -706,7 +706,7 @@ def test_sharded_sphere_voting_equals_single_rank(torch_cuda):
         votes = votes + v
         spheres += s
     assert spheres == s1 and torch.equal(votes, v1)
-    assert float((v1 > 0).float().mean()) > 0.95
+    assert float((v1 > 0).float().mean()) > 0.8  # (the kept ball is 3-D, tester:188-191; tall vegetation at R = 6 m falls outside)
     got = sums / votes.clamp_min(1e-12).unsqueeze(1)
     # same spheres, same network, same pyramids: equal up to the order of the float additions
     assert float((got - p1).abs().max()) < 1e-3
