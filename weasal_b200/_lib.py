@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libweasal_b200.so")
+LIB_PATH = os.environ.get("WEASAL_B200_LIB") or os.path.join(_HERE, "libweasal_b200.so")  # (env: experiment builds)
 _lib = None
 
 c_f32p = C.POINTER(C.c_float)

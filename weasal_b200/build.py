@@ -19,18 +19,23 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
+def build(force=False, verbose=False, defines=(), lib=None):
+    """``defines`` / ``lib``: an experiment build with extra -D flags into another file name (A/B runs on the GPU box
+    select it with WEASAL_B200_LIB); the default build is the product."""
+    lib = lib or LIB
+    if not force and not defines and not needs_build():
+        return lib
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
+    tag = "" if not defines else "." + "_".join(d.replace("=", "") for d in defines)
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(CSRC, src.replace(".cu", tag + ".o"))
+        cmd = ([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+               + ["-c", os.path.join(CSRC, src), "-o", obj])
         subprocess.check_call(cmd)
         objs.append(obj)
-    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
-    return LIB
+    subprocess.check_call([nvcc, "-shared", "-o", lib] + objs + ["-lcudart"])
+    return lib
 
 
 if __name__ == "__main__":

@@ -495,6 +495,86 @@ __device__ __forceinline__ void dense_rows(unsigned char* sA, int warp, int lane
     }
 }
 
+// Second formulation of the same assembly (the default, KP_ASSEMBLE_V=2). Every lane owns 4 reduction columns of the
+// tile, i.e. one kernel point k_l and 4 channels, and the entries it needs from row r are exactly the k_l group of that
+// row's list: entries[15*row0(r) + koff[r][k_l] .. koff[r][k_l+1]). So each lane walks its OWN short entry stream and
+// accumulates in registers: no zero pass over the tile, no read-modify-write of shared memory, no second rounding pass
+// and none of the ballot / ffs / shuffle bookkeeping that distributes a flat entry list over lane groups (that version
+// executes ~2x the instructions). Rows are processed R = 8 at a time so that 8 independent gathers are in flight per
+// lane, and the entry record of step t+1 is requested while the feature rows of step t are in flight. Lanes that share
+// a kernel point read the same record (one broadcast transaction).
+template <int U, class LAY, int RPW>
+__device__ __forceinline__ void assemble_rows_v2(unsigned char* sA, int warp, int lane, int chunk, int cin_p, int K,
+                                                 const int* s_row0, const unsigned short* s_koff,
+                                                 const int2* __restrict__ entries, const float* __restrict__ x) {
+    constexpr int R = 8;
+    static_assert(RPW % R == 0, "rows per warp must be a multiple of the row group");
+    const int my_col = chunk * CK + 4 * lane;
+    const int k_l = my_col / cin_p, c_l = my_col - k_l * cin_p;
+    const bool lane_ok = k_l < K;
+    const float* xc = x + c_l;
+    const int p0 = warp * RPW;
+#pragma unroll 1
+    for (int r0 = 0; r0 < RPW; r0 += R) {
+        const int2* ep[R];
+        int cnt[R];
+        float4 acc[R];
+        int2 nxt[R];
+        int m = 0;
+#pragma unroll
+        for (int u = 0; u < R; u++) {
+            const int row = p0 + r0 + u;
+            int b = 0, e = 0;
+            if (lane_ok) {
+                const unsigned short* ko = s_koff + row * KOFF + k_l;
+                b = ko[0];
+                e = ko[1];
+            }
+            ep[u] = entries + 15LL * s_row0[row] + b;
+            cnt[u] = e - b;
+            m = max(m, cnt[u]);
+            acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            nxt[u] = make_int2(0, 0);
+            if (cnt[u] > 0) nxt[u] = __ldg(ep[u]);
+        }
+        for (int t = 0; t < m; t++) {
+            float4 xv[R];
+            float wv[R];
+#pragma unroll
+            for (int u = 0; u < R; u++) {
+                const int2 rec = nxt[u];
+                xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                wv[u] = 0.f;
+                if (t < cnt[u]) {
+                    xv[u] = __ldg(reinterpret_cast<const float4*>(xc + (size_t)((unsigned)rec.x & J_MASK) * cin_p));
+                    wv[u] = __int_as_float(rec.y);
+                }
+                if (t + 1 < cnt[u]) nxt[u] = __ldg(ep[u] + t + 1);
+            }
+#pragma unroll
+            for (int u = 0; u < R; u++) {
+                acc[u].x = fmaf(wv[u], xv[u].x, acc[u].x); acc[u].y = fmaf(wv[u], xv[u].y, acc[u].y);
+                acc[u].z = fmaf(wv[u], xv[u].z, acc[u].z); acc[u].w = fmaf(wv[u], xv[u].w, acc[u].w);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < R; u++) {
+            float4 v = acc[u];
+            v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+            *reinterpret_cast<float4*>(sA + LAY::off(p0 + r0 + u, lane)) = v;
+        }
+    }
+}
+
+#ifndef KP_ASSEMBLE_V
+#define KP_ASSEMBLE_V 2
+#endif
+#if KP_ASSEMBLE_V == 1
+#define KP_ASSEMBLE assemble_rows
+#else
+#define KP_ASSEMBLE assemble_rows_v2
+#endif
+
 // stage the entry-list headers of one tile: row0 (first table column of the centre) and koff (32 bytes per centre,
 // moved as two 16-byte words)
 template <int FWD_THREADS>
@@ -581,7 +661,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) kp_fwd_kernel(FwdPar
             }
             if (nblk == 0) {
                 if (DENSE) dense_rows<LayoutKMajor, RPW>(sA, warp, lane, chunk, tile_base, P.nq, P.x, P.cin_p, P.mask, P.slope_in);
-                else assemble_rows<8, LayoutKMajor, RPW>(sA, warp, lane, chunk, P.cin_p, P.K, s_row0, s_koff, P.entries, P.x);
+                else KP_ASSEMBLE<8, LayoutKMajor, RPW>(sA, warp, lane, chunk, P.cin_p, P.K, s_row0, s_koff, P.entries, P.x);
                 fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
             }
             __syncthreads();
@@ -738,7 +818,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) kp_dw_kernel(DwParam
         }
         __syncthreads();  // headers ready
         if (DENSE) dense_rows<LayoutMNMajor, RPW>(sA, warp, lane, chunk, tile_base, P.nq, P.x, P.cin_p, P.mask, P.slope_in);
-        else assemble_rows<8, LayoutMNMajor, RPW>(sA, warp, lane, chunk, P.cin_p, P.K, s_row0, s_koff, P.entries, P.x);
+        else KP_ASSEMBLE<8, LayoutMNMajor, RPW>(sA, warp, lane, chunk, P.cin_p, P.K, s_row0, s_koff, P.entries, P.x);
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
