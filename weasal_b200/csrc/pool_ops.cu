@@ -7,9 +7,14 @@
 
 namespace kp {
 
-// lanes stride the channels; the neighbour loop is outermost so each index is read once per row, and a lane keeps the
-// running maxima of its (up to CPL) channels in registers. C > 32*CPL falls back to repeating the sweep per block of
-// 32*CPL channels.
+// A warp owns a query row. The row's indices are read 32 at a time (one per lane) and the real ones compacted with a
+// ballot (about half of a distance-sorted, shadow-padded row is padding); the warp then walks the real neighbours four at
+// a time, each lane keeping the running maxima of its (up to CPL) channels, so that 4 x CPL feature loads are in flight
+// per lane instead of one dependent index load + one feature load per neighbour.
+// Semantics of blocks.py:93-112: out = max over the row of xpad[idx], xpad = x with one zero row, so a shadow entry
+// contributes the value 0 (argmax -1, no gradient); among equal values the earliest real neighbour wins, and a shadow's
+// 0 replaces the running maximum only when it is strictly greater (as if the padding came last, which is where the
+// search puts it); a row without real neighbours gives 0.
 template <typename IdxT, int CPL>
 __global__ void __launch_bounds__(256) max_pool_fwd_kernel(const float* __restrict__ x, int ns, int C,
                                                           const IdxT* __restrict__ idx, int nq, int H, int stride,
@@ -23,15 +28,41 @@ __global__ void __launch_bounds__(256) max_pool_fwd_kernel(const float* __restri
         int bj[CPL];
 #pragma unroll
         for (int u = 0; u < CPL; u++) { best[u] = 0.f; bj[u] = -1; }
-        for (int h = 0; h < H; h++) {
-            const long long j = (long long)row[h];
-            const bool real = j >= 0 && j < ns;
+        bool first = true, shadow_seen = false;
+        for (int hb = 0; hb < H; hb += 32) {
+            const long long jl = (hb + lane < H) ? (long long)row[hb + lane] : -1;
+            const bool real_l = jl >= 0 && jl < ns;
+            unsigned m = __ballot_sync(0xffffffffu, real_l);
+            shadow_seen = shadow_seen || (__ballot_sync(0xffffffffu, !real_l && hb + lane < H) != 0u);
+            while (m) {
+                int jv[4];
+                float v[4][CPL];
 #pragma unroll
-            for (int u = 0; u < CPL; u++) {
-                const int c = cb + u * 32 + lane;
-                const float v = (real && c < C) ? __ldg(x + (size_t)j * C + c) : 0.f;
-                if (h == 0 || v > best[u]) { best[u] = v; bj[u] = real ? (int)j : -1; }
+                for (int q = 0; q < 4; q++) {
+                    const int src = m ? (__ffs(m) - 1) : 0;
+                    jv[q] = m ? (int)__shfl_sync(0xffffffffu, jl, src) : -1;
+                    m &= m - 1u;
+#pragma unroll
+                    for (int u = 0; u < CPL; u++) {
+                        const int c = cb + u * 32 + lane;
+                        v[q][u] = (jv[q] >= 0 && c < C) ? __ldg(x + (size_t)jv[q] * C + c) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (jv[q] >= 0) {
+#pragma unroll
+                        for (int u = 0; u < CPL; u++)
+                            if (first || v[q][u] > best[u]) { best[u] = v[q][u]; bj[u] = jv[q]; }
+                        first = false;
+                    }
+                }
             }
+        }
+        if (shadow_seen) {
+#pragma unroll
+            for (int u = 0; u < CPL; u++)
+                if (first || 0.f > best[u]) { best[u] = 0.f; bj[u] = -1; }
         }
 #pragma unroll
         for (int u = 0; u < CPL; u++) {
