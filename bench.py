@@ -210,6 +210,8 @@ def run_ours(args):
     def net_step(batch, allreduce=True):
         return trainer.step(batch) if allreduce else eager._body(batch)
 
+    stamps = []  # (host time at which a step was launched, its pyramid's build time, time get() waited) of the last run
+
     def run_steps(first, n, e2e, allreduce=True, clocks=None, on_batch=None):
         """n steps over batches first, first+1, ...: the pyramid of step t+1 is built on the prefetcher's side stream
         (one native call, the counterpart of the reference's DataLoader workers) while step t trains. The pipeline
@@ -221,6 +223,7 @@ def run_ours(args):
             prefetch.submit(src[b]["points"], src[b]["features"], src[b]["labels"], batches[b]["lengths"])
 
         pts = 0
+        stamps.clear()
         done = []  # one event per launched step: the host stays at most two steps ahead of the GPU
         ahead = os.environ.get("WEASAL_BENCH_PREFETCH", "1") != "0"  # 0: build each pyramid when its step starts (A/B)
         if n > 0 and ahead:
@@ -233,6 +236,7 @@ def run_ours(args):
             if len(done) >= 2:
                 done.pop(0).synchronize()
             t_l0 = time.perf_counter()
+            stamps.append((t_l0, prefetch.stats[-1][0], prefetch.stats[-1][1]))
             loss = net_step(batch, allreduce)
             ev = torch.cuda.Event()
             ev.record()
@@ -286,6 +290,9 @@ def run_ours(args):
     run_steps(0, N_BATCHES, True)
     torch.cuda.synchronize()
     clocks = ClockSampler(local)
+    for _ in range(3):  # the first NVML reads of a process take 10-35 ms (seen as a one-off stall in the first timed step)
+        clocks.sample()
+    clocks.rows.clear()
     launches0 = _lib.launch_count()
     timed(W, 0, False)
     launches0 = _lib.launch_count()
@@ -296,6 +303,11 @@ def run_ours(args):
     ms, pts = timed(0, K, False, clocks if rank == 0 else None)
     if prof_range:
         torch.cuda.profiler.stop()
+    iv = np.diff([a[0] for a in stamps]) * 1e3 if len(stamps) > 2 else np.zeros(1)
+    pacing = {"launch_interval_ms": {"min": float(iv.min()), "median": float(np.median(iv)), "max": float(iv.max())},
+              "pyramid_build_ms_median": float(np.median([a[1] for a in stamps]) * 1e3) if stamps else None,
+              "get_wait_ms_median": float(np.median([a[2] for a in stamps]) * 1e3) if stamps else None,
+              "launch_intervals_ms": [round(float(v), 2) for v in iv]}
     # library kernels launched in the timed region: the pyramid's (counted live) + those inside the replayed graphs
     gpu_launches = _lib.launch_count() - launches0 + (trainer.n_graphed - g0) * trainer.launches_per_replay
     graphed_steps = trainer.n_graphed - g0
@@ -383,7 +395,7 @@ def run_ours(args):
                        "harness_linear_precision": "tf32"},
             "e2e": {"value": e2e_pts / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / K},
-            "gpu_launches": int(gpu_launches), "gpu_launches_per_step": gpu_launches / max(K, 1),
+            "pacing": pacing, "gpu_launches": int(gpu_launches), "gpu_launches_per_step": gpu_launches / max(K, 1),
             "clocks": clk, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
             "grad_allreduce_bytes": reducer.bytes() if world > 1 else 0,
         }
