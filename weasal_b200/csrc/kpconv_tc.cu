@@ -261,11 +261,15 @@ __global__ void __launch_bounds__(INF_WARPS * 32) kp_influence_kernel(const floa
     const int npairs = K * hn;
     const int my_first = min(lane * hn, npairs);  // first pair of kernel point `lane` (lanes 0..15)
     int myoff = 0, run = 0;
-    int k = hn > 0 ? lane / hn : 0;
-    int h = hn > 0 ? lane % hn : 0;
+    // pair p = (kernel point p / hn, neighbour p % hn). hn <= 128 and p < 1920, so the quotient comes exactly from one
+    // float multiply: (p + 0.5) / hn stays at least 0.5 / 128 away from an integer, far above the rounding error
+    const float inv_hn = hn > 0 ? 1.f / (float)hn : 0.f;
     int base = 0;
     for (; base < npairs; base += 32) {
-        const bool valid = base + lane < npairs;
+        const int p = base + lane;
+        const bool valid = p < npairs;
+        const int k = (int)(((float)p + 0.5f) * inv_hn);
+        const int h = p - k * hn;
         float w = 0.f;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) {
@@ -281,8 +285,6 @@ __global__ void __launch_bounds__(INF_WARPS * 32) kp_influence_kernel(const floa
         }
         if (my_first >= base && my_first < base + 32) myoff = run + __popc(m & ((1u << (my_first - base)) - 1u));
         run += __popc(m);
-        h += 32;
-        while (h >= hn && hn > 0) { h -= hn; k++; }
     }
     if (my_first >= base) myoff = run;  // kernel points that start at or after the end of the sweep
     if (lane < 16) koff_row[lane] = (unsigned short)myoff;
