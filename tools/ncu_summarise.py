@@ -43,6 +43,8 @@ def main():
         acc = {}
         for d in data:
             k = re.sub(r"[<(].*", "", d[name_i]).replace("void ", "").replace("kp::", "")
+            if re.search(r"<\(int\)\d+, \(bool\)1>|<\d+, 1>", d[name_i]):
+                k += "_dense"  # the dense (unary block) instantiation of kp_fwd / kp_dw is reported separately
             b = float(d[ri].replace(",", "")) * UNIT.get(units[ri], 1.0) + float(d[wi].replace(",", "")) * UNIT.get(units[wi], 1.0)
             a = acc.setdefault(k, [0, 0.0])
             a[0] += 1
