@@ -210,6 +210,7 @@ def run_ours(args):
     def net_step(batch, allreduce=True):
         return trainer.step(batch) if allreduce else eager._body(batch)
 
+    loss_pinned = torch.zeros(4, dtype=torch.float32).pin_memory()
     stamps = []  # (host time at which a step was launched, its pyramid's build time, time get() waited) of the last run
 
     def run_steps(first, n, e2e, allreduce=True, clocks=None, on_batch=None):
@@ -234,26 +235,33 @@ def run_ours(args):
                 submit(it)
             batch = prefetch.get()
             if len(done) >= 2:
-                done.pop(0).synchronize()
+                ev0, slot0 = done.pop(0)
+                ev0.synchronize()
+                if e2e:
+                    loss_host = float(loss_pinned[slot0])  # the device -> host read of that step's result
             t_l0 = time.perf_counter()
             stamps.append((t_l0, prefetch.stats[-1][0], prefetch.stats[-1][1]))
             loss = net_step(batch, allreduce)
+            if e2e:  # the step's result travels to pinned host memory behind the step; it is read two steps later, so
+                loss_pinned[it % 4].copy_(loss, non_blocking=True)  # the host never drains the GPU inside the loop
             ev = torch.cuda.Event()
             ev.record()
-            done.append(ev)
+            done.append((ev, it % 4))
             if ahead and it + 1 < first + n:
                 submit(it + 1)  # after this step's launch: the GPU starts on step t while the host prepares batch t+1
             if os.environ.get("WEASAL_DEBUG") and rank == 0:
                 print(f"[bench] {'e2e' if e2e else 'dev'} step {it}: build {prefetch.stats[-1][0] * 1e3:.2f} ms, get() waited "
                       f"{prefetch.stats[-1][1] * 1e3:.2f} ms, net launches {(time.perf_counter() - t_l0) * 1e3:.2f} ms",
                       file=sys.stderr)
-            if e2e:
-                loss_host = loss.item()  # device -> host read of the step's result
             if clocks is not None and (it - first) % max(n // 8, 1) == 0:
                 clocks.sample()  # the step's kernels are still in flight here: a reading under load
             if on_batch is not None:
                 on_batch(batch)
             pts += batches[it % N_BATCHES]["points"].shape[0]
+        for ev0, slot0 in done:  # the last steps' results are read before the call returns (inside the timed region)
+            ev0.synchronize()
+            if e2e:
+                loss_host = float(loss_pinned[slot0])
         return pts
 
     def timed(n_warm, n_steps, e2e, clocks=None):
