@@ -183,7 +183,9 @@ def run_ours(args):
     torch.manual_seed(args.seed)  # identical initial weights on every rank
     net = KPFCNNHarness(ncfg, KPConv).to(dev)
     net.train()
-    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.98, weight_decay=1e-3)
+    # (fused: weight decay + momentum + update of all parameters in one multi-tensor kernel)
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.98, weight_decay=1e-3,
+                          fused=os.environ.get("WEASAL_BENCH_FUSED_SGD", "1") == "1")
     reducer = GradAllReducer(net.parameters())
 
     dev_batches = [{k: torch.from_numpy(v).to(dev) for k, v in b.items() if k != "lengths"} for b in batches]

@@ -238,6 +238,10 @@ int kp_max_pool_backward_dev(const float* d_out, const int* argmax, int nq, int 
                              void* stream);
 int kp_closest_pool_dev(const float* src, int ns, int channels, const void* inds, int idx_is_i64, int nq,
                         int idx_stride, float* dst, int backward, void* stream);
+/* Same with a row stride (in elements, >= channels) on src: a gradient that is a column slice of a wider matrix — the
+ * backward of the decoder's torch.cat (models/architectures.py:339-340) — is read in place, not copied first. */
+int kp_closest_pool_strided_dev(const float* src, int src_row_stride, int ns, int channels, const void* inds,
+                                int idx_is_i64, int nq, int idx_stride, float* dst, int backward, void* stream);
 
 #ifdef __cplusplus
 }

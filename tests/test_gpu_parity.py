@@ -498,6 +498,14 @@ def test_pooling_ops_match_reference_formulation(torch_cuda):
         assert torch.allclose(x1.grad, x2.grad, rtol=0, atol=1e-5)
     y = ops.max_pool(x, idx.to(torch.int32))
     assert torch.equal(y, ref_max(x))
+    # closest_pool backward reads a gradient that is a column slice of a wider matrix (torch.cat backward) in place
+    wide = torch.from_numpy(rng.normal(size=(nq, C_ + 11)).astype(np.float32)).cuda()
+    gs = wide[:, 5:5 + C_]
+    assert not gs.is_contiguous()
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ops.closest_pool(xa, idx).backward(gs)
+    ops.closest_pool(xb, idx).backward(gs.contiguous())
+    assert torch.allclose(xa.grad, xb.grad, rtol=0, atol=1e-5)
 
 
 def test_batch_query_more_than_256_neighbours_escalates(torch_cuda):

@@ -49,7 +49,7 @@ int max_pool_fwd_device(const float* x, int ns, int C, const void* idx, int is_i
                         float* out, int* arg, cudaStream_t stream);
 int max_pool_bwd_device(const float* dout, const int* arg, int nq, int C, float* dx, int ns, cudaStream_t stream);
 int closest_pool_device(const float* src, int ns, int C, const void* idx, int is_i64, int nq, int stride, float* dst,
-                        int backward, cudaStream_t stream);
+                        int backward, int src_ld, cudaStream_t stream);
 }  // namespace kp
 
 using namespace kp;
@@ -286,7 +286,13 @@ int kp_max_pool_backward_dev(const float* d_out, const int* argmax, int nq, int 
 }
 int kp_closest_pool_dev(const float* src, int ns, int channels, const void* inds, int idx_is_i64, int nq,
                         int idx_stride, float* dst, int backward, void* stream) {
-    return closest_pool_device(src, ns, channels, inds, idx_is_i64, nq, idx_stride, dst, backward, (cudaStream_t)stream);
+    return closest_pool_device(src, ns, channels, inds, idx_is_i64, nq, idx_stride, dst, backward, channels,
+                               (cudaStream_t)stream);
+}
+int kp_closest_pool_strided_dev(const float* src, int src_row_stride, int ns, int channels, const void* inds,
+                                int idx_is_i64, int nq, int idx_stride, float* dst, int backward, void* stream) {
+    return closest_pool_device(src, ns, channels, inds, idx_is_i64, nq, idx_stride, dst, backward, src_row_stride,
+                               (cudaStream_t)stream);
 }
 
 }  // extern "C"

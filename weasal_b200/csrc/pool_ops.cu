@@ -86,16 +86,16 @@ __global__ void __launch_bounds__(256) max_pool_bwd_kernel(const float* __restri
 template <typename IdxT>
 __global__ void __launch_bounds__(256) closest_pool_kernel(const float* __restrict__ src, int ns, int C,
                                                           const IdxT* __restrict__ idx, int nq, int stride,
-                                                          float* __restrict__ dst, int backward) {
+                                                          float* __restrict__ dst, int backward, int src_ld) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= nq) return;
     const long long j = (long long)idx[(size_t)i * stride];
     const bool real = j >= 0 && j < ns;
     if (!backward) {
-        for (int c = lane; c < C; c += 32) dst[(size_t)i * C + c] = real ? src[(size_t)j * C + c] : 0.f;
+        for (int c = lane; c < C; c += 32) dst[(size_t)i * C + c] = real ? src[(size_t)j * src_ld + c] : 0.f;
     } else if (real) {
-        for (int c = lane; c < C; c += 32) atomicAdd(&dst[(size_t)j * C + c], src[(size_t)i * C + c]);
+        for (int c = lane; c < C; c += 32) atomicAdd(&dst[(size_t)j * C + c], src[(size_t)i * src_ld + c]);
     }
 }
 
@@ -122,12 +122,15 @@ int max_pool_bwd_device(const float* dout, const int* arg, int nq, int C, float*
     return KP_OK;
 }
 
+// src_ld: row stride of src in elements (>= C): a gradient that is a column slice of a wider matrix (the backward of the
+// decoder's torch.cat) is read in place instead of being copied first
 int closest_pool_device(const float* src, int ns, int C, const void* idx, int is_i64, int nq, int stride, float* dst,
-                        int backward, cudaStream_t stream) {
+                        int backward, int src_ld, cudaStream_t stream) {
+    if (src_ld < C) return fail(KP_ERR_ARG, "closest_pool: source row stride smaller than the channel count");
     if (backward) KP_CUDA(cudaMemsetAsync(dst, 0, (size_t)ns * C * sizeof(float), stream));
     if (nq == 0 || C == 0) return KP_OK;
-    if (is_i64) closest_pool_kernel<long long><<<ceil_div(nq, 8), 256, 0, stream>>>(src, ns, C, (const long long*)idx, nq, stride, dst, backward);
-    else closest_pool_kernel<int><<<ceil_div(nq, 8), 256, 0, stream>>>(src, ns, C, (const int*)idx, nq, stride, dst, backward);
+    if (is_i64) closest_pool_kernel<long long><<<ceil_div(nq, 8), 256, 0, stream>>>(src, ns, C, (const long long*)idx, nq, stride, dst, backward, src_ld);
+    else closest_pool_kernel<int><<<ceil_div(nq, 8), 256, 0, stream>>>(src, ns, C, (const int*)idx, nq, stride, dst, backward, src_ld);
     KP_CHECK_LAUNCH();
     return KP_OK;
 }

@@ -336,11 +336,17 @@ class ClosestPoolFunction(torch.autograd.Function):
     def backward(ctx, d_out):
         (idx,) = ctx.saved_tensors
         ns, i64, stride = ctx.meta
-        do = _f32c(d_out)
+        # the gradient of a torch.cat input is a column slice of a wider matrix: read it in place (row stride) instead
+        # of copying it (the copy was 21 us per decoder level)
+        if d_out.dtype == torch.float32 and d_out.dim() == 2 and d_out.stride(1) == 1 and d_out.stride(0) >= d_out.shape[1]:
+            do, ld = d_out, d_out.stride(0)
+        else:
+            do = _f32c(d_out)
+            ld = do.shape[1]
         nq, C_ = do.shape
         dx = torch.empty((ns, C_), dtype=torch.float32, device=do.device)
-        _lib.check(_lib.lib().kp_closest_pool_dev(do.data_ptr(), ns, C_, idx.data_ptr(), i64, nq, stride,
-                                                  dx.data_ptr(), 1, _stream()), "closest_pool_backward")
+        _lib.check(_lib.lib().kp_closest_pool_strided_dev(do.data_ptr(), ld, ns, C_, idx.data_ptr(), i64, nq, stride,
+                                                          dx.data_ptr(), 1, _stream()), "closest_pool_backward")
         return dx, None
 
 
