@@ -62,14 +62,14 @@ def kpconv_sweep(S, Ls, nb):
         x = torch.randn(n, C, device=dev, requires_grad=True)
         w = (torch.randn(15, C, C, device=dev) / C ** 0.5).requires_grad_(True)
         kp = torch.randn(15, 3, device=dev) * 0.4
-        ms_f, y = timeit(lambda: ops.kpconv(S, S, nb, x, w, kp, 0.4), warm=1, reps=3)
+        ms_f, y = timeit(lambda: ops.kpconv(S, S, nb, x, w, kp, 0.4), warm=3, reps=5)
         g = torch.randn_like(y)
 
         def fb():
             yy = ops.kpconv(S, S, nb, x, w, kp, 0.4)
             yy.backward(g)
             return yy
-        ms_fb, _ = timeit(fb, warm=1, reps=3)
+        ms_fb, _ = timeit(fb, warm=3, reps=5)  # (the first calls size allocator pools of a few hundred MB)
         H = nb.shape[1]
         bytes_f = 4 * n * H + 24 * n + 4 * n * C * 2 + 4 * 15 * C * C
         flops = 2 * n * 15 * C * C
