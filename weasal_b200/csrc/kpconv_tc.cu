@@ -935,6 +935,35 @@ static int build_lists(Scratch& S, const float* centres, int nc, const float* ot
 
 static int pad4(int c) { return (c + 3) & ~3; }
 
+// How many CTAs share the reduction axis of one 128-point tile. A CTA costs (its chunks + ~1 chunk of fixed work:
+// TMEM allocation, headers, epilogue), CTAs run in waves of `slots` (2 per SM for the 8-warp kernels, 1 for the 16-warp
+// ones), and a split pays a zero-fill plus an atomic epilogue. The previous rule (fill 296 slots, never look at the
+// wave count) ran the 146-tile layer as 438 CTAs = 1.5 waves of 3 chunks where 292 CTAs = 1 wave of 4 chunks is shorter,
+// and split the 252-tile layer in two for nothing. WEASAL_KSPLIT_MODEL=0 restores it (A/B runs).
+static int pick_ksplit(int n_tiles, int n_chunks, int slots) {
+    static const bool model = !(getenv("WEASAL_KSPLIT_MODEL") && atoi(getenv("WEASAL_KSPLIT_MODEL")) == 0);
+    static const bool deterministic = getenv("WEASAL_KPCONV_DETERMINISTIC") && atoi(getenv("WEASAL_KPCONV_DETERMINISTIC")) != 0;
+    if (deterministic) return 1;  // one CTA per tile: bit-reproducible sums, slower on the deep layers
+    if (!model) {
+        int ks = ceil_div(2 * 148, n_tiles);
+        if (ks > n_chunks) ks = n_chunks;
+        if (ks > 16) ks = 16;
+        if (ks < 1) ks = 1;
+        return ceil_div(n_chunks, ceil_div(n_chunks, ks));  // no empty splits
+    }
+    int best = 1;
+    double best_cost = 1e30;
+    for (int ks = 1; ks <= n_chunks && ks <= 16; ks++) {
+        const int cps = ceil_div(n_chunks, ks);
+        if (ceil_div(n_chunks, cps) != ks) continue;  // would leave empty splits
+        const double waves = (double)ceil_div((long long)n_tiles * ks, slots);
+        const double cost = waves * (cps + 1.0) + (ks > 1 ? 0.5 * waves : 0.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = ks; }
+    }
+    return best;
+}
+
+
 // opt-in dynamic shared memory: raise a kernel's limit only when a launch needs more than it already has
 template <typename KernelT>
 static cudaError_t set_smem(KernelT kernel, size_t bytes) {
@@ -985,22 +1014,15 @@ static int run_forward(const char* tag, Scratch& S, int nc, const int* rowptr, i
     P.mask = nullptr; P.slope_in = 1.f; P.bias = nullptr; P.slope_out = 1.f;
     // split the reduction across CTAs when the tiles alone cannot fill the 148 SMs (two CTAs each)
     const int n_tiles = ceil_div(nc, TILE_M);
-    int ksplit = ceil_div(2 * 148, n_tiles);
-    if (ksplit > n_chunks) ksplit = n_chunks;
-    if (ksplit > 16) ksplit = 16;
-    if (ksplit < 1) ksplit = 1;
-    ksplit = ceil_div(n_chunks, ceil_div(n_chunks, ksplit));  // no empty splits
     // Split partial sums meet in `out` through float atomics, so their order (the last bits of the result) varies from
-    // run to run. WEASAL_KPCONV_DETERMINISTIC=1 keeps one CTA per tile: bit-reproducible forward / dX, slower on the
-    // deep layers.
-    static const bool deterministic = getenv("WEASAL_KPCONV_DETERMINISTIC") && atoi(getenv("WEASAL_KPCONV_DETERMINISTIC")) != 0;
-    if (deterministic) ksplit = 1;
+    // run to run; WEASAL_KPCONV_DETERMINISTIC=1 keeps one CTA per tile.
+    const size_t smem = (size_t)A_BYTES + (size_t)NB * CK * 4 + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
+    const int ksplit = pick_ksplit(n_tiles, n_chunks, smem <= (size_t)SMEM_TWO_CTAS ? 2 * 148 : 148);
     P.ksplit = ksplit;
     if (ksplit > 1) KP_CUDA(cudaMemsetAsync(out, 0, (size_t)nc * cout * sizeof(float), stream));
     uint32_t cols = 32;
     while ((int)cols < n_nblk * NB) cols <<= 1;
     P.tmem_cols = cols;
-    const size_t smem = (size_t)A_BYTES + (size_t)NB * CK * 4 + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
     if (smem <= (size_t)SMEM_TWO_CTAS) {
         KP_CUDA(set_smem(kp_fwd_kernel<8, false>, smem));
         ProfileScope ps(tag, stream);
@@ -1133,7 +1155,8 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
         const int n_slices = ceil_div(cout_p, P.NB);
         const int n_chunks = ceil_div((long long)K * cin_p, CK);
         P.n_tiles = ceil_div(nq, TILE_M);
-        int splits = (2 * 148) / (n_chunks * n_slices);
+        const size_t smem = (size_t)4 * MN_LBO + (size_t)dw_b_bytes(P.NB) + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
+        int splits = (smem <= (size_t)SMEM_TWO_CTAS ? 2 * 148 : 148) / (n_chunks * n_slices);  // one wave of CTAs
         if (splits < 1) splits = 1;
         if (splits > P.n_tiles) splits = P.n_tiles;
         P.n_splits = splits;
@@ -1142,7 +1165,6 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
         uint32_t cols = 32;
         while ((int)cols < P.NB) cols <<= 1;
         P.tmem_cols = cols;
-        const size_t smem = (size_t)4 * MN_LBO + (size_t)dw_b_bytes(P.NB) + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
         if (smem <= (size_t)SMEM_TWO_CTAS) {
             KP_CUDA(set_smem(kp_dw_kernel<8, false>, smem));
             ProfileScope ps("kp_dw", stream);
@@ -1235,19 +1257,13 @@ static int run_dense(const char* tag, Scratch& S, int n, const float* a, int aco
         P.out = out + o0; P.cout = co; P.ldo = ldo;
         P.mask = mask; P.slope_in = slope_in;
         P.bias = bias ? bias + o0 : nullptr; P.slope_out = slope_out;
-        int ksplit = ceil_div(2 * 148, n_tiles);
-        if (ksplit > n_chunks) ksplit = n_chunks;
-        if (ksplit > 16) ksplit = 16;
-        if (ksplit < 1) ksplit = 1;
-        ksplit = ceil_div(n_chunks, ceil_div(n_chunks, ksplit));
-        static const bool deterministic = getenv("WEASAL_KPCONV_DETERMINISTIC") && atoi(getenv("WEASAL_KPCONV_DETERMINISTIC")) != 0;
-        if (deterministic) ksplit = 1;
+        const size_t smem = (size_t)A_BYTES + (size_t)NB * CK * 4 + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
+        const int ksplit = pick_ksplit(n_tiles, n_chunks, smem <= (size_t)SMEM_TWO_CTAS ? 2 * 148 : 148);
         P.ksplit = ksplit;
         if (ksplit > 1) KP_CUDA(cudaMemset2DAsync(out + o0, (size_t)ldo * 4, 0, (size_t)co * 4, n, stream));
         uint32_t cols = 32;
         while ((int)cols < n_nblk * NB) cols <<= 1;
         P.tmem_cols = cols;
-        const size_t smem = (size_t)A_BYTES + (size_t)NB * CK * 4 + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
         if (smem <= (size_t)SMEM_TWO_CTAS) {
             KP_CUDA(set_smem(kp_fwd_kernel<8, true>, smem));
             ProfileScope ps(tag, stream);
@@ -1327,7 +1343,8 @@ int linear_backward_device(const float* x, int n, int cin, const float* w, int c
     const int n_slices = ceil_div(cin_p16, P.NB);
     const int n_chunks = ceil_div(cout_p, CK);
     P.n_tiles = ceil_div(n, TILE_M);
-    int splits = (2 * 148) / (n_chunks * n_slices);
+    const size_t smem = (size_t)4 * MN_LBO + (size_t)dw_b_bytes(P.NB) + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
+    int splits = (smem <= (size_t)SMEM_TWO_CTAS ? 2 * 148 : 148) / (n_chunks * n_slices);  // one wave of CTAs
     if (splits < 1) splits = 1;
     if (splits > P.n_tiles) splits = P.n_tiles;
     P.n_splits = splits;
@@ -1336,7 +1353,6 @@ int linear_backward_device(const float* x, int n, int cin, const float* w, int c
     uint32_t cols = 32;
     while ((int)cols < P.NB) cols <<= 1;
     P.tmem_cols = cols;
-    const size_t smem = (size_t)4 * MN_LBO + (size_t)dw_b_bytes(P.NB) + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
     if (smem <= (size_t)SMEM_TWO_CTAS) {
         KP_CUDA(set_smem(kp_dw_kernel<8, true>, smem));
         ProfileScope ps("lin_dw", stream);
