@@ -238,3 +238,22 @@ def test_layer_plan_and_rotation_draw_order_follow_the_reference_walk():
     # no CPU path: the builder refuses host tensors
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         pyramid.NativeBuild(torch.zeros(4, 3), [4], cfg)
+
+
+def test_vote_schedule_covers_the_tile_and_shards_partition_it():
+    """Host logic of the sharded voting inference: the visiting schedule's kept discs (0.7 * in_radius) cover the tile
+    in every pass, and the round-robin shards of the sphere batches are a partition."""
+    from weasal_b200.distributed import shard_indices
+    from weasal_b200.voting import vote_centres
+    R, lo, hi = 10.0, np.array([0.0, -5.0]), np.array([83.0, 47.0])
+    c = vote_centres(lo, hi, R, num_votes=3, seed=2)
+    per_pass = len(c) // 3
+    assert c.dtype == np.float32 and len(c) == 3 * per_pass
+    g = np.stack(np.meshgrid(np.linspace(lo[0], hi[0], 60), np.linspace(lo[1], hi[1], 40), indexing="ij"), -1).reshape(-1, 2)
+    first = c[:per_pass]
+    d = np.sqrt(((g[:, None, :] - first[None, :, :]) ** 2).sum(2)).min(1)
+    assert d.max() <= 0.7 * R  # un-jittered pass: every tile position lies inside some kept disc
+    n_batches = 17
+    shards = [shard_indices(n_batches, r, 4) for r in range(4)]
+    assert sorted(sum(shards, [])) == list(range(n_batches))
+    assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
