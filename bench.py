@@ -13,9 +13,7 @@ Prints ONE JSON line (rank 0).
 import argparse
 import json
 import os
-import subprocess
 import sys
-import threading
 import time
 
 import numpy as np

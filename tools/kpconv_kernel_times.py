@@ -4,7 +4,7 @@ build of the library (e.g. one compiled with -DKP_ASSEMBLE_V=1) for A/B comparis
 
     python tools/kpconv_kernel_times.py
 """
-import ctypes as C, json, os, sys
+import ctypes as C, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.getcwd())
 from weasal_b200 import ops, _lib

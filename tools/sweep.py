@@ -4,7 +4,6 @@ Writes one JSON object per line to stdout."""
 import json
 import os
 import sys
-import time
 
 import numpy as np
 import torch
