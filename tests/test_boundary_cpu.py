@@ -257,3 +257,91 @@ def test_vote_schedule_covers_the_tile_and_shards_partition_it():
     shards = [shard_indices(n_batches, r, 4) for r in range(4)]
     assert sorted(sum(shards, [])) == list(range(n_batches))
     assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
+
+
+def test_static_padding_is_invisible_to_the_reference_operator_chain():
+    """The claim the CUDA-graph engine rests on (weasal_b200/engine.py), checked on the REFERENCE's own formulation
+    (oracle/kpconv_torch.py + the harness network on CPU, float64 so that the algebra shows, not summation order):
+    padding every layer to a fixed row count — points 1e6, index rows filled with the shadow value (= the padded
+    support count), features 0, labels ignore_index — changes neither the loss nor any parameter gradient, and the
+    logits of the real rows are the same. Widening the matrices with shadow COLUMNS is equally invisible to KPConv and
+    closest_pool; max_pool sees one more zero candidate on rows that had no shadow entry at all (blocks.py:104 pads with
+    a zero row) — the dependence on the batch's widest row that the reference has too (its matrix width is Hmax)."""
+    import torch.nn.functional as F
+    from oracle.kpconv_torch import KPConvTorch
+    from oracle.pyramid_ref import segmentation_inputs_cpu
+    from weasal_b200.net import CfgView, KPFCNNHarness, max_pool, net_config
+    from weasal_b200.pyramid import DeviceBatch
+    from weasal_b200.synthetic import make_batch
+    ncfg = dict(net_config("vaihingen_pl"), dropout=0.0, first_features_dim=16)
+    view = CfgView(ncfg)
+    b = make_batch("vaihingen_pl", seed=5, batch_num=2, in_radius=4.0)
+    np.random.seed(0)
+    li = segmentation_inputs_cpu(b["points"], b["features"], b["labels"] % 9, b["lengths"], view,
+                                 random_grid_orient=False, use_ref=oracle.ref_available())
+    L = (len(li) - 2) // 5
+    n = [li[l].shape[0] for l in range(L)]
+    cap = [m + 7 + 3 * l for l, m in enumerate(n)]  # every layer gets some padding
+
+    def pad_rows(a, rows, value):
+        out = np.full((rows,) + a.shape[1:], value, a.dtype)
+        out[:a.shape[0]] = a
+        return out
+
+    def pad_idx(m, rows, ns_real, ns_cap, extra_cols):
+        if m.shape[0] == 0:
+            return m
+        m = np.where(m == ns_real, ns_cap, m)  # the shadow value follows the support tensor's row count
+        out = np.full((rows, m.shape[1] + extra_cols), ns_cap, m.dtype)
+        out[:m.shape[0], :m.shape[1]] = m
+        return out
+
+    def padded(extra_cols):
+        pl = list(li)
+        for l in range(L):
+            pl[l] = pad_rows(li[l], cap[l], np.float32(1e6))
+            pl[L + l] = pad_idx(li[L + l], cap[l], n[l], cap[l], extra_cols)
+            if l + 1 < L:
+                pl[2 * L + l] = pad_idx(li[2 * L + l], cap[l + 1], n[l], cap[l], extra_cols)
+                pl[3 * L + l] = pad_idx(li[3 * L + l], cap[l], n[l + 1], cap[l + 1], extra_cols)
+        pl[5 * L] = pad_rows(li[5 * L], cap[0], np.float32(0))
+        pl[5 * L + 1] = pad_rows(li[5 * L + 1], cap[0], -100)
+        return pl
+
+    def to_t(lst):
+        out = []
+        for a in lst:
+            t = torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a
+            out.append(t.double() if torch.is_tensor(t) and t.is_floating_point() else t)
+        return out
+
+    np.random.seed(1)
+    torch.manual_seed(1)
+    net = KPFCNNHarness(ncfg, KPConvTorch).double()
+    res = []
+    for lst in (li, padded(0)):
+        net.zero_grad(set_to_none=True)
+        batch = DeviceBatch(to_t(lst))
+        logits = net(batch)
+        loss = F.cross_entropy(logits, batch.labels)
+        loss.backward()
+        res.append((float(loss.detach()), logits.detach()[:n[0]].clone(),
+                    [p.grad.clone() for p in net.parameters() if p.grad is not None]))
+    assert abs(res[0][0] - res[1][0]) <= 1e-12 * max(abs(res[0][0]), 1.0)
+    assert float((res[0][1] - res[1][1]).abs().max()) <= 1e-12 * float(res[0][1].abs().max())
+    assert len(res[0][2]) == len(res[1][2]) > 10
+    for ga, gb in zip(res[0][2], res[1][2]):
+        assert float((ga - gb).abs().max()) <= 1e-11 * max(float(ga.abs().max()), 1e-30)
+    # extra shadow columns: KPConv is unchanged; max_pool changes only on rows that had no shadow entry
+    wide = DeviceBatch(to_t(padded(3)))
+    plain = DeviceBatch(to_t(li))
+    x = torch.randn(n[0], 8, dtype=torch.float64) - 0.5
+    xw = torch.cat([x, torch.zeros(cap[0] - n[0], 8, dtype=torch.float64)])
+    conv = net.encoder[2].conv.__class__(15, 3, 8, 8, 0.24, 0.6).double()
+    ya = conv(plain.points[1], plain.points[0], plain.pools[0], x)
+    yb = conv(wide.points[1], wide.points[0], wide.pools[0], xw)
+    assert float((ya - yb[:n[1]]).abs().max()) <= 1e-12
+    ma, mb = max_pool(x, plain.pools[0]), max_pool(xw, wide.pools[0])
+    full_rows = (plain.pools[0] < n[0]).all(1)
+    assert torch.equal(ma[~full_rows], mb[:n[1]][~full_rows])
+    assert torch.equal(torch.clamp(ma[full_rows], min=0.0), mb[:n[1]][full_rows])

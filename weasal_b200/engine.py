@@ -10,7 +10,14 @@ labels are ``ignore_index``), the whole step is captured once and replayed per b
 
 Padded rows change nothing on the real rows: KPConv / max_pool / closest_pool of a row without neighbours is zero and
 no real row refers to a padded one; the reference's BatchNorm is the identity on these 2-D features (blocks.py:453-463),
-so there are no batch statistics to pollute; the loss ignores padded labels.
+so there are no batch statistics to pollute; the loss ignores padded labels. (tests/test_boundary_cpu.py checks this
+on the reference's own operator chain in float64: loss, real-row logits and every parameter gradient are identical.)
+One reference quirk is visible through the fixed WIDTHS: ``max_pool`` pads with a zero row (blocks.py:104), so a shadow
+entry contributes 0 to the maximum; a row that fills the batch's widest matrix has no shadow entry in the reference's
+layout (width = Hmax of that batch) but has one here (width = the limit), i.e. its maximum is clamped at 0 — exactly
+what the reference computes for the same sphere in a batch with a wider Hmax. KPConv and closest_pool are unaffected
+(shadow terms are zeros in a sum / not the first column). Removing the difference needs the true width as a device
+scalar inside max_pool (round 2).
 
 A batch that does not fit the capacities, or whose rows were cropped by a limit (the symmetric-table shortcut of the
 conv matrices then does not hold), takes the ordinary eager step with the same kernels.
