@@ -345,3 +345,22 @@ def test_static_padding_is_invisible_to_the_reference_operator_chain():
     full_rows = (plain.pools[0] < n[0]).all(1)
     assert torch.equal(ma[~full_rows], mb[:n[1]][~full_rows])
     assert torch.equal(torch.clamp(ma[full_rows], min=0.0), mb[:n[1]][full_rows])
+
+
+def test_conv_neighbour_relation_is_symmetric_in_f32():
+    """What the symmetric-table shortcut of KPConv's backward (kp_kpconv_backward_sym_dev) assumes, checked on the CPU
+    oracle and, when available, the compiled reference cores: for queries == supports without a crop, j is in row i
+    exactly when i is in row j, because ((a-b)^2 summed in f32) is exactly symmetric."""
+    from weasal_b200.synthetic import make_batch
+    b = make_batch("vaihingen_pl", seed=9, batch_num=2, in_radius=5.0)
+    P, Lb = b["points"], b["lengths"]
+    fns = [oracle.batch_neighbors] + ([oracle.ref_batch_neighbors] if oracle.ref_available() else [])
+    for fn in fns:
+        for r in (0.6, 1.2):
+            nb = fn(P, P, Lb, Lb, r)
+            n = len(P)
+            rows = np.repeat(np.arange(n), nb.shape[1])
+            real = nb.ravel() < n
+            pairs = set(zip(rows[real].tolist(), nb.ravel()[real].tolist()))
+            assert all((j, i) in pairs for (i, j) in pairs)
+            assert all((i, i) in pairs for i in range(n))  # every point is its own (closest) neighbour
