@@ -119,7 +119,7 @@ int kp_grid_subsample_dev(const float* points, int n, const int* batches, int nb
  *   lengths0 [nb]; conv_radius / pool_radius / up_radius / sample_dl [n_layers] (conv_radius[l] == 0: no conv search at
  *   layer l; pool / upsample / sample_dl entries of the last layer are ignored); rot [n_layers-1][nb][3][3] f32 grid
  *   orientations or NULL; limits [n_layers] neighbourhood limits or NULL (0 = unlimited).
- * Outputs are carved from the caller's DEVICE `slab` (slab_bytes); offsets [5*n_layers + 2] receives byte offsets into it:
+ * Outputs are carved from the caller's DEVICE `slab` (slab_bytes); offsets [5*n_layers + 3] receives byte offsets into it:
  *   [0,L) points of layer l ([n,3] f32; layer 0 = -1, the caller's points0), [L,2L) conv matrices [n_l, stride],
  *   [2L,3L) pool matrices [n_{l+1}, stride], [3L,4L) upsample matrices [n_l, stride], [4L,5L) batch lengths (int32
  *   [nb]); -1 = absent. n_out [L], lengths_out [L*nb], widths [3*L] (true maximum neighbour counts, conv / pool /
@@ -140,7 +140,8 @@ int kp_pyramid_build_dev(const float* points0, int n0, const int* lengths0, int 
  * is the SUPPORT layer's n_cap (so that "index == row count of the support tensor" still marks a shadow, the convention
  * of models/blocks.py:278/357), the optional layer-0 features [n0,fdim] f32 with 0 and labels [n0] int64 with
  * label_pad (DEVICE pointers or NULL; they travel in the slab so the consumer copies one buffer). Layer 0's points
- * live in the slab too (offsets[0] >= 0); offsets has 5*n_layers + 2 entries ([5L] features, [5L+1] labels). The slab
+ * live in the slab too (offsets[0] >= 0); offsets has 5*n_layers + 3 entries ([5L] features, [5L+1] labels, [5L+2] the 3*n_layers true widths as int32,
+ * conv / pool / upsample blocks of L, for kp_max_pool_forward_width_dev). The slab
  * layout depends on (n_cap, limits / cap, nb, fdim) alone. Padded query rows have no neighbours and nothing refers to
  * a padded support row, so every operator of the path computes the same values on the real rows. A layer that outgrows
  * its capacity returns KP_ERR_CAPACITY with *need_cap = -(layer + 1). */
@@ -234,6 +235,11 @@ int kp_linear_backward_dev(const float* x, int n, int cin, const float* weight, 
  */
 int kp_max_pool_forward_dev(const float* x, int ns, int channels, const void* inds, int idx_is_i64, int nq, int H,
                             int idx_stride, float* out, int* argmax, void* stream);
+/* Same with the matrix' TRUE width as a device scalar (d_width, int32): columns at or beyond *d_width are ignored. For
+ * fixed-width (static-shape) matrices: the reference's matrix is only as wide as the batch's widest row
+ * (cpp_neighbors/wrapper.cpp:211), so a full row has no shadow entry and no zero candidate in the maximum. */
+int kp_max_pool_forward_width_dev(const float* x, int ns, int channels, const void* inds, int idx_is_i64, int nq, int H,
+                                  int idx_stride, const int* d_width, float* out, int* argmax, void* stream);
 int kp_max_pool_backward_dev(const float* d_out, const int* argmax, int nq, int channels, float* d_x, int ns,
                              void* stream);
 int kp_closest_pool_dev(const float* src, int ns, int channels, const void* inds, int idx_is_i64, int nq,

@@ -639,6 +639,17 @@ def test_static_pyramid_layout_and_overflow_fallback(torch_cuda):
             m = mine[:rows, :w]
             assert torch.equal(torch.where(ref == ns_ref, torch.full_like(ref, ns_cap), ref), m)
             assert bool((mine[:rows, w:] == ns_cap).all()) and bool((mine[rows:] == ns_cap).all())
+    # max_pool on the fixed-width matrix with its true width == max_pool on the ordinary matrix, bit for bit; without
+    # the width, rows as wide as the matrix get the extra zero candidate of a shadow column
+    from weasal_b200 import ops
+    x0 = torch.randn(len(P), 16, device=dev) - 0.5
+    xpad = torch.cat([x0, torch.zeros(n_cap[0] - len(P), 16, device=dev)])
+    m_dyn = ops.max_pool(x0, want[2][0])
+    assert int(got.pool_widths[0]) == want[2][0].shape[1]
+    assert torch.equal(m_dyn, ops.max_pool(xpad, got.pools[0], got.pool_widths[0])[:m_dyn.shape[0]])
+    full = (want[2][0] < len(P)).all(1)
+    m_wide = ops.max_pool(xpad, got.pools[0])[:m_dyn.shape[0]]
+    assert torch.equal(torch.clamp(m_dyn[full], min=0), m_wide[full]) and torch.equal(m_dyn[~full], m_wide[~full])
     assert torch.equal(got.features[:len(P)], Fe) and bool((got.features[len(P):] == 0).all())
     assert torch.equal(got.labels[:len(P)], Lb) and bool((got.labels[len(P):] == -100).all())
     pf.close()

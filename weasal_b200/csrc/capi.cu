@@ -46,7 +46,7 @@ int pyramid_build_device(const float* pts0, int n0, const int* lens0, int nb, in
                          const int* n_cap, const float* feats, int fdim, const long long* labels, long long label_pad,
                          cudaStream_t stream);
 int max_pool_fwd_device(const float* x, int ns, int C, const void* idx, int is_i64, int nq, int H, int stride,
-                        float* out, int* arg, cudaStream_t stream);
+                        float* out, int* arg, const int* d_width, cudaStream_t stream);
 int max_pool_bwd_device(const float* dout, const int* arg, int nq, int C, float* dx, int ns, cudaStream_t stream);
 int closest_pool_device(const float* src, int ns, int C, const void* idx, int is_i64, int nq, int stride, float* dst,
                         int backward, int src_ld, cudaStream_t stream);
@@ -278,7 +278,13 @@ int kp_linear_backward_dev(const float* x, int n, int cin, const float* weight, 
 
 int kp_max_pool_forward_dev(const float* x, int ns, int channels, const void* inds, int idx_is_i64, int nq, int H,
                             int idx_stride, float* out, int* argmax, void* stream) {
-    return max_pool_fwd_device(x, ns, channels, inds, idx_is_i64, nq, H, idx_stride, out, argmax, (cudaStream_t)stream);
+    return max_pool_fwd_device(x, ns, channels, inds, idx_is_i64, nq, H, idx_stride, out, argmax, nullptr,
+                               (cudaStream_t)stream);
+}
+int kp_max_pool_forward_width_dev(const float* x, int ns, int channels, const void* inds, int idx_is_i64, int nq, int H,
+                                  int idx_stride, const int* d_width, float* out, int* argmax, void* stream) {
+    return max_pool_fwd_device(x, ns, channels, inds, idx_is_i64, nq, H, idx_stride, out, argmax, d_width,
+                               (cudaStream_t)stream);
 }
 int kp_max_pool_backward_dev(const float* d_out, const int* argmax, int nq, int channels, float* d_x, int ns,
                              void* stream) {

@@ -18,10 +18,14 @@ namespace kp {
 template <typename IdxT, int CPL>
 __global__ void __launch_bounds__(256) max_pool_fwd_kernel(const float* __restrict__ x, int ns, int C,
                                                           const IdxT* __restrict__ idx, int nq, int H, int stride,
-                                                          float* __restrict__ out, int* __restrict__ arg) {
+                                                          float* __restrict__ out, int* __restrict__ arg,
+                                                          const int* __restrict__ d_width) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= nq) return;
+    // d_width (optional, device scalar): the matrix' true width; columns beyond it do not exist for this operator (a
+    // fixed-width matrix must not hand a full row the extra zero candidate of a shadow column, see engine.py)
+    if (d_width) H = min(H, max(*d_width, 0));
     const IdxT* row = idx + (size_t)i * stride;
     for (int cb = 0; cb < C; cb += 32 * CPL) {
         float best[CPL];
@@ -100,14 +104,14 @@ __global__ void __launch_bounds__(256) closest_pool_kernel(const float* __restri
 }
 
 int max_pool_fwd_device(const float* x, int ns, int C, const void* idx, int is_i64, int nq, int H, int stride,
-                        float* out, int* arg, cudaStream_t stream) {
+                        float* out, int* arg, const int* d_width, cudaStream_t stream) {
     if (nq == 0 || C == 0) return KP_OK;
     if (C <= 64) {
-        if (is_i64) max_pool_fwd_kernel<long long, 2><<<ceil_div(nq, 8), 256, 0, stream>>>(x, ns, C, (const long long*)idx, nq, H, stride, out, arg);
-        else max_pool_fwd_kernel<int, 2><<<ceil_div(nq, 8), 256, 0, stream>>>(x, ns, C, (const int*)idx, nq, H, stride, out, arg);
+        if (is_i64) max_pool_fwd_kernel<long long, 2><<<ceil_div(nq, 8), 256, 0, stream>>>(x, ns, C, (const long long*)idx, nq, H, stride, out, arg, d_width);
+        else max_pool_fwd_kernel<int, 2><<<ceil_div(nq, 8), 256, 0, stream>>>(x, ns, C, (const int*)idx, nq, H, stride, out, arg, d_width);
     } else {
-        if (is_i64) max_pool_fwd_kernel<long long, 8><<<ceil_div(nq, 8), 256, 0, stream>>>(x, ns, C, (const long long*)idx, nq, H, stride, out, arg);
-        else max_pool_fwd_kernel<int, 8><<<ceil_div(nq, 8), 256, 0, stream>>>(x, ns, C, (const int*)idx, nq, H, stride, out, arg);
+        if (is_i64) max_pool_fwd_kernel<long long, 8><<<ceil_div(nq, 8), 256, 0, stream>>>(x, ns, C, (const long long*)idx, nq, H, stride, out, arg, d_width);
+        else max_pool_fwd_kernel<int, 8><<<ceil_div(nq, 8), 256, 0, stream>>>(x, ns, C, (const int*)idx, nq, H, stride, out, arg, d_width);
     }
     KP_CHECK_LAUNCH();
     return KP_OK;

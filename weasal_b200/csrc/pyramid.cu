@@ -71,9 +71,9 @@ struct PendingSearch {
 // layout of the integer outputs (all HOST arrays):
 //   n_out[L]              points per layer
 //   lens_out[L*nb]        batch lengths per layer
-//   offs[5*L+2]           slab byte offsets: [0,L) points (layer 0: -1, the caller's own tensor), [L,2L) conv matrices,
+//   offs[5*L+3]           slab byte offsets: [0,L) points (layer 0: -1, the caller's own tensor), [L,2L) conv matrices,
 //                         [2L,3L) pool matrices, [3L,4L) upsample matrices, [4L,5L) lengths (int32 [nb]); -1 = absent;
-//                         [5L] features, [5L+1] labels (static mode only)
+//                         [5L] features, [5L+1] labels, [5L+2] true widths int32 [3L] (static mode only)
 //   widths[3*L]           true maximum neighbour count of the conv / pool / upsample search of each layer
 //   strides[3*L]          row stride (columns stored) of those matrices
 // Static mode (n_cap != null): every layer has a FIXED row count n_cap[l] (its points, its matrices and the layer-0
@@ -90,7 +90,7 @@ int pyramid_build_device(const float* pts0, int n0, const int* lens0, int nb, in
                          cudaStream_t stream) {
     if (n0 <= 0 || nb <= 0 || L <= 0 || L > 16 || cap <= 0) return fail(KP_ERR_ARG, "pyramid: bad sizes");
     const int isz = idx_is_i64 ? 8 : 4;
-    for (int i = 0; i < 5 * L + 2; i++) offs[i] = -1;
+    for (int i = 0; i < 5 * L + 3; i++) offs[i] = -1;
     if (n_cap && n0 > n_cap[0]) {
         *need_cap = -1;
         return fail(KP_ERR_CAPACITY, "pyramid: layer 0 has more points than its static capacity");
@@ -156,6 +156,7 @@ int pyramid_build_device(const float* pts0, int n0, const int* lens0, int nb, in
             offs[5 * L + 1] = lo;
             if (lo >= 0 && (rc = pad_copy<long long>(labels, n0, (long long*)(sl.base + lo), n_cap[0], label_pad, stream)) != KP_OK) return rc;
         }
+        offs[5 * L + 2] = sl.take((long long)3 * L * 4);  // the true widths, uploaded once they are known
         if (po >= 0) cur = (const float*)(sl.base + po);
     }
     for (int l = 0; l < L; l++) {
@@ -250,6 +251,10 @@ int pyramid_build_device(const float* pts0, int n0, const int* lens0, int nb, in
     if (want_cap > cap) {
         *need_cap = want_cap;
         return fail(KP_ERR_CAPACITY, "pyramid: neighbour rows wider than cap");
+    }
+    if (n_cap && offs[5 * L + 2] >= 0) {  // fixed-width consumers (max_pool) need the true widths on the device
+        if ((rc = upload_small(widths, (size_t)3 * L * 4, sl.base + offs[5 * L + 2], stream)) != KP_OK) return rc;
+        KP_CUDA(cudaStreamSynchronize(stream));
     }
     *need_bytes = sl.off;
     return KP_OK;

@@ -16,8 +16,9 @@ One reference quirk is visible through the fixed WIDTHS: ``max_pool`` pads with 
 entry contributes 0 to the maximum; a row that fills the batch's widest matrix has no shadow entry in the reference's
 layout (width = Hmax of that batch) but has one here (width = the limit), i.e. its maximum is clamped at 0 — exactly
 what the reference computes for the same sphere in a batch with a wider Hmax. KPConv and closest_pool are unaffected
-(shadow terms are zeros in a sum / not the first column). Removing the difference needs the true width as a device
-scalar inside max_pool (round 2).
+(shadow terms are zeros in a sum / not the first column). The static layout therefore carries every matrix' true width
+as a device scalar (``batch.pool_widths``) and max_pool ignores the columns beyond it (kp_max_pool_forward_width_dev),
+which removes the difference.
 
 A batch that does not fit the capacities, or whose rows were cropped by a limit (the symmetric-table shortcut of the
 conv matrices then does not hold), takes the ordinary eager step with the same kernels.
@@ -103,7 +104,9 @@ class GraphedTrainStep:
         must not survive from one batch's data to the next)."""
         P, Nn, Po, Up, Le = nbld.views(self.slab, mark_symmetric=True)
         f, lb = nbld.static_extras(self.slab)
-        return DeviceBatch(P + Nn + Po + Up + Le + [f, lb])
+        batch = DeviceBatch(P + Nn + Po + Up + Le + [f, lb])
+        batch.pool_widths = nbld.static_pool_widths(self.slab)  # max_pool ignores the columns beyond the true width
+        return batch
 
     def _capture(self, batch):
         nbld, dev = batch.build, batch.static_slab.device

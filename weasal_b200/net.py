@@ -19,11 +19,12 @@ import os
 UNARY_FUSED_MAX_CHANNELS = int(os.environ.get("WEASAL_UNARY_MAX_C", "64"))
 
 
-def max_pool(x, inds):
-    """blocks.py:93-112: shadow row is zeros, so shadow entries contribute 0 to the max."""
+def max_pool(x, inds, width=None):
+    """blocks.py:93-112: shadow row is zeros, so shadow entries contribute 0 to the max. ``width``: the true width of a
+    fixed-width matrix (int32 device scalar, static-shape batches), columns beyond it are ignored."""
     if x.is_cuda:
         from . import ops
-        return ops.max_pool(x, inds)
+        return ops.max_pool(x, inds, width)
     xp = torch.cat((x, torch.zeros_like(x[:1, :])), 0)  # CPU: the reference's own formulation (reference arm only)
     idx = inds.unsqueeze(2).expand(-1, -1, xp.shape[1])
     return xp.unsqueeze(1).expand(-1, inds.shape[1], -1).gather(0, idx).max(dim=1)[0]
@@ -84,7 +85,8 @@ class ConvBlock(nn.Module):
         if self.kind == 'simple':
             return F.leaky_relu(self.conv(q, s, idx, x), 0.1)
         y = self.unary2(F.leaky_relu(self.conv(q, s, idx, self.unary1(x)), 0.1))
-        sc = self.shortcut(max_pool(x, idx) if self.strided else x)
+        widths = getattr(batch, "pool_widths", None)
+        sc = self.shortcut(max_pool(x, idx, widths[l] if widths is not None else None) if self.strided else x)
         return F.leaky_relu(y + sc, 0.1)
 
 

@@ -290,16 +290,24 @@ class MaxPoolFunction(torch.autograd.Function):
     """models/blocks.py:93-112 as one gather-max kernel; backward routes each gradient to the winning support row."""
 
     @staticmethod
-    def forward(ctx, x, inds):
-        _need_cuda(x, inds)
+    def forward(ctx, x, inds, width=None):
+        """``width``: optional int32 CUDA scalar tensor holding the matrix' true width (fixed-width matrices)."""
+        _need_cuda(x, inds, width)
         xx = _f32c(x)
         idx, i64, H, stride = _idx_args(inds)
         ns, C_ = xx.shape
         nq = idx.shape[0]
         out = torch.empty((nq, C_), dtype=torch.float32, device=xx.device)
         arg = torch.empty((nq, C_), dtype=torch.int32, device=xx.device)
-        _lib.check(_lib.lib().kp_max_pool_forward_dev(xx.data_ptr(), ns, C_, idx.data_ptr(), i64, nq, H, stride,
-                                                      out.data_ptr(), arg.data_ptr(), _stream()), "max_pool")
+        if width is not None:
+            if width.dtype != torch.int32:
+                raise RuntimeError("max_pool: width must be an int32 tensor")
+            _lib.check(_lib.lib().kp_max_pool_forward_width_dev(xx.data_ptr(), ns, C_, idx.data_ptr(), i64, nq, H, stride,
+                                                                width.data_ptr(), out.data_ptr(), arg.data_ptr(),
+                                                                _stream()), "max_pool")
+        else:
+            _lib.check(_lib.lib().kp_max_pool_forward_dev(xx.data_ptr(), ns, C_, idx.data_ptr(), i64, nq, H, stride,
+                                                          out.data_ptr(), arg.data_ptr(), _stream()), "max_pool")
         ctx.save_for_backward(arg)
         ctx.ns = ns
         return out
@@ -312,7 +320,7 @@ class MaxPoolFunction(torch.autograd.Function):
         dx = torch.empty((ctx.ns, C_), dtype=torch.float32, device=do.device)
         _lib.check(_lib.lib().kp_max_pool_backward_dev(do.data_ptr(), arg.data_ptr(), nq, C_, dx.data_ptr(), ctx.ns,
                                                        _stream()), "max_pool_backward")
-        return dx, None
+        return dx, None, None
 
 
 class ClosestPoolFunction(torch.autograd.Function):
@@ -350,8 +358,8 @@ class ClosestPoolFunction(torch.autograd.Function):
         return dx, None
 
 
-def max_pool(x, inds):
-    return MaxPoolFunction.apply(x, inds)
+def max_pool(x, inds, width=None):
+    return MaxPoolFunction.apply(x, inds, width)
 
 
 def closest_pool(x, inds):

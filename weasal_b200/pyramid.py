@@ -235,7 +235,7 @@ class NativeBuild:
             self.limits[:min(L, len(neighborhood_limits))] = np.asarray(neighborhood_limits, np.int64)[:L]
         self.order, self.dtype, self.cap = order, index_dtype, int(cap)
         self.isz = 8 if index_dtype == torch.int64 else 4
-        self.offs = np.zeros(5 * L + 2, np.int64)
+        self.offs = np.zeros(5 * L + 3, np.int64)
         self.n_cap = np.ascontiguousarray(n_cap, dtype=np.int32) if n_cap is not None else None
         self.feats = self.labs = None
         self.label_pad = int(label_pad)
@@ -260,6 +260,7 @@ class NativeBuild:
             tot += al(int(nc[0]) * self.feats.shape[1] * 4)
         if self.labs is not None:
             tot += al(int(nc[0]) * 8)
+        tot += al(3 * L * 4)
         for l in range(L):
             tot += al(self.nb * 4)
             if self.conv_r[l] > 0:
@@ -344,6 +345,12 @@ class NativeBuild:
             if Nn[l].shape[0] and sym:
                 Nn[l]._kp_symmetric = True
         return P, Nn, Po, Up, Le
+
+    def static_pool_widths(self, slab):
+        """Per layer, the true width of the pool matrix as an int32 device scalar (view of the slab), for max_pool."""
+        o = int(self.offs[5 * self.L + 2])
+        w = slab[o:o + 12 * self.L].view(torch.int32)
+        return [w[self.L + l:self.L + l + 1] for l in range(self.L)]
 
     def static_extras(self, slab):
         """(features [n_cap0, fdim], labels [n_cap0]) views of a static slab (None where not supplied)."""
@@ -521,6 +528,8 @@ class PyramidPrefetcher:
         batch = DeviceBatch(P + Nn + Po + Up + Le + [feats, labs], extras)
         batch.build, batch.no_crop = nbld, nbld.no_crop()
         batch.static_slab = slab[:nbld.static_slab_bytes()] if nbld.n_cap is not None else None
+        if nbld.n_cap is not None:
+            batch.pool_widths = nbld.static_pool_widths(slab)
         batch.n_points = int(nbld.n_out[0])
         return batch
 
