@@ -364,3 +364,61 @@ def test_conv_neighbour_relation_is_symmetric_in_f32():
             pairs = set(zip(rows[real].tolist(), nb.ravel()[real].tolist()))
             assert all((j, i) in pairs for (i, j) in pairs)
             assert all((i, i) in pairs for i in range(n))  # every point is its own (closest) neighbour
+
+
+def test_dropin_registers_the_reference_module_names():
+    """dropin.install(): the reference's import statements (datasets/common.py:30-31
+    `import cpp_wrappers.cpp_subsampling.grid_subsampling as cpp_subsampling`, `...radius_neighbors as cpp_neighbors`)
+    resolve to the B200 bindings, with the reference's call conventions (keyword-only options)."""
+    import importlib
+    import inspect
+    import sys
+    saved = {k: v for k, v in sys.modules.items() if k.startswith("cpp_wrappers")}
+    try:
+        from weasal_b200 import dropin, grid_subsampling, radius_neighbors
+        assert dropin.install(patch_kpconv=False) is True
+        rn = importlib.import_module("cpp_wrappers.cpp_neighbors.radius_neighbors")
+        gs = importlib.import_module("cpp_wrappers.cpp_subsampling.grid_subsampling")
+        assert rn is radius_neighbors and gs is grid_subsampling
+        sig = inspect.signature(rn.batch_query)
+        assert list(sig.parameters)[:4] == ["queries", "supports", "q_batches", "s_batches"]
+        assert sig.parameters["radius"].kind is inspect.Parameter.KEYWORD_ONLY
+        for fn, opts in ((gs.subsample, ("features", "classes", "sampleDl", "method", "verbose")),
+                         (gs.subsample_batch, ("features", "classes", "sampleDl", "method", "max_p", "verbose"))):
+            ps = inspect.signature(fn).parameters
+            assert all(ps[o].kind is inspect.Parameter.KEYWORD_ONLY for o in opts)
+    finally:
+        for k in [k for k in sys.modules if k.startswith("cpp_wrappers")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_tf32_operands_meet_the_parity_bar_and_bf16_does_not():
+    """The operand-precision decision of the KPConv contraction, reproduced on the CPU from the
+    reference's own golden KPConv case: rounding both operands of sum_k WF_k @ W_k to TF32 (10-bit mantissa, round to
+    nearest) keeps the output within 1e-3 of the fp32 reference; bf16 operands (7-bit mantissa) do not."""
+    g = np.load(os.path.join(GOLDEN, "kpconv_ref.npz"))
+    name = "c64_64"
+    q, s, idx, x, w, kp = (g[f"{name}.{k}"] for k in ("q_pts", "s_pts", "idx", "x", "weights", "kernel_points"))
+    ext = float(g[f"{name}.extent"])
+    ref = g[f"{name}.out"].astype(np.float64)
+    s_pad = np.vstack([s, np.full((1, 3), 1e6, np.float32)]).astype(np.float64)
+    x_pad = np.vstack([x, np.zeros((1, x.shape[1]), np.float32)]).astype(np.float64)
+    nb = s_pad[idx] - q[:, None, :].astype(np.float64)                                   # [Nq,H,3]
+    d = np.sqrt(((nb[:, :, None, :] - kp[None, None].astype(np.float64)) ** 2).sum(3))  # [Nq,H,K]
+    wgt = np.clip(1.0 - d / ext, 0.0, None)
+    wf = np.einsum("nhk,nhc->nkc", wgt, x_pad[idx]).astype(np.float32)                   # the fp32 A operand
+
+    def round_mantissa(a, bits):  # round-to-nearest-even on the fp32 bit pattern, keeping `bits` mantissa bits
+        u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+        drop = 23 - bits
+        u = (u + ((1 << (drop - 1)) - 1) + ((u >> drop) & 1)) >> drop << drop
+        return u.astype(np.uint32).view(np.float32).astype(np.float64)
+
+    errs = {}
+    for tag, bits in (("tf32", 10), ("bf16", 7)):
+        out = np.einsum("nkc,kco->no", round_mantissa(wf, bits), round_mantissa(w, bits))
+        errs[tag] = float(np.abs(out - ref).max() / np.abs(ref).max())
+    exact = np.einsum("nkc,kco->no", wf.astype(np.float64), w.astype(np.float64))
+    assert float(np.abs(exact - ref).max() / np.abs(ref).max()) < 1e-5  # the restatement itself matches the reference
+    assert errs["tf32"] < 5e-4 and errs["bf16"] > 1e-3, errs  # measured: 3.0e-4 and 2.4e-3
