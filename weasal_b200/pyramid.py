@@ -424,7 +424,9 @@ class PyramidPrefetcher:
     The worker runs nothing but ONE native call per batch (kp_pyramid_build_dev, GIL released): argument arrays,
     host->device copies and the output slab are prepared by ``submit`` and the tensor views by ``get``, both on the
     caller's thread, so the two threads hardly ever compete for the interpreter. Output slabs live in a ring of
-    ``slots`` buffers; a slot is reused only after the consumer's stream has passed the step that read it.
+    ``slots`` buffers; a slot is reused only after the consumer's stream has passed the step that read it: ``get()``
+    marks the PREVIOUS batch as consumed (everything launched on the current stream so far), so launch a batch's work
+    before asking for the next one and keep at most ``slots - 1`` batches alive.
     Grid orientations are drawn from ``np.random`` at submit time, in submission order."""
 
     def __init__(self, config, device="cuda", neighborhood_limits=None, random_grid_orient=True, order="reference",
