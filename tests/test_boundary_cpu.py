@@ -422,3 +422,44 @@ def test_tf32_operands_meet_the_parity_bar_and_bf16_does_not():
     exact = np.einsum("nkc,kco->no", wf.astype(np.float64), w.astype(np.float64))
     assert float(np.abs(exact - ref).max() / np.abs(ref).max()) < 1e-5  # the restatement itself matches the reference
     assert errs["tf32"] < 5e-4 and errs["bf16"] > 1e-3, errs  # measured: 3.0e-4 and 2.4e-3
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="needs the reference checkout")
+def test_dropin_patches_the_reference_blocks_module():
+    """dropin.install() against the REAL reference sources (in a subprocess: importing them rebinds `datasets`,
+    `utils`, `models`): models.blocks.KPConv becomes the B200 module, max_pool / closest_pool dispatch on the device
+    and still run the reference's own code on CPU tensors, and the reference's block_decider builds blocks around the
+    replacement class."""
+    import subprocess
+    import sys
+    code = r"""
+import os, sys, types
+ROOT, REF = sys.argv[1], "/root/reference"
+sys.path.insert(0, ROOT)
+for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.cm"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules["torch_scatter"] = types.ModuleType("torch_scatter")
+for n in ("datasets", "utils", "models", "kernels"):
+    m = types.ModuleType(n); m.__path__ = [os.path.join(REF, n)]; sys.modules[n] = m
+sys.path.insert(0, REF); os.chdir(REF)
+import torch
+import models.blocks as B
+ref_max, ref_closest, ref_kpconv = B.max_pool, B.closest_pool, B.KPConv
+from weasal_b200 import dropin, kpconv
+assert dropin.install() is True
+assert B.KPConv is kpconv.KPConv and B.KPConv is not ref_kpconv
+assert B.max_pool is not ref_max and B.closest_pool is not ref_closest
+x = torch.randn(50, 6); idx = torch.randint(0, 51, (20, 5))
+assert torch.equal(B.max_pool(x, idx), ref_max(x, idx)) and torch.equal(B.closest_pool(x, idx), ref_closest(x, idx))
+dropin.install()  # idempotent
+assert torch.equal(B.max_pool(x, idx), ref_max(x, idx))
+class Cfg:
+    num_kernel_points = 15; in_points_dim = 3; KP_extent = 1.2; conv_radius = 2.5; fixed_kernel_points = 'center'
+    KP_influence = 'linear'; aggregation_mode = 'sum'; use_batch_norm = True; batch_norm_momentum = 0.02
+    modulated = False; deformable = False
+blk = B.block_decider('resnetb', 0.6, 32, 64, 0, Cfg())
+assert isinstance(blk.KPConv, kpconv.KPConv) and blk.KPConv.weights.shape == (15, 16, 16)
+print("OK")
+"""
+    out = subprocess.run([sys.executable, "-c", code, ROOT], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stderr[-2000:]
