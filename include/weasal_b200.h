@@ -43,6 +43,10 @@ void kp_free_host(void* p);
  * into buf (returns the length, -1 if buf is too small) and clears the records. */
 void kp_profile_enable(int on);
 int kp_profile_read(char* buf, int buflen);
+/* Host-side planning only (no device work; exported so that the CPU tests can check it): over how many CTAs the KPConv /
+ * unary kernels split the reduction axis of one 128-point tile, given the tiles, the 128-column chunks of that axis and
+ * the CTAs the device holds at once (296 for the 8-warp kernels, 148 for the 16-warp ones). */
+int kp_plan_ksplit(int n_tiles, int n_chunks, int slots);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Batch radius search.

@@ -463,3 +463,24 @@ print("OK")
 """
     out = subprocess.run([sys.executable, "-c", code, ROOT], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stderr[-2000:]
+
+
+def test_reduction_split_plan():
+    """kp_plan_ksplit (host logic of the KPConv / unary launches): splits never leave a CTA without chunks, stay within
+    16, use one CTA per tile when the tiles already fill the device, prefer one full wave to one and a half (the
+    146-tile layer of the benchmark: 2 splits, not 3) and do not split the 252-tile layer at all."""
+    from weasal_b200 import _lib
+    L = _lib.lib()
+    for tiles in (1, 16, 66, 146, 252, 318, 1000, 5000):
+        for chunks in (1, 2, 4, 8, 15, 30, 60):
+            for slots in (148, 296):
+                ks = L.kp_plan_ksplit(tiles, chunks, slots)
+                assert 1 <= ks <= min(chunks, 16)
+                cps = -(-chunks // ks)
+                assert -(-chunks // cps) == ks  # no empty split
+    assert L.kp_plan_ksplit(5000, 8, 296) == 1
+    assert L.kp_plan_ksplit(146, 8, 296) == 2
+    assert L.kp_plan_ksplit(252, 4, 296) == 1
+    assert L.kp_plan_ksplit(66, 15, 148) == 2
+    assert L.kp_plan_ksplit(16, 30, 148) > 4   # few tiles, long reduction: spread it
+    assert L.kp_plan_ksplit(0, 4, 296) < 0     # KP_ERR_ARG

@@ -25,7 +25,7 @@ SYMBOLS = ["kp_last_error", "kp_version", "kp_launch_count", "kp_free_host", "kp
            "kp_kpconv_backward_kept_dev", "kp_transpose_table_dev", "kp_kpconv_wf_dev", "kp_kpconv_dx_atomic_dev", "kp_profile_enable",
            "kp_profile_read", "kp_max_pool_forward_dev", "kp_max_pool_backward_dev", "kp_closest_pool_dev",
            "kp_pyramid_build_dev", "kp_pyramid_build_static_dev", "kp_kpconv_backward_sym_dev",
-           "kp_linear_forward_dev", "kp_linear_backward_dev", "kp_closest_pool_strided_dev", "kp_max_pool_forward_width_dev"]
+           "kp_linear_forward_dev", "kp_linear_backward_dev", "kp_closest_pool_strided_dev", "kp_max_pool_forward_width_dev", "kp_plan_ksplit"]
 
 
 def lib():
@@ -79,6 +79,7 @@ def lib():
                                               C.c_int, vp, vp, C.c_int, vp, C.c_longlong, vp, C.c_longlong, vp, vp, vp,
                                               vp, vp, vp, vp, vp]
     L.kp_closest_pool_strided_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.kp_plan_ksplit.argtypes = [C.c_int, C.c_int, C.c_int]
     L.kp_linear_forward_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_float, vp, vp]
     L.kp_linear_backward_dev.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_float, vp, vp, vp, vp]
     _lib = L

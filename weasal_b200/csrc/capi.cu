@@ -35,6 +35,7 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
 int transpose_table_entry(const void* idx, int idx_is_i64, int nq, int H, int idx_stride, int ns, int* rowptr,
                           int* col_sorted, cudaStream_t stream);
 int profile_read(char* buf, int buflen);
+int plan_ksplit(int n_tiles, int n_chunks, int slots);
 int linear_forward_device(const float* x, int n, int cin, const float* w, const float* bias, int cout, float slope,
                           float* y, cudaStream_t stream);
 int linear_backward_device(const float* x, int n, int cin, const float* w, int cout, const float* y, float slope,
@@ -73,6 +74,10 @@ long long kp_launch_count(void) { return g_launch_count.load(); }
 void kp_free_host(void* p) { free(p); }
 void kp_profile_enable(int on) { g_profile_on = on != 0; }
 int kp_profile_read(char* buf, int buflen) { return profile_read(buf, buflen); }
+int kp_plan_ksplit(int n_tiles, int n_chunks, int slots) {
+    if (n_tiles <= 0 || n_chunks <= 0 || slots <= 0) return fail(KP_ERR_ARG, "plan_ksplit: bad sizes");
+    return plan_ksplit(n_tiles, n_chunks, slots);
+}
 
 int kp_batch_query_dev(const float* queries, int nq, const float* supports, int ns, const int* q_batches,
                        const int* s_batches, int nb, float radius, void* out, int out_is_i64, int cap, int* hmax,

@@ -1212,6 +1212,9 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
     return KP_OK;
 }
 
+// host-side planning, exported for tests (no device work)
+int plan_ksplit(int n_tiles, int n_chunks, int slots) { return pick_ksplit(n_tiles, n_chunks, slots); }
+
 // ------------------------------------------------------------------------------------------ dense linear layers
 // The unary blocks around every KPConv (models/blocks.py:467-507 UnaryBlock: Linear without bias -> BatchNorm, which
 // is the identity on these 2-D features or a bias when use_bn is off, blocks.py:453-465 -> LeakyReLU(0.1)) run on the same
