@@ -12,7 +12,6 @@ the reference itself on seeded synthetic inputs:
 """
 import os
 import sys
-import types
 
 import numpy as np
 
@@ -22,48 +21,13 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 import oracle  # noqa: E402
-from weasal_b200.synthetic import make_batch  # noqa: E402
+from weasal_b200.synthetic import make_als_tile, make_batch  # noqa: E402
 
 
 def install_reference_import_harness():
-    """make models.blocks / datasets.common importable without their GUI deps."""
-    import torch
-
-    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.cm"):
-        sys.modules.setdefault(name, types.ModuleType(name))
-    ts = types.ModuleType("torch_scatter")
-    sys.modules["torch_scatter"] = ts
-    for n in ("datasets", "utils", "models", "kernels"):
-        m = types.ModuleType(n)
-        m.__path__ = [os.path.join(REF, n)]
-        sys.modules[n] = m
-    for n in ("cpp_wrappers", "cpp_wrappers.cpp_subsampling", "cpp_wrappers.cpp_neighbors"):
-        m = types.ModuleType(n)
-        m.__path__ = []
-        sys.modules[n] = m
-    gs = types.ModuleType("cpp_wrappers.cpp_subsampling.grid_subsampling")
-
-    def subsample(points, features=None, classes=None, sampleDl=0.1, method="barycenters", verbose=0):
-        return oracle.ref_subsample(points, features, classes, sampleDl)
-
-    def subsample_batch(points, batches, features=None, classes=None, sampleDl=0.1, method="barycenters",
-                        max_p=0, verbose=0):
-        return oracle.ref_subsample_batch(points, batches, features, classes, sampleDl, max_p)
-
-    gs.subsample, gs.subsample_batch = subsample, subsample_batch
-    sys.modules[gs.__name__] = gs
-    sys.modules["cpp_wrappers.cpp_subsampling"].grid_subsampling = gs
-    rn = types.ModuleType("cpp_wrappers.cpp_neighbors.radius_neighbors")
-
-    def batch_query(queries, supports, q_batches, s_batches, radius=0.1):
-        return oracle.ref_batch_neighbors(queries, supports, q_batches, s_batches, radius)
-
-    rn.batch_query = batch_query
-    sys.modules[rn.__name__] = rn
-    sys.modules["cpp_wrappers.cpp_neighbors"].radius_neighbors = rn
-    sys.path.insert(0, REF)
-    os.chdir(REF)  # load_kernels uses the relative path kernels/dispositions (kernel_points.py:410)
-    torch.Tensor.cuda = lambda self, *a, **k: self
+    """SURVEY.md Appendix A.2 (shared with the tests: oracle/ref_harness.py), extension modules backed by oracle/_ref."""
+    from oracle import ref_harness
+    ref_harness.install(REF, backend="oracle_ref")
 
 
 def golden_kpconv():
@@ -178,12 +142,116 @@ def golden_pyramid():
     np.savez_compressed(os.path.join(HERE, "pyramid_ref.npz"), **out)
 
 
+PL_ARCH = ['simple', 'resnetb', 'resnetb_strided', 'resnetb', 'resnetb_strided', 'resnetb', 'resnetb_strided', 'resnetb',
+           'resnetb_strided', 'resnetb', 'nearest_upsample', 'unary', 'nearest_upsample', 'unary', 'nearest_upsample',
+           'unary', 'nearest_upsample', 'unary']
+
+
+def golden_pyramid_dales():
+    """The DALES PseudoLabel walk (train_DALES_PseudoLabel.py:98-121: dl 0.4, 5 layers, conv_radius 2.5) on spheres cut
+    from a tile that was first subsampled at dl like the dataset does (DALES_PseudoLabel.py load_subsampled_clouds),
+    with neighbourhood limits that bite on some layers (crop ties are exercised). Index matrices are stored as uint16
+    (every layer has < 65535 points)."""
+    from datasets.common import PointCloudDataset
+    from weasal_b200.synthetic import extract_spheres, make_als_tile, pick_centres
+
+    class Cfg:
+        first_subsampling_dl = 0.4
+        conv_radius = 2.5
+        deform_radius = 6.0
+        architecture = PL_ARCH
+
+    tile, _, _ = make_als_tile(41, 60.0, 14.0)
+    sub = oracle.ref_subsample(tile, sampleDl=0.4)
+    centres = pick_centres(sub, 2, 12.0, 42)
+    pts, lens, _ = extract_spheres(sub, centres, 12.0)
+    ds = PointCloudDataset("x")
+    ds.config = Cfg()
+    ds.neighborhood_limits = [26, 40, 48, 50, 40]
+    np.random.seed(4321)
+    feats = np.ones((len(pts), 1), np.float32)
+    li = ds.segmentation_inputs(pts, feats, np.zeros(len(pts), np.int64), lens)
+    L = (len(li) - 2) // 5
+    out = {"in_pts": pts, "in_lens": lens, "limits": np.asarray(ds.neighborhood_limits, np.int32),
+           "seed": np.int64(4321), "L": np.int64(L)}
+    for l in range(L):
+        assert len(li[l]) < 65535
+        out[f"points{l}"] = li[l]
+        out[f"neighbors{l}"] = li[L + l].astype(np.uint16)
+        out[f"pools{l}"] = li[2 * L + l].astype(np.uint16)
+        out[f"upsamples{l}"] = li[3 * L + l].astype(np.uint16)
+        out[f"lengths{l}"] = np.asarray(li[4 * L + l], np.int32)
+        print("dales", l, li[l].shape, li[L + l].shape, li[2 * L + l].shape, li[3 * L + l].shape)
+    np.savez_compressed(os.path.join(HERE, "pyramid_dales_ref.npz"), **out)
+
+
+WIDE_CASES = [("w128_128", 128, 128), ("w256_256", 256, 256), ("w512_512", 512, 512), ("w512_256", 512, 256),
+              ("w256_32", 256, 32), ("w32_256", 32, 256)]
+
+
+def wide_inputs(seed, n, cin, cout):
+    """x, weights, d_out of a wide case from numpy's PCG64 stream (the test regenerates them: only outputs are stored)."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, cin), dtype=np.float32)
+    w = (rng.standard_normal((15, cin, cout), dtype=np.float32) / np.float32(np.sqrt(cin * 4.0))).astype(np.float32)
+    d_out = rng.standard_normal((n, cout), dtype=np.float32)
+    return x, w, d_out
+
+
+def golden_kpconv_wide():
+    """The wide layers of the DALES net (128 -> 512 channels, train_DALES_PseudoLabel.py:120) and of the WL attention
+    heads (256->32, 32->256, 512->256: models/blocks.py:778-784, 844-849, 909, 981) from the reference's own KPConv on
+    one shared geometry of > 5000 points (42 tiles of 128: the multi-wave / split-reduction paths are active). To keep the
+    fixture small only the geometry, the kernel points and SAMPLES of the outputs are stored (256 rows of out and dX,
+    every 8th / 4th row and column of dW); x, weights and d_out are regenerated from a seeded numpy stream."""
+    import torch
+    from models.blocks import KPConv
+
+    tile, _, _ = make_als_tile(51, 64.0, 14.0)
+    dl = 0.96
+    pts = oracle.ref_subsample(tile, sampleDl=dl)
+    lens = np.asarray([len(pts)], np.int32)
+    radius = dl * 2.5
+    extent = radius / 2.5
+    idx = oracle.ref_batch_neighbors(pts, pts, lens, lens, radius).astype(np.int64)
+    n = len(pts)
+    assert 5000 < n < 65535, n
+    rows = np.sort(np.random.default_rng(9).choice(n, 256, replace=False))
+    out = {"pts": pts, "idx": idx.astype(np.uint16), "rows": rows.astype(np.int32), "extent": np.float32(extent),
+           "radius": np.float32(radius)}
+    q = torch.from_numpy(pts)
+    for ci, (name, cin, cout) in enumerate(WIDE_CASES):
+        np.random.seed(200 + ci)
+        torch.manual_seed(200 + ci)
+        conv = KPConv(15, 3, cin, cout, extent, radius)
+        x_np, w_np, do_np = wide_inputs(300 + ci, n, cin, cout)
+        with torch.no_grad():
+            conv.weights.copy_(torch.from_numpy(w_np))
+        x = torch.from_numpy(x_np).requires_grad_(True)
+        y = conv(q, q, torch.from_numpy(idx), x)
+        y.backward(torch.from_numpy(do_np))
+        sc, so = max(cin // 64, 1), max(cout // 64, 1)
+        out.update({f"{name}.kernel_points": conv.kernel_points.detach().numpy(), f"{name}.seed": np.int64(300 + ci),
+                    f"{name}.out_rows": y.detach().numpy()[rows], f"{name}.dx_rows": x.grad.numpy()[rows],
+                    f"{name}.dw_sub": conv.weights.grad.numpy()[:, ::sc, ::so].copy(),
+                    f"{name}.dw_stride": np.asarray([sc, so], np.int32),
+                    f"{name}.out_absmax": np.float32(y.detach().abs().max()),
+                    f"{name}.dx_absmax": np.float32(x.grad.abs().max()),
+                    f"{name}.dw_absmax": np.float32(conv.weights.grad.abs().max())})
+        print(name, n, idx.shape, float(y.abs().max()))
+    np.savez_compressed(os.path.join(HERE, "kpconv_wide_ref.npz"), **out)
+
+
 if __name__ == "__main__":
     oracle.build()
     install_reference_import_harness()
-    golden_kpconv()
-    golden_precompute()
-    golden_pyramid()
+    only_new = "--new" in sys.argv  # keep the round-1 fixtures byte-identical: generate the added ones only
+    if not only_new:
+        golden_kpconv()
+        golden_precompute()
+        golden_pyramid()
+    golden_pyramid_dales()
+    golden_kpconv_wide()
     os.chdir(ROOT)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

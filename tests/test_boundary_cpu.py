@@ -484,3 +484,45 @@ def test_reduction_split_plan():
     assert L.kp_plan_ksplit(66, 15, 148) == 2
     assert L.kp_plan_ksplit(16, 30, 148) > 4   # few tiles, long reduction: spread it
     assert L.kp_plan_ksplit(0, 4, 296) < 0     # KP_ERR_ARG
+
+
+def test_kernel_points_table_and_recipe():
+    """weasal_b200.kernel_points carries the reference's cached 15-point disposition as a constant and applies the
+    reference's recipe (kernels/kernel_points.py:452-487) from the same np.random stream: the centre stays at the
+    origin up to the N(0, 0.01) noise, the others sit at ~0.66 of the radius, and a seeded call reproduces the committed
+    values. When a copy of the reference is on the machine the result must equal its load_kernels bit for bit."""
+    from weasal_b200 import kernel_points as kpm
+    t = kpm.K015_CENTER_3D
+    assert t.shape == (15, 3) and t.dtype == np.float64 and not t[0].any()
+    r = np.linalg.norm(t[1:], axis=1)
+    assert abs(r.mean() - 0.66) < 0.01 and r.min() > 0.6 and r.max() < 0.7
+    np.random.seed(42)
+    got = kpm.load_kernels(0.6, 15, dimension=3, fixed="center")
+    assert got.dtype == np.float32 and got.shape == (15, 3)
+    want_first_rows = np.array([[0.006060549, 0.003381847, 0.001674248], [-0.27230382, 0.07972425, 0.279908]], np.float32)
+    assert np.allclose(got[:2], want_first_rows, rtol=0, atol=1e-7), got[:2]
+    with pytest.raises(NotImplementedError):
+        kpm.load_kernels(0.6, 13, dimension=3, fixed="center")
+    from oracle import ref_harness
+    root = ref_harness.find_root()
+    if root is None:
+        return
+    import subprocess
+    import sys
+    code = r"""
+import os, sys, types
+import numpy as np
+ROOT, REF = sys.argv[1], sys.argv[2]
+sys.path.insert(0, ROOT)
+from oracle import ref_harness
+ref_harness.install(REF)
+from kernels.kernel_points import load_kernels as ref_load
+from weasal_b200.kernel_points import load_kernels
+for seed, radius in ((0, 0.6), (1, 1.2), (7, 9.6)):
+    np.random.seed(seed); a = ref_load(radius, 15, dimension=3, fixed='center'); s1 = np.random.rand()
+    np.random.seed(seed); b = load_kernels(radius, 15, dimension=3, fixed='center'); s2 = np.random.rand()
+    assert a.dtype == b.dtype and np.array_equal(a, b) and s1 == s2, (seed, np.abs(a - b).max())
+print("OK")
+"""
+    out = subprocess.run([sys.executable, "-c", code, ROOT, root], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stderr[-2000:]

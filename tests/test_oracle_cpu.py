@@ -127,3 +127,72 @@ def test_rotation_restatement():
     assert np.array_equal(oracle.rotate(p, R), ref)
     ref_t = np.sum(np.expand_dims(p, 2) * R.T, axis=1)  # common.py:134
     assert np.array_equal(oracle.rotate(p, R, transpose=True), ref_t)
+
+
+PL_ARCH5 = ['simple', 'resnetb', 'resnetb_strided', 'resnetb', 'resnetb_strided', 'resnetb', 'resnetb_strided', 'resnetb',
+            'resnetb_strided', 'resnetb', 'nearest_upsample', 'unary', 'nearest_upsample', 'unary', 'nearest_upsample',
+            'unary', 'nearest_upsample', 'unary']
+
+
+@pytest.mark.parametrize("fixture,dl0,arch", [("pyramid_ref.npz", 0.24, PL_ARCH5[:8] + PL_ARCH5[10:16]),
+                                              ("pyramid_dales_ref.npz", 0.4, PL_ARCH5)])
+def test_oracle_pyramid_equals_reference_up_to_exact_ties(fixture, dl0, arch):
+    """The restated pyramid walk on the restated cores ((d2, index) order) against the reference's own
+    segmentation_inputs output, Vaihingen3D and DALES walks: points bit-exact, index matrices identical once groups of
+    exactly equal d2 are canonicalised; differences are admitted only inside the tie group a crop column cut."""
+    from conftest import assert_same_up_to_ties
+    from oracle.pyramid_ref import segmentation_inputs_cpu
+    g = np.load(os.path.join(GOLDEN, fixture))
+
+    class Cfg:
+        first_subsampling_dl = dl0
+        conv_radius = 2.5
+        deform_radius = 6.0
+        architecture = arch
+
+    np.random.seed(int(g["seed"]))
+    li = segmentation_inputs_cpu(g["in_pts"], None, None, g["in_lens"], Cfg(), neighborhood_limits=list(g["limits"]),
+                                 use_ref=False)
+    L = int(g["L"])
+    assert (len(li) - 2) // 5 == L
+    for l in range(L):
+        assert np.array_equal(li[l], g[f"points{l}"])
+        for off, nm in ((L, "neighbors"), (2 * L, "pools"), (3 * L, "upsamples")):
+            ref = g[f"{nm}{l}"].astype(np.int64)
+            if ref.size:
+                q = li[l + 1] if nm == "pools" else li[l]
+                s = li[l + 1] if nm == "upsamples" else li[l]
+                assert_same_up_to_ties(q, s, li[off + l], ref, f"{nm}{l}")
+
+
+def test_tie_canonicalisation_detects_real_mismatches():
+    from conftest import assert_same_up_to_ties
+    rng = np.random.default_rng(0)
+    base = rng.uniform(0, 2, (60, 3)).astype(np.float32)
+    s = np.concatenate([base, base], 0)  # every point twice: exact ties everywhere
+    L = np.array([len(s)], np.int32)
+    mine = oracle.batch_neighbors(s, s, L, L, 0.6).astype(np.int64)
+    swapped = mine.copy()
+    swapped[:, [0, 1]] = swapped[:, [1, 0]]  # self and its duplicate: d2 = 0 both, order is arbitrary in the reference
+    n_perm, n_crop = assert_same_up_to_ties(s, s, mine, swapped, "dup")
+    assert n_perm == len(s) and n_crop == 0
+    wrong = mine.copy()
+    i = int(np.argmax((mine < len(s)).sum(1)))
+    wrong[i, 2] = (wrong[i, 2] + 1) % len(s) if (wrong[i, 2] + 1) % len(s) not in wrong[i] else wrong[i, 2]
+    far = int(np.setdiff1d(np.arange(len(s)), mine[i])[0])
+    wrong[i, 2] = far  # a support that is NOT within the radius
+    with pytest.raises(AssertionError):
+        assert_same_up_to_ties(s, s, mine, wrong, "wrong")
+
+
+def test_oracle_kpconv_matches_reference_wide_golden():
+    """One of the wide cases (256 -> 32 on 17k points) through the f64 oracle against the reference's sampled fp32 outputs."""
+    g = np.load(os.path.join(GOLDEN, "kpconv_wide_ref.npz"))
+    name, cin, cout = "w256_32", 256, 32
+    pts, idx, rows = g["pts"], g["idx"].astype(np.int64), g["rows"].astype(np.int64)
+    rng = np.random.default_rng(int(g[f"{name}.seed"]))
+    x = rng.standard_normal((len(pts), cin), dtype=np.float32)
+    w = (rng.standard_normal((15, cin, cout), dtype=np.float32) / np.float32(np.sqrt(cin * 4.0))).astype(np.float32)
+    kp = g[f"{name}.kernel_points"]
+    out = oracle.kpconv_forward(pts[rows], pts, idx[rows], x, w, kp, float(g["extent"]))
+    assert rel_err(out, g[f"{name}.out_rows"]) < 3e-6

@@ -32,9 +32,12 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    if not os.environ.get("WEASAL_B200_LIB"):
         from . import build as _build
-        _build.build()
+        # a no-op when the library is newer than every source; rebuilds after an edit of csrc/ or the header, so a stale
+        # library is never loaded silently. Without nvcc (a box that only received the prebuilt .so) the check is skipped.
+        if not os.path.exists(LIB_PATH) or (_build.needs_build() and os.path.exists(_build.nvcc_path())):
+            _build.build()
     L = C.CDLL(LIB_PATH)
     L.kp_last_error.restype = C.c_char_p
     L.kp_launch_count.restype = C.c_longlong

@@ -11,11 +11,16 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 
+def nvcc_path():
+    return os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "weasal_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    deps.append(os.path.join(HERE, "..", "include", "weasal_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -25,7 +30,7 @@ def build(force=False, verbose=False, defines=(), lib=None):
     lib = lib or LIB
     if not force and not defines and not needs_build():
         return lib
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    nvcc = nvcc_path()
     objs = []
     tag = "" if not defines else "." + "_".join(d.replace("=", "") for d in defines)
     for src in SOURCES:

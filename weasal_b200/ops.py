@@ -331,6 +331,8 @@ class ClosestPoolFunction(torch.autograd.Function):
         _need_cuda(x, inds)
         xx = _f32c(x)
         idx, i64, H, stride = _idx_args(inds)
+        if H == 0:  # the reference indexes inds[:, 0] (blocks.py:87): an index error there, an error here
+            raise IndexError("closest_pool: the index matrix has no columns")
         ns, C_ = xx.shape
         nq = idx.shape[0]
         out = torch.empty((nq, C_), dtype=torch.float32, device=xx.device)

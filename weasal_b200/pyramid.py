@@ -457,7 +457,10 @@ class PyramidPrefetcher:
         self.thread = threading.Thread(target=self._run, name="weasal-pyramid", daemon=True)
         self.thread.start()
 
-    def submit(self, points, features, labels, lengths, extras=None):
+    def submit(self, points, features, labels, lengths, extras=None, inputs_ready=False):
+        """``inputs_ready``: the caller guarantees that CUDA input tensors were completed long ago (e.g. a resident data
+        set); otherwise the side stream first waits for everything queued so far on the caller's current stream, which
+        may still be writing them (e.g. spheres just cut out of a cloud on the device)."""
         import ctypes as C
         lens = np.ascontiguousarray(lengths.cpu().numpy() if torch.is_tensor(lengths) else lengths, dtype=np.int32).reshape(-1)
         rot = draw_grid_rotations(self.cfg, len(lens), self.orient)
@@ -471,6 +474,13 @@ class PyramidPrefetcher:
 
         slot = self.n_sub % len(self.slabs)
         self.n_sub += 1
+        cuda_inputs = [t for t in (points, features, labels) if torch.is_tensor(t) and t.is_cuda]
+        if cuda_inputs and not inputs_ready:
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(self.dev))
+            self.side.wait_event(ready)
+        for t in cuda_inputs:  # allocated on the caller's stream, read on the side stream: tell the caching allocator
+            t.record_stream(self.side)
         with torch.cuda.stream(self.side):
             if self.free_ev[slot] is not None:
                 self.side.wait_event(self.free_ev[slot])  # the step that read this slot's previous batch has finished
