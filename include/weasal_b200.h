@@ -175,35 +175,68 @@ int kp_kpconv_backward_dev(const float* q_pts, int nq, const float* s_pts, int n
                            int cout, const float* kernel_points, int K, float KP_extent, const float* d_out,
                            float* d_x, float* d_weights, void* stream);
 
-/* Training variant: the forward pass leaves its influence entry lists (which depend only on the geometry and the kernel
- * points) in two caller-owned device buffers of the sizes kp_kpconv_lists_bytes reports, and the backward pass of the
- * same call reuses them instead of rebuilding them. Backward also accepts the transposed neighbour table
- * (kp_transpose_table_dev: CSR over the supports, rowptr int32 [ns+2] = ns+1 row pointers followed by the longest
- * row's length, col int32 [nq*H]), which depends on the index
- * matrix only and can therefore be shared by every KPConv that uses that matrix; NULL = build it internally.
+/* Training variant: the forward pass leaves its influence lists (which depend only on the geometry and the kernel
+ * points) in two caller-owned device buffers of the sizes kp_kpconv_lists_bytes reports (`lists_hdr`: 4 control ints +
+ * one header of 272 ints per tile of 128 centres; `lists_entries`: (neighbour | row << 25, weight) records, worst case
+ * 15 per table cell), and the backward pass of the same call reuses them instead of rebuilding them. Backward also
+ * accepts the transposed neighbour table (kp_transpose_table_dev: CSR over the supports, rowptr int32 [ns+2] = ns+1 row
+ * pointers followed by the longest row's length, col int32 [nq*H]), which depends on the index matrix only and can
+ * therefore be shared by every KPConv that uses that matrix; NULL = build it internally.
  * Results are identical to the plain pair above. */
 int kp_transpose_table_dev(const void* neighb_inds, int idx_is_i64, int nq, int H, int idx_stride, int ns,
                            int* rowptr, int* col, void* stream);
-void kp_kpconv_lists_bytes(int nq, int H, long long* koff_bytes, long long* entries_bytes);
+void kp_kpconv_lists_bytes(int nq, int H, long long* hdr_bytes, long long* entries_bytes);
 int kp_kpconv_forward_keep_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
                                int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,
                                int cout, const float* kernel_points, int K, float KP_extent, float* out,
-                               void* lists_koff, void* lists_entries, void* stream);
+                               void* lists_hdr, void* lists_entries, void* stream);
 int kp_kpconv_backward_kept_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
                                 int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,
                                 int cout, const float* kernel_points, int K, float KP_extent, const float* d_out,
-                                float* d_x, float* d_weights, const void* lists_koff, const void* lists_entries,
+                                float* d_x, float* d_weights, const void* lists_hdr, const void* lists_entries,
                                 const int* t_rowptr, const int* t_col, void* stream);
+
+/* Split form, for callers that know the geometry before the features (a training loop builds the lists of batch t+1 in
+ * its prefetch stage, on a side stream, while batch t trains; KPConv's forward / backward of models/blocks.py:238-374
+ * then starts at the tensor-core kernels):
+ *   kp_kpconv_lists_build_dev  lists of one pass. Forward and dW: centres = q_pts, others = s_pts, the index matrix as
+ *       given, kp_sign = +1. dX: centres = s_pts, others = q_pts, the TRANSPOSED table (t_rowptr / t_col from
+ *       kp_transpose_table_dev with n_pairs = nq*H, or the matrix itself when it is symmetric), kp_sign = -1.
+ *       entries_cap = capacity of lists_entries in records; when a calibrated capacity is exceeded the overflow flag
+ *       lists_hdr[1] is set (the affected tiles are left empty) and the caller must rebuild with a larger buffer.
+ *   kp_kpconv_apply_lists_dev  out[nc, cout] = (gather of x[n_x_rows, cin] through the lists) x weights. Forward:
+ *       transpose_w = 0, weights [K, cin, cout]. dX: x = d_out, cin = the conv's out_channels, cout = its in_channels,
+ *       transpose_w = 1 and the conv's own weights [K, cout, cin]. weights_packed != 0: `weights` holds the operand
+ *       images made by kp_pack_weights_dev (kind 0 / 1). out_slope != 1: LeakyReLU fused into the epilogue.
+ *   kp_kpconv_dw_lists_dev     d_weights [K, cin, cout] = gather^T x d_out (overwritten), lists of the forward pass. */
+int kp_kpconv_lists_build_dev(const float* centres, int nc, const float* others, int no, const void* neighb_inds,
+                              int idx_is_i64, int H, int idx_stride, const int* t_rowptr, const int* t_col,
+                              long long n_pairs, const float* kernel_points, int K, float kp_sign, float KP_extent,
+                              void* lists_hdr, void* lists_entries, long long entries_cap, void* stream);
+int kp_kpconv_apply_lists_dev(int nc, const float* x, int n_x_rows, int cin, const float* weights, int weights_packed,
+                              int transpose_w, int cout, int K, const void* lists_hdr, const void* lists_entries,
+                              float* out, float out_slope, void* stream);
+int kp_kpconv_dw_lists_dev(int nq, const float* x, int ns, int cin, const float* d_out, int cout, int K,
+                           const void* lists_hdr, const void* lists_entries, float* d_weights, void* stream);
+
+/* Operand images of the tensor-core contractions (TF32-rounded weights in the UMMA shared-memory layout, one image per
+ * 64 reduction columns). One launch packs any number of them: a training step calls it once per step for every KPConv
+ * and unary block instead of once per operator call. kinds: 0 KPConv forward (weights [K,cin,cout]), 1 KPConv dX (same
+ * weights, read transposed), 2 linear forward (weight [cout,cin]), 3 linear dX (same weight). kinds / Ks / cins / couts /
+ * weights / images are HOST arrays of n_jobs entries (device pointers inside); kp_pack_image_floats = image size. */
+long long kp_pack_image_floats(int kind, int K, int cin, int cout);
+int kp_pack_weights_dev(int n_jobs, const int* kinds, const float* const* weights, const int* Ks, const int* cins,
+                        const int* couts, float* const* images, void* stream);
 
 /* Backward for a SYMMETRIC neighbour table: queries == supports (pts [n,3]) and no row lost a neighbour to a crop, as
  * for the conv matrices `neighbors[l]` of datasets/common.py:505 when no neighbourhood limit bites. Then j is in row i
  * exactly when i is in row j (the f32 squared distance is exactly symmetric), the table is its own transpose and the
  * dX pass needs no transposed copy. The caller asserts the symmetry; results equal kp_kpconv_backward_dev's.
- * lists_koff / lists_entries: the forward pass's lists (kp_kpconv_forward_keep_dev) or NULL. */
+ * lists_hdr / lists_entries: the forward pass's lists (kp_kpconv_forward_keep_dev) or NULL. */
 int kp_kpconv_backward_sym_dev(const float* pts, int n, const void* neighb_inds, int idx_is_i64, int H, int idx_stride,
                                const float* x, int cin, const float* weights, int cout, const float* kernel_points,
                                int K, float KP_extent, const float* d_out, float* d_x, float* d_weights,
-                               const void* lists_koff, const void* lists_entries, void* stream);
+                               const void* lists_hdr, const void* lists_entries, void* stream);
 
 /* fp32 CUDA-core pieces (bring-up / cross-check of the tensor-core path; not the product path):
  *   wf [nq, K*cin] = kernel-point-weighted neighbour features; dx [ns,cin] += adjoint scatter of dwf [nq,K*cin]. */
@@ -228,6 +261,14 @@ int kp_linear_forward_dev(const float* x, int n, int cin, const float* weight, c
                           float negative_slope, float* y, void* stream);
 int kp_linear_backward_dev(const float* x, int n, int cin, const float* weight, int cout, const float* y,
                            float negative_slope, const float* d_y, float* d_x, float* d_weight, void* stream);
+/* The same with ready-made operand images (kp_pack_weights_dev kinds 2 / 3) and the two halves of the backward pass as
+ * separate calls, so that a caller can run them on different streams. */
+int kp_linear_forward_packed_dev(const float* x, int n, int cin, const float* images, const float* bias, int cout,
+                                 float negative_slope, float* y, void* stream);
+int kp_linear_dx_packed_dev(int n, int cin, const float* images_t, int cout, const float* y, float negative_slope,
+                            const float* d_y, float* d_x, void* stream);
+int kp_linear_dw_dev(const float* x, int n, int cin, int cout, const float* y, float negative_slope, const float* d_y,
+                     float* d_weight, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Pooling gathers next to KPConv (the callers' side of the path).

@@ -76,16 +76,34 @@ def main():
     same = same and bool(torch.equal(batch_a.features, batch_b.features)) and bool(torch.equal(batch_a.labels, batch_b.labels))
     L = len(batch_b.points)
 
+    def run(net, batch, slope=None):
+        """forward + loss + backward with a fixed dropout mask; ``slope`` overrides every LeakyReLU's negative_slope
+        (an attribute of the reference's own modules: with slope 1 the network has no activation kinks left)"""
+        for m in net.modules():
+            if isinstance(m, torch.nn.LeakyReLU):
+                m.negative_slope = 0.1 if slope is None else slope
+        net.zero_grad(set_to_none=True)
+        torch.manual_seed(11)
+        out = net(batch, cfg)
+        loss = net.loss(out, batch.labels)
+        loss.backward()
+        return out.detach().clone(), float(loss), {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
+
     # (1) stock reference operator
     np.random.seed(3)
     torch.manual_seed(3)
     net_ref = KPFCNN(cfg, list(range(n_cls)), []).to(dev)
     net_ref.train()
     stock_kpconv = B.KPConv
-    torch.manual_seed(11)
-    out_ref = net_ref(batch_a, cfg)
-    loss_ref = net_ref.loss(out_ref, batch_a.labels)
-    loss_ref.backward()
+    out_ref, loss_ref, g_ref = run(net_ref, batch_a)
+    out_ref_lin, _, g_ref_lin = run(net_ref, batch_a, slope=1.0)
+    # sensitivity of the STOCK network to a perturbation of the size of one TF32 rounding (2^-11 relative) of its input
+    # features: how far parameter gradients move when a LeakyReLU / max-pool decision flips somewhere
+    feats0 = batch_a.features.clone()
+    torch.manual_seed(99)
+    batch_a.features = feats0 * (1 + 2.0 ** -11 * torch.randn_like(feats0))
+    out_pert, _, g_pert = run(net_ref, batch_a)
+    batch_a.features = feats0
 
     # (2) the drop-in
     assert dropin.install() is True and B.KPConv is kpconv.KPConv and B.KPConv is not stock_kpconv
@@ -93,32 +111,35 @@ def main():
     torch.manual_seed(3)
     net_new = KPFCNN(cfg, list(range(n_cls)), []).to(dev)
     n_conv = sum(isinstance(m, kpconv.KPConv) for m in net_new.modules())
-    missing = net_new.load_state_dict(net_ref.state_dict(), strict=True)
+    net_new.load_state_dict(net_ref.state_dict(), strict=True)
     net_new.train()
-    torch.manual_seed(11)
-    out_new = net_new(batch_b, cfg)
-    loss_new = net_new.loss(out_new, batch_b.labels)
-    loss_new.backward()
+    out_new, loss_new, g_new = run(net_new, batch_b)
+    out_new_lin, _, g_new_lin = run(net_new, batch_b, slope=1.0)
     torch.cuda.synchronize()
 
     def rel(a, r):
         return float((a - r).abs().max() / r.abs().max().clamp_min(1e-30))
 
-    grads = {}
-    for (n1, p1), (n2, p2) in zip(net_ref.named_parameters(), net_new.named_parameters()):
-        assert n1 == n2
-        if p1.grad is None or p2.grad is None:
-            assert p1.grad is None and p2.grad is None, n1   # the identity BatchNorm layers: no grad on either side
-            continue
-        grads[n1] = rel(p2.grad, p1.grad)
-    worst = max(grads, key=grads.get)
+    def grad_rel(ga, gr):
+        assert set(ga) == set(gr)   # the identity BatchNorm layers have no grad on either side
+        per = {n: rel(ga[n], gr[n]) for n in gr}
+        worst = max(per, key=per.get)
+        va, vr = torch.cat([ga[n].flatten() for n in gr]), torch.cat([gr[n].flatten() for n in gr])
+        return per[worst], worst, float((va - vr).norm() / vr.norm())
+
+    gmax, gworst, gl2 = grad_rel(g_new, g_ref)
+    lmax, lworst, ll2 = grad_rel(g_new_lin, g_ref_lin)
+    pmax, pworst, pl2 = grad_rel(g_pert, g_ref)
     print(json.dumps({
         "config": cfg_name, "points": int(len(b["points"])), "layers": L, "pyramid_tensors_compared": n_tensors,
         "pyramid_paths_identical": bool(same), "kpconv_modules_swapped": int(n_conv),
         "state_dict_keys": len(net_ref.state_dict()), "logits_rel": rel(out_new, out_ref),
-        "loss_ref": float(loss_ref), "loss_new": float(loss_new), "n_grads": len(grads),
-        "grad_rel_max": grads[worst], "grad_rel_worst": worst,
-        "grad_rel_kpconv_max": max(v for k, v in grads.items() if "KPConv" in k)}))
+        "loss_ref": loss_ref, "loss_new": loss_new, "n_grads": len(g_ref),
+        "grad_rel_max": gmax, "grad_rel_worst": gworst, "grad_rel_l2": gl2,
+        "linear_logits_rel": rel(out_new_lin, out_ref_lin), "linear_grad_rel_max": lmax, "linear_grad_rel_worst": lworst,
+        "linear_grad_rel_l2": ll2,
+        "stock_perturbed_logits_rel": rel(out_pert, out_ref), "stock_perturbed_grad_rel_max": pmax,
+        "stock_perturbed_grad_rel_l2": pl2}))
 
 
 if __name__ == "__main__":

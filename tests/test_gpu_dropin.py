@@ -31,4 +31,11 @@ def test_unmodified_reference_kpfcnn_on_the_dropin(cfg_name, in_radius, batch_nu
     assert r["logits_rel"] < TOL, r
     assert abs(r["loss_new"] - r["loss_ref"]) < TOL * abs(r["loss_ref"]), r
     assert r["n_grads"] >= 40
-    assert r["grad_rel_max"] < TOL, r
+    # parameter gradients: 1e-3 on the whole gradient vector (norm-wise). The worst single parameter is not a property
+    # of the operator: the STOCK network, fed features perturbed by one TF32 rounding (2^-11 relative), moves its own
+    # per-parameter gradients by 1-6e-2 (a LeakyReLU / max-pool decision flips on one of the few deep-layer points), so
+    # that measured sensitivity, not 1e-3, bounds the per-parameter maximum. Without activation kinks
+    # (negative_slope = 1 on both networks) the same comparison is reported as linear_*.
+    assert r["grad_rel_l2"] < TOL, r
+    assert r["linear_grad_rel_l2"] < TOL and r["linear_logits_rel"] < TOL, r
+    assert r["grad_rel_max"] < 3.0 * max(r["stock_perturbed_grad_rel_max"], TOL), r

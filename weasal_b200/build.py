@@ -30,6 +30,15 @@ def build(force=False, verbose=False, defines=(), lib=None):
     lib = lib or LIB
     if not force and not defines and not needs_build():
         return lib
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:  # several ranks may arrive here at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not defines and not needs_build():
+            return lib
+        return _build_locked(force, verbose, defines, lib)
+
+
+def _build_locked(force, verbose, defines, lib):
     nvcc = nvcc_path()
     objs = []
     tag = "" if not defines else "." + "_".join(d.replace("=", "") for d in defines)
@@ -39,7 +48,8 @@ def build(force=False, verbose=False, defines=(), lib=None):
                + ["-c", os.path.join(CSRC, src), "-o", obj])
         subprocess.check_call(cmd)
         objs.append(obj)
-    subprocess.check_call([nvcc, "-shared", "-o", lib] + objs + ["-lcudart"])
+    subprocess.check_call([nvcc, "-shared", "-o", lib + ".tmp"] + objs + ["-lcudart"])
+    os.replace(lib + ".tmp", lib)
     return lib
 
 

@@ -23,23 +23,35 @@ int kpconv_wf_device(const float* q, int nq, const float* s, int ns, const void*
 int kpconv_dx_atomic_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
                             int idx_stride, const float* dwf, int cin, const float* kp, int K, float extent, float* dx,
                             cudaStream_t stream);
-void kpconv_lists_bytes(int nq, int H, long long* koff_bytes, long long* entries_bytes);
+void kpconv_lists_bytes(int nc, long long n_pairs, long long* hdr_bytes, long long* entries_bytes);
 int kpconv_forward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
                           int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
-                          float extent, float* out, void* lists_koff, void* lists_entries, cudaStream_t stream);
+                          float extent, float* out, void* lists_hdr, void* lists_entries, cudaStream_t stream);
 int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
                            int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
-                           float extent, const float* dout, float* dx, float* dw, const void* lists_koff,
+                           float extent, const float* dout, float* dx, float* dw, const void* lists_hdr,
                            const void* lists_entries, const int* t_rowptr, const int* t_col, int table_symmetric,
                            cudaStream_t stream);
+int kpconv_lists_build_device(const float* centres, int nc, const float* others, int no, const void* idx, int idx_is_i64,
+                              int H, int idx_stride, const int* rowptr, const int* col, long long n_pairs,
+                              const float* kp, int K, float kp_sign, float extent, void* hdr, void* entries,
+                              long long entries_cap, cudaStream_t stream);
+int kpconv_apply_lists_device(int nc, const float* x, int n_x_rows, int cin, const float* w, int w_packed, int transpose_w,
+                              int cout, int K, const void* hdr, const void* entries, float* out, float slope_out,
+                              cudaStream_t stream);
+int kpconv_dw_lists_device(int nq, const float* x, int ns, int cin, const float* dout, int cout, int K, const void* hdr,
+                           const void* entries, float* dw, cudaStream_t stream);
+long long pack_image_floats(int kind, int K, int cin, int cout);
+int pack_weights_device(int n_jobs, const int* kinds, const float* const* weights, const int* Ks, const int* cins,
+                        const int* couts, float* const* images, cudaStream_t stream);
 int transpose_table_entry(const void* idx, int idx_is_i64, int nq, int H, int idx_stride, int ns, int* rowptr,
                           int* col_sorted, cudaStream_t stream);
 int profile_read(char* buf, int buflen);
 int plan_ksplit(int n_tiles, int n_chunks, int slots);
-int linear_forward_device(const float* x, int n, int cin, const float* w, const float* bias, int cout, float slope,
-                          float* y, cudaStream_t stream);
-int linear_backward_device(const float* x, int n, int cin, const float* w, int cout, const float* y, float slope,
-                           const float* dy, float* dx, float* dw, cudaStream_t stream);
+int linear_forward_device(const float* x, int n, int cin, const float* w, int w_packed, const float* bias, int cout,
+                          float slope, float* y, cudaStream_t stream);
+int linear_backward_device(const float* x, int n, int cin, const float* w, int w_packed, int cout, const float* y,
+                           float slope, const float* dy, float* dx, float* dw, cudaStream_t stream);
 int pyramid_build_device(const float* pts0, int n0, const int* lens0, int nb, int L, const float* conv_r,
                          const float* pool_r, const float* up_r, const float* dl, const float* rot, const int* limits,
                          int order, int idx_is_i64, int cap, void* slab, long long slab_bytes, long long* offs, int* n_out,
@@ -203,34 +215,64 @@ int kp_kpconv_forward_dev(const float* q_pts, int nq, const float* s_pts, int ns
                                  kernel_points, K, KP_extent, out, nullptr, nullptr, (cudaStream_t)stream);
 }
 
-void kp_kpconv_lists_bytes(int nq, int H, long long* koff_bytes, long long* entries_bytes) {
-    kpconv_lists_bytes(nq, H, koff_bytes, entries_bytes);
+void kp_kpconv_lists_bytes(int nq, int H, long long* hdr_bytes, long long* entries_bytes) {
+    kpconv_lists_bytes(nq, (long long)nq * H, hdr_bytes, entries_bytes);
+}
+
+int kp_kpconv_lists_build_dev(const float* centres, int nc, const float* others, int no, const void* neighb_inds,
+                              int idx_is_i64, int H, int idx_stride, const int* t_rowptr, const int* t_col,
+                              long long n_pairs, const float* kernel_points, int K, float kp_sign, float KP_extent,
+                              void* lists_hdr, void* lists_entries, long long entries_cap, void* stream) {
+    return kpconv_lists_build_device(centres, nc, others, no, neighb_inds, idx_is_i64, H, idx_stride, t_rowptr, t_col,
+                                     n_pairs, kernel_points, K, kp_sign, KP_extent, lists_hdr, lists_entries, entries_cap,
+                                     (cudaStream_t)stream);
+}
+
+int kp_kpconv_apply_lists_dev(int nc, const float* x, int n_x_rows, int cin, const float* weights, int weights_packed,
+                              int transpose_w, int cout, int K, const void* lists_hdr, const void* lists_entries,
+                              float* out, float out_slope, void* stream) {
+    return kpconv_apply_lists_device(nc, x, n_x_rows, cin, weights, weights_packed, transpose_w, cout, K, lists_hdr,
+                                     lists_entries, out, out_slope, (cudaStream_t)stream);
+}
+
+int kp_kpconv_dw_lists_dev(int nq, const float* x, int ns, int cin, const float* d_out, int cout, int K,
+                           const void* lists_hdr, const void* lists_entries, float* d_weights, void* stream) {
+    return kpconv_dw_lists_device(nq, x, ns, cin, d_out, cout, K, lists_hdr, lists_entries, d_weights, (cudaStream_t)stream);
+}
+
+long long kp_pack_image_floats(int kind, int K, int cin, int cout) { return pack_image_floats(kind, K, cin, cout); }
+
+int kp_pack_weights_dev(int n_jobs, const int* kinds, const float* const* weights, const int* Ks, const int* cins,
+                        const int* couts, float* const* images, void* stream) {
+    if (n_jobs < 0 || (n_jobs > 0 && (!kinds || !weights || !Ks || !cins || !couts || !images)))
+        return fail(KP_ERR_ARG, "pack_weights: bad arguments");
+    return pack_weights_device(n_jobs, kinds, weights, Ks, cins, couts, images, (cudaStream_t)stream);
 }
 
 int kp_kpconv_forward_keep_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
                                int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,
                                int cout, const float* kernel_points, int K, float KP_extent, float* out,
-                               void* lists_koff, void* lists_entries, void* stream) {
+                               void* lists_hdr, void* lists_entries, void* stream) {
     return kpconv_forward_device(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, weights, cout,
-                                 kernel_points, K, KP_extent, out, lists_koff, lists_entries, (cudaStream_t)stream);
+                                 kernel_points, K, KP_extent, out, lists_hdr, lists_entries, (cudaStream_t)stream);
 }
 
 int kp_kpconv_backward_kept_dev(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
                                 int idx_is_i64, int H, int idx_stride, const float* x, int cin, const float* weights,
                                 int cout, const float* kernel_points, int K, float KP_extent, const float* d_out,
-                                float* d_x, float* d_weights, const void* lists_koff, const void* lists_entries,
+                                float* d_x, float* d_weights, const void* lists_hdr, const void* lists_entries,
                                 const int* t_rowptr, const int* t_col, void* stream) {
     return kpconv_backward_device(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, H, idx_stride, x, cin, weights, cout,
-                                  kernel_points, K, KP_extent, d_out, d_x, d_weights, lists_koff, lists_entries,
+                                  kernel_points, K, KP_extent, d_out, d_x, d_weights, lists_hdr, lists_entries,
                                   t_rowptr, t_col, 0, (cudaStream_t)stream);
 }
 
 int kp_kpconv_backward_sym_dev(const float* pts, int n, const void* neighb_inds, int idx_is_i64, int H, int idx_stride,
                                const float* x, int cin, const float* weights, int cout, const float* kernel_points,
                                int K, float KP_extent, const float* d_out, float* d_x, float* d_weights,
-                               const void* lists_koff, const void* lists_entries, void* stream) {
+                               const void* lists_hdr, const void* lists_entries, void* stream) {
     return kpconv_backward_device(pts, n, pts, n, neighb_inds, idx_is_i64, H, idx_stride, x, cin, weights, cout,
-                                  kernel_points, K, KP_extent, d_out, d_x, d_weights, lists_koff, lists_entries, nullptr,
+                                  kernel_points, K, KP_extent, d_out, d_x, d_weights, lists_hdr, lists_entries, nullptr,
                                   nullptr, 1, (cudaStream_t)stream);
 }
 
@@ -274,11 +316,23 @@ int kp_pyramid_build_static_dev(const float* points0, int n0, const int* lengths
 
 int kp_linear_forward_dev(const float* x, int n, int cin, const float* weight, const float* bias, int cout,
                           float negative_slope, float* y, void* stream) {
-    return linear_forward_device(x, n, cin, weight, bias, cout, negative_slope, y, (cudaStream_t)stream);
+    return linear_forward_device(x, n, cin, weight, 0, bias, cout, negative_slope, y, (cudaStream_t)stream);
+}
+int kp_linear_forward_packed_dev(const float* x, int n, int cin, const float* images, const float* bias, int cout,
+                                 float negative_slope, float* y, void* stream) {
+    return linear_forward_device(x, n, cin, images, 1, bias, cout, negative_slope, y, (cudaStream_t)stream);
 }
 int kp_linear_backward_dev(const float* x, int n, int cin, const float* weight, int cout, const float* y,
                            float negative_slope, const float* d_y, float* d_x, float* d_weight, void* stream) {
-    return linear_backward_device(x, n, cin, weight, cout, y, negative_slope, d_y, d_x, d_weight, (cudaStream_t)stream);
+    return linear_backward_device(x, n, cin, weight, 0, cout, y, negative_slope, d_y, d_x, d_weight, (cudaStream_t)stream);
+}
+int kp_linear_dx_packed_dev(int n, int cin, const float* images_t, int cout, const float* y, float negative_slope,
+                            const float* d_y, float* d_x, void* stream) {
+    return linear_backward_device(nullptr, n, cin, images_t, 1, cout, y, negative_slope, d_y, d_x, nullptr, (cudaStream_t)stream);
+}
+int kp_linear_dw_dev(const float* x, int n, int cin, int cout, const float* y, float negative_slope, const float* d_y,
+                     float* d_weight, void* stream) {
+    return linear_backward_device(x, n, cin, nullptr, 0, cout, y, negative_slope, d_y, nullptr, d_weight, (cudaStream_t)stream);
 }
 
 int kp_max_pool_forward_dev(const float* x, int ns, int channels, const void* inds, int idx_is_i64, int nq, int H,

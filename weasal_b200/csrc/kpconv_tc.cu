@@ -1,6 +1,6 @@
-// KPConv forward / backward for sm_100a: sparse kernel-point gather on CUDA cores feeding tcgen05 (TF32 in,
-// FP32 accumulate in TMEM) — replaces models/blocks.py:238-374 (rigid, 'linear' influence, 'sum' aggregation) and the
-// autograd backward of that expression.
+// KPConv forward / backward for sm_100a: sparse kernel-point gather on CUDA cores feeding tcgen05 (TF32 in, FP32
+// accumulate in TMEM) through a warp-specialised, multi-stage shared-memory pipeline — replaces models/blocks.py:238-374
+// (rigid, 'linear' influence, 'sum' aggregation) and the autograd backward of that expression.
 //
 //   out[i,:] = sum_k ( sum_h w[i,k,h] * x[idx[i,h],:] ) @ W[k],   w = max(0, 1 - ||(s[idx[i,h]] - q[i]) - kp[k]|| / ext)
 //
@@ -10,20 +10,28 @@
 //     and only the dense second contraction [P x (K*Cin)] x [(K*Cin) x Cout] goes to the tensor cores.
 //   * bf16 operands give ~1.6e-3 relative error on that contraction, above the 1e-3 parity bar; TF32 operands
 //     rounded to nearest give ~4e-4. Hence kind::tf32.
+//   * the sparse gather reads Nq*H_real*Cin*4 bytes out of L2 (~4-5x the bytes the tensor core consumes), so the kernel
+//     is bound by how many gathers the producer warps keep in flight; the pipeline exists to keep them issuing.
 //
 // Kernels
-//   kp_influence   one warp per centre point: influence weights of every (neighbour, kernel point) pair, compacted
-//                  into per-point entry lists grouped by kernel point: entry = (neighbour index | k << 27, weight).
-//                  A centre's list lives in its own slot of 15 entries per table column, so no allocation / atomics.
-//   kp_pack_w      W[k,c,o] -> TF32-rounded B-operand images, one per 128-column chunk of the (k,c) reduction axis,
-//                  already in the UMMA K-major core-matrix layout (so a CTA fetches a chunk with one bulk copy).
-//   kp_fwd         one CTA per 128 points. Per chunk: warps assemble the A tile [128 x 128] in shared memory from the
-//                  entry lists (gathered float4 rows of x, all loads of a batch in flight together), one thread issues
-//                  16 tcgen05.mma (M128 x N x K8) accumulating into TMEM; epilogue tcgen05.ld -> global.
+//   kp_lists       one CTA per tile of 128 centre points: influence weights of every (neighbour, kernel point) pair,
+//                  compacted into ONE FLAT LIST PER (tile, kernel point), sorted by row: entry = (neighbour index | row
+//                  in tile << 25, weight). A tile header holds, per kernel point, the list's start at every 8-row block.
+//                  The lists depend on the geometry and the (frozen) kernel points only: a training step builds them in
+//                  its prefetch stage, off the training stream.
+//   kp_pack_w      W[k,c,o] -> TF32-rounded B-operand images, one per 64-column chunk of the (k,c) reduction axis,
+//                  already in the UMMA K-major core-matrix layout (a CTA fetches a chunk with one bulk copy).
+//   kp_fwd         one CTA per 128-point tile (x a slice of the reduction axis on deep layers). Warp roles: 8 PRODUCER
+//                  warps assemble A chunks [128 x 64] into a ring of shared-memory stages (each lane group walks one flat
+//                  list segment: U independent float4 gathers in flight, accumulation in registers, one store per row);
+//                  1 LOADER warp streams the packed weight chunks with cp.async.bulk into its own ring; 1 MMA warp
+//                  issues tcgen05.mma.kind::tf32 (M128 x N x K8) into TMEM and releases stages with tcgen05.commit;
+//                  the producer warps drain TMEM at the end (fused bias / LeakyReLU / split-reduction atomics).
 //                  Backward-dX is the same kernel run on the transposed neighbour table with W^T and -kp
 //                  (atomics-free segmented scatter).
-//   kp_dw          dW[(k,c),o] = sum_i WF[i,(k,c)] * dOut[i,o]: the same A tile consumed MN-major (M = (k,c) rows,
-//                  K = points) against the dOut tile, accumulated in TMEM across a CTA's point tiles, then added to dW.
+//   kp_dw          dW[(k,c),o] = sum_i WF[i,(k,c)] * dOut[i,o]: stages of 64 points, the A tile consumed MN-major
+//                  (M = (k,c) rows, K = points) against the dOut tile, same producer / MMA roles, accumulated in TMEM
+//                  across a CTA's point tiles, then added to dW.
 #include "common.cuh"
 
 #include <cstdlib>
@@ -34,22 +42,38 @@
 namespace kp {
 
 // ------------------------------------------------------------------------------------------------------- constants
-constexpr int TILE_M = 128;      // points per CTA tile (= UMMA M)
-constexpr int CK = 128;          // reduction columns per chunk
-// Warps per CTA (template parameter NW of the kernels): the A-tile assembly is latency bound and wants as many warps in
-// flight as the SM holds. Shapes whose shared memory lets two CTAs share an SM run 8 warps per CTA (the second CTA's
-// assembly overlaps the first one's MMA / barrier phases); shapes with one CTA per SM run 16 warps.
-constexpr int SMEM_TWO_CTAS = 110 * 1024;
-constexpr int KOFF = 16;         // per-point cumulative entry counts per kernel point (K <= 15)
-constexpr int K_SHIFT = 27;      // entry.x = neighbour index | (kernel point << 27)
-constexpr unsigned J_MASK = (1u << K_SHIFT) - 1u;
-// A tile, UMMA canonical no-swizzle layout: element (row p, col c) at
-//   (p/8)*A_SBO + (c/4)*A_LBO + (p%8)*16 + (c%4)*4     (8 rows x 16 bytes core matrices)
-// A_LBO carries 16 bytes of padding so that a warp writing one row (32 lanes x 16 B) is bank-conflict free.
+constexpr int TILE_M = 128;       // centre points per tile (= UMMA M of the forward / dX kernels)
+constexpr int RB = 8;             // rows per row block (= one core-matrix row group)
+constexpr int NRB = TILE_M / RB;  // 16 row blocks per tile
+constexpr int TOFF_RB = NRB + 1;  // per kernel point: list position at the start of every row block, plus its end
+constexpr int TOFF_PER_TILE = 16 * TOFF_RB;   // 272 ints per tile; slot [15][0] = the tile's first entry, [15][1] = count
+constexpr int ROW_SHIFT = 25;     // entry.x = neighbour index | (row in tile << 25)
+constexpr unsigned J_MASK = (1u << ROW_SHIFT) - 1u;
+constexpr int K_SHIFT = 27;       // scratch lists (per row, grouped by kernel point): index | (kernel point << 27)
+constexpr unsigned JS_MASK = (1u << K_SHIFT) - 1u;
+
+constexpr int NPW = 8;            // producer warps (they are also the epilogue warps: two per TMEM lane quadrant)
+constexpr int LOADER_WARP = NPW, MMA_WARP = NPW + 1;
+constexpr int WS_THREADS = (NPW + 2) * 32;
+constexpr int FWD_CK = 64;        // reduction columns per forward stage
+constexpr int DW_CK = 128;        // reduction columns (= UMMA M) per dW CTA
+constexpr int DW_PT = 64;         // points per dW stage
+constexpr int MAX_STAGES = 4;
+
+// forward A stage [128 rows x 64 cols], UMMA canonical K-major no-swizzle layout: element (row p, col c) at
+//   (c/4)*A_LBO + (p/8)*A_SBO + (p%8)*16 + (c%4)*4     (8 rows x 16 bytes core matrices)
+// A_LBO carries 16 bytes of padding so that lanes writing one row are spread over the banks.
 constexpr int A_SBO = 128;
-constexpr int A_LBO = 16 * 128 + 16;          // 2064
-constexpr int A_BYTES = (CK / 4) * A_LBO;     // 66048
+constexpr int A_LBO = 16 * 128 + 16;              // 2064
+constexpr int A_STAGE = (FWD_CK / 4) * A_LBO;     // 33024
 constexpr int B_SBO = 128;
+// dW stages, MN-major SWIZZLE_128B_BASE32B (the only MN-major layout tcgen05 accepts for 32-bit operands,
+// cute::UMMA::Layout_MN_SW128_32B_Atom): rows of 32 elements (128 B) along M/N, 4 consecutive K values (points) = 4
+// consecutive rows (512 B atom), byte-address bits [5,7) XORed with bits [7,9). Element (m, k) at
+//   (m/32)*MN_LBO + (k/4)*MN_SBO + (k%4)*128 + ((((m%32)/8) ^ (k%4))*32) + (m%8)*4
+constexpr int MN_SBO = 512;
+constexpr int MN_LBO = (DW_PT / 4) * MN_SBO;      // 8 KiB per group of 32 M/N values
+constexpr int DW_A_STAGE = (DW_CK / 32) * MN_LBO; // 32 KiB
 
 // --------------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -59,6 +83,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -108,7 +135,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {  // arrives on `bar` when every MMA issued so far is done
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
@@ -129,9 +156,12 @@ __device__ __forceinline__ float to_tf32(float f) {  // round to nearest, ties a
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(f));
     return __uint_as_float(u);
 }
+__device__ __forceinline__ float4 to_tf32(float4 v) {
+    return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+}
 
-// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor, version 1):
-// [0,14) start>>4, [16,30) leading (K-direction) byte offset>>4, [32,46) stride (M/N-direction) byte offset>>4
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// [0,14) start>>4, [16,30) leading byte offset>>4, [32,46) stride byte offset>>4, [61,64) layout type
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo, uint32_t layout_type = 0) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
            (1ull << 46) | ((uint64_t)layout_type << 61);
@@ -159,330 +189,369 @@ __device__ __forceinline__ float influence_w(float rx, float ry, float rz, float
     return fmaxf(0.f, 1.f - sqrtf(dx * dx + dy * dy + dz * dz) * inv_ext);
 }
 
-// Entry lists. Centre i owns the slot entries[15 * row0(i) ...), row0 = i*H (padded table) or rowptr[i] (CSR): 15
-// entries per table column is the exact worst case, so the list never overflows and needs no allocator. Inside the
-// slot the entries are packed, grouped by kernel point (koff[i][k] = first entry of kernel point k, koff[i][15] =
-// count), each group in table-column order.
-constexpr int INF_WARPS = 8;
+constexpr int LST_WARPS = 16;     // warps per list-building CTA: 8 rows of the tile each
+constexpr int LST_ROWS = TILE_M / LST_WARPS;
 constexpr int INF_MAX_ROW = 128;  // real neighbours staged per centre in shared memory (longer rows: two-pass path)
 
-// any row length: lanes = neighbours, one pass to count per kernel point, one to write
-__device__ __forceinline__ void influence_long_row(const float* __restrict__ others, int no, const Table& T, size_t pos0,
-                                               int cnt_row, float cx, float cy, float cz, const float* s_kp,
-                                               float inv_ext, unsigned short* __restrict__ koff_row,
-                                               int2* __restrict__ my_entries, int lane) {
+// any row length (rare: more than INF_MAX_ROW neighbours): one pass over the row per kernel point, lanes = neighbours;
+// the groups come out in kernel-point order, each in table-column order (scratch format)
+__device__ __noinline__ void influence_long_row(const float* __restrict__ others, int no, const Table& T, size_t pos0,
+                                                int cnt_row, float cx, float cy, float cz, const float* s_kp, int K,
+                                                float inv_ext, unsigned short* koff_row, int2* __restrict__ my_entries,
+                                                int lane) {
     const unsigned lt_mask = (1u << lane) - 1u;
-    int cnt[15];
-#pragma unroll
-    for (int k = 0; k < 15; k++) cnt[k] = 0;
-    for (int hb = 0; hb < cnt_row; hb += 32) {
-        const int h = hb + lane;
-        long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
-        const bool valid = j >= 0 && j < no;
-        if (!__any_sync(0xffffffffu, valid)) continue;
-        float rx = 0.f, ry = 0.f, rz = 0.f;
-        if (valid) { rx = others[3 * j] - cx; ry = others[3 * j + 1] - cy; rz = others[3 * j + 2] - cz; }
-#pragma unroll
-        for (int k = 0; k < 15; k++) {
-            const float w = valid ? influence_w(rx, ry, rz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext) : 0.f;
-            cnt[k] += __popc(__ballot_sync(0xffffffffu, w > 0.f));
-        }
-    }
-    int run[16];
-    int total = 0;
-#pragma unroll
-    for (int k = 0; k < 15; k++) { run[k] = total; total += cnt[k]; }
-    run[15] = total;
-    int mine = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) mine = (lane == k) ? run[k] : mine;
-    if (lane < 16) koff_row[lane] = (unsigned short)mine;
-    if (total == 0) return;
-    for (int hb = 0; hb < cnt_row; hb += 32) {
-        const int h = hb + lane;
-        long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
-        const bool valid = j >= 0 && j < no;
-        if (!__any_sync(0xffffffffu, valid)) continue;
-        float rx = 0.f, ry = 0.f, rz = 0.f;
-        if (valid) { rx = others[3 * j] - cx; ry = others[3 * j + 1] - cy; rz = others[3 * j + 2] - cz; }
-#pragma unroll
-        for (int k = 0; k < 15; k++) {
-            const float w = valid ? influence_w(rx, ry, rz, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext) : 0.f;
+    int run = 0;
+    for (int k = 0; k < 15; k++) {
+        if (lane == 0) koff_row[k] = (unsigned short)run;
+        if (k >= K) continue;
+        const float kx = s_kp[3 * k], ky = s_kp[3 * k + 1], kz = s_kp[3 * k + 2];
+        for (int hb = 0; hb < cnt_row; hb += 32) {
+            const int h = hb + lane;
+            long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
+            const bool valid = j >= 0 && j < no;
+            float w = 0.f;
+            if (valid) w = influence_w(others[3 * j] - cx, others[3 * j + 1] - cy, others[3 * j + 2] - cz, kx, ky, kz, inv_ext);
             const unsigned m = __ballot_sync(0xffffffffu, w > 0.f);
             if (w > 0.f) {
                 int2 e;
                 e.x = (int)((unsigned)j | ((unsigned)k << K_SHIFT));
                 e.y = __float_as_int(w);
-                my_entries[run[k] + __popc(m & lt_mask)] = e;
+                my_entries[run + __popc(m & lt_mask)] = e;
             }
-            run[k] += __popc(m);
+            run += __popc(m);
         }
     }
+    if (lane == 0) koff_row[15] = (unsigned short)run;
+    __syncwarp();
 }
 
-// One warp per centre. The real neighbours of the row are compacted into shared memory (shadow entries dropped), then
-// the warp sweeps the (kernel point, neighbour) pairs in kernel-point-major order, 32 pairs per step, one influence
-// evaluation per lane: ballot-compacting the non-zero weights in that order yields the list already grouped by kernel
-// point and ordered by table column, in a single pass.
-__global__ void __launch_bounds__(INF_WARPS * 32) kp_influence_kernel(const float* __restrict__ centres, int nc,
-                                                                     const float* __restrict__ others, int no, Table T,
-                                                                     const float* __restrict__ kp, int K, float kp_sign,
-                                                                     float inv_ext, unsigned short* __restrict__ koff,
-                                                                     int2* __restrict__ entries) {
+// One CTA per tile of 128 centres.
+//   Phase A (one warp per centre at a time, 8 centres per warp): the real neighbours of the row are compacted into
+//     shared memory (shadow entries dropped), then the warp sweeps the (kernel point, neighbour) pairs in kernel-point-
+//     major order, 32 pairs per step, one influence evaluation per lane; ballot-compacting the non-zero weights yields the
+//     row's list grouped by kernel point, written to the row's slot of a scratch buffer (15 entries per table cell is the
+//     exact worst case, so no allocation), with the group starts kept in shared memory.
+//   Scan: per kernel point, the exclusive prefix of the group sizes over the 128 rows = each row's place in the tile's
+//     flat list of that kernel point; the tile takes its range of the compact entry buffer with one atomicAdd.
+//   Phase B: the rows' groups are copied from the scratch slots (still in L2) to their place in the flat lists.
+struct ListsOut {
+    int* toff;        // [n_tiles][16][17]
+    int2* entries;    // compact, `cap` entries
+    int* ctl;         // [0] = entries used so far (atomic cursor), [1] = overflow flag
+    long long cap;
+};
+
+__global__ void __launch_bounds__(LST_WARPS * 32, 2) kp_lists_kernel(const float* __restrict__ centres, int nc,
+                                                                 const float* __restrict__ others, int no, Table T,
+                                                                 const float* __restrict__ kp, int K, float kp_sign,
+                                                                 float inv_ext, int2* __restrict__ scratch, ListsOut L) {
     __shared__ float s_kp[16 * 3];
-    __shared__ float4 s_nb[INF_WARPS][INF_MAX_ROW];
+    __shared__ float4 s_nb[LST_WARPS][INF_MAX_ROW];
+    __shared__ unsigned short s_koff[TILE_M][16];  // per row: start of kernel point k's group in the row's slot; [15] = count
+    __shared__ int s_pos[15][TILE_M + 1];          // per kernel point: exclusive prefix of the group sizes over the rows
+    __shared__ int s_start[17];                    // list starts inside the tile's range; [15] = tile total; [16] = range base
     if (threadIdx.x < 48) s_kp[threadIdx.x] = (threadIdx.x < 3 * K) ? kp_sign * kp[threadIdx.x] : 1e30f;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * INF_WARPS + warp;
-    if (i >= nc) return;
+    const int tile = blockIdx.x;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const float cx = centres[3 * (size_t)i], cy = centres[3 * (size_t)i + 1], cz = centres[3 * (size_t)i + 2];
-    size_t row0, pos0;
-    int cnt_row;
-    if (T.rowptr) { row0 = (size_t)T.rowptr[i]; pos0 = row0; cnt_row = T.rowptr[i + 1] - T.rowptr[i]; }
-    else { row0 = (size_t)i * T.H; pos0 = (size_t)i * T.stride; cnt_row = T.H; }
-    int2* my_entries = entries + 15 * row0;
-    unsigned short* koff_row = koff + (size_t)i * KOFF;
-    if (cnt_row > INF_MAX_ROW) return;  // kp_influence_long_kernel takes these rows
     float4* nb = s_nb[warp];
-    int hn = 0;
-    for (int hb = 0; hb < cnt_row; hb += 32) {
-        const int h = hb + lane;
-        long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
-        const bool valid = j >= 0 && j < no;
-        const unsigned m = __ballot_sync(0xffffffffu, valid);
-        if (valid)
-            nb[hn + __popc(m & lt_mask)] = make_float4(others[3 * j] - cx, others[3 * j + 1] - cy, others[3 * j + 2] - cz,
-                                                       __int_as_float((int)j));
-        hn += __popc(m);
-    }
-    __syncwarp();
-    const int npairs = K * hn;
-    const int my_first = min(lane * hn, npairs);  // first pair of kernel point `lane` (lanes 0..15)
-    int myoff = 0, run = 0;
-    // pair p = (kernel point p / hn, neighbour p % hn). hn <= 128 and p < 1920, so the quotient comes exactly from one
-    // float multiply: (p + 0.5) / hn stays at least 0.5 / 128 away from an integer, far above the rounding error
-    const float inv_hn = hn > 0 ? 1.f / (float)hn : 0.f;
-    int base = 0;
-    for (; base < npairs; base += 32) {
-        const int p = base + lane;
-        const bool valid = p < npairs;
-        const int k = (int)(((float)p + 0.5f) * inv_hn);
-        const int h = p - k * hn;
-        float w = 0.f;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
-            v = nb[h];
-            w = influence_w(v.x, v.y, v.z, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, w > 0.f);
-        if (w > 0.f) {
-            int2 e;
-            e.x = (int)((unsigned)__float_as_int(v.w) | ((unsigned)k << K_SHIFT));
-            e.y = __float_as_int(w);
-            my_entries[run + __popc(m & lt_mask)] = e;
-        }
-        if (my_first >= base && my_first < base + 32) myoff = run + __popc(m & ((1u << (my_first - base)) - 1u));
-        run += __popc(m);
-    }
-    if (my_first >= base) myoff = run;  // kernel points that start at or after the end of the sweep
-    if (lane < 16) koff_row[lane] = (unsigned short)myoff;
-}
 
-// rows longer than INF_MAX_ROW (only possible for very dense tables); every other warp exits at once
-__global__ void __launch_bounds__(INF_WARPS * 32) kp_influence_long_kernel(const float* __restrict__ centres, int nc,
-                                                                          const float* __restrict__ others, int no,
-                                                                          Table T, const float* __restrict__ kp, int K,
-                                                                          float kp_sign, float inv_ext,
-                                                                          unsigned short* __restrict__ koff,
-                                                                          int2* __restrict__ entries) {
-    if (T.rowptr && T.rowptr[nc + 1] <= INF_MAX_ROW) return;  // CSR tables record their longest row after the pointers
-    __shared__ float s_kp[16 * 3];
-    if (threadIdx.x < 48) s_kp[threadIdx.x] = (threadIdx.x < 3 * K) ? kp_sign * kp[threadIdx.x] : 1e30f;
+    for (int rr = 0; rr < LST_ROWS; rr++) {
+        const int row = warp * LST_ROWS + rr;
+        const int i = tile * TILE_M + row;
+        unsigned short* koff_row = s_koff[row];
+        if (i >= nc) {
+            if (lane < 16) koff_row[lane] = 0;
+            continue;
+        }
+        const float cx = centres[3 * (size_t)i], cy = centres[3 * (size_t)i + 1], cz = centres[3 * (size_t)i + 2];
+        size_t row0, pos0;
+        int cnt_row;
+        if (T.rowptr) { row0 = (size_t)T.rowptr[i]; pos0 = row0; cnt_row = T.rowptr[i + 1] - T.rowptr[i]; }
+        else { row0 = (size_t)i * T.H; pos0 = (size_t)i * T.stride; cnt_row = T.H; }
+        int2* my_entries = scratch + 15 * row0;
+        if (cnt_row > INF_MAX_ROW) {
+            influence_long_row(others, no, T, pos0, cnt_row, cx, cy, cz, s_kp, K, inv_ext, koff_row, my_entries, lane);
+            continue;
+        }
+        int hn = 0;
+        for (int hb = 0; hb < cnt_row; hb += 32) {
+            const int h = hb + lane;
+            long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
+            const bool valid = j >= 0 && j < no;
+            const unsigned m = __ballot_sync(0xffffffffu, valid);
+            if (valid)
+                nb[hn + __popc(m & lt_mask)] = make_float4(others[3 * j] - cx, others[3 * j + 1] - cy, others[3 * j + 2] - cz,
+                                                           __int_as_float((int)j));
+            hn += __popc(m);
+        }
+        __syncwarp();
+        const int npairs = K * hn;
+        const int my_first = min(lane * hn, npairs);  // first pair of kernel point `lane` (lanes 0..15)
+        int myoff = 0, run = 0;
+        // pair p = (kernel point p / hn, neighbour p % hn). hn <= 128 and p < 1920, so the quotient comes exactly from one
+        // float multiply: (p + 0.5) / hn stays at least 0.5 / 128 away from an integer, far above the rounding error
+        const float inv_hn = hn > 0 ? 1.f / (float)hn : 0.f;
+        int base = 0;
+        for (; base < npairs; base += 32) {
+            const int p = base + lane;
+            const bool valid = p < npairs;
+            const int k = (int)(((float)p + 0.5f) * inv_hn);
+            const int h = p - k * hn;
+            float w = 0.f;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                v = nb[h];
+                w = influence_w(v.x, v.y, v.z, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, w > 0.f);
+            if (w > 0.f) {
+                int2 e;
+                e.x = (int)((unsigned)__float_as_int(v.w) | ((unsigned)k << K_SHIFT));
+                e.y = __float_as_int(w);
+                my_entries[run + __popc(m & lt_mask)] = e;
+            }
+            if (my_first >= base && my_first < base + 32) myoff = run + __popc(m & ((1u << (my_first - base)) - 1u));
+            run += __popc(m);
+        }
+        if (my_first >= base) myoff = run;  // kernel points that start at or after the end of the sweep
+        if (lane < 16) koff_row[lane] = (unsigned short)myoff;
+        __syncwarp();  // the staging row is reused by the next centre
+    }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * INF_WARPS + (threadIdx.x >> 5);
-    if (i >= nc) return;
-    size_t row0, pos0;
-    int cnt_row;
-    if (T.rowptr) { row0 = (size_t)T.rowptr[i]; pos0 = row0; cnt_row = T.rowptr[i + 1] - T.rowptr[i]; }
-    else { row0 = (size_t)i * T.H; pos0 = (size_t)i * T.stride; cnt_row = T.H; }
-    if (cnt_row <= INF_MAX_ROW) return;
-    influence_long_row(others, no, T, pos0, cnt_row, centres[3 * (size_t)i], centres[3 * (size_t)i + 1],
-                       centres[3 * (size_t)i + 2], s_kp, inv_ext, koff + (size_t)i * KOFF, entries + 15 * row0, lane);
+
+    // per kernel point: exclusive prefix over the rows (warp w takes kernel points w, w + 16, ...)
+    for (int k = warp; k < 15; k += LST_WARPS) {
+        int carry = 0;
+        for (int r0 = 0; r0 < TILE_M; r0 += 32) {
+            const int r = r0 + lane;
+            const int c = (int)s_koff[r][k + 1] - (int)s_koff[r][k];
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            s_pos[k][r] = carry + incl - c;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) s_pos[k][TILE_M] = carry;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int len = lane < 15 ? s_pos[lane][TILE_M] : 0;
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane < 16) s_start[lane] = incl - len;  // [15] = total
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int base = 0;
+        if (lane == 0) {
+            base = total > 0 ? atomicAdd(L.ctl, total) : 0;
+            if ((long long)base + total > L.cap) {  // (only possible for a caller-bounded buffer: the batch takes the
+                atomicExch(L.ctl + 1, 1);           //  slow path, the tile is left empty)
+                base = -1;
+            }
+            s_start[16] = base;
+        }
+    }
+    __syncthreads();
+    const int base = s_start[16];
+    int* toff = L.toff + (size_t)tile * TOFF_PER_TILE;
+    for (int t = threadIdx.x; t < TOFF_PER_TILE; t += LST_WARPS * 32) {
+        const int k = t / TOFF_RB, rb = t - k * TOFF_RB;
+        int v;
+        if (k < 15) v = base < 0 ? 0 : s_start[k] + s_pos[k][rb * RB];
+        else v = rb == 0 ? (base < 0 ? 0 : base) : (rb == 1 ? (base < 0 ? 0 : s_start[15]) : 0);
+        toff[t] = v;
+    }
+    if (base < 0) return;
+    int2* dst = L.entries + base;
+    for (int rr = 0; rr < LST_ROWS; rr++) {
+        const int row = warp * LST_ROWS + rr;
+        const int i = tile * TILE_M + row;
+        if (i >= nc) break;
+        const unsigned short* ko = s_koff[row];
+        const int total = ko[15];
+        if (total == 0) continue;
+        const size_t row0 = T.rowptr ? (size_t)T.rowptr[i] : (size_t)i * T.H;
+        const int2* src = scratch + 15 * row0;
+        for (int e = lane; e < total; e += 32) {
+            int2 rec = src[e];
+            const int k = (int)((unsigned)rec.x >> K_SHIFT);
+            rec.x = (int)(((unsigned)rec.x & JS_MASK) | ((unsigned)row << ROW_SHIFT));
+            dst[s_start[k] + s_pos[k][row] + (e - (int)ko[k])] = rec;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------- weight pack
 // images[chunk][nblk] : NB rows (output channels) x CK reduction columns, K-major core-matrix layout:
 //   element (n, col) at (n/8)*128 + (col/4)*(NB*16) + (n%8)*16 + (col%4)*4 bytes.  col <-> (k, c) = (col / cin_p, col % cin_p)
 // value = tf32(W[k*sk + c*sc + n*sn]) inside the valid range, else 0.
-__global__ void __launch_bounds__(256) kp_pack_w_kernel(const float* __restrict__ W, int K, int cin, int cin_p, int cout,
-                                                       long long sk, long long sc, long long sn, int NB, int n_nblk,
-                                                       int n_chunks, float* __restrict__ images) {
-    const long long total = (long long)n_chunks * n_nblk * NB * CK;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        // t enumerates destination floats linearly (coalesced stores)
-        const long long img = t / ((long long)NB * CK);
-        const int r = (int)(t % ((long long)NB * CK));
-        const int chunk = (int)(img / n_nblk), nblk = (int)(img % n_nblk);
-        const int j = r / (NB * 4);          // 16-byte K chunk
-        const int rem = r % (NB * 4);
-        const int n8 = rem / 32, in8 = rem % 32;
-        const int n = n8 * 8 + in8 / 4, e = in8 % 4;
-        const int col = chunk * CK + j * 4 + e;
-        const int k = col / cin_p, c = col % cin_p;
-        const int ng = nblk * NB + n;
-        float v = 0.f;
-        if (k < K && c < cin && ng < cout) v = to_tf32(W[k * sk + c * sc + ng * sn]);
-        images[t] = v;
+struct PackJob {
+    const float* W;
+    float* images;
+    long long sk, sc, sn;
+    int K, cin, cin_p, cout, NB, n_nblk, n_chunks;
+    long long first;  // first destination float of this job in the launch-wide enumeration
+};
+constexpr int PACK_MAX_JOBS = 64;
+struct PackJobs {
+    int n;
+    long long total;
+    PackJob job[PACK_MAX_JOBS];
+};
+
+__device__ __forceinline__ void pack_one(const PackJob& J, long long t) {
+    const long long per_img = (long long)J.NB * FWD_CK;
+    const long long img = t / per_img;
+    const int r = (int)(t - img * per_img);
+    const int chunk = (int)(img / J.n_nblk), nblk = (int)(img - (long long)chunk * J.n_nblk);
+    const int j = r / (J.NB * 4);          // 16-byte K chunk
+    const int rem = r - j * (J.NB * 4);
+    const int n8 = rem >> 5, in8 = rem & 31;
+    const int n = n8 * 8 + (in8 >> 2), e = in8 & 3;
+    const int col = chunk * FWD_CK + j * 4 + e;
+    const int k = col / J.cin_p, c = col - k * J.cin_p;
+    const int ng = nblk * J.NB + n;
+    float v = 0.f;
+    if (k < J.K && c < J.cin && ng < J.cout) v = to_tf32(J.W[k * J.sk + c * J.sc + ng * J.sn]);
+    J.images[t] = v;
+}
+
+// every job of a launch in one grid-stride enumeration of destination floats (coalesced stores); the job of an element
+// is found by a short linear search over the (few) job boundaries
+__global__ void __launch_bounds__(256) kp_pack_w_kernel(const __grid_constant__ PackJobs P) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < P.total; t += (long long)gridDim.x * blockDim.x) {
+        int j = 0;
+        while (j + 1 < P.n && t >= P.job[j + 1].first) j++;
+        pack_one(P.job[j], t - P.job[j].first);
     }
 }
 
-// zero-pad the channel dimension to a multiple of 4 (float4 gathers)
+// zero-pad the channel dimension (float4 gathers need a row pitch the lane groups divide)
 __global__ void __launch_bounds__(256) kp_pad_cols_kernel(const float* __restrict__ src, long long rows, int c, int c_p,
                                                          float* __restrict__ dst) {
     const long long total = rows * c_p;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const long long r = t / c_p;
-        const int cc = (int)(t % c_p);
+        const int cc = (int)(t - r * c_p);
         dst[t] = cc < c ? src[r * c + cc] : 0.f;
     }
 }
 
-// ---------------------------------------------------------------------------------- A-tile assembly (shared by fwd, dW)
-// Where the 16 bytes (4 consecutive reduction columns 4*lane..4*lane+3) of tile row p live in shared memory.
+// ------------------------------------------------------------------------------------- A-stage producers (fwd, dW)
+// Where the 16 bytes (4 consecutive reduction columns = column group cg) of stage row p live in shared memory.
 struct LayoutKMajor {  // forward: UMMA K-major, no swizzle (see A_SBO / A_LBO above)
-    static __device__ __forceinline__ int off(int p, int lane) { return lane * A_LBO + (p >> 3) * A_SBO + (p & 7) * 16; }
+    static __device__ __forceinline__ int off(int p, int cg) { return cg * A_LBO + (p >> 3) * A_SBO + (p & 7) * 16; }
 };
-// dW: the same tile consumed MN-major (M = reduction column, K = point). For 32-bit operands the only MN-major shared
-// memory layout the tensor core accepts is SWIZZLE_128B_BASE32B (cute::UMMA::Layout_MN_SW128_32B_Atom): rows of 32
-// elements (128 B) along M, 4 consecutive K values = 4 consecutive rows (512 B atom), byte-address bits [5,7) XORed
-// with bits [7,9). Element (m, k) at
-//   (m/32)*MN_LBO + (k/4)*MN_SBO + (k%4)*128 + ((((m%32)/8) ^ (k%4))*32) + (m%8)*4
-constexpr int MN_SBO = 512;                     // next group of 4 K values (points)
-constexpr int MN_LBO = (TILE_M / 4) * MN_SBO;   // next group of 32 M values: 16 KiB
-struct LayoutMNMajor {
-    static __device__ __forceinline__ int off(int p, int lane) {
-        return (lane >> 3) * MN_LBO + (p >> 2) * MN_SBO + (p & 3) * 128 + ((((lane & 7) >> 1) ^ (p & 3)) << 5) + (lane & 1) * 16;
+struct LayoutMNMajor {  // dW: M = reduction column (cg = 4 of them), K = point p (see MN_SBO / MN_LBO above)
+    static __device__ __forceinline__ int off(int p, int cg) {
+        return (cg >> 3) * MN_LBO + (p >> 2) * MN_SBO + (p & 3) * 128 + ((((cg & 7) >> 1) ^ (p & 3)) << 5) + (cg & 1) * 16;
     }
 };
 
-// Warp `warp` owns tile rows [warp*RPW, warp*RPW + RPW). For chunk `chunk` it zeroes them, walks the entry lists of
-// its points restricted to the chunk's kernel points (flattened across the points, 32 entries per batch), gathers
-// float4 feature rows with U loads in flight per lane and accumulates w * x into the rows, then rounds them to TF32.
-template <int U, class LAY, int RPW>
-__device__ __forceinline__ void assemble_rows(unsigned char* sA, int warp, int lane, int chunk, int cin_p, int K,
-                                              const int* s_row0, const unsigned short* s_koff,
-                                              const int2* __restrict__ entries, const float* __restrict__ x) {
-    const int col0 = chunk * CK;
-    const int kfirst = col0 / cin_p;
-    const int klast = min(K - 1, (col0 + CK - 1) / cin_p);
-    const int my_col = col0 + 4 * lane;
-    const int k_l = my_col / cin_p, c_l = my_col % cin_p;
-    const int p0 = warp * RPW;
-#pragma unroll
-    for (int r = 0; r < RPW; r++)
-        *reinterpret_cast<float4*>(sA + LAY::off(p0 + r, lane)) = make_float4(0.f, 0.f, 0.f, 0.f);
-    long long start = 0;
-    int cnt = 0;
-    if (lane < RPW && kfirst < K) {
-        const unsigned short* ko = s_koff + (p0 + lane) * KOFF;
-        start = 15LL * s_row0[p0 + lane] + ko[kfirst];
-        cnt = (int)ko[klast + 1] - (int)ko[kfirst];
+// How a stage is shared out. A stage is (rows x columns) = 128 x 64 (forward) or 64 x 128 (dW): 2048 float4 cells for
+// the 256 producer lanes, i.e. every lane owns ONE column group (4 reduction columns = one kernel point, 4 channels) of
+// ONE block of 8 rows. Lanes are bundled into groups of G = seg_len / 4 (seg_len = min(Cin, 64) consecutive columns of
+// one kernel point): a group owns a (segment, row block) unit and walks exactly the entries of the tile's flat list of
+// that kernel point that fall into the row block, toff[k][rb] .. toff[k][rb + 1]: sorted by row, so the lane accumulates
+// in registers while the row stays the same and stores a finished row ONCE (rows without entries are stored as zeros on
+// the way): no zero-fill pass, no read-modify-write of shared memory, no per-row pointer chasing, and the entry records
+// of a unit are consecutive in memory. U entries are in flight per lane (their records first, then their float4 gathers).
+struct GatherGeom {
+    int g_log2;      // log2(G)
+    int seg_len;     // min(cin_p, 64)
+    int cin_p, K;
+};
+
+template <class LAY, int NRBS, int U>
+__device__ __forceinline__ void produce_sparse(unsigned char* sA, int warp, int lane, const GatherGeom& gg, int col_base,
+                                               int rb_base, const int* __restrict__ toff_tile,
+                                               const int2* __restrict__ ent, const float* __restrict__ x) {
+    const int G = 1 << gg.g_log2;
+    const int g = (warp << (5 - gg.g_log2)) + (lane >> gg.g_log2);
+    const int li = lane & (G - 1);
+    const int s = g / NRBS, rb = g - s * NRBS;
+    const int cg = s * G + li;
+    const int col = col_base + s * gg.seg_len;
+    const int k = col / gg.cin_p;
+    const int c0 = col - k * gg.cin_p + 4 * li;
+    int a = 0, b = 0;
+    if (k < gg.K) {
+        a = __ldg(toff_tile + k * TOFF_RB + rb_base + rb);
+        b = __ldg(toff_tile + k * TOFF_RB + rb_base + rb + 1);
     }
-    int incl = cnt;
+    const int2* __restrict__ ep = ent + a;
+    const int n = b - a;
+    const float* __restrict__ xc = x + c0;
+    const int p0 = rb * RB;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cur = 0;
+    int2 rec[U];
 #pragma unroll
-    for (int o = 1; o < RPW; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    const int E = __shfl_sync(0xffffffffu, incl, RPW - 1);
-    const int excl = incl - cnt;
-    const float* xc = x + c_l;
-    const int kc = klast - kfirst + 1;  // kernel points in this chunk (lanes with equal k_l form a group)
-    for (int b0 = 0; b0 < E; b0 += 32) {
-        const int e = b0 + lane;
-        int pt = 0;
+    for (int u = 0; u < U; u++) rec[u] = u < n ? __ldg(ep + u) : make_int2(0, 0);
+    for (int e0 = 0; e0 < n; e0 += U) {
+        float4 xv[U];
+        float wv[U];
+        int rv[U];
 #pragma unroll
-        for (int t = 0; t < RPW - 1; t++) pt += (__shfl_sync(0xffffffffu, incl, t) <= e) ? 1 : 0;
-        const long long pstart = __shfl_sync(0xffffffffu, start, pt);
-        const int pexcl = __shfl_sync(0xffffffffu, excl, pt);
-        int2 rec = make_int2(0, 0);
-        int ek = -1;
-        if (e < E) {
-            rec = entries[pstart + (e - pexcl)];
-            ek = (int)((unsigned)rec.x >> K_SHIFT);
-            rec.x = (int)(((unsigned)rec.x & J_MASK) | ((unsigned)pt << K_SHIFT));  // the kernel point is implied by the
-        }                                                                          // consuming lane group: carry the row
-        // Each lane group (lanes sharing a kernel point) walks ITS entries of the batch; groups advance together, so
-        // one step serves up to kc entries.
-        unsigned mymask = 0;
-        for (int g = 0; g < kc; g++) {
-            const unsigned m = __ballot_sync(0xffffffffu, ek == kfirst + g);
-            if (k_l == kfirst + g) mymask = m;
+        for (int u = 0; u < U; u++) {
+            xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            wv[u] = __int_as_float(rec[u].y);
+            rv[u] = (int)(((unsigned)rec[u].x >> ROW_SHIFT) & (RB - 1));
+            if (e0 + u < n) xv[u] = __ldg(reinterpret_cast<const float4*>(xc + (size_t)((unsigned)rec[u].x & J_MASK) * gg.cin_p));
         }
-        int steps = __popc(mymask);
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
-        for (int g = 0; g < steps; g += U) {
-            float4 xv[U];
-            float wv[U];
-            int ov[U];
+        for (int u = 0; u < U; u++) rec[u] = e0 + U + u < n ? __ldg(ep + e0 + U + u) : make_int2(0, 0);
 #pragma unroll
-            for (int u = 0; u < U; u++) {
-                const bool have = mymask != 0u;
-                const int ee = have ? (__ffs(mymask) - 1) : 0;
-                mymask &= mymask - 1u;
-                const unsigned jp = (unsigned)__shfl_sync(0xffffffffu, rec.x, ee);
-                const float w = __int_as_float(__shfl_sync(0xffffffffu, rec.y, ee));
-                ov[u] = LAY::off(p0 + (int)(jp >> K_SHIFT), lane);  // (row, lane) are coupled by the swizzle
-                wv[u] = have ? w : 0.f;
-                xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (have) xv[u] = __ldg(reinterpret_cast<const float4*>(xc + (size_t)(jp & J_MASK) * cin_p));
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                if (wv[u] != 0.f) {
-                    float4* a = reinterpret_cast<float4*>(sA + ov[u]);
-                    float4 v = *a;
-                    v.x = fmaf(wv[u], xv[u].x, v.x); v.y = fmaf(wv[u], xv[u].y, v.y);
-                    v.z = fmaf(wv[u], xv[u].z, v.z); v.w = fmaf(wv[u], xv[u].w, v.w);
-                    *a = v;
+        for (int u = 0; u < U; u++) {
+            if (e0 + u < n) {
+                if (rv[u] != cur) {
+                    *reinterpret_cast<float4*>(sA + LAY::off(p0 + cur, cg)) = to_tf32(acc);
+                    for (int r = cur + 1; r < rv[u]; r++)
+                        *reinterpret_cast<float4*>(sA + LAY::off(p0 + r, cg)) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    cur = rv[u];
                 }
+                acc.x = fmaf(wv[u], xv[u].x, acc.x); acc.y = fmaf(wv[u], xv[u].y, acc.y);
+                acc.z = fmaf(wv[u], xv[u].z, acc.z); acc.w = fmaf(wv[u], xv[u].w, acc.w);
             }
         }
     }
-#pragma unroll
-    for (int r = 0; r < RPW; r++) {
-        float4* a = reinterpret_cast<float4*>(sA + LAY::off(p0 + r, lane));
-        float4 v = *a;
-        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-        *a = v;
-    }
+    *reinterpret_cast<float4*>(sA + LAY::off(p0 + cur, cg)) = to_tf32(acc);
+    for (int r = cur + 1; r < RB; r++)
+        *reinterpret_cast<float4*>(sA + LAY::off(p0 + r, cg)) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// Dense variant of the A tile (linear layers next to KPConv: the A operand is a plain row-major matrix): warp `warp`
-// copies its RPW rows of columns [chunk*CK, chunk*CK + CK) from a[n, ld], optionally scaled by the LeakyReLU derivative
-// taken from `mask` (same shape: factor 1 where mask > 0, `slope` elsewhere), rounded to TF32. All RPW loads of a lane are
-// independent and issued together.
-template <class LAY, int RPW>
-__device__ __forceinline__ void dense_rows(unsigned char* sA, int warp, int lane, int chunk, int tile_base, int n,
-                                           const float* __restrict__ a, int ld, const float* __restrict__ mask,
-                                           float slope) {
-    const int col = chunk * CK + 4 * lane;
-    const int p0 = warp * RPW;
-    float4 v[RPW];
+// Dense variant (linear layers next to KPConv: the A operand is a plain row-major matrix a[n, ld]): the lane's 8 cells
+// are 8 independent float4 loads, optionally scaled by the LeakyReLU derivative taken from `mask` (same shape: factor 1
+// where mask > 0, `slope` elsewhere), rounded to TF32.
+template <class LAY, int NRBS>
+__device__ __forceinline__ void produce_dense(unsigned char* sA, int warp, int lane, int col_base, int row_base, int n,
+                                              const float* __restrict__ a, int ld, const float* __restrict__ mask,
+                                              float slope) {
+    constexpr int NCG = 256 / NRBS;                 // column groups per stage (16 forward, 32 dW)
+    const int t = warp * 32 + lane;
+    const int cg = t % NCG, rb = t / NCG;
+    const int col = col_base + 4 * cg;
+    const int p0 = rb * RB;
+    float4 v[RB];
 #pragma unroll
-    for (int r = 0; r < RPW; r++) {
-        const int i = tile_base + p0 + r;
+    for (int r = 0; r < RB; r++) {
+        const int i = row_base + p0 + r;
         v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < n && col < ld) v[r] = __ldg(reinterpret_cast<const float4*>(a + (size_t)i * ld + col));
     }
     if (mask) {
 #pragma unroll
-        for (int r = 0; r < RPW; r++) {
-            const int i = tile_base + p0 + r;
+        for (int r = 0; r < RB; r++) {
+            const int i = row_base + p0 + r;
             if (i < n && col < ld) {
                 const float4 y = __ldg(reinterpret_cast<const float4*>(mask + (size_t)i * ld + col));
                 v[r].x *= y.x > 0.f ? 1.f : slope; v[r].y *= y.y > 0.f ? 1.f : slope;
@@ -491,126 +560,24 @@ __device__ __forceinline__ void dense_rows(unsigned char* sA, int warp, int lane
         }
     }
 #pragma unroll
-    for (int r = 0; r < RPW; r++) {
-        v[r].x = to_tf32(v[r].x); v[r].y = to_tf32(v[r].y); v[r].z = to_tf32(v[r].z); v[r].w = to_tf32(v[r].w);
-        *reinterpret_cast<float4*>(sA + LAY::off(p0 + r, lane)) = v[r];
-    }
-}
-
-// Second formulation of the same assembly (the default, KP_ASSEMBLE_V=2). Every lane owns 4 reduction columns of the
-// tile, i.e. one kernel point k_l and 4 channels, and the entries it needs from row r are exactly the k_l group of that
-// row's list: entries[15*row0(r) + koff[r][k_l] .. koff[r][k_l+1]). So each lane walks its OWN short entry stream and
-// accumulates in registers: no zero pass over the tile, no read-modify-write of shared memory, no second rounding pass
-// and none of the ballot / ffs / shuffle bookkeeping that distributes a flat entry list over lane groups (that version
-// executes ~2x the instructions). Rows are processed R = 8 at a time so that 8 independent gathers are in flight per
-// lane, and the entry record of step t+1 is requested while the feature rows of step t are in flight. Lanes that share
-// a kernel point read the same record (one broadcast transaction).
-template <int U, class LAY, int RPW>
-__device__ __forceinline__ void assemble_rows_v2(unsigned char* sA, int warp, int lane, int chunk, int cin_p, int K,
-                                                 const int* s_row0, const unsigned short* s_koff,
-                                                 const int2* __restrict__ entries, const float* __restrict__ x) {
-    constexpr int R = 8;
-    static_assert(RPW % R == 0, "rows per warp must be a multiple of the row group");
-    const int my_col = chunk * CK + 4 * lane;
-    const int k_l = my_col / cin_p, c_l = my_col - k_l * cin_p;
-    const bool lane_ok = k_l < K;
-    const float* xc = x + c_l;
-    const int p0 = warp * RPW;
-#pragma unroll 1
-    for (int r0 = 0; r0 < RPW; r0 += R) {
-        const int2* ep[R];
-        int cnt[R];
-        float4 acc[R];
-        int2 nxt[R];
-        int m = 0;
-#pragma unroll
-        for (int u = 0; u < R; u++) {
-            const int row = p0 + r0 + u;
-            int b = 0, e = 0;
-            if (lane_ok) {
-                const unsigned short* ko = s_koff + row * KOFF + k_l;
-                b = ko[0];
-                e = ko[1];
-            }
-            ep[u] = entries + 15LL * s_row0[row] + b;
-            cnt[u] = e - b;
-            m = max(m, cnt[u]);
-            acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            nxt[u] = make_int2(0, 0);
-            if (cnt[u] > 0) nxt[u] = __ldg(ep[u]);
-        }
-        for (int t = 0; t < m; t++) {
-            float4 xv[R];
-            float wv[R];
-#pragma unroll
-            for (int u = 0; u < R; u++) {
-                const int2 rec = nxt[u];
-                xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                wv[u] = 0.f;
-                if (t < cnt[u]) {
-                    xv[u] = __ldg(reinterpret_cast<const float4*>(xc + (size_t)((unsigned)rec.x & J_MASK) * cin_p));
-                    wv[u] = __int_as_float(rec.y);
-                }
-                if (t + 1 < cnt[u]) nxt[u] = __ldg(ep[u] + t + 1);
-            }
-#pragma unroll
-            for (int u = 0; u < R; u++) {
-                acc[u].x = fmaf(wv[u], xv[u].x, acc[u].x); acc[u].y = fmaf(wv[u], xv[u].y, acc[u].y);
-                acc[u].z = fmaf(wv[u], xv[u].z, acc[u].z); acc[u].w = fmaf(wv[u], xv[u].w, acc[u].w);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < R; u++) {
-            float4 v = acc[u];
-            v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-            *reinterpret_cast<float4*>(sA + LAY::off(p0 + r0 + u, lane)) = v;
-        }
-    }
-}
-
-#ifndef KP_ASSEMBLE_V
-#define KP_ASSEMBLE_V 2
-#endif
-#if KP_ASSEMBLE_V == 1
-#define KP_ASSEMBLE assemble_rows
-#else
-#define KP_ASSEMBLE assemble_rows_v2
-#endif
-
-// stage the entry-list headers of one tile: row0 (first table column of the centre) and koff (32 bytes per centre,
-// moved as two 16-byte words)
-template <int FWD_THREADS>
-__device__ __forceinline__ void stage_headers(int tile_base, int n, int H, const int* __restrict__ rowptr,
-                                              const unsigned short* __restrict__ koff, int* s_row0,
-                                              unsigned short* s_koff) {
-    for (int t = threadIdx.x; t < TILE_M; t += FWD_THREADS) {
-        const int i = tile_base + t;
-        s_row0[t] = (i < n) ? (rowptr ? rowptr[i] : i * H) : 0;
-    }
-    const uint4* src = reinterpret_cast<const uint4*>(koff);
-    uint4* dst = reinterpret_cast<uint4*>(s_koff);
-    for (int t = threadIdx.x; t < TILE_M * 2; t += FWD_THREADS) {
-        const int i = tile_base + (t >> 1);
-        dst[t] = (i < n) ? __ldg(src + (size_t)i * 2 + (t & 1)) : make_uint4(0u, 0u, 0u, 0u);
-    }
+    for (int r = 0; r < RB; r++) *reinterpret_cast<float4*>(sA + LAY::off(p0 + r, cg)) = to_tf32(v[r]);
 }
 
 // --------------------------------------------------------------------------------------------------------- forward
 struct FwdParams {
     int nq;              // centre points (rows of out)
-    const float* x;      // [n_other, cin_p] features gathered through the entry lists
-    int cin_p, K;
-    const int* rowptr;   // CSR row pointers of the centres' table, or null for a padded table of width H
-    int H;
-    const unsigned short* koff;
+    const float* x;      // [n_other, cin_p] features gathered through the lists (dense mode: the A matrix [nq, cin_p])
+    GatherGeom gg;
+    const int* toff;     // tile headers (sparse mode)
     const int2* entries;
-    const float* images; // packed weights [n_chunks][n_nblk][NB*CK]
+    const float* images; // packed weights [n_chunks][n_nblk][NB*64]
     int NB, n_nblk, n_chunks;
     int ksplit;          // CTAs along the reduction (blockIdx.y); > 1 => partial sums are added atomically into out
+    int stages;
     float* out;          // [nq, cout] with row stride ldo (pre-zeroed when ksplit > 1)
     int cout, ldo;
     uint32_t tmem_cols;
-    // dense mode (template DENSE): A = x[nq, cin_p] itself, optionally times the LeakyReLU derivative read from mask
+    // dense mode (template DENSE): optional LeakyReLU-derivative mask on the A matrix
     const float* mask;
     float slope_in;
     // epilogue (ksplit == 1 only): out = leaky(acc + bias, slope_out); bias may be null, slope_out = 1 disables
@@ -618,182 +585,226 @@ struct FwdParams {
     float slope_out;
 };
 
-template <int NW, bool DENSE>
-__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) kp_fwd_kernel(FwdParams P) {
-    constexpr int FWD_THREADS = NW * 32, RPW = TILE_M / NW, NWARPS = NW;
+// shared memory: [stages] A stages, [stages] B stages, barriers. Barrier use: a_full[s] counts the 8 producer warps,
+// b_full[s] the loader's expect_tx + the bulk copy's bytes; a_empty / b_empty / acc_full are arrived on by tcgen05.commit.
+struct FwdBars {
+    uint64_t a_full[MAX_STAGES], a_empty[MAX_STAGES], b_full[MAX_STAGES], b_empty[MAX_STAGES], acc_full;
+    uint32_t tmem;
+};
+
+template <bool DENSE>
+__global__ void __launch_bounds__(WS_THREADS, 2) kp_fwd_kernel(const __grid_constant__ FwdParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    const int S = P.stages;
+    const int b_bytes = P.NB * FWD_CK * 4;
     unsigned char* sA = smem;
-    unsigned char* sB = smem + A_BYTES;
-    const int b_bytes = P.NB * CK * 4;
-    unsigned short* s_koff = reinterpret_cast<unsigned short*>(sB + b_bytes);
-    int* s_row0 = reinterpret_cast<int*>(s_koff + TILE_M * KOFF);
-    uint64_t* bar_b = reinterpret_cast<uint64_t*>(s_row0 + TILE_M);
-    uint64_t* bar_mma = bar_b + 1;
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_mma + 1);
+    unsigned char* sB = smem + (size_t)S * A_STAGE;
+    FwdBars* bars = reinterpret_cast<FwdBars*>(sB + (size_t)S * b_bytes);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile_base = blockIdx.x * TILE_M;
+    const int tile = blockIdx.x, tile_base = tile * TILE_M;
     const int cps = (P.n_chunks + P.ksplit - 1) / P.ksplit;
     const int c0 = blockIdx.y * cps, c1 = min(P.n_chunks, c0 + cps);
     if (c0 >= c1) return;
+    const int n_loc = c1 - c0;
 
     if (tid == 0) {
-        mbar_init(bar_b, 1);
-        mbar_init(bar_mma, 1);
+        for (int s = 0; s < S; s++) {
+            mbar_init(&bars->a_full[s], NPW);
+            mbar_init(&bars->a_empty[s], 1);
+            mbar_init(&bars->b_full[s], 1);
+            mbar_init(&bars->b_empty[s], 1);
+        }
+        mbar_init(&bars->acc_full, 1);
         fence_mbar_init();
     }
-    __syncwarp();
-    if (warp == 0) tmem_alloc(s_tmem, P.tmem_cols);
-    if (!DENSE) stage_headers<FWD_THREADS>(tile_base, P.nq, P.H, P.rowptr, P.koff, s_row0, s_koff);
+    if (warp == MMA_WARP) tmem_alloc(&bars->tmem, P.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *s_tmem;
-    const uint32_t idesc = make_idesc(TILE_M, P.NB, 0, 0);
-    const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
-    const uint32_t b_lbo = (uint32_t)P.NB * 16u;
+    const uint32_t tmem = bars->tmem;
 
-    int step = 0;  // one MMA group (chunk, nblk) per step; bar_b / bar_mma complete once per step
-    for (int chunk = c0; chunk < c1; chunk++) {
-        for (int nblk = 0; nblk < P.n_nblk; nblk++, step++) {
-            if (step > 0) mbar_wait(bar_mma, (uint32_t)((step - 1) & 1));  // previous MMAs done: A and B reusable
-            if (tid == 0) {
-                mbar_expect_tx(bar_b, (uint32_t)b_bytes);
-                bulk_g2s(sB, P.images + ((size_t)chunk * P.n_nblk + nblk) * (size_t)P.NB * CK, (uint32_t)b_bytes, bar_b);
+    if (warp < NPW) {
+        // ===== producers: A chunk `it` -> stage it % S =====
+        const int* toff_tile = nullptr;
+        const int2* ent = nullptr;
+        if (!DENSE) {
+            toff_tile = P.toff + (size_t)tile * TOFF_PER_TILE;
+            ent = P.entries + __ldg(toff_tile + 15 * TOFF_RB);
+        }
+        for (int it = 0; it < n_loc; it++) {
+            const int s = it % S, use = it / S;
+            if (use > 0) mbar_wait(&bars->a_empty[s], (uint32_t)((use - 1) & 1));
+            unsigned char* a = sA + (size_t)s * A_STAGE;
+            const int col_base = (c0 + it) * FWD_CK;
+            if (DENSE) produce_dense<LayoutKMajor, NRB>(a, warp, lane, col_base, tile_base, P.nq, P.x, P.gg.cin_p, P.mask, P.slope_in);
+            else produce_sparse<LayoutKMajor, NRB, 4>(a, warp, lane, P.gg, col_base, 0, toff_tile, ent, P.x);
+            fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->a_full[s]);
+        }
+    } else if (warp == LOADER_WARP) {
+        // ===== loader: packed weight chunk of step t -> B stage t % S =====
+        if (lane == 0) {
+            const int n_steps = n_loc * P.n_nblk;
+            for (int t = 0; t < n_steps; t++) {
+                const int s = t % S, use = t / S;
+                if (use > 0) mbar_wait(&bars->b_empty[s], (uint32_t)((use - 1) & 1));
+                const int chunk = c0 + t / P.n_nblk, nblk = t % P.n_nblk;
+                mbar_expect_tx(&bars->b_full[s], (uint32_t)b_bytes);
+                bulk_g2s(sB + (size_t)s * b_bytes, P.images + ((size_t)chunk * P.n_nblk + nblk) * (size_t)P.NB * FWD_CK,
+                         (uint32_t)b_bytes, &bars->b_full[s]);
             }
-            if (nblk == 0) {
-                if (DENSE) dense_rows<LayoutKMajor, RPW>(sA, warp, lane, chunk, tile_base, P.nq, P.x, P.cin_p, P.mask, P.slope_in);
-                else KP_ASSEMBLE<8, LayoutKMajor, RPW>(sA, warp, lane, chunk, P.cin_p, P.K, s_row0, s_koff, P.entries, P.x);
-                fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
-            }
-            __syncthreads();
-            if (tid == 0) {
-                mbar_wait(bar_b, (uint32_t)(step & 1));
-                tc_fence_after();
-#pragma unroll 1
-                for (int kk = 0; kk < CK / 8; kk++) {  // K = 8 per tf32 MMA = two 16-byte K chunks
-                    const uint64_t ad = make_desc(a_addr + kk * 2 * A_LBO, A_LBO, A_SBO);
-                    const uint64_t bd = make_desc(b_addr + kk * 2 * b_lbo, b_lbo, B_SBO);
-                    umma_tf32(tmem + (uint32_t)(nblk * P.NB), ad, bd, idesc, (chunk > c0 || kk > 0) ? 1u : 0u);
+        }
+    } else {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(TILE_M, P.NB, 0, 0);
+            const uint32_t b_lbo = (uint32_t)P.NB * 16u;
+            int t = 0;
+            for (int it = 0; it < n_loc; it++) {
+                const int s = it % S;
+                mbar_wait(&bars->a_full[s], (uint32_t)((it / S) & 1));
+                const uint32_t a_addr = smem_u32(sA + (size_t)s * A_STAGE);
+                for (int nblk = 0; nblk < P.n_nblk; nblk++, t++) {
+                    const int sb = t % S;
+                    mbar_wait(&bars->b_full[sb], (uint32_t)((t / S) & 1));
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(sB + (size_t)sb * b_bytes);
+#pragma unroll
+                    for (int kk = 0; kk < FWD_CK / 8; kk++) {  // K = 8 per tf32 MMA = two 16-byte K chunks
+                        const uint64_t ad = make_desc(a_addr + kk * 2 * A_LBO, A_LBO, A_SBO);
+                        const uint64_t bd = make_desc(b_addr + kk * 2 * b_lbo, b_lbo, B_SBO);
+                        umma_tf32(tmem + (uint32_t)(nblk * P.NB), ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&bars->b_empty[sb]);
                 }
-                umma_commit(bar_mma);
+                umma_commit(&bars->a_empty[s]);
             }
+            umma_commit(&bars->acc_full);
         }
     }
-    mbar_wait(bar_mma, (uint32_t)((step - 1) & 1));
-    tc_fence_after();
 
-    // epilogue: warp w reads TMEM lanes 32*(w%4).., column blocks of 16 dealt round-robin over the 4 warps of a quadrant
-    const int row = tile_base + 32 * (warp & 3) + lane;
-    const int n_cb = (P.n_nblk * P.NB) / 16;
-    const bool vec = (P.cout & 3) == 0 && (P.ldo & 3) == 0;
-    const bool post = P.ksplit == 1 && (P.bias != nullptr || P.slope_out != 1.f);
-    for (int cb = warp >> 2; cb < n_cb; cb += NWARPS / 4) {
-        float v[16];
-        tmem_ld16(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cb * 16), v);
-        if (post) {
+    // ===== epilogue: the producer warps drain TMEM (warp w: lanes 32*(w%4).., column blocks of 16 dealt over w/4) =====
+    if (warp < NPW) {
+        mbar_wait(&bars->acc_full, 0u);
+        tc_fence_after();
+        const int row = tile_base + 32 * (warp & 3) + lane;
+        const int n_cb = (P.n_nblk * P.NB) / 16;
+        const bool vec = (P.cout & 3) == 0 && (P.ldo & 3) == 0;
+        const bool post = P.ksplit == 1 && (P.bias != nullptr || P.slope_out != 1.f);
+        for (int cb = warp >> 2; cb < n_cb; cb += NPW / 4) {
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cb * 16), v);
+            if (post) {
 #pragma unroll
-            for (int t = 0; t < 16; t++) {
-                float a = v[t];
-                if (P.bias && cb * 16 + t < P.cout) a += __ldg(P.bias + cb * 16 + t);
-                v[t] = a > 0.f ? a : a * P.slope_out;
+                for (int t = 0; t < 16; t++) {
+                    float a = v[t];
+                    if (P.bias && cb * 16 + t < P.cout) a += __ldg(P.bias + cb * 16 + t);
+                    v[t] = a > 0.f ? a : a * P.slope_out;
+                }
             }
-        }
-        if (row < P.nq) {
-            float* o = P.out + (size_t)row * P.ldo + cb * 16;
+            if (row < P.nq) {
+                float* o = P.out + (size_t)row * P.ldo + cb * 16;
 #pragma unroll
-            for (int t = 0; t < 16; t += 4) {
-                if (vec && cb * 16 + t < P.cout) {
-                    const float4 f = make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]);
-                    if (P.ksplit > 1) atomicAdd(reinterpret_cast<float4*>(o + t), f);
-                    else *reinterpret_cast<float4*>(o + t) = f;
-                } else if (!vec) {
+                for (int t = 0; t < 16; t += 4) {
+                    if (vec && cb * 16 + t < P.cout) {
+                        const float4 f = make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]);
+                        if (P.ksplit > 1) atomicAdd(reinterpret_cast<float4*>(o + t), f);
+                        else *reinterpret_cast<float4*>(o + t) = f;
+                    } else if (!vec) {
 #pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (cb * 16 + t + u < P.cout) {
-                            if (P.ksplit > 1) atomicAdd(o + t + u, v[t + u]);
-                            else o[t + u] = v[t + u];
-                        }
+                        for (int u = 0; u < 4; u++)
+                            if (cb * 16 + t + u < P.cout) {
+                                if (P.ksplit > 1) atomicAdd(o + t + u, v[t + u]);
+                                else o[t + u] = v[t + u];
+                            }
+                    }
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, P.tmem_cols);
+    if (warp == MMA_WARP) tmem_dealloc(tmem, P.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------------------- dW
-// B tile = dOut[tile points, NB outputs], also MN-major SWIZZLE_128B_BASE32B: element (n, p) by the formula above
-// with m = n. Size = ceil(NB/32) * MN_LBO.
+// B stage = dOut[64 points, NB outputs], MN-major SWIZZLE_128B_BASE32B like the A stage (m = output column).
 __host__ __device__ constexpr int dw_b_bytes(int NB) { return ((NB + 31) / 32) * MN_LBO; }
 
 struct DwParams {
     int nq;
     const float* x;      // [ns, cin_p]
-    int cin, cin_p, K, H;
-    const unsigned short* koff;
+    GatherGeom gg;
+    int cin;
+    const int* toff;
     const int2* entries;
     const float* dout;   // [nq, cout]
     int cout, NB;        // NB = output columns handled per CTA (<= 256), slice index = blockIdx.z
-    int n_tiles, n_splits;
+    int n_tiles, n_splits, stages;
     float* dw;           // [K, cin, cout], pre-zeroed
     uint32_t tmem_cols;
-    // dense mode: A = x[nq, cin_p] itself (times the LeakyReLU derivative read from mask), see dense_rows
+    // dense mode: A = x[nq, cin_p] itself (times the LeakyReLU derivative read from mask), see produce_dense
     const float* mask;
     float slope_in;
 };
 
-template <int NW, bool DENSE>
-__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) kp_dw_kernel(DwParams P) {
-    constexpr int FWD_THREADS = NW * 32, RPW = TILE_M / NW, NWARPS = NW;
+struct DwBars {
+    uint64_t full[MAX_STAGES], empty[MAX_STAGES], acc_full;
+    uint32_t tmem;
+};
+
+template <bool DENSE>
+__global__ void __launch_bounds__(WS_THREADS, 2) kp_dw_kernel(const __grid_constant__ DwParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* sA = smem;                       // 4 * MN_LBO = 64 KiB, 1024-aligned (swizzle uses address bits)
-    unsigned char* sB = smem + 4 * MN_LBO;
+    const int S = P.stages;
     const int b_bytes = dw_b_bytes(P.NB);
-    unsigned short* s_koff = reinterpret_cast<unsigned short*>(sB + b_bytes);
-    int* s_row0 = reinterpret_cast<int*>(s_koff + TILE_M * KOFF);
-    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(s_row0 + TILE_M);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_mma + 1);
+    const int stage_bytes = DW_A_STAGE + b_bytes;  // both multiples of 1024 (the swizzle uses address bits)
+    DwBars* bars = reinterpret_cast<DwBars*>(smem + (size_t)S * stage_bytes);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int chunk = blockIdx.x, split = blockIdx.y, n0 = blockIdx.z * P.NB;
     if (split >= P.n_tiles) return;  // uniform: nothing to do for this CTA
+    const int my_tiles = (P.n_tiles - split + P.n_splits - 1) / P.n_splits;
+    const int n_steps = my_tiles * (TILE_M / DW_PT);
 
     if (tid == 0) {
-        mbar_init(bar_mma, 1);
+        for (int s = 0; s < S; s++) {
+            mbar_init(&bars->full[s], NPW);
+            mbar_init(&bars->empty[s], 1);
+        }
+        mbar_init(&bars->acc_full, 1);
         fence_mbar_init();
     }
-    __syncwarp();
-    if (warp == 0) tmem_alloc(s_tmem, P.tmem_cols);
+    if (warp == MMA_WARP) tmem_alloc(&bars->tmem, P.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *s_tmem;
-    const uint32_t idesc = make_idesc(TILE_M, P.NB, 1, 1);
-    const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+    const uint32_t tmem = bars->tmem;
 
-    int step = 0;
-    for (int tile = split; tile < P.n_tiles; tile += P.n_splits, step++) {
-        const int tile_base = tile * TILE_M;
-        if (step > 0) mbar_wait(bar_mma, (uint32_t)((step - 1) & 1));
-        if (!DENSE) stage_headers<FWD_THREADS>(tile_base, P.nq, P.H, nullptr, P.koff, s_row0, s_koff);
-        // dOut tile -> B (TF32): the warp's RPW rows x NB/4 float4 items are dealt round-robin to the lanes, eight loads
-        // in flight per lane (a row-at-a-time loop costs RPW dependent global-memory round trips per tile)
-        {
-            const int nv = P.NB >> 2;
-            const int items = RPW * nv;
-            const bool vec4 = (P.cout & 3) == 0;
-            for (int base = 0; base < items; base += 32 * 8) {
-                float4 v[8];
+    if (warp < NPW) {
+        // ===== producers: step t = (tile, half): A stage [64 points x 128 columns] + dOut stage [64 points x NB] =====
+        const int nv = P.NB >> 2;
+        const bool vec4 = (P.cout & 3) == 0;
+        for (int t = 0; t < n_steps; t++) {
+            const int s = t % S, use = t / S;
+            const int tile = split + (t >> 1) * P.n_splits, half = t & 1;
+            const int row_base = tile * TILE_M + half * DW_PT;
+            if (use > 0) mbar_wait(&bars->empty[s], (uint32_t)((use - 1) & 1));
+            unsigned char* a = smem + (size_t)s * stage_bytes;
+            unsigned char* b = a + DW_A_STAGE;
+            // dOut rows -> B stage (TF32): 64 rows x NB/4 float4 items dealt over the 256 lanes, 4 loads in flight
+            const int items = DW_PT * nv;
+            for (int base = warp * 32 + lane; base < items; base += 4 * NPW * 32) {
+                float4 v[4];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int t = base + u * 32 + lane;
+                for (int u = 0; u < 4; u++) {
+                    const int q = base + u * NPW * 32;
                     v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (t < items) {
-                        const int r = t / nv, n4 = t - r * nv;
-                        const int i = tile_base + warp * RPW + r;
-                        const int n = n0 + n4 * 4;
+                    if (q < items) {
+                        const int r = q / nv, n4 = q - r * nv;
+                        const int i = row_base + r, n = n0 + n4 * 4;
                         if (i < P.nq && n < P.cout) {
                             const float* src = P.dout + (size_t)i * P.cout + n;
                             if (vec4) v[u] = __ldg(reinterpret_cast<const float4*>(src));
@@ -807,64 +818,77 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) kp_dw_kernel(DwParam
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int t = base + u * 32 + lane;
-                    if (t < items) {
-                        const int r = t / nv, n4 = t - r * nv;
-                        float4 w = v[u];
-                        w.x = to_tf32(w.x); w.y = to_tf32(w.y); w.z = to_tf32(w.z); w.w = to_tf32(w.w);
-                        *reinterpret_cast<float4*>(sB + LayoutMNMajor::off(warp * RPW + r, n4)) = w;
+                for (int u = 0; u < 4; u++) {
+                    const int q = base + u * NPW * 32;
+                    if (q < items) {
+                        const int r = q / nv, n4 = q - r * nv;
+                        *reinterpret_cast<float4*>(b + LayoutMNMajor::off(r, n4)) = to_tf32(v[u]);
                     }
                 }
             }
-        }
-        __syncthreads();  // headers ready
-        if (DENSE) dense_rows<LayoutMNMajor, RPW>(sA, warp, lane, chunk, tile_base, P.nq, P.x, P.cin_p, P.mask, P.slope_in);
-        else KP_ASSEMBLE<8, LayoutMNMajor, RPW>(sA, warp, lane, chunk, P.cin_p, P.K, s_row0, s_koff, P.entries, P.x);
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-#pragma unroll 1
-            for (int kk = 0; kk < TILE_M / 8; kk++) {  // K = 8 points per MMA
-                // MN-major swizzled descriptors: "leading" offset = next 32-element group along M/N, "stride" offset =
-                // next group of 4 K values; 8 points per MMA = two K groups = 1024 B
-                const uint64_t ad = make_desc(a_addr + kk * 2 * MN_SBO, MN_LBO, MN_SBO, LAYOUT_SW128_BASE32B);
-                const uint64_t bd = make_desc(b_addr + kk * 2 * MN_SBO, MN_LBO, MN_SBO, LAYOUT_SW128_BASE32B);
-                umma_tf32(tmem, ad, bd, idesc, (step > 0 || kk > 0) ? 1u : 0u);
+            if (DENSE) {
+                produce_dense<LayoutMNMajor, DW_PT / RB>(a, warp, lane, chunk * DW_CK, row_base, P.nq, P.x, P.gg.cin_p, P.mask, P.slope_in);
+            } else {
+                const int* toff_tile = P.toff + (size_t)tile * TOFF_PER_TILE;
+                const int2* ent = P.entries + __ldg(toff_tile + 15 * TOFF_RB);
+                produce_sparse<LayoutMNMajor, DW_PT / RB, 4>(a, warp, lane, P.gg, chunk * DW_CK, half * (DW_PT / RB), toff_tile, ent, P.x);
             }
-            umma_commit(bar_mma);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->full[s]);
+        }
+    } else if (warp == MMA_WARP) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(DW_CK, P.NB, 1, 1);
+            for (int t = 0; t < n_steps; t++) {
+                const int s = t % S;
+                mbar_wait(&bars->full[s], (uint32_t)((t / S) & 1));
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes), b_addr = a_addr + DW_A_STAGE;
+#pragma unroll
+                for (int kk = 0; kk < DW_PT / 8; kk++) {  // K = 8 points per MMA
+                    // MN-major swizzled descriptors: "leading" offset = next 32-element group along M/N, "stride" offset =
+                    // next group of 4 K values; 8 points per MMA = two K groups = 1024 B
+                    const uint64_t ad = make_desc(a_addr + kk * 2 * MN_SBO, MN_LBO, MN_SBO, LAYOUT_SW128_BASE32B);
+                    const uint64_t bd = make_desc(b_addr + kk * 2 * MN_SBO, MN_LBO, MN_SBO, LAYOUT_SW128_BASE32B);
+                    umma_tf32(tmem, ad, bd, idesc, (t > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(&bars->empty[s]);
+            }
+            umma_commit(&bars->acc_full);
         }
     }
-    mbar_wait(bar_mma, (uint32_t)((step - 1) & 1));
-    tc_fence_after();
 
-    // epilogue: TMEM lane r = reduction column chunk*CK + r = (k, c); add into dW[k, c, n0 + col]
-    const int r = 32 * (warp & 3) + lane;
-    const int col = chunk * CK + r;
-    const int k = col / P.cin_p, c = col % P.cin_p;
-    const bool row_ok = k < P.K && c < P.cin;
-    const bool vec = (P.cout & 3) == 0;
-    for (int cb = warp >> 2; cb < P.NB / 16; cb += NWARPS / 4) {
-        float v[16];
-        tmem_ld16(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cb * 16), v);
-        if (row_ok) {
-            float* o = P.dw + ((size_t)k * P.cin + c) * P.cout + n0 + cb * 16;
+    // epilogue: TMEM lane r = reduction column chunk*128 + r = (k, c); add into dW[k, c, n0 + col]
+    if (warp < NPW) {
+        mbar_wait(&bars->acc_full, 0u);
+        tc_fence_after();
+        const int r = 32 * (warp & 3) + lane;
+        const int col = chunk * DW_CK + r;
+        const int k = col / P.gg.cin_p, c = col - k * P.gg.cin_p;
+        const bool row_ok = k < P.gg.K && c < P.cin;
+        const bool vec = (P.cout & 3) == 0;
+        for (int cb = warp >> 2; cb < P.NB / 16; cb += NPW / 4) {
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cb * 16), v);
+            if (row_ok) {
+                float* o = P.dw + ((size_t)k * P.cin + c) * P.cout + n0 + cb * 16;
 #pragma unroll
-            for (int t = 0; t < 16; t += 4) {
-                if (vec && n0 + cb * 16 + t < P.cout) {
-                    atomicAdd(reinterpret_cast<float4*>(o + t), make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]));
-                } else if (!vec) {
+                for (int t = 0; t < 16; t += 4) {
+                    if (vec && n0 + cb * 16 + t < P.cout) {
+                        atomicAdd(reinterpret_cast<float4*>(o + t), make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]));
+                    } else if (!vec) {
 #pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (n0 + cb * 16 + t + u < P.cout) atomicAdd(o + t + u, v[t + u]);
+                        for (int u = 0; u < 4; u++)
+                            if (n0 + cb * 16 + t + u < P.cout) atomicAdd(o + t + u, v[t + u]);
+                    }
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, P.tmem_cols);
+    if (warp == MMA_WARP) tmem_dealloc(tmem, P.tmem_cols);
 }
 
 // ----------------------------------------------------------------------------------------- transposed neighbour table
@@ -908,38 +932,65 @@ __global__ void __launch_bounds__(256) kp_tr_sort_kernel(const int* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------- host side
+static int pad4(int c) { return (c + 3) & ~3; }
+// row pitch of a gathered matrix: the lane groups of the producers cover min(pitch, 64) columns of one kernel point, so
+// the pitch is a power of two up to 64 or a multiple of 64
+static int pad_gather(int c) {
+    if (c > 64) return (c + 63) & ~63;
+    int p = 4;
+    while (p < c) p <<= 1;
+    return p;
+}
+static GatherGeom make_geom(int cin_p, int K) {
+    GatherGeom g;
+    g.cin_p = cin_p;
+    g.K = K;
+    g.seg_len = cin_p < FWD_CK ? cin_p : FWD_CK;
+    g.g_log2 = 0;
+    while ((4 << g.g_log2) < g.seg_len) g.g_log2++;
+    return g;
+}
+
+// Caller-visible list buffers: `hdr` = 4 control ints (entries used, overflow flag, 2 spare) followed by the tile
+// headers, `entries` = the compact entry array.
+constexpr int LISTS_CTL_INTS = 4;
 struct Lists {
-    unsigned short* koff;
+    int* hdr;
     int2* entries;
+    long long cap;
+    const int* toff() const { return hdr + LISTS_CTL_INTS; }
 };
 
+void kpconv_lists_bytes(int nc, long long n_pairs, long long* hdr_bytes, long long* entries_bytes) {
+    const long long tiles = nc > 0 ? (nc + TILE_M - 1) / TILE_M : 1;
+    *hdr_bytes = (LISTS_CTL_INTS + tiles * TOFF_PER_TILE) * 4;
+    *entries_bytes = (n_pairs > 0 ? n_pairs : 1) * 15 * 8;  // exact worst case; callers with calibrated bounds pass less
+}
+
 static int build_lists(Scratch& S, const float* centres, int nc, const float* others, int no, const Table& T,
-                       long long n_pairs, int max_row, const float* kp, int K, float kp_sign, float extent, Lists* L,
-                       cudaStream_t stream, void* ext_koff = nullptr, void* ext_entries = nullptr) {
+                       long long n_pairs, const float* kp, int K, float kp_sign, float extent, Lists* L,
+                       cudaStream_t stream) {
     if (n_pairs * 15 >= (1LL << 31)) return fail(KP_ERR_UNSUPPORTED, "kpconv: neighbour table too large (Nq*H*15 >= 2^31)");
-    L->koff = ext_koff ? (unsigned short*)ext_koff : S.alloc<unsigned short>((size_t)nc * KOFF);
-    L->entries = ext_entries ? (int2*)ext_entries : S.alloc<int2>((size_t)(n_pairs > 0 ? n_pairs : 1) * 15);
-    if (S.status != KP_OK) return S.status;
-    ProfileScope ps("kp_influence", stream);
-    kp_influence_kernel<<<ceil_div(nc, INF_WARPS), INF_WARPS * 32, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign,
-                                                                             1.f / extent, L->koff, L->entries);
-    if (max_row == 0 || max_row > INF_MAX_ROW) {  // CSR rows of unknown length, or a padded table wider than the staging
-        KP_CHECK_LAUNCH();
-        kp_influence_long_kernel<<<ceil_div(nc, INF_WARPS), INF_WARPS * 32, 0, stream>>>(centres, nc, others, no, T, kp, K,
-                                                                                      kp_sign, 1.f / extent, L->koff,
-                                                                                      L->entries);
+    const int n_tiles = ceil_div(nc, TILE_M);
+    if (!L->hdr) {
+        L->hdr = S.alloc<int>((size_t)LISTS_CTL_INTS + (size_t)n_tiles * TOFF_PER_TILE);
+        L->cap = (n_pairs > 0 ? n_pairs : 1) * 15;
+        L->entries = S.alloc<int2>((size_t)L->cap);
     }
+    int2* scratch = S.alloc<int2>((size_t)(n_pairs > 0 ? n_pairs : 1) * 15);
+    if (S.status != KP_OK) return S.status;
+    ProfileScope ps("kp_lists", stream);
+    KP_CUDA(cudaMemsetAsync(L->hdr, 0, LISTS_CTL_INTS * sizeof(int), stream));
+    ListsOut O;
+    O.toff = L->hdr + LISTS_CTL_INTS; O.entries = L->entries; O.ctl = L->hdr; O.cap = L->cap;
+    kp_lists_kernel<<<n_tiles, LST_WARPS * 32, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, 1.f / extent, scratch, O);
     KP_CHECK_LAUNCH();
     return KP_OK;
 }
 
-static int pad4(int c) { return (c + 3) & ~3; }
-
 // How many CTAs share the reduction axis of one 128-point tile. A CTA costs (its chunks + ~1 chunk of fixed work:
-// TMEM allocation, headers, epilogue), CTAs run in waves of `slots` (2 per SM for the 8-warp kernels, 1 for the 16-warp
-// ones), and a split pays a zero-fill plus an atomic epilogue. The previous rule (fill 296 slots, never look at the
-// wave count) ran the 146-tile layer as 438 CTAs = 1.5 waves of 3 chunks where 292 CTAs = 1 wave of 4 chunks is shorter,
-// and split the 252-tile layer in two for nothing. WEASAL_KSPLIT_MODEL=0 restores it (A/B runs).
+// TMEM allocation, pipeline fill, epilogue), CTAs run in waves of `slots` (2 per SM when two CTAs fit an SM, else 1),
+// and a split pays a zero-fill plus an atomic epilogue. WEASAL_KSPLIT_MODEL=0: fill the slots without looking at waves.
 static int pick_ksplit(int n_tiles, int n_chunks, int slots) {
     static const bool model = !(getenv("WEASAL_KSPLIT_MODEL") && atoi(getenv("WEASAL_KSPLIT_MODEL")) == 0);
     static const bool deterministic = getenv("WEASAL_KPCONV_DETERMINISTIC") && atoi(getenv("WEASAL_KPCONV_DETERMINISTIC")) != 0;
@@ -962,7 +1013,7 @@ static int pick_ksplit(int n_tiles, int n_chunks, int slots) {
     }
     return best;
 }
-
+int plan_ksplit(int n_tiles, int n_chunks, int slots) { return pick_ksplit(n_tiles, n_chunks, slots); }
 
 // opt-in dynamic shared memory: raise a kernel's limit only when a launch needs more than it already has
 template <typename KernelT>
@@ -977,63 +1028,150 @@ static cudaError_t set_smem(KernelT kernel, size_t bytes) {
     return e;
 }
 
-// out[nc, cout] = sum over entry lists of w * x[j, :] contracted with W (strides sk, sc, sn over (k, c_in, n_out))
-static int run_forward(const char* tag, Scratch& S, int nc, const int* rowptr, int H, const float* x, int n_x_rows, int cin,
-                       const Lists& L, const float* W, long long sk, long long sc, long long sn, int cout, int K,
-                       float* out, cudaStream_t stream) {
-    const int cin_p = pad4(cin);
-    const float* xg = x;
-    if (cin_p != cin) {
-        float* xp = S.alloc<float>((size_t)n_x_rows * cin_p);
-        if (S.status != KP_OK) return S.status;
-        const long long tot = (long long)n_x_rows * cin_p;
-        kp_pad_cols_kernel<<<ceil_div(tot, 256) < 2048 ? ceil_div(tot, 256) : 2048, 256, 0, stream>>>(x, n_x_rows, cin, cin_p, xp);
-        KP_CHECK_LAUNCH();
-        xg = xp;
-    }
+constexpr size_t SMEM_TWO_CTAS = 112 * 1024;  // dynamic shared memory up to which two CTAs share an SM
+
+// shape of the packed weight images of one contraction [*, K*cin_p] x [K*cin_p, cout]
+struct ImgShape {
+    int NB, n_nblk, n_chunks;
+    long long floats() const { return (long long)n_chunks * n_nblk * NB * FWD_CK; }
+};
+static int img_shape(int K, int cin_p, int cout, ImgShape* s) {
     const int cout_p = (cout + 15) & ~15;
-    const int NB = cout_p < 256 ? cout_p : 256;
-    const int n_nblk = ceil_div(cout_p, NB);
-    if (n_nblk * NB > 512) return fail(KP_ERR_UNSUPPORTED, "kpconv: out_channels > 512");
-    const int n_chunks = ceil_div((long long)K * cin_p, CK);
-    float* images = S.alloc<float>((size_t)n_chunks * n_nblk * NB * CK);
-    if (S.status != KP_OK) return S.status;
-    {
-        const long long total = (long long)n_chunks * n_nblk * NB * CK;
-        const int grid = ceil_div(total, 256) < 4096 ? ceil_div(total, 256) : 4096;
-        ProfileScope ps("kp_pack_w", stream);
-        kp_pack_w_kernel<<<grid, 256, 0, stream>>>(W, K, cin, cin_p, cout, sk, sc, sn, NB, n_nblk, n_chunks, images);
-        KP_CHECK_LAUNCH();
-    }
+    s->NB = cout_p < 256 ? cout_p : 256;
+    s->n_nblk = ceil_div(cout_p, s->NB);
+    if (s->n_nblk * s->NB > 512) return fail(KP_ERR_UNSUPPORTED, "kpconv: more than 512 output channels in one pass");
+    s->n_chunks = ceil_div((long long)K * cin_p, FWD_CK);
+    return KP_OK;
+}
+
+static int launch_pack(const PackJobs& J, cudaStream_t stream) {
+    if (J.n == 0 || J.total == 0) return KP_OK;
+    const int grid = ceil_div(J.total, 256) < 2368 ? ceil_div(J.total, 256) : 2368;
+    ProfileScope ps("kp_pack_w", stream);
+    kp_pack_w_kernel<<<grid, 256, 0, stream>>>(J);
+    KP_CHECK_LAUNCH();
+    return KP_OK;
+}
+static void add_pack_job(PackJobs& J, const float* W, float* images, long long sk, long long sc, long long sn, int K, int cin,
+                         int cin_p, int cout, const ImgShape& sh) {
+    PackJob& j = J.job[J.n++];
+    j.W = W; j.images = images; j.sk = sk; j.sc = sc; j.sn = sn; j.K = K; j.cin = cin; j.cin_p = cin_p; j.cout = cout;
+    j.NB = sh.NB; j.n_nblk = sh.n_nblk; j.n_chunks = sh.n_chunks;
+    j.first = J.total;
+    J.total += sh.floats();
+}
+
+// out[nc, cout] (row stride ldo) = A · images, A = the sparse gather through the lists (or the dense matrix x[nc, cin_p])
+static int launch_fwd(const char* tag, bool dense, int nc, const float* x, const GatherGeom& gg, const int* toff,
+                      const int2* entries, const float* images, const ImgShape& sh, float* out, int cout, int ldo,
+                      const float* mask, float slope_in, const float* bias, float slope_out, cudaStream_t stream,
+                      int* ksplit_used = nullptr) {
     FwdParams P;
-    P.nq = nc; P.x = xg; P.cin_p = cin_p; P.K = K;
-    P.rowptr = rowptr; P.H = H;
-    P.koff = L.koff; P.entries = L.entries;
-    P.images = images; P.NB = NB; P.n_nblk = n_nblk; P.n_chunks = n_chunks;
-    P.out = out; P.cout = cout; P.ldo = cout;
-    P.mask = nullptr; P.slope_in = 1.f; P.bias = nullptr; P.slope_out = 1.f;
-    // split the reduction across CTAs when the tiles alone cannot fill the 148 SMs (two CTAs each)
+    P.nq = nc; P.x = x; P.gg = gg; P.toff = toff; P.entries = entries;
+    P.images = images; P.NB = sh.NB; P.n_nblk = sh.n_nblk; P.n_chunks = sh.n_chunks;
+    P.out = out; P.cout = cout; P.ldo = ldo;
+    P.mask = mask; P.slope_in = slope_in; P.bias = bias; P.slope_out = slope_out;
     const int n_tiles = ceil_div(nc, TILE_M);
-    // Split partial sums meet in `out` through float atomics, so their order (the last bits of the result) varies from
-    // run to run; WEASAL_KPCONV_DETERMINISTIC=1 keeps one CTA per tile.
-    const size_t smem = (size_t)A_BYTES + (size_t)NB * CK * 4 + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
-    const int ksplit = pick_ksplit(n_tiles, n_chunks, smem <= (size_t)SMEM_TWO_CTAS ? 2 * 148 : 148);
+    const size_t per_stage = (size_t)A_STAGE + (size_t)sh.NB * FWD_CK * 4;
+    const int stages = sh.NB == 128 ? 3 : 2;
+    const size_t smem = stages * per_stage + sizeof(FwdBars) + 64;
+    P.stages = stages;
+    // split the reduction across CTAs when the tiles alone cannot fill the SMs. Split partial sums meet in `out`
+    // through float atomics, so their order (the last bits of the result) varies from run to run;
+    // WEASAL_KPCONV_DETERMINISTIC=1 keeps one CTA per tile.
+    const int ksplit = pick_ksplit(n_tiles, sh.n_chunks, smem <= SMEM_TWO_CTAS ? 2 * 148 : 148);
     P.ksplit = ksplit;
-    if (ksplit > 1) KP_CUDA(cudaMemsetAsync(out, 0, (size_t)nc * cout * sizeof(float), stream));
+    if (ksplit_used) *ksplit_used = ksplit;
+    if (ksplit > 1) KP_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)cout * 4, nc, stream));
     uint32_t cols = 32;
-    while ((int)cols < n_nblk * NB) cols <<= 1;
+    while ((int)cols < sh.n_nblk * sh.NB) cols <<= 1;
     P.tmem_cols = cols;
-    if (smem <= (size_t)SMEM_TWO_CTAS) {
-        KP_CUDA(set_smem(kp_fwd_kernel<8, false>, smem));
-        ProfileScope ps(tag, stream);
-        kp_fwd_kernel<8, false><<<dim3(n_tiles, ksplit), 256, smem, stream>>>(P);
+    ProfileScope ps(tag, stream);
+    if (dense) {
+        KP_CUDA(set_smem(kp_fwd_kernel<true>, smem));
+        kp_fwd_kernel<true><<<dim3(n_tiles, ksplit), WS_THREADS, smem, stream>>>(P);
     } else {
-        KP_CUDA(set_smem(kp_fwd_kernel<16, false>, smem));
-        ProfileScope ps(tag, stream);
-        kp_fwd_kernel<16, false><<<dim3(n_tiles, ksplit), 512, smem, stream>>>(P);
+        KP_CUDA(set_smem(kp_fwd_kernel<false>, smem));
+        kp_fwd_kernel<false><<<dim3(n_tiles, ksplit), WS_THREADS, smem, stream>>>(P);
     }
     KP_CHECK_LAUNCH();
     return KP_OK;
+}
+
+// dw[K, cin, cout] (+)= A^T · dout, A as above; dw must be zeroed by the caller
+static int launch_dw(const char* tag, bool dense, int nq, const float* x, const GatherGeom& gg, int cin, const int* toff,
+                     const int2* entries, const float* dout, int cout, float* dw, const float* mask, float slope_in,
+                     cudaStream_t stream) {
+    const int cout_p = (cout + 15) & ~15;
+    DwParams P;
+    P.nq = nq; P.x = x; P.gg = gg; P.cin = cin; P.toff = toff; P.entries = entries;
+    P.dout = dout; P.cout = cout;
+    P.NB = cout_p < 256 ? cout_p : 256;
+    const int n_slices = ceil_div(cout_p, P.NB);
+    const int n_chunks = ceil_div((long long)gg.K * gg.cin_p, DW_CK);
+    P.n_tiles = ceil_div(nq, TILE_M);
+    const size_t per_stage = (size_t)DW_A_STAGE + (size_t)dw_b_bytes(P.NB);
+    const int stages = P.NB == 128 ? 3 : 2;
+    const size_t smem = stages * per_stage + sizeof(DwBars) + 64;
+    P.stages = stages;
+    int splits = (smem <= SMEM_TWO_CTAS ? 2 * 148 : 148) / (n_chunks * n_slices);  // one wave of CTAs
+    if (splits < 1) splits = 1;
+    if (splits > P.n_tiles) splits = P.n_tiles;
+    P.n_splits = splits;
+    P.dw = dw;
+    P.mask = mask; P.slope_in = slope_in;
+    uint32_t cols = 32;
+    while ((int)cols < P.NB) cols <<= 1;
+    P.tmem_cols = cols;
+    ProfileScope ps(tag, stream);
+    if (dense) {
+        KP_CUDA(set_smem(kp_dw_kernel<true>, smem));
+        kp_dw_kernel<true><<<dim3(n_chunks, splits, n_slices), WS_THREADS, smem, stream>>>(P);
+    } else {
+        KP_CUDA(set_smem(kp_dw_kernel<false>, smem));
+        kp_dw_kernel<false><<<dim3(n_chunks, splits, n_slices), WS_THREADS, smem, stream>>>(P);
+    }
+    KP_CHECK_LAUNCH();
+    return KP_OK;
+}
+
+// rows padded to the pitch the consumers need
+static int padded_to(Scratch& S, const float* src, long long n, int c, int c_p, const float** dst, cudaStream_t stream) {
+    *dst = src;
+    if (c_p == c) return KP_OK;
+    float* p = S.alloc<float>((size_t)(n > 0 ? n : 1) * c_p);
+    if (S.status != KP_OK) return S.status;
+    const long long tot = n * c_p;
+    if (tot > 0) {
+        kp_pad_cols_kernel<<<ceil_div(tot, 256) < 2048 ? ceil_div(tot, 256) : 2048, 256, 0, stream>>>(src, n, c, c_p, p);
+        KP_CHECK_LAUNCH();
+    }
+    *dst = p;
+    return KP_OK;
+}
+
+// out[nc, cout] = (sparse gather of x[n_x_rows, cin] through L) contracted with W (strides sk, sc, sn over (k, c_in,
+// n_out)), or with ready-made images when `images` is non-null
+static int apply_lists(const char* tag, Scratch& S, int nc, const float* x, int n_x_rows, int cin, const Lists& L,
+                       const float* W, long long sk, long long sc, long long sn, const float* images, int cout, int K,
+                       float* out, float slope_out, cudaStream_t stream) {
+    const int cin_p = pad_gather(cin);
+    const float* xg;
+    int rc = padded_to(S, x, n_x_rows, cin, cin_p, &xg, stream);
+    if (rc != KP_OK) return rc;
+    ImgShape sh;
+    if ((rc = img_shape(K, cin_p, cout, &sh)) != KP_OK) return rc;
+    if (!images) {
+        float* img = S.alloc<float>((size_t)sh.floats());
+        if (S.status != KP_OK) return S.status;
+        PackJobs J;
+        J.n = 0; J.total = 0;
+        add_pack_job(J, W, img, sk, sc, sn, K, cin, cin_p, cout, sh);
+        if ((rc = launch_pack(J, stream)) != KP_OK) return rc;
+        images = img;
+    }
+    return launch_fwd(tag, false, nc, xg, make_geom(cin_p, K), L.toff(), L.entries, images, sh, out, cout, cout, nullptr,
+                      1.f, nullptr, slope_out, stream);
 }
 
 static int check_args(int nq, int ns, int H, int idx_stride, int cin, int cout, int K, float extent) {
@@ -1041,21 +1179,40 @@ static int check_args(int nq, int ns, int H, int idx_stride, int cin, int cout, 
     if (K <= 0 || K > 15) return fail(KP_ERR_UNSUPPORTED, "kpconv: kernel_size must be 1..15");
     if (!(extent > 0.f)) return fail(KP_ERR_ARG, "kpconv: KP_extent must be positive");
     if (H > 4096) return fail(KP_ERR_UNSUPPORTED, "kpconv: more than 4096 neighbour columns");
-    if ((long long)ns >= (1LL << K_SHIFT) || (long long)nq >= (1LL << K_SHIFT))
-        return fail(KP_ERR_UNSUPPORTED, "kpconv: more than 2^27 points in one call");
+    if ((long long)ns >= (1LL << ROW_SHIFT) || (long long)nq >= (1LL << ROW_SHIFT))
+        return fail(KP_ERR_UNSUPPORTED, "kpconv: more than 2^25 points in one call");
     return KP_OK;
 }
 
-// lists_koff / lists_entries (optional, caller-owned device buffers of kpconv_lists_bytes): the forward pass leaves
-// the influence entry lists there so that backward can reuse them instead of rebuilding them.
-void kpconv_lists_bytes(int nq, int H, long long* koff_bytes, long long* entries_bytes) {
-    *koff_bytes = (long long)(nq > 0 ? nq : 1) * KOFF * 2;
-    *entries_bytes = (long long)(nq > 0 ? nq : 1) * (H > 0 ? H : 1) * 15 * 8;
+// Standalone list construction (the prefetch stage of a training step, or a caller that keeps the lists of a static
+// geometry): centres / others are the roles of the pass the lists are for (forward and dW: centres = queries, others =
+// supports, kp_sign = +1; dX: centres = supports, others = queries, table = the transposed one, kp_sign = -1).
+int kpconv_lists_build_device(const float* centres, int nc, const float* others, int no, const void* idx, int idx_is_i64,
+                              int H, int idx_stride, const int* rowptr, const int* col, long long n_pairs,
+                              const float* kp, int K, float kp_sign, float extent, void* hdr, void* entries,
+                              long long entries_cap, cudaStream_t stream) {
+    if (nc <= 0 || no <= 0 || K <= 0 || K > 15 || !(extent > 0.f) || !hdr || !entries || entries_cap <= 0)
+        return fail(KP_ERR_ARG, "kpconv_lists_build: bad arguments");
+    if ((long long)nc >= (1LL << ROW_SHIFT) || (long long)no >= (1LL << ROW_SHIFT))
+        return fail(KP_ERR_UNSUPPORTED, "kpconv: more than 2^25 points in one call");
+    Scratch S(stream);
+    Table T;
+    if (rowptr) { T.idx = col; T.rowptr = rowptr; T.H = 0; T.stride = 0; T.is_i64 = 0; }
+    else {
+        if (H <= 0 || idx_stride < H) return fail(KP_ERR_ARG, "kpconv_lists_build: bad table");
+        T.idx = idx; T.rowptr = nullptr; T.H = H; T.stride = idx_stride; T.is_i64 = idx_is_i64;
+        n_pairs = (long long)nc * H;
+    }
+    Lists L;
+    L.hdr = (int*)hdr; L.entries = (int2*)entries; L.cap = entries_cap;
+    return build_lists(S, centres, nc, others, no, T, n_pairs, kp, K, kp_sign, extent, &L, stream);
 }
 
+// lists_hdr / lists_entries (optional, caller-owned device buffers of kpconv_lists_bytes): the forward pass leaves
+// the influence lists there so that backward can reuse them instead of rebuilding them.
 int kpconv_forward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
                           int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
-                          float extent, float* out, void* lists_koff, void* lists_entries, cudaStream_t stream) {
+                          float extent, float* out, void* lists_hdr, void* lists_entries, cudaStream_t stream) {
     int rc = check_args(nq, ns, H, idx_stride, cin, cout, K, extent);
     if (rc != KP_OK) return rc;
     if (nq == 0) return KP_OK;
@@ -1067,9 +1224,48 @@ int kpconv_forward_device(const float* q, int nq, const float* s, int ns, const 
     Table T;
     T.idx = idx; T.rowptr = nullptr; T.H = H; T.stride = idx_stride; T.is_i64 = idx_is_i64;
     Lists L;
-    rc = build_lists(S, q, nq, s, ns, T, (long long)nq * H, H, kp, K, 1.f, extent, &L, stream, lists_koff, lists_entries);
+    L.hdr = (int*)lists_hdr; L.entries = (int2*)lists_entries; L.cap = (long long)nq * H * 15;
+    if (!lists_hdr || !lists_entries) L.hdr = nullptr;
+    rc = build_lists(S, q, nq, s, ns, T, (long long)nq * H, kp, K, 1.f, extent, &L, stream);
     if (rc != KP_OK) return rc;
-    return run_forward("kp_fwd", S, nq, nullptr, H, x, ns, cin, L, w, (long long)cin * cout, cout, 1, cout, K, out, stream);
+    return apply_lists("kp_fwd", S, nq, x, ns, cin, L, w, (long long)cin * cout, cout, 1, nullptr, cout, K, out, 1.f, stream);
+}
+
+// Forward-type pass over ready-made lists (also the dX pass: x = dOut, lists = the transposed ones, weights read
+// transposed). w_packed != 0: `w` holds ready-made images (kp_pack_weights_dev); transpose_w: W'[k][o][c] = W[k][c][o].
+int kpconv_apply_lists_device(int nc, const float* x, int n_x_rows, int cin, const float* w, int w_packed, int transpose_w,
+                              int cout, int K, const void* hdr, const void* entries, float* out, float slope_out,
+                              cudaStream_t stream) {
+    if (nc < 0 || n_x_rows < 0 || cin <= 0 || cout <= 0 || K <= 0 || K > 15 || !hdr || !entries)
+        return fail(KP_ERR_ARG, "kpconv_apply_lists: bad arguments");
+    if (nc == 0) return KP_OK;
+    Scratch S(stream);
+    Lists L;
+    L.hdr = (int*)hdr; L.entries = (int2*)entries; L.cap = 0;
+    // B(col = (k, c), n) with c over this call's `cin` gathered channels and n over its `cout` produced channels.
+    // Forward: W[k][c][n], strides (cin*cout, cout, 1). dX (this call's cin = the conv's out_channels Co, cout = its
+    // in_channels Ci): B((k, o), c) = W[k][c][o] = W[k*Ci*Co + c*Co + o], strides (Ci*Co, 1, Co) = (cin*cout, 1, cin).
+    const long long sk = (long long)cin * cout;
+    const long long sc = transpose_w ? 1 : cout;
+    const long long sn = transpose_w ? cin : 1;
+    return apply_lists(transpose_w ? "kp_fwd_dx" : "kp_fwd", S, nc, x, n_x_rows, cin, L, w_packed ? nullptr : w, sk, sc, sn,
+                       w_packed ? w : nullptr, cout, K, out, slope_out, stream);
+}
+
+// dW over ready-made (query-centred) lists; d_w [K, cin, cout] is overwritten
+int kpconv_dw_lists_device(int nq, const float* x, int ns, int cin, const float* dout, int cout, int K, const void* hdr,
+                           const void* entries, float* dw, cudaStream_t stream) {
+    if (nq < 0 || ns < 0 || cin <= 0 || cout <= 0 || K <= 0 || K > 15 || !hdr || !entries)
+        return fail(KP_ERR_ARG, "kpconv_dw_lists: bad arguments");
+    KP_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * cin * cout * sizeof(float), stream));
+    if (nq == 0 || ns == 0) return KP_OK;
+    Scratch S(stream);
+    const int cin_p = pad_gather(cin);
+    const float* xg;
+    int rc = padded_to(S, x, ns, cin, cin_p, &xg, stream);
+    if (rc != KP_OK) return rc;
+    return launch_dw("kp_dw", false, nq, xg, make_geom(cin_p, K), cin, (const int*)hdr + LISTS_CTL_INTS, (const int2*)entries,
+                     dout, cout, dw, nullptr, 1.f, stream);
 }
 
 // Transposed neighbour table (CSR over the supports): row j lists, in ascending order, the centres i whose row contains
@@ -1110,7 +1306,7 @@ int transpose_table_entry(const void* idx, int idx_is_i64, int nq, int H, int id
 
 int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const void* idx, int idx_is_i64, int H,
                            int idx_stride, const float* x, int cin, const float* w, int cout, const float* kp, int K,
-                           float extent, const float* dout, float* dx, float* dw, const void* lists_koff,
+                           float extent, const float* dout, float* dx, float* dw, const void* lists_hdr,
                            const void* lists_entries, const int* t_rowptr, const int* t_col, int table_symmetric,
                            cudaStream_t stream) {
     int rc = check_args(nq, ns, H, idx_stride, cin, cout, K, extent);
@@ -1124,70 +1320,32 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
     Scratch S(stream);
     const long long n_pairs = (long long)nq * H;
 
-    // ---- dW: entry lists centred on the queries (same as forward)
+    // ---- dW: lists centred on the queries (same as forward)
     {
         Table T;
         T.idx = idx; T.rowptr = nullptr; T.H = H; T.stride = idx_stride; T.is_i64 = idx_is_i64;
         Lists L;
-        if (lists_koff && lists_entries) {  // left behind by the forward pass
-            L.koff = (unsigned short*)lists_koff;
-            L.entries = (int2*)lists_entries;
+        L.hdr = nullptr;
+        if (lists_hdr && lists_entries) {  // left behind by the forward pass
+            L.hdr = (int*)lists_hdr; L.entries = (int2*)lists_entries; L.cap = n_pairs * 15;
         } else {
-            rc = build_lists(S, q, nq, s, ns, T, n_pairs, H, kp, K, 1.f, extent, &L, stream);
+            rc = build_lists(S, q, nq, s, ns, T, n_pairs, kp, K, 1.f, extent, &L, stream);
             if (rc != KP_OK) return rc;
         }
-        const int cin_p = pad4(cin);
-        const float* xg = x;
-        if (cin_p != cin) {
-            float* xp = S.alloc<float>((size_t)ns * cin_p);
-            if (S.status != KP_OK) return S.status;
-            const int grid = ceil_div((long long)ns * cin_p, 256) < 2048 ? ceil_div((long long)ns * cin_p, 256) : 2048;
-            kp_pad_cols_kernel<<<grid, 256, 0, stream>>>(x, ns, cin, cin_p, xp);
-            KP_CHECK_LAUNCH();
-            xg = xp;
-        }
-        const int cout_p = (cout + 15) & ~15;
-        DwParams P;
-        P.nq = nq; P.x = xg; P.cin = cin; P.cin_p = cin_p; P.K = K; P.H = H;
-        P.koff = L.koff; P.entries = L.entries;
-        P.dout = dout; P.cout = cout;
-        P.NB = cout_p < 256 ? cout_p : 256;
-        const int n_slices = ceil_div(cout_p, P.NB);
-        const int n_chunks = ceil_div((long long)K * cin_p, CK);
-        P.n_tiles = ceil_div(nq, TILE_M);
-        const size_t smem = (size_t)4 * MN_LBO + (size_t)dw_b_bytes(P.NB) + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
-        int splits = (smem <= (size_t)SMEM_TWO_CTAS ? 2 * 148 : 148) / (n_chunks * n_slices);  // one wave of CTAs
-        if (splits < 1) splits = 1;
-        if (splits > P.n_tiles) splits = P.n_tiles;
-        P.n_splits = splits;
-        P.dw = dw;
-        P.mask = nullptr; P.slope_in = 1.f;
-        uint32_t cols = 32;
-        while ((int)cols < P.NB) cols <<= 1;
-        P.tmem_cols = cols;
-        if (smem <= (size_t)SMEM_TWO_CTAS) {
-            KP_CUDA(set_smem(kp_dw_kernel<8, false>, smem));
-            ProfileScope ps("kp_dw", stream);
-            kp_dw_kernel<8, false><<<dim3(n_chunks, splits, n_slices), 256, smem, stream>>>(P);
-        } else {
-            KP_CUDA(set_smem(kp_dw_kernel<16, false>, smem));
-            ProfileScope ps("kp_dw", stream);
-            kp_dw_kernel<16, false><<<dim3(n_chunks, splits, n_slices), 512, smem, stream>>>(P);
-        }
-        KP_CHECK_LAUNCH();
+        const int cin_p = pad_gather(cin);
+        const float* xg;
+        if ((rc = padded_to(S, x, ns, cin, cin_p, &xg, stream)) != KP_OK) return rc;
+        rc = launch_dw("kp_dw", false, nq, xg, make_geom(cin_p, K), cin, L.toff(), L.entries, dout, cout, dw, nullptr, 1.f, stream);
+        if (rc != KP_OK) return rc;
     }
 
     // ---- dX: the forward kernel on the transposed table, with W^T and -kp
+    Table T;
+    long long t_pairs = n_pairs;
     if (table_symmetric) {
         // queries == supports and no row was cropped: j is in row i exactly when i is in row j (the f32 distance is
         // exactly symmetric), so the table is its own transpose and no CSR copy is needed
-        Table T;
         T.idx = idx; T.rowptr = nullptr; T.H = H; T.stride = idx_stride; T.is_i64 = idx_is_i64;
-        Lists L;
-        rc = build_lists(S, s, ns, q, nq, T, n_pairs, H, kp, K, -1.f, extent, &L, stream);
-        if (rc != KP_OK) return rc;
-        rc = run_forward("kp_fwd_dx", S, ns, nullptr, H, dout, nq, cout, L, w, (long long)cin * cout, 1, cout, cin, K, dx, stream);
-        if (rc != KP_OK) return rc;
     } else {
         const int* rowptr = t_rowptr;
         const int* col_sorted = t_col;
@@ -1200,104 +1358,129 @@ int kpconv_backward_device(const float* q, int nq, const float* s, int ns, const
             rowptr = rp;
             col_sorted = cs;
         }
-        Table T;
         T.idx = col_sorted; T.rowptr = rowptr; T.H = 0; T.stride = 0; T.is_i64 = 0;
-        Lists L;
-        rc = build_lists(S, s, ns, q, nq, T, n_pairs, 0, kp, K, -1.f, extent, &L, stream);
-        if (rc != KP_OK) return rc;
-        // W'[k][c' = o][n' = c] = W[k][c][o]
-        rc = run_forward("kp_fwd_dx", S, ns, rowptr, 0, dout, nq, cout, L, w, (long long)cin * cout, 1, cout, cin, K, dx, stream);
-        if (rc != KP_OK) return rc;
     }
-    return KP_OK;
+    Lists L;
+    L.hdr = nullptr;
+    rc = build_lists(S, s, ns, q, nq, T, t_pairs, kp, K, -1.f, extent, &L, stream);
+    if (rc != KP_OK) return rc;
+    // W'[k][c' = o][n' = c] = W[k][c][o]
+    return apply_lists("kp_fwd_dx", S, ns, dout, nq, cout, L, w, (long long)cin * cout, 1, cout, nullptr, cin, K, dx, 1.f, stream);
 }
 
-// host-side planning, exported for tests (no device work)
-int plan_ksplit(int n_tiles, int n_chunks, int slots) { return pick_ksplit(n_tiles, n_chunks, slots); }
+// ------------------------------------------------------------------------------------------------ weight packing API
+// One launch packs the operand images of any number of contractions (a training step calls it once, right after the
+// optimizer step / before the forward pass, for every KPConv (W and W^T) and every unary block).
+//   kind 0: KPConv forward   W[K, cin, cout]           -> images of [K*pad(cin)] x cout
+//   kind 1: KPConv dX        W[K, cin, cout] transposed -> images of [K*pad(cout)] x cin
+//   kind 2: linear forward   W[cout, cin] (nn.Linear)   -> images of [pad4(cin)] x cout         (y = x W^T)
+//   kind 3: linear dX        W[cout, cin]               -> images of [pad4(cout)] x cin         (dx = g W)
+long long pack_image_floats(int kind, int K, int cin, int cout) {
+    ImgShape sh;
+    int rc;
+    switch (kind) {
+        case 0: rc = img_shape(K, pad_gather(cin), cout, &sh); break;
+        case 1: rc = img_shape(K, pad_gather(cout), cin, &sh); break;
+        case 2: rc = img_shape(1, pad4(cin), cout < 512 ? cout : 512, &sh); break;
+        case 3: rc = img_shape(1, pad4(cout), cin < 512 ? cin : 512, &sh); break;
+        default: return -1;
+    }
+    if (rc != KP_OK) return -1;
+    if (kind == 2) return sh.floats() * ceil_div(cout, 512);
+    if (kind == 3) return sh.floats() * ceil_div(cin, 512);
+    return sh.floats();
+}
+
+int pack_weights_device(int n_jobs, const int* kinds, const float* const* weights, const int* Ks, const int* cins,
+                        const int* couts, float* const* images, cudaStream_t stream) {
+    PackJobs J;
+    J.n = 0; J.total = 0;
+    for (int i = 0; i < n_jobs; i++) {
+        const int K = Ks[i], cin = cins[i], cout = couts[i];
+        ImgShape sh;
+        int rc;
+        if (kinds[i] == 0) {
+            if ((rc = img_shape(K, pad_gather(cin), cout, &sh)) != KP_OK) return rc;
+            add_pack_job(J, weights[i], images[i], (long long)cin * cout, cout, 1, K, cin, pad_gather(cin), cout, sh);
+        } else if (kinds[i] == 1) {
+            if ((rc = img_shape(K, pad_gather(cout), cin, &sh)) != KP_OK) return rc;
+            add_pack_job(J, weights[i], images[i], (long long)cin * cout, 1, cout, K, cout, pad_gather(cout), cin, sh);
+        } else if (kinds[i] == 2 || kinds[i] == 3) {
+            // dense layers: output slices of up to 512 columns (TMEM), one job per slice, images back to back
+            const int a_cols = kinds[i] == 2 ? cin : cout, o_cols = kinds[i] == 2 ? cout : cin;
+            long long off = 0;
+            for (int o0 = 0; o0 < o_cols; o0 += 512) {
+                const int co = o_cols - o0 < 512 ? o_cols - o0 : 512;
+                if ((rc = img_shape(1, pad4(a_cols), co, &sh)) != KP_OK) return rc;
+                if (J.n >= PACK_MAX_JOBS) {
+                    if ((rc = launch_pack(J, stream)) != KP_OK) return rc;
+                    J.n = 0; J.total = 0;
+                }
+                // kind 2: B(c, o) = W[o*cin + c]: sc = 1, sn = cin; kind 3: B(o, c) = W[o*cin + c]: sc = cin, sn = 1
+                if (kinds[i] == 2) add_pack_job(J, weights[i] + (long long)o0 * cin, images[i] + off, 0, 1, cin, 1, a_cols, pad4(a_cols), co, sh);
+                else add_pack_job(J, weights[i] + o0, images[i] + off, 0, cin, 1, 1, a_cols, pad4(a_cols), co, sh);
+                off += sh.floats();
+            }
+            continue;
+        } else return fail(KP_ERR_ARG, "pack_weights: unknown kind");
+        if (J.n >= PACK_MAX_JOBS - 1) {
+            if ((rc = launch_pack(J, stream)) != KP_OK) return rc;
+            J.n = 0; J.total = 0;
+        }
+    }
+    return launch_pack(J, stream);
+}
 
 // ------------------------------------------------------------------------------------------ dense linear layers
 // The unary blocks around every KPConv (models/blocks.py:467-507 UnaryBlock: Linear without bias -> BatchNorm, which
 // is the identity on these 2-D features or a bias when use_bn is off, blocks.py:453-465 -> LeakyReLU(0.1)) run on the same
-// tcgen05 pipeline with a dense A tile: one kernel for y = leaky(x W^T + b), one for dx = (dy * leaky'(y)) W, one for
-// dW = (dy * leaky'(y))^T x. The library GEMMs they replace pick 9-18 CTAs for the weight gradients of the shallow
-// layers (a 40k-row reduction into a 16x32 matrix) and need separate activation / bias kernels.
+// tcgen05 pipeline with a dense A stage: one kernel for y = leaky(x W^T + b), one for dx = (dy * leaky'(y)) W, one for
+// dW = (dy * leaky'(y))^T x.
 __global__ void __launch_bounds__(256) kp_bias_act_kernel(float* __restrict__ y, long long n, int cout, int ld,
                                                          const float* __restrict__ bias, float slope) {
     const long long total = n * cout;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const long long r = t / cout;
-        const int c = (int)(t % cout);
+        const int c = (int)(t - r * cout);
         float a = y[r * ld + c] + (bias ? bias[c] : 0.f);
         y[r * ld + c] = a > 0.f ? a : a * slope;
     }
 }
 
-// out[n, cout] (row stride ldo) = leaky( (a ⊙ leaky'(mask))[n, acols] · B + bias ), B(c, o) = W[c*sc + o*sn]
+// out[n, cout] (row stride ldo) = leaky( (a ⊙ leaky'(mask))[n, acols] · B + bias ), B(c, o) = W[c*sc + o*sn], or ready-made
+// images (slices of 512 output columns back to back, pack kinds 2 / 3)
 static int run_dense(const char* tag, Scratch& S, int n, const float* a, int acols, int acols_valid, const float* mask,
-                     float slope_in, const float* W, long long sc, long long sn, int cout, const float* bias,
-                     float slope_out, float* out, int ldo, cudaStream_t stream) {
-    const int n_tiles = ceil_div(n, TILE_M);
-    const int n_chunks = ceil_div(acols, CK);
+                     float slope_in, const float* W, long long sc, long long sn, const float* images, int cout,
+                     const float* bias, float slope_out, float* out, int ldo, cudaStream_t stream) {
+    long long img_off = 0;
     for (int o0 = 0; o0 < cout; o0 += 512) {  // TMEM holds 512 accumulator columns
         const int co = cout - o0 < 512 ? cout - o0 : 512;
-        const int cout_p = (co + 15) & ~15;
-        const int NB = cout_p < 256 ? cout_p : 256;
-        const int n_nblk = ceil_div(cout_p, NB);
-        float* images = S.alloc<float>((size_t)n_chunks * n_nblk * NB * CK);
-        if (S.status != KP_OK) return S.status;
-        {
-            const long long total = (long long)n_chunks * n_nblk * NB * CK;
-            const int grid = ceil_div(total, 256) < 4096 ? ceil_div(total, 256) : 4096;
-            ProfileScope ps("lin_pack_w", stream);
-            kp_pack_w_kernel<<<grid, 256, 0, stream>>>(W + (long long)o0 * sn, 1, acols_valid, acols, co, 0, sc, sn, NB, n_nblk,
-                                                       n_chunks, images);
-            KP_CHECK_LAUNCH();
+        ImgShape sh;
+        int rc = img_shape(1, acols, co, &sh);
+        if (rc != KP_OK) return rc;
+        const float* img = images ? images + img_off : nullptr;
+        img_off += sh.floats();
+        if (!img) {
+            float* p = S.alloc<float>((size_t)sh.floats());
+            if (S.status != KP_OK) return S.status;
+            PackJobs J;
+            J.n = 0; J.total = 0;
+            add_pack_job(J, W + (long long)o0 * sn, p, 0, sc, sn, 1, acols_valid, acols, co, sh);
+            if ((rc = launch_pack(J, stream)) != KP_OK) return rc;
+            img = p;
         }
-        FwdParams P;
-        P.nq = n; P.x = a; P.cin_p = acols; P.K = 1;
-        P.rowptr = nullptr; P.H = 0; P.koff = nullptr; P.entries = nullptr;
-        P.images = images; P.NB = NB; P.n_nblk = n_nblk; P.n_chunks = n_chunks;
-        P.out = out + o0; P.cout = co; P.ldo = ldo;
-        P.mask = mask; P.slope_in = slope_in;
-        P.bias = bias ? bias + o0 : nullptr; P.slope_out = slope_out;
-        const size_t smem = (size_t)A_BYTES + (size_t)NB * CK * 4 + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
-        const int ksplit = pick_ksplit(n_tiles, n_chunks, smem <= (size_t)SMEM_TWO_CTAS ? 2 * 148 : 148);
-        P.ksplit = ksplit;
-        if (ksplit > 1) KP_CUDA(cudaMemset2DAsync(out + o0, (size_t)ldo * 4, 0, (size_t)co * 4, n, stream));
-        uint32_t cols = 32;
-        while ((int)cols < n_nblk * NB) cols <<= 1;
-        P.tmem_cols = cols;
-        if (smem <= (size_t)SMEM_TWO_CTAS) {
-            KP_CUDA(set_smem(kp_fwd_kernel<8, true>, smem));
-            ProfileScope ps(tag, stream);
-            kp_fwd_kernel<8, true><<<dim3(n_tiles, ksplit), 256, smem, stream>>>(P);
-        } else {
-            KP_CUDA(set_smem(kp_fwd_kernel<16, true>, smem));
-            ProfileScope ps(tag, stream);
-            kp_fwd_kernel<16, true><<<dim3(n_tiles, ksplit), 512, smem, stream>>>(P);
-        }
-        KP_CHECK_LAUNCH();
+        GatherGeom gg = make_geom(acols, 1);
+        int ksplit = 1;  // (launch_fwd decides the split; a split finishes bias / activation in a separate pass)
+        rc = launch_fwd(tag, true, n, a, gg, nullptr, nullptr, img, sh, out + o0, co, ldo, mask, slope_in,
+                        bias ? bias + o0 : nullptr, slope_out, stream, &ksplit);
+        if (rc != KP_OK) return rc;
         if (ksplit > 1 && (bias || slope_out != 1.f)) {  // the split partial sums met through atomics: finish separately
             const long long total = (long long)n * co;
             const int grid = ceil_div(total, 256) < 2368 ? ceil_div(total, 256) : 2368;
-            kp_bias_act_kernel<<<grid, 256, 0, stream>>>(out + o0, n, co, ldo, P.bias, slope_out);
+            kp_bias_act_kernel<<<grid, 256, 0, stream>>>(out + o0, n, co, ldo, bias ? bias + o0 : nullptr, slope_out);
             KP_CHECK_LAUNCH();
         }
     }
-    return KP_OK;
-}
-
-// rows padded to a multiple of 4 columns when needed (float4 loads of the dense A tile)
-static int padded_cols(Scratch& S, const float* src, int n, int c, const float** dst, int* c_p, cudaStream_t stream) {
-    *c_p = pad4(c);
-    *dst = src;
-    if (*c_p == c) return KP_OK;
-    float* p = S.alloc<float>((size_t)n * *c_p);
-    if (S.status != KP_OK) return S.status;
-    const long long tot = (long long)n * *c_p;
-    kp_pad_cols_kernel<<<ceil_div(tot, 256) < 2048 ? ceil_div(tot, 256) : 2048, 256, 0, stream>>>(src, n, c, *c_p, p);
-    KP_CHECK_LAUNCH();
-    *dst = p;
     return KP_OK;
 }
 
@@ -1307,66 +1490,42 @@ static int check_linear(int n, int cin, int cout, float slope) {
     return KP_OK;
 }
 
-// y[n, cout] = leaky(x[n, cin] · w[cout, cin]^T + bias, slope); bias may be null; slope = 1: no activation
-int linear_forward_device(const float* x, int n, int cin, const float* w, const float* bias, int cout, float slope,
-                          float* y, cudaStream_t stream) {
+// y[n, cout] = leaky(x[n, cin] · w[cout, cin]^T + bias, slope); bias may be null; slope = 1: no activation.
+// w_packed: `w` holds images made by pack kind 2.
+int linear_forward_device(const float* x, int n, int cin, const float* w, int w_packed, const float* bias, int cout,
+                          float slope, float* y, cudaStream_t stream) {
     int rc = check_linear(n, cin, cout, slope);
     if (rc != KP_OK || n == 0) return rc;
     Scratch S(stream);
     const float* xa;
-    int cin_p;
-    if ((rc = padded_cols(S, x, n, cin, &xa, &cin_p, stream)) != KP_OK) return rc;
-    return run_dense("lin_fwd", S, n, xa, cin_p, cin, nullptr, 1.f, w, 1, cin, cout, bias, slope, y, cout, stream);
+    const int cin_p = pad4(cin);
+    if ((rc = padded_to(S, x, n, cin, cin_p, &xa, stream)) != KP_OK) return rc;
+    return run_dense("lin_fwd", S, n, xa, cin_p, cin, nullptr, 1.f, w_packed ? nullptr : w, 1, cin, w_packed ? w : nullptr, cout,
+                     bias, slope, y, cout, stream);
 }
 
 // dx[n, cin] = g · w, dw[cout, cin] = g^T · x with g = dy ⊙ leaky'(y) (y = the forward OUTPUT, or null when the layer
-// has no activation); dx may be null. dw is overwritten.
-int linear_backward_device(const float* x, int n, int cin, const float* w, int cout, const float* y, float slope,
-                           const float* dy, float* dx, float* dw, cudaStream_t stream) {
+// has no activation); dx may be null. dw is overwritten. w_packed: `w` holds images made by pack kind 3 (dx only).
+int linear_backward_device(const float* x, int n, int cin, const float* w, int w_packed, int cout, const float* y,
+                           float slope, const float* dy, float* dx, float* dw, cudaStream_t stream) {
     int rc = check_linear(n, cin, cout, slope);
     if (rc != KP_OK) return rc;
-    KP_CUDA(cudaMemsetAsync(dw, 0, (size_t)cin * cout * sizeof(float), stream));
+    if (dw) KP_CUDA(cudaMemsetAsync(dw, 0, (size_t)cin * cout * sizeof(float), stream));
     if (n == 0) return KP_OK;
     Scratch S(stream);
     const float *ga, *ya = y;
-    int cout_p;
-    if ((rc = padded_cols(S, dy, n, cout, &ga, &cout_p, stream)) != KP_OK) return rc;
-    if (y && cout_p != cout && (rc = padded_cols(S, y, n, cout, &ya, &cout_p, stream)) != KP_OK) return rc;
+    const int cout_p = pad4(cout);
+    if ((rc = padded_to(S, dy, n, cout, cout_p, &ga, stream)) != KP_OK) return rc;
+    if (y && (rc = padded_to(S, y, n, cout, cout_p, &ya, stream)) != KP_OK) return rc;
     if (dx) {
-        rc = run_dense("lin_dx", S, n, ga, cout_p, cout, ya, slope, w, cin, 1, cin, nullptr, 1.f, dx, cin, stream);
+        rc = run_dense("lin_dx", S, n, ga, cout_p, cout, ya, slope, w_packed ? nullptr : w, cin, 1, w_packed ? w : nullptr, cin,
+                       nullptr, 1.f, dx, cin, stream);
         if (rc != KP_OK) return rc;
     }
-    // dW[o, c] = sum_i g[i, o] x[i, c]: kp_dw with A = g (M = o), B tile = x rows (N = c)
-    DwParams P;
-    P.nq = n; P.x = ga; P.cin = cout; P.cin_p = cout_p; P.K = 1; P.H = 0;
-    P.koff = nullptr; P.entries = nullptr;
-    P.dout = x; P.cout = cin;
-    const int cin_p16 = (cin + 15) & ~15;
-    P.NB = cin_p16 < 256 ? cin_p16 : 256;
-    const int n_slices = ceil_div(cin_p16, P.NB);
-    const int n_chunks = ceil_div(cout_p, CK);
-    P.n_tiles = ceil_div(n, TILE_M);
-    const size_t smem = (size_t)4 * MN_LBO + (size_t)dw_b_bytes(P.NB) + TILE_M * KOFF * 2 + TILE_M * 4 + 64;
-    int splits = (smem <= (size_t)SMEM_TWO_CTAS ? 2 * 148 : 148) / (n_chunks * n_slices);  // one wave of CTAs
-    if (splits < 1) splits = 1;
-    if (splits > P.n_tiles) splits = P.n_tiles;
-    P.n_splits = splits;
-    P.dw = dw;
-    P.mask = ya; P.slope_in = slope;
-    uint32_t cols = 32;
-    while ((int)cols < P.NB) cols <<= 1;
-    P.tmem_cols = cols;
-    if (smem <= (size_t)SMEM_TWO_CTAS) {
-        KP_CUDA(set_smem(kp_dw_kernel<8, true>, smem));
-        ProfileScope ps("lin_dw", stream);
-        kp_dw_kernel<8, true><<<dim3(n_chunks, splits, n_slices), 256, smem, stream>>>(P);
-    } else {
-        KP_CUDA(set_smem(kp_dw_kernel<16, true>, smem));
-        ProfileScope ps("lin_dw", stream);
-        kp_dw_kernel<16, true><<<dim3(n_chunks, splits, n_slices), 512, smem, stream>>>(P);
-    }
-    KP_CHECK_LAUNCH();
-    return KP_OK;
+    if (!dw) return KP_OK;
+    // dW[o, c] = sum_i g[i, o] x[i, c]: kp_dw with A = g (M = o), B stage = x rows (N = c)
+    GatherGeom gg = make_geom(cout_p, 1);
+    return launch_dw("lin_dw", true, n, ga, gg, cout, nullptr, nullptr, x, cin, dw, ya, slope, stream);
 }
 
 }  // namespace kp
