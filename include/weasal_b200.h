@@ -202,7 +202,8 @@ int kp_kpconv_backward_kept_dev(const float* q_pts, int nq, const float* s_pts, 
  *   kp_kpconv_lists_build_dev  lists of one pass. Forward and dW: centres = q_pts, others = s_pts, the index matrix as
  *       given, kp_sign = +1. dX: centres = s_pts, others = q_pts, the TRANSPOSED table (t_rowptr / t_col from
  *       kp_transpose_table_dev with n_pairs = nq*H, or the matrix itself when it is symmetric), kp_sign = -1.
- *       entries_cap = capacity of lists_entries in records; when a calibrated capacity is exceeded the overflow flag
+ *       entries_cap = capacity of lists_entries in records (the buffer itself must hold entries_cap + 2: the kernels fetch
+ *       16-byte aligned windows); when a calibrated capacity is exceeded the overflow flag
  *       lists_hdr[1] is set (the affected tiles are left empty) and the caller must rebuild with a larger buffer.
  *   kp_kpconv_apply_lists_dev  out[nc, cout] = (gather of x[n_x_rows, cin] through the lists) x weights. Forward:
  *       transpose_w = 0, weights [K, cin, cout]. dX: x = d_out, cin = the conv's out_channels, cout = its in_channels,

@@ -1,1 +1,3 @@
-for c in "vaihingen_pl 9.0 3" "dales_pl 7.0 2" "vaihingen_pl 16.0 3"; do timeout 600 python tests/ref_dropin_script.py $c 2>&1 | tail -3; done
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "kpconv or linear" 2>&1 | tail -4
+timeout 300 python tools/kpconv_kernel_times.py 2>&1 | tail -6
+timeout 600 python tools/sweep.py 1000000 2>&1 | grep kpconv

@@ -52,9 +52,10 @@ constexpr unsigned J_MASK = (1u << ROW_SHIFT) - 1u;
 constexpr int K_SHIFT = 27;       // scratch lists (per row, grouped by kernel point): index | (kernel point << 27)
 constexpr unsigned JS_MASK = (1u << K_SHIFT) - 1u;
 
-constexpr int NPW = 8;            // producer warps (they are also the epilogue warps: two per TMEM lane quadrant)
-constexpr int LOADER_WARP = NPW, MMA_WARP = NPW + 1;
-constexpr int WS_THREADS = (NPW + 2) * 32;
+// Producer warps per CTA (template parameter NPW of the kernels; they are also the epilogue warps): 8 where two CTAs
+// share an SM (every lane owns 8 rows of one column group), 16 where the stages of a wide layer leave room for one CTA
+// only (4 rows per lane): the gather is latency bound, so an SM wants ~16 producer warps either way. Two more warps
+// follow them: the weight loader and the MMA issuer.
 constexpr int FWD_CK = 64;        // reduction columns per forward stage
 constexpr int DW_CK = 128;        // reduction columns (= UMMA M) per dW CTA
 constexpr int DW_PT = 64;         // points per dW stage
@@ -87,24 +88,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the time hint (ns) runs out: neither a spin
+// (a plain try_wait loop returned every ~20 ns and took 37 % of the kernel's issue slots away from the producers, ncu
+// capture profiles/r2_ncu_ws_v2_spin.csv) nor a nanosleep back-off (which adds its quantum to every hand-over of the ring).
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(4000u)
         : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    // bounded spin: a barrier that never completes (a malformed descriptor, a lost bulk copy) traps instead of
-    // hanging the GPU; 2^26 polls is seconds, far beyond any legitimate wait here
+    // bounded: a barrier that never completes (a malformed descriptor, a lost bulk copy) traps instead of hanging the GPU
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); spins++)
-        if (spins > (1u << 26)) __trap();
+        if (spins > (1u << 22)) __trap();
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -470,12 +473,16 @@ struct GatherGeom {
     int cin_p, K;
 };
 
-template <class LAY, int NRBS, int U>
+// RPL = rows per lane: 8 (8 producer warps), or 4 (16 warps: two lane groups share a unit, each walks the unit's entries
+// and takes the rows of its half).
+template <class LAY, int NRBS, int U, int RPL>
 __device__ __forceinline__ void produce_sparse(unsigned char* sA, int warp, int lane, const GatherGeom& gg, int col_base,
                                                int rb_base, const int* __restrict__ toff_tile,
                                                const int2* __restrict__ ent, const float* __restrict__ x) {
     const int G = 1 << gg.g_log2;
-    const int g = (warp << (5 - gg.g_log2)) + (lane >> gg.g_log2);
+    const int gi = (warp << (5 - gg.g_log2)) + (lane >> gg.g_log2);
+    const int g = RPL == RB ? gi : (gi >> 1);
+    const int r_lo = RPL == RB ? 0 : (gi & 1) * RPL, r_hi = r_lo + RPL;
     const int li = lane & (G - 1);
     const int s = g / NRBS, rb = g - s * NRBS;
     const int cg = s * G + li;
@@ -492,7 +499,7 @@ __device__ __forceinline__ void produce_sparse(unsigned char* sA, int warp, int 
     const float* __restrict__ xc = x + c0;
     const int p0 = rb * RB;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int cur = 0;
+    int cur = r_lo;
     int2 rec[U];
 #pragma unroll
     for (int u = 0; u < U; u++) rec[u] = u < n ? __ldg(ep + u) : make_int2(0, 0);
@@ -505,13 +512,14 @@ __device__ __forceinline__ void produce_sparse(unsigned char* sA, int warp, int 
             xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             wv[u] = __int_as_float(rec[u].y);
             rv[u] = (int)(((unsigned)rec[u].x >> ROW_SHIFT) & (RB - 1));
-            if (e0 + u < n) xv[u] = __ldg(reinterpret_cast<const float4*>(xc + (size_t)((unsigned)rec[u].x & J_MASK) * gg.cin_p));
+            if (e0 + u >= n || (RPL != RB && (rv[u] < r_lo || rv[u] >= r_hi))) rv[u] = -1;   // not mine
+            if (rv[u] >= 0) xv[u] = __ldg(reinterpret_cast<const float4*>(xc + (size_t)((unsigned)rec[u].x & J_MASK) * gg.cin_p));
         }
 #pragma unroll
         for (int u = 0; u < U; u++) rec[u] = e0 + U + u < n ? __ldg(ep + e0 + U + u) : make_int2(0, 0);
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            if (e0 + u < n) {
+            if (rv[u] >= 0) {
                 if (rv[u] != cur) {
                     *reinterpret_cast<float4*>(sA + LAY::off(p0 + cur, cg)) = to_tf32(acc);
                     for (int r = cur + 1; r < rv[u]; r++)
@@ -525,32 +533,32 @@ __device__ __forceinline__ void produce_sparse(unsigned char* sA, int warp, int 
         }
     }
     *reinterpret_cast<float4*>(sA + LAY::off(p0 + cur, cg)) = to_tf32(acc);
-    for (int r = cur + 1; r < RB; r++)
+    for (int r = cur + 1; r < r_hi; r++)
         *reinterpret_cast<float4*>(sA + LAY::off(p0 + r, cg)) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // Dense variant (linear layers next to KPConv: the A operand is a plain row-major matrix a[n, ld]): the lane's 8 cells
 // are 8 independent float4 loads, optionally scaled by the LeakyReLU derivative taken from `mask` (same shape: factor 1
 // where mask > 0, `slope` elsewhere), rounded to TF32.
-template <class LAY, int NRBS>
+template <class LAY, int NRBS, int RPL>
 __device__ __forceinline__ void produce_dense(unsigned char* sA, int warp, int lane, int col_base, int row_base, int n,
                                               const float* __restrict__ a, int ld, const float* __restrict__ mask,
                                               float slope) {
     constexpr int NCG = 256 / NRBS;                 // column groups per stage (16 forward, 32 dW)
     const int t = warp * 32 + lane;
-    const int cg = t % NCG, rb = t / NCG;
+    const int cg = t % NCG;
     const int col = col_base + 4 * cg;
-    const int p0 = rb * RB;
-    float4 v[RB];
+    const int p0 = (t / NCG) * RPL;
+    float4 v[RPL];
 #pragma unroll
-    for (int r = 0; r < RB; r++) {
+    for (int r = 0; r < RPL; r++) {
         const int i = row_base + p0 + r;
         v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < n && col < ld) v[r] = __ldg(reinterpret_cast<const float4*>(a + (size_t)i * ld + col));
     }
     if (mask) {
 #pragma unroll
-        for (int r = 0; r < RB; r++) {
+        for (int r = 0; r < RPL; r++) {
             const int i = row_base + p0 + r;
             if (i < n && col < ld) {
                 const float4 y = __ldg(reinterpret_cast<const float4*>(mask + (size_t)i * ld + col));
@@ -560,7 +568,7 @@ __device__ __forceinline__ void produce_dense(unsigned char* sA, int warp, int l
         }
     }
 #pragma unroll
-    for (int r = 0; r < RB; r++) *reinterpret_cast<float4*>(sA + LAY::off(p0 + r, cg)) = to_tf32(v[r]);
+    for (int r = 0; r < RPL; r++) *reinterpret_cast<float4*>(sA + LAY::off(p0 + r, cg)) = to_tf32(v[r]);
 }
 
 // --------------------------------------------------------------------------------------------------------- forward
@@ -592,8 +600,9 @@ struct FwdBars {
     uint32_t tmem;
 };
 
-template <bool DENSE>
-__global__ void __launch_bounds__(WS_THREADS, 2) kp_fwd_kernel(const __grid_constant__ FwdParams P) {
+template <bool DENSE, int NPW>
+__global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_fwd_kernel(const __grid_constant__ FwdParams P) {
+    constexpr int LOADER_WARP = NPW, MMA_WARP = NPW + 1, RPL = RB * 8 / NPW;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int S = P.stages;
     const int b_bytes = P.NB * FWD_CK * 4;
@@ -637,8 +646,8 @@ __global__ void __launch_bounds__(WS_THREADS, 2) kp_fwd_kernel(const __grid_cons
             if (use > 0) mbar_wait(&bars->a_empty[s], (uint32_t)((use - 1) & 1));
             unsigned char* a = sA + (size_t)s * A_STAGE;
             const int col_base = (c0 + it) * FWD_CK;
-            if (DENSE) produce_dense<LayoutKMajor, NRB>(a, warp, lane, col_base, tile_base, P.nq, P.x, P.gg.cin_p, P.mask, P.slope_in);
-            else produce_sparse<LayoutKMajor, NRB, 4>(a, warp, lane, P.gg, col_base, 0, toff_tile, ent, P.x);
+            if (DENSE) produce_dense<LayoutKMajor, NRB, RPL>(a, warp, lane, col_base, tile_base, P.nq, P.x, P.gg.cin_p, P.mask, P.slope_in);
+            else produce_sparse<LayoutKMajor, NRB, 4, RPL>(a, warp, lane, P.gg, col_base, 0, toff_tile, ent, P.x);
             fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->a_full[s]);
@@ -688,6 +697,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) kp_fwd_kernel(const __grid_cons
     // ===== epilogue: the producer warps drain TMEM (warp w: lanes 32*(w%4).., column blocks of 16 dealt over w/4) =====
     if (warp < NPW) {
         mbar_wait(&bars->acc_full, 0u);
+        __syncwarp();
         tc_fence_after();
         const int row = tile_base + 32 * (warp & 3) + lane;
         const int n_cb = (P.n_nblk * P.NB) / 16;
@@ -755,8 +765,9 @@ struct DwBars {
     uint32_t tmem;
 };
 
-template <bool DENSE>
-__global__ void __launch_bounds__(WS_THREADS, 2) kp_dw_kernel(const __grid_constant__ DwParams P) {
+template <bool DENSE, int NPW>
+__global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_dw_kernel(const __grid_constant__ DwParams P) {
+    constexpr int LOADER_WARP = NPW, MMA_WARP = NPW + 1, RPL = RB * 8 / NPW;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int S = P.stages;
     const int b_bytes = dw_b_bytes(P.NB);
@@ -827,11 +838,11 @@ __global__ void __launch_bounds__(WS_THREADS, 2) kp_dw_kernel(const __grid_const
                 }
             }
             if (DENSE) {
-                produce_dense<LayoutMNMajor, DW_PT / RB>(a, warp, lane, chunk * DW_CK, row_base, P.nq, P.x, P.gg.cin_p, P.mask, P.slope_in);
+                produce_dense<LayoutMNMajor, DW_PT / RB, RPL>(a, warp, lane, chunk * DW_CK, row_base, P.nq, P.x, P.gg.cin_p, P.mask, P.slope_in);
             } else {
                 const int* toff_tile = P.toff + (size_t)tile * TOFF_PER_TILE;
                 const int2* ent = P.entries + __ldg(toff_tile + 15 * TOFF_RB);
-                produce_sparse<LayoutMNMajor, DW_PT / RB, 4>(a, warp, lane, P.gg, chunk * DW_CK, half * (DW_PT / RB), toff_tile, ent, P.x);
+                produce_sparse<LayoutMNMajor, DW_PT / RB, 4, RPL>(a, warp, lane, P.gg, chunk * DW_CK, half * (DW_PT / RB), toff_tile, ent, P.x);
             }
             fence_proxy_async();
             __syncwarp();
@@ -862,6 +873,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) kp_dw_kernel(const __grid_const
     // epilogue: TMEM lane r = reduction column chunk*128 + r = (k, c); add into dW[k, c, n0 + col]
     if (warp < NPW) {
         mbar_wait(&bars->acc_full, 0u);
+        __syncwarp();
         tc_fence_after();
         const int r = 32 * (warp & 3) + lane;
         const int col = chunk * DW_CK + r;
@@ -1028,7 +1040,7 @@ static cudaError_t set_smem(KernelT kernel, size_t bytes) {
     return e;
 }
 
-constexpr size_t SMEM_TWO_CTAS = 112 * 1024;  // dynamic shared memory up to which two CTAs share an SM
+constexpr size_t SMEM_TWO_CTAS = 113 * 1024;  // dynamic shared memory up to which two CTAs share an SM (228 KiB / 2 - 1 KiB)
 
 // shape of the packed weight images of one contraction [*, K*cin_p] x [K*cin_p, cout]
 struct ImgShape {
@@ -1087,13 +1099,16 @@ static int launch_fwd(const char* tag, bool dense, int nc, const float* x, const
     while ((int)cols < sh.n_nblk * sh.NB) cols <<= 1;
     P.tmem_cols = cols;
     ProfileScope ps(tag, stream);
-    if (dense) {
-        KP_CUDA(set_smem(kp_fwd_kernel<true>, smem));
-        kp_fwd_kernel<true><<<dim3(n_tiles, ksplit), WS_THREADS, smem, stream>>>(P);
-    } else {
-        KP_CUDA(set_smem(kp_fwd_kernel<false>, smem));
-        kp_fwd_kernel<false><<<dim3(n_tiles, ksplit), WS_THREADS, smem, stream>>>(P);
-    }
+    const dim3 grid(n_tiles, ksplit);
+    const bool two = smem <= SMEM_TWO_CTAS;
+#define KP_LAUNCH_FWD(D, W)                                                     \
+    do {                                                                        \
+        KP_CUDA(set_smem(kp_fwd_kernel<D, W>, smem));                           \
+        kp_fwd_kernel<D, W><<<grid, (W + 2) * 32, smem, stream>>>(P);           \
+    } while (0)
+    if (dense) { if (two) KP_LAUNCH_FWD(true, 8); else KP_LAUNCH_FWD(true, 16); }
+    else { if (two) KP_LAUNCH_FWD(false, 8); else KP_LAUNCH_FWD(false, 16); }
+#undef KP_LAUNCH_FWD
     KP_CHECK_LAUNCH();
     return KP_OK;
 }
@@ -1124,13 +1139,16 @@ static int launch_dw(const char* tag, bool dense, int nq, const float* x, const 
     while ((int)cols < P.NB) cols <<= 1;
     P.tmem_cols = cols;
     ProfileScope ps(tag, stream);
-    if (dense) {
-        KP_CUDA(set_smem(kp_dw_kernel<true>, smem));
-        kp_dw_kernel<true><<<dim3(n_chunks, splits, n_slices), WS_THREADS, smem, stream>>>(P);
-    } else {
-        KP_CUDA(set_smem(kp_dw_kernel<false>, smem));
-        kp_dw_kernel<false><<<dim3(n_chunks, splits, n_slices), WS_THREADS, smem, stream>>>(P);
-    }
+    const dim3 grid(n_chunks, splits, n_slices);
+    const bool two = smem <= SMEM_TWO_CTAS;
+#define KP_LAUNCH_DW(D, W)                                                      \
+    do {                                                                        \
+        KP_CUDA(set_smem(kp_dw_kernel<D, W>, smem));                            \
+        kp_dw_kernel<D, W><<<grid, (W + 2) * 32, smem, stream>>>(P);            \
+    } while (0)
+    if (dense) { if (two) KP_LAUNCH_DW(true, 8); else KP_LAUNCH_DW(true, 16); }
+    else { if (two) KP_LAUNCH_DW(false, 8); else KP_LAUNCH_DW(false, 16); }
+#undef KP_LAUNCH_DW
     KP_CHECK_LAUNCH();
     return KP_OK;
 }
