@@ -195,15 +195,24 @@ def run_ours(args):
     # the batches, like the reference's sampler calibration (batch_limit / neighborhood_limits): rows padded to a
     # per-layer capacity, neighbourhood limits chosen so that no row is cropped (results equal the unlimited pyramid).
     use_graph = os.environ.get("WEASAL_BENCH_GRAPH", "1") != "0"  # "eager": static batches, eager launches (ncu lists)
-    n_cap = limits = None
+    n_cap = limits = plans = None
+    from weasal_b200.engine import calibrate_conv_plans
+    from weasal_b200.net import fused_linear_weights
+    from weasal_b200.plan import WeightPacker
+    # weight-only work (TF32 operand images of every KPConv / unary block): one launch per step
+    packer = WeightPacker(net, fused_linear_weights(net)) if os.environ.get("WEASAL_BENCH_PACKER", "1") == "1" else None
     if use_graph:
         n_cap, limits = calibrate_static_caps(view, [b["points"] for b in dev_batches], [b["lengths"] for b in batches])
-    prefetch = pyramid.PyramidPrefetcher(view, dev, neighborhood_limits=limits, n_cap=n_cap)
+        # geometry-only work (influence lists, transposed tables of all 10 KPConv): built by the prefetch stage
+        if os.environ.get("WEASAL_BENCH_PLANS", "1") == "1":
+            plans = calibrate_conv_plans(net, view, [b["points"] for b in dev_batches], [b["lengths"] for b in batches],
+                                         n_cap, limits)
+    prefetch = pyramid.PyramidPrefetcher(view, dev, neighborhood_limits=limits, n_cap=n_cap, plans=plans)
     trainer = GraphedTrainStep(net, opt, F.cross_entropy, reducer=reducer if world > 1 else None, clip_value=100.0,
-                               use_graph=os.environ.get("WEASAL_BENCH_GRAPH", "1") == "1")
-    eager = GraphedTrainStep(net, opt, F.cross_entropy, reducer=None, clip_value=100.0)  # profile leg: no collective
+                               use_graph=os.environ.get("WEASAL_BENCH_GRAPH", "1") == "1", plans=plans, packer=packer)
+    eager = GraphedTrainStep(net, opt, F.cross_entropy, reducer=None, clip_value=100.0, packer=packer)  # profile leg: no collective
     if use_graph:  # capture before the prefetch pipeline runs (nothing else issues CUDA work meanwhile)
-        prefetch.submit(dev_batches[0]["points"], dev_batches[0]["features"], dev_batches[0]["labels"], batches[0]["lengths"])
+        prefetch.submit(dev_batches[0]["points"], dev_batches[0]["features"], dev_batches[0]["labels"], batches[0]["lengths"], inputs_ready=True)
         trainer.prepare(prefetch.get())
         torch.cuda.synchronize()
 
@@ -221,7 +230,7 @@ def run_ours(args):
 
         def submit(it):
             b = it % N_BATCHES
-            prefetch.submit(src[b]["points"], src[b]["features"], src[b]["labels"], batches[b]["lengths"])
+            prefetch.submit(src[b]["points"], src[b]["features"], src[b]["labels"], batches[b]["lengths"], inputs_ready=True)
 
         pts = 0
         stamps.clear()

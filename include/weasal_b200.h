@@ -220,6 +220,24 @@ int kp_kpconv_apply_lists_dev(int nc, const float* x, int n_x_rows, int cin, con
 int kp_kpconv_dw_lists_dev(int nq, const float* x, int ns, int cin, const float* d_out, int cout, int K,
                            const void* lists_hdr, const void* lists_entries, float* d_weights, void* stream);
 
+/* All of a batch's geometry-only KPConv work in ONE call, for a prefetch thread: the jobs run in order on `stream`.
+ *   kind 0  lists over a padded index matrix (centres, others, neighb_inds / idx_is_i64 / H / idx_stride, kernel points,
+ *           kp_sign, KP_extent) -> (hdr, entries, entries_cap)        [kp_kpconv_lists_build_dev]
+ *   kind 1  transposed table of a padded index matrix with nc rows over `no` supports -> (rowptr [no+2], col [nc*H])
+ *                                                                    [kp_transpose_table_dev]
+ *   kind 2  lists over a CSR table (rowptr, col of an earlier kind-1 job, n_pairs = its nc*H) -> (hdr, entries, cap)
+ * overflow_flag (optional DEVICE int): set to 1 when any list outgrew its entries_cap. */
+typedef struct kp_list_job {
+    int kind;
+    const float* centres; int nc;
+    const float* others; int no;
+    const void* neighb_inds; int idx_is_i64, H, idx_stride;
+    int* rowptr; int* col; long long n_pairs;
+    const float* kernel_points; int K; float kp_sign, KP_extent;
+    void* hdr; void* entries; long long entries_cap;
+} kp_list_job;
+int kp_kpconv_prepare_dev(const kp_list_job* jobs, int n_jobs, int* overflow_flag, void* stream);
+
 /* Operand images of the tensor-core contractions (TF32-rounded weights in the UMMA shared-memory layout, one image per
  * 64 reduction columns). One launch packs any number of them: a training step calls it once per step for every KPConv
  * and unary block instead of once per operator call. kinds: 0 KPConv forward (weights [K,cin,cout]), 1 KPConv dX (same

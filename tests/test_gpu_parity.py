@@ -321,6 +321,67 @@ def test_kpconv_random_shapes_vs_oracle(cin, cout, H, torch_cuda):
     assert rel_max(dw, o_dw) < KP_TOL and rel_l2(dw, o_dw) < KP_TOL
 
 
+def test_kpconv_prefetched_lists_and_packed_weights_equal_the_plain_operator(torch_cuda):
+    """The split form of the operator (lists built ahead by kp_kpconv_prepare_dev for forward / dX incl. the transposed
+    table of a strided conv, weights packed by one kp_pack_weights_dev launch, dW and dX as separate calls) gives the
+    plain operator's results (up to the order of the float atomics that join split reductions)."""
+    torch = torch_cuda
+    import ctypes as C
+    from weasal_b200 import _lib, ops
+    from weasal_b200.kpconv import KPConv
+    from weasal_b200.plan import ConvPlans, ConvSpec, WeightPacker
+    b = make_batch("vaihingen_pl", seed=12, batch_num=2, in_radius=8.0)
+    dev = torch.device("cuda")
+    P0 = torch.from_numpy(b["points"]).to(dev)
+    lens = b["lengths"]
+    P1, lens1 = ops.grid_subsample(P0, lens, sampleDl=0.48)
+    P1 = P1.contiguous()
+    conv_idx = ops.batch_query(P0, P0, lens, lens, 0.6)
+    pool_idx = ops.batch_query(P1, P0, lens1, lens, 0.6)
+    np.random.seed(3)
+    torch.manual_seed(3)
+    for strided, (q, idx) in ((False, (P0, conv_idx)), (True, (P1, pool_idx))):
+        idx = idx.contiguous()
+        conv = KPConv(15, 3, 16, 32, 0.24, 0.6).to(dev)
+        x = torch.randn(P0.shape[0], 16, device=dev)
+        g = torch.randn(q.shape[0], 32, device=dev)
+        # plain operator
+        x1 = x.clone().requires_grad_(True)
+        y1 = conv(q, P0, idx, x1)
+        y1.backward(g)
+        dw1, dx1 = conv.weights.grad.clone(), x1.grad.clone()
+        conv.weights.grad = None
+        # split form
+        sp = ConvSpec(0, strided, conv)
+        n_cap = [P0.shape[0], P1.shape[0]]
+        H = idx.shape[1]
+        used = 15 * idx.shape[0] * H
+        plans = ConvPlans([sp], n_cap, [H, H], [H, H], [used])
+        buf = torch.zeros(plans.nbytes, dtype=torch.uint8, device=dev)
+        jobs = plans.jobs([P0, P1], [idx, None], [idx, None], idx.dtype == torch.int64, buf)
+        assert len(jobs) == (3 if strided else 2)
+        plans.run(jobs, buf, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert int(buf[:4].view(torch.int32)[0]) == 0
+        idx2 = idx.clone()
+        plans.attach(buf, [idx2, None], [idx2, None])
+        packer = WeightPacker(conv)
+        packer.pack()
+        x2 = x.clone().requires_grad_(True)
+        y2 = conv(q, P0, idx2, x2)
+        y2.backward(g)
+        packer.release()
+        # (same kernels on the same lists; reductions split across CTAs meet through float atomics, so last bits may differ)
+        assert rel_max(y2.detach().cpu().numpy(), y1.detach().cpu().numpy()) < 1e-5, strided
+        assert rel_max(x2.grad.cpu().numpy(), dx1.cpu().numpy()) < 1e-5, strided
+        assert rel_max(conv.weights.grad.cpu().numpy(), dw1.cpu().numpy()) < 1e-5, strided
+        # a list buffer that is too small raises the overflow flag instead of writing out of bounds
+        small = ConvPlans([sp], n_cap, [H, H], [H, H], [64])
+        buf_s = torch.zeros(small.nbytes, dtype=torch.uint8, device=dev)
+        small.run(small.jobs([P0, P1], [idx, None], [idx, None], idx.dtype == torch.int64, buf_s), buf_s,
+                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert int(buf_s[:4].view(torch.int32)[0]) == 1
+
+
 def test_kpconv_all_shadow_rows_and_linearity(torch_cuda):
     torch = torch_cuda
     from weasal_b200 import ops
@@ -611,9 +672,12 @@ def test_batch_query_no_supports_at_all(torch_cuda):
 
 
 # ------------------------------------------------------------------------------------------ static shapes + CUDA graph
-def test_graphed_static_step_matches_eager_dynamic_step(torch_cuda):
+@pytest.mark.parametrize("prefetched", [False, True])
+def test_graphed_static_step_matches_eager_dynamic_step(prefetched, torch_cuda):
     """The training step replayed from a CUDA graph over padded static-shape batches computes what the eager step
-    computes over the ordinary batches: same losses, same parameters after three SGD steps (dropout off)."""
+    computes over the ordinary batches: same losses, same parameters after three SGD steps (dropout off).
+    ``prefetched``: the KPConv influence lists / transposed tables come from the prefetch stage (plan.ConvPlans) and the
+    weight images from one packing launch per step (plan.WeightPacker), dW and dX forked onto two streams."""
     torch = torch_cuda
     import copy
     import torch.nn.functional as F
@@ -636,14 +700,23 @@ def test_graphed_static_step_matches_eager_dynamic_step(torch_cuda):
     losses = []
     for net, caps in ((net_a, None), (net_b, n_cap)):
         opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-3)
-        tr = GraphedTrainStep(net, opt, F.cross_entropy, clip_value=100.0)
+        plans = packer = None
+        if caps and prefetched:
+            from weasal_b200.engine import calibrate_conv_plans
+            from weasal_b200.net import fused_linear_weights
+            from weasal_b200.plan import WeightPacker
+            plans = calibrate_conv_plans(net, view, P, [b["lengths"] for b in data], n_cap, limits, random_grid_orient=False)
+            packer = WeightPacker(net, fused_linear_weights(net))
+            assert len(plans.specs) == 10 and len(packer.jobs) >= 20
+        tr = GraphedTrainStep(net, opt, F.cross_entropy, clip_value=100.0, plans=plans, packer=packer)
         pf = pyramid.PyramidPrefetcher(view, dev, neighborhood_limits=limits if caps else None, n_cap=caps,
-                                       random_grid_orient=False)
+                                       random_grid_orient=False, plans=plans)
         ls = []
         for i in range(3):
             pf.submit(P[i], Fe[i], Lb[i], data[i]["lengths"])
             batch = pf.get()
             assert (batch.static_slab is not None) == (caps is not None)
+            assert (batch.plan_buf is not None) == (plans is not None)
             ls.append(float(tr.step(batch)))
         pf.close()
         assert (tr.n_graphed, tr.n_eager) == ((3, 0) if caps else (0, 3))

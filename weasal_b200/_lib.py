@@ -27,7 +27,8 @@ SYMBOLS = ["kp_last_error", "kp_version", "kp_launch_count", "kp_free_host", "kp
            "kp_pyramid_build_dev", "kp_pyramid_build_static_dev", "kp_kpconv_backward_sym_dev",
            "kp_linear_forward_dev", "kp_linear_backward_dev", "kp_closest_pool_strided_dev", "kp_max_pool_forward_width_dev", "kp_plan_ksplit",
            "kp_kpconv_lists_build_dev", "kp_kpconv_apply_lists_dev", "kp_kpconv_dw_lists_dev", "kp_pack_image_floats",
-           "kp_pack_weights_dev", "kp_linear_forward_packed_dev", "kp_linear_dx_packed_dev", "kp_linear_dw_dev"]
+           "kp_pack_weights_dev", "kp_linear_forward_packed_dev", "kp_linear_dx_packed_dev", "kp_linear_dw_dev",
+           "kp_kpconv_prepare_dev"]
 
 
 def lib():
@@ -98,8 +99,18 @@ def lib():
     L.kp_linear_forward_packed_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_float, vp, vp]
     L.kp_linear_dx_packed_dev.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_float, vp, vp, vp]
     L.kp_linear_dw_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_float, vp, vp, vp]
+    L.kp_kpconv_prepare_dev.argtypes = [vp, C.c_int, vp, vp]
     _lib = L
     return L
+
+
+class ListJob(C.Structure):
+    """struct kp_list_job of include/weasal_b200.h"""
+    _fields_ = [("kind", C.c_int), ("centres", vp), ("nc", C.c_int), ("others", vp), ("no", C.c_int),
+                ("neighb_inds", vp), ("idx_is_i64", C.c_int), ("H", C.c_int), ("idx_stride", C.c_int),
+                ("rowptr", vp), ("col", vp), ("n_pairs", C.c_longlong),
+                ("kernel_points", vp), ("K", C.c_int), ("kp_sign", C.c_float), ("KP_extent", C.c_float),
+                ("hdr", vp), ("entries", vp), ("entries_cap", C.c_longlong)]
 
 
 def last_error():

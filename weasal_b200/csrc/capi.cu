@@ -42,6 +42,7 @@ int kpconv_apply_lists_device(int nc, const float* x, int n_x_rows, int cin, con
 int kpconv_dw_lists_device(int nq, const float* x, int ns, int cin, const float* dout, int cout, int K, const void* hdr,
                            const void* entries, float* dw, cudaStream_t stream);
 long long pack_image_floats(int kind, int K, int cin, int cout);
+int kpconv_prepare_device(const kp_list_job* jobs, int n_jobs, int* overflow_flag, cudaStream_t stream);
 int pack_weights_device(int n_jobs, const int* kinds, const float* const* weights, const int* Ks, const int* cins,
                         const int* couts, float* const* images, cudaStream_t stream);
 int transpose_table_entry(const void* idx, int idx_is_i64, int nq, int H, int idx_stride, int ns, int* rowptr,
@@ -241,6 +242,10 @@ int kp_kpconv_dw_lists_dev(int nq, const float* x, int ns, int cin, const float*
 }
 
 long long kp_pack_image_floats(int kind, int K, int cin, int cout) { return pack_image_floats(kind, K, cin, cout); }
+
+int kp_kpconv_prepare_dev(const kp_list_job* jobs, int n_jobs, int* overflow_flag, void* stream) {
+    return kpconv_prepare_device(jobs, n_jobs, overflow_flag, (cudaStream_t)stream);
+}
 
 int kp_pack_weights_dev(int n_jobs, const int* kinds, const float* const* weights, const int* Ks, const int* cins,
                         const int* couts, float* const* images, void* stream) {

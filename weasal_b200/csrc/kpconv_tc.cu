@@ -36,6 +36,7 @@
 
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -242,6 +243,7 @@ struct ListsOut {
     int2* entries;    // compact, `cap` entries
     int* ctl;         // [0] = entries used so far (atomic cursor), [1] = overflow flag
     long long cap;
+    int* overflow;    // optional: one flag shared by all lists of a batch (set together with ctl[1])
 };
 
 __global__ void __launch_bounds__(LST_WARPS * 32, 2) kp_lists_kernel(const float* __restrict__ centres, int nc,
@@ -357,6 +359,7 @@ __global__ void __launch_bounds__(LST_WARPS * 32, 2) kp_lists_kernel(const float
             base = total > 0 ? atomicAdd(L.ctl, total) : 0;
             if ((long long)base + total > L.cap) {  // (only possible for a caller-bounded buffer: the batch takes the
                 atomicExch(L.ctl + 1, 1);           //  slow path, the tile is left empty)
+                if (L.overflow) atomicExch(L.overflow, 1);
                 base = -1;
             }
             s_start[16] = base;
@@ -981,7 +984,7 @@ void kpconv_lists_bytes(int nc, long long n_pairs, long long* hdr_bytes, long lo
 
 static int build_lists(Scratch& S, const float* centres, int nc, const float* others, int no, const Table& T,
                        long long n_pairs, const float* kp, int K, float kp_sign, float extent, Lists* L,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, int* overflow = nullptr) {
     if (n_pairs * 15 >= (1LL << 31)) return fail(KP_ERR_UNSUPPORTED, "kpconv: neighbour table too large (Nq*H*15 >= 2^31)");
     const int n_tiles = ceil_div(nc, TILE_M);
     if (!L->hdr) {
@@ -994,7 +997,7 @@ static int build_lists(Scratch& S, const float* centres, int nc, const float* ot
     ProfileScope ps("kp_lists", stream);
     KP_CUDA(cudaMemsetAsync(L->hdr, 0, LISTS_CTL_INTS * sizeof(int), stream));
     ListsOut O;
-    O.toff = L->hdr + LISTS_CTL_INTS; O.entries = L->entries; O.ctl = L->hdr; O.cap = L->cap;
+    O.toff = L->hdr + LISTS_CTL_INTS; O.entries = L->entries; O.ctl = L->hdr; O.cap = L->cap; O.overflow = overflow;
     kp_lists_kernel<<<n_tiles, LST_WARPS * 32, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, 1.f / extent, scratch, O);
     KP_CHECK_LAUNCH();
     return KP_OK;
@@ -1027,12 +1030,15 @@ static int pick_ksplit(int n_tiles, int n_chunks, int slots) {
 }
 int plan_ksplit(int n_tiles, int n_chunks, int slots) { return pick_ksplit(n_tiles, n_chunks, slots); }
 
-// opt-in dynamic shared memory: raise a kernel's limit only when a launch needs more than it already has
+// opt-in dynamic shared memory: a kernel's limit is only ever raised. The attribute belongs to the process, not to the
+// calling thread (autograd runs backward passes on its own thread), so the bookkeeping is process-wide too.
 template <typename KernelT>
 static cudaError_t set_smem(KernelT kernel, size_t bytes) {
-    static thread_local std::map<std::pair<const void*, int>, size_t> have;  // (kernel, device) -> current limit
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> have;  // (kernel, device) -> current limit
     int dev = 0;
     cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
     size_t& h = have[{(const void*)kernel, dev}];
     if (bytes <= h) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -1224,6 +1230,46 @@ int kpconv_lists_build_device(const float* centres, int nc, const float* others,
     Lists L;
     L.hdr = (int*)hdr; L.entries = (int2*)entries; L.cap = entries_cap;
     return build_lists(S, centres, nc, others, no, T, n_pairs, kp, K, kp_sign, extent, &L, stream);
+}
+
+int transpose_table_device(Scratch& S, const void* idx, int idx_is_i64, int nq, int H, int idx_stride, int ns,
+                           int* rowptr, int* col_sorted, cudaStream_t stream);
+
+// Everything the KPConv calls of one batch need besides features and weights, in ONE call (a training loop issues it
+// from its prefetch thread right after the pyramid): jobs run in order on `stream`.
+int kpconv_prepare_device(const kp_list_job* jobs, int n_jobs, int* overflow_flag, cudaStream_t stream) {
+    if (n_jobs < 0 || (n_jobs > 0 && !jobs)) return fail(KP_ERR_ARG, "kpconv_prepare: bad arguments");
+    Scratch S(stream);
+    ArenaHold hold(S);  // every job's scratch stays valid until the call returns (jobs overlap on the stream)
+    if (overflow_flag) KP_CUDA(cudaMemsetAsync(overflow_flag, 0, sizeof(int), stream));
+    for (int i = 0; i < n_jobs; i++) {
+        const kp_list_job& J = jobs[i];
+        int rc;
+        if (J.kind == 1) {
+            if (J.nc < 0 || J.no <= 0 || J.H <= 0 || J.idx_stride < J.H || !J.rowptr || !J.col)
+                return fail(KP_ERR_ARG, "kpconv_prepare: bad transpose job");
+            rc = transpose_table_device(S, J.neighb_inds, J.idx_is_i64, J.nc, J.H, J.idx_stride, J.no, J.rowptr, J.col, stream);
+        } else if (J.kind == 0 || J.kind == 2) {
+            if (J.nc <= 0 || J.no <= 0 || J.K <= 0 || J.K > 15 || !(J.KP_extent > 0.f) || !J.hdr || !J.entries || J.entries_cap <= 0)
+                return fail(KP_ERR_ARG, "kpconv_prepare: bad list job");
+            Table T;
+            long long n_pairs;
+            if (J.kind == 2) {
+                T.idx = J.col; T.rowptr = J.rowptr; T.H = 0; T.stride = 0; T.is_i64 = 0;
+                n_pairs = J.n_pairs;
+            } else {
+                if (J.H <= 0 || J.idx_stride < J.H) return fail(KP_ERR_ARG, "kpconv_prepare: bad table");
+                T.idx = J.neighb_inds; T.rowptr = nullptr; T.H = J.H; T.stride = J.idx_stride; T.is_i64 = J.idx_is_i64;
+                n_pairs = (long long)J.nc * J.H;
+            }
+            Lists L;
+            L.hdr = (int*)J.hdr; L.entries = (int2*)J.entries; L.cap = J.entries_cap;
+            rc = build_lists(S, J.centres, J.nc, J.others, J.no, T, n_pairs, J.kernel_points, J.K, J.kp_sign, J.KP_extent, &L,
+                             stream, overflow_flag);
+        } else return fail(KP_ERR_ARG, "kpconv_prepare: unknown job kind");
+        if (rc != KP_OK) return rc;
+    }
+    return KP_OK;
 }
 
 // lists_hdr / lists_entries (optional, caller-owned device buffers of kpconv_lists_bytes): the forward pass leaves

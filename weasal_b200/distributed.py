@@ -41,6 +41,18 @@ class GradAllReducer:
         torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)])
 
 
+    @torch.no_grad()
+    def allreduce_flat(self, flat):
+        """Average a flat gradient buffer in place: ONE collective, no copies (the captured training step gathers the
+        gradients into ``flat`` inside its graph and reads them back from there)."""
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:  # (gloo, the CPU tests: no AVG)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(dist.get_world_size(self.group))
+
 def shard_indices(n_items, rank, world_size):
     """Round-robin shard of sphere (or batch) indices: rank r takes r, r + W, r + 2W, ..."""
     return list(range(rank, n_items, world_size))

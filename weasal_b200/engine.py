@@ -58,29 +58,58 @@ def calibrate_static_caps(config, point_sets, length_sets, row_margin=1.05, row_
     return n_cap, limits
 
 
+def calibrate_conv_plans(net, config, point_sets, length_sets, n_cap, limits, random_grid_orient=True, margin=1.3):
+    """The fixed layout of the prefetched KPConv lists (weasal_b200.plan.ConvPlans) for ``net``: capacities of the entry
+    buffers from a calibration pass over the given batches (records actually needed, plus a margin; a batch that
+    outgrows them takes the eager step)."""
+    from .plan import ConvPlans, conv_specs, measure_entries
+    from .pyramid import DeviceBatch, segmentation_inputs
+    specs = conv_specs(net)
+    need = None
+    for pts, lens in zip(point_sets, length_sets):
+        li = segmentation_inputs(pts, None, None, lens, config, neighborhood_limits=limits,
+                                 random_grid_orient=random_grid_orient, native=True)
+        used = measure_entries(specs, DeviceBatch(li))
+        need = used if need is None else [max(a, b) for a, b in zip(need, used)]
+    caps = [int(v * margin) + 4096 for v in need]
+    return ConvPlans(specs, n_cap, limits, limits, caps)
+
+
 class GraphedTrainStep:
     """forward -> loss -> backward (-> gradient all-reduce) -> clip -> optimizer step of a static-shape batch, captured
-    once into a CUDA graph and replayed per batch.
+    once into CUDA graphs and replayed per batch.
 
-        trainer = GraphedTrainStep(net, optimizer, loss_fn, reducer=reducer, clip_value=100.0)
-        loss = trainer.step(batch)          # batch from PyramidPrefetcher(..., n_cap=..., neighborhood_limits=...)
+        trainer = GraphedTrainStep(net, optimizer, loss_fn, reducer=reducer, clip_value=100.0, plans=plans, packer=packer)
+        loss = trainer.step(batch)          # batch from PyramidPrefetcher(..., n_cap=..., neighborhood_limits=..., plans=plans)
 
     ``loss_fn(logits, labels)``; ``net(batch)`` consumes a :class:`DeviceBatch`. The returned loss is a device scalar
-    (the graph's static output for graphed steps)."""
+    (the graph's static output for graphed steps).
 
-    def __init__(self, net, optimizer, loss_fn, reducer=None, clip_value=None, warmup=3, use_graph=True):
+    One GPU: ONE graph (weight packing, forward, loss, backward, clip, optimizer). With a ``reducer`` (data parallel): graph A
+    = packing, forward, loss, backward and one multi-tensor copy of the gradients into a flat buffer; then ONE eager NCCL
+    all-reduce (average) of that buffer; then graph B = clip + optimizer step reading gradients that are views of the flat
+    buffer. Both graphs address the flat buffer and the captured gradient tensors directly, so an eager fall-back step in
+    between (which re-creates ``p.grad``) cannot leave a later replay with stale gradients."""
+
+    def __init__(self, net, optimizer, loss_fn, reducer=None, clip_value=None, warmup=3, use_graph=True, plans=None,
+                 packer=None):
         self.use_graph = use_graph  # False: every batch takes the eager step (profiling under ncu)
         self.net, self.opt, self.loss_fn, self.reducer, self.clip, self.warmup = net, optimizer, loss_fn, reducer, clip_value, warmup
-        self.graph = None
+        self.plans, self.packer = plans, packer
+        self.graph = self.graph_tail = None
         self.slab = None          # the graph's input: one static slab, every tensor of the batch is a view of it
+        self.plan_buf = None      # ... and the prefetched KPConv lists of the batch
         self.layout = None        # (offsets, n_cap, strides) of the captured layout
         self.loss = None
+        self.flat = None          # flat gradient buffer (data parallel)
         self.launches_per_replay = 0   # library kernels inside one replay (bench.py's gpu_launches)
         self.n_graphed = self.n_eager = 0
         self.tail_in_graph = True
 
     # ------------------------------------------------------------------------------------------------------ the step
     def _head(self, batch):
+        if self.packer is not None:
+            self.packer.pack()   # operand images of every layer's weights: one launch
         logits = self.net(batch)
         loss = self.loss_fn(logits, batch.labels)
         self.opt.zero_grad(set_to_none=True)
@@ -106,11 +135,14 @@ class GraphedTrainStep:
         f, lb = nbld.static_extras(self.slab)
         batch = DeviceBatch(P + Nn + Po + Up + Le + [f, lb])
         batch.pool_widths = nbld.static_pool_widths(self.slab)  # max_pool ignores the columns beyond the true width
+        if self.plan_buf is not None:
+            self.plans.attach(self.plan_buf, batch.neighbors, batch.pools)
         return batch
 
     def _capture(self, batch):
         nbld, dev = batch.build, batch.static_slab.device
         self.slab = torch.empty_like(batch.static_slab)
+        self.plan_buf = torch.empty_like(batch.plan_buf) if (self.plans is not None and batch.plan_buf is not None) else None
         self.layout = (nbld.offs.copy(), nbld.n_cap.copy(), nbld.strides.copy())
         params = [p for p in self.net.parameters()]
         saved = [p.detach().clone() for p in params]
@@ -120,6 +152,8 @@ class GraphedTrainStep:
         s.wait_stream(cur)
         with torch.cuda.stream(s):
             self.slab.copy_(batch.static_slab)
+            if self.plan_buf is not None:
+                self.plan_buf.copy_(batch.plan_buf)
             for _ in range(self.warmup):  # sizes the allocator pools, the library's scratch arena (per stream) and the
                 self._body(self._static_batch(nbld))  # optimizer's momentum buffers before anything is recorded
         cur.wait_stream(s)
@@ -127,11 +161,30 @@ class GraphedTrainStep:
         self.opt.zero_grad(set_to_none=True)
         g = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        # With a gradient all-reduce the graph ends after backward and the collective + clip + optimizer (a handful
-        # of multi-tensor launches) stay eager: the collective keeps its place in the process group's own stream order.
         self.tail_in_graph = self.reducer is None
-        with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
-            self.loss = self._body(self._static_batch(nbld)) if self.tail_in_graph else self._head(self._static_batch(nbld))
+        if self.tail_in_graph:
+            with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
+                self.loss = self._body(self._static_batch(nbld))
+        else:
+            # graph A ends with the gradients gathered into one flat buffer; graph B (clip + optimizer) reads them there
+            with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
+                self.loss = self._head(self._static_batch(nbld))
+                with_grad = [p for p in params if p.grad is not None]
+                self.flat = torch.empty(sum(p.numel() for p in with_grad), dtype=torch.float32, device=dev)
+                views, o = [], 0
+                for p in with_grad:
+                    views.append(self.flat[o:o + p.numel()].view_as(p))
+                    o += p.numel()
+                torch._foreach_copy_(views, [p.grad for p in with_grad])
+            self._grad_params, self._grad_views = with_grad, views
+            for p, v in zip(with_grad, views):
+                p.grad = v
+            gt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gt, stream=s, pool=g.pool(), capture_error_mode="thread_local"):
+                if self.clip is not None:
+                    torch.nn.utils.clip_grad_value_(with_grad, self.clip)
+                self.opt.step()
+            self.graph_tail = gt
         self.launches_per_replay = _lib.launch_count() - n0
         self.graph = g
         # the warm-up steps must not count as training: parameters back to their values, momentum buffers that did
@@ -150,6 +203,8 @@ class GraphedTrainStep:
     def _fits(self, batch):
         if not self.use_graph or getattr(batch, "static_slab", None) is None or not batch.no_crop:
             return False
+        if self.plans is not None and getattr(batch, "plan_buf", None) is None:
+            return False   # a list outgrew its calibrated capacity: this batch builds its lists on the fly (eager step)
         if self.layout is None:
             return True
         nbld = batch.build
@@ -164,12 +219,18 @@ class GraphedTrainStep:
     def step(self, batch):
         if not self._fits(batch):
             self.n_eager += 1
-            return self._body(batch)
+            if self.graph_tail is not None:   # the eager step uses its own gradient tensors
+                self.opt.zero_grad(set_to_none=True)
+            loss = self._body(batch)
+            return loss
         if self.graph is None:
             self._capture(batch)
         self.slab.copy_(batch.static_slab, non_blocking=True)
+        if self.plan_buf is not None:
+            self.plan_buf.copy_(batch.plan_buf, non_blocking=True)
         self.graph.replay()
         if not self.tail_in_graph:
-            self._tail()
+            self.reducer.allreduce_flat(self.flat)
+            self.graph_tail.replay()
         self.n_graphed += 1
         return self.loss

@@ -60,6 +60,12 @@ class Unary(nn.Module):
         return F.leaky_relu(x, 0.1) if self.relu else x
 
 
+def fused_linear_weights(net):
+    """``nn.Linear`` weights of the unary blocks that run on the fused tcgen05 linear kernels (for plan.WeightPacker)."""
+    return [m.mlp.weight for m in net.modules()
+            if isinstance(m, Unary) and max(m.mlp.in_features, m.mlp.out_features) <= UNARY_FUSED_MAX_CHANNELS]
+
+
 class ConvBlock(nn.Module):
     """'simple', 'resnetb' or 'resnetb_strided' block at pyramid level `layer`."""
 

@@ -196,6 +196,21 @@ class KPConvFunction(torch.autograd.Function):
         nq, ns = q.shape[0], s.shape[0]
         L = _lib.lib()
         lists = None
+        plan = _find_plan(neighb_inds, kernel_points)
+        if plan is not None and kpconv_impl() != "simt":
+            # the geometry-only half of the operator (influence lists, transposed table) was built ahead of time by the
+            # prefetch stage (weasal_b200.plan); the weights may come as ready-made operand images (WeightPacker)
+            img = getattr(weights, "_kp_packed", None)
+            out = torch.empty((nq, cout), dtype=torch.float32, device=q.device)
+            wsrc = img["fwd"] if img is not None else w
+            _lib.check(L.kp_kpconv_apply_lists_dev(nq, xx.data_ptr(), ns, cin, wsrc.data_ptr(), 1 if img is not None else 0, 0,
+                                                   cout, K, plan.f_hdr.data_ptr(), plan.f_ent.data_ptr(), out.data_ptr(), 1.0,
+                                                   _stream()), "kpconv_apply_lists")
+            ctx.plan, ctx.img = plan, img
+            ctx.save_for_backward(xx, w)
+            ctx.shape = (nq, ns)
+            return out
+        ctx.plan = None
         if kpconv_impl() == "simt":  # fp32 cross-check path (CUDA-core gather + library GEMM), not the product path
             wf = torch.empty((nq, K * cin), dtype=torch.float32, device=q.device)
             _lib.check(L.kp_kpconv_wf_dev(q.data_ptr(), nq, s.data_ptr(), ns, idx.data_ptr(), i64, H, stride,
@@ -228,6 +243,8 @@ class KPConvFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
+        if ctx.plan is not None:
+            return KPConvFunction._backward_planned(ctx, d_out)
         q, s, idx, xx, w, kp = ctx.saved_tensors
         i64, H, stride, ext = ctx.meta
         K, cin, cout = w.shape
@@ -279,6 +296,60 @@ class KPConvFunction(torch.autograd.Function):
                                                      tr[1].data_ptr(), _stream()),
                        "kpconv_backward")
         return None, None, None, dx, dw, None, None
+
+
+def _backward_planned(ctx, d_out):
+    """dW and dX over the prefetched lists: two independent kernels, forked onto two streams (capturable: the fork and
+    the join are event dependencies) so that each one's tail overlaps the other's head."""
+    xx, w = ctx.saved_tensors
+    plan, img = ctx.plan, ctx.img
+    nq, ns = ctx.shape
+    K, cin, cout = w.shape
+    do = _f32c(d_out)
+    L = _lib.lib()
+    dev = do.device
+    dx = dw = None
+    cur = torch.cuda.current_stream(dev)
+    side = _side_stream(dev) if (ctx.needs_input_grad[3] and ctx.needs_input_grad[4] and _FORK_BACKWARD) else None
+    if ctx.needs_input_grad[4]:
+        dw = torch.empty((K, cin, cout), dtype=torch.float32, device=dev)
+        if side is not None:
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                _lib.check(L.kp_kpconv_dw_lists_dev(nq, xx.data_ptr(), ns, cin, do.data_ptr(), cout, K, plan.f_hdr.data_ptr(),
+                                                    plan.f_ent.data_ptr(), dw.data_ptr(), _stream()), "kpconv_dw_lists")
+        else:
+            _lib.check(L.kp_kpconv_dw_lists_dev(nq, xx.data_ptr(), ns, cin, do.data_ptr(), cout, K, plan.f_hdr.data_ptr(),
+                                                plan.f_ent.data_ptr(), dw.data_ptr(), _stream()), "kpconv_dw_lists")
+    if ctx.needs_input_grad[3]:
+        dx = torch.empty((ns, cin), dtype=torch.float32, device=dev)
+        wsrc = img["dx"] if img is not None else w
+        _lib.check(L.kp_kpconv_apply_lists_dev(ns, do.data_ptr(), nq, cout, wsrc.data_ptr(), 1 if img is not None else 0, 1, cin,
+                                               K, plan.d_hdr.data_ptr(), plan.d_ent.data_ptr(), dx.data_ptr(), 1.0, _stream()),
+                   "kpconv_apply_lists")
+    if side is not None:
+        cur.wait_stream(side)
+        for t in (xx, do, dw):
+            t.record_stream(side)
+    return None, None, None, dx, dw, None, None
+
+
+KPConvFunction._backward_planned = staticmethod(_backward_planned)
+
+_FORK_BACKWARD = os.environ.get("WEASAL_FORK_BACKWARD", "1") != "0"
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(dev)
+    return _SIDE[key]
+
+
+def _find_plan(neighb_inds, kernel_points):
+    plans = getattr(neighb_inds, "_kp_plans", None)
+    return plans.get(kernel_points.data_ptr()) if plans else None
 
 
 def kpconv(q_pts, s_pts, neighb_inds, x, weights, kernel_points, KP_extent):
@@ -381,8 +452,15 @@ class LinearActFunction(torch.autograd.Function):
         n, cin = xx.shape
         cout = w.shape[0]
         y = torch.empty((n, cout), dtype=torch.float32, device=xx.device)
-        _lib.check(_lib.lib().kp_linear_forward_dev(xx.data_ptr(), n, cin, w.data_ptr(), b.data_ptr() if b is not None else None,
-                                                    cout, float(slope), y.data_ptr(), _stream()), "linear_forward")
+        img = getattr(weight, "_kp_packed", None)
+        if img is not None:
+            _lib.check(_lib.lib().kp_linear_forward_packed_dev(xx.data_ptr(), n, cin, img["fwd"].data_ptr(),
+                                                               b.data_ptr() if b is not None else None, cout, float(slope),
+                                                               y.data_ptr(), _stream()), "linear_forward")
+        else:
+            _lib.check(_lib.lib().kp_linear_forward_dev(xx.data_ptr(), n, cin, w.data_ptr(), b.data_ptr() if b is not None else None,
+                                                        cout, float(slope), y.data_ptr(), _stream()), "linear_forward")
+        ctx.img = img
         ctx.save_for_backward(xx, w, y)
         ctx.slope, ctx.has_bias = float(slope), bias is not None
         return y
@@ -402,6 +480,30 @@ class LinearActFunction(torch.autograd.Function):
             db = g.sum(0)
         dx = torch.empty((n, cin), dtype=torch.float32, device=xx.device) if ctx.needs_input_grad[0] else None
         dw = torch.empty((cout, cin), dtype=torch.float32, device=xx.device)
+        if ctx.img is not None:
+            # dW and dX as two kernels on two streams (see _backward_planned), dX from the ready-made transposed images
+            L = _lib.lib()
+            yp = y.data_ptr() if act else None
+            sl = ctx.slope if act else 1.0
+            dev = g.device
+            cur = torch.cuda.current_stream(dev)
+            side = _side_stream(dev) if (dx is not None and _FORK_BACKWARD) else None
+            if side is not None:
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    _lib.check(L.kp_linear_dw_dev(xx.data_ptr(), n, cin, cout, yp, sl, g.data_ptr(), dw.data_ptr(), _stream()),
+                               "linear_dw")
+            else:
+                _lib.check(L.kp_linear_dw_dev(xx.data_ptr(), n, cin, cout, yp, sl, g.data_ptr(), dw.data_ptr(), _stream()),
+                           "linear_dw")
+            if dx is not None:
+                _lib.check(L.kp_linear_dx_packed_dev(n, cin, ctx.img["dx"].data_ptr(), cout, yp, sl, g.data_ptr(), dx.data_ptr(),
+                                                     _stream()), "linear_dx")
+            if side is not None:
+                cur.wait_stream(side)
+                for t in (xx, y, g, dw):
+                    t.record_stream(side)
+            return dx, dw, db, None
         _lib.check(_lib.lib().kp_linear_backward_dev(xx.data_ptr(), n, cin, w.data_ptr(), cout,
                                                      y.data_ptr() if act else None, ctx.slope if act else 1.0,
                                                      g.data_ptr(), dx.data_ptr() if dx is not None else None,

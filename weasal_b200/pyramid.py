@@ -430,7 +430,7 @@ class PyramidPrefetcher:
     Grid orientations are drawn from ``np.random`` at submit time, in submission order."""
 
     def __init__(self, config, device="cuda", neighborhood_limits=None, random_grid_orient=True, order="reference",
-                 index_dtype=torch.int64, slots=3, n_cap=None):
+                 index_dtype=torch.int64, slots=3, n_cap=None, plans=None):
         """``n_cap``: per-layer row capacities -> batches come in the static layout of kp_pyramid_build_static_dev
         (features and labels inside the slab; ``batch.static_slab`` set) for :class:`weasal_b200.engine.GraphedTrainStep`;
         a batch that does not fit falls back to the ordinary layout."""
@@ -442,6 +442,11 @@ class PyramidPrefetcher:
             self.dev = torch.device("cuda", torch.cuda.current_device())
         self.cfg, self.limits, self.orient, self.order, self.dtype = config, neighborhood_limits, random_grid_orient, order, index_dtype
         self.n_cap = list(n_cap) if n_cap is not None else None
+        # plans (weasal_b200.plan.ConvPlans, static layout only): the influence lists / transposed tables of every KPConv
+        # of the network are built right behind the pyramid, by the same worker on the same stream
+        self.plans = plans if n_cap is not None else None
+        self.plan_bufs = [None] * slots
+        self.plan_jobs = [None] * slots      # (slab address, buffer address, ctypes job table) per ring slot
         # high priority: the pyramid's ~150 small kernels slot in between the training stream's big ones instead of
         # queueing behind them (a build took 4.2 ms instead of 2.0 ms when the training stream ran ahead)
         self.side = torch.cuda.Stream(self.dev, priority=-1)
@@ -489,6 +494,8 @@ class PyramidPrefetcher:
                                n_cap=self.n_cap, features=feats, labels=labs)
             if self.slabs[slot] is None or self.slabs[slot].numel() < nbld.slab_bytes():
                 self.slabs[slot] = torch.empty(int(nbld.slab_bytes() * 1.25), dtype=torch.uint8, device=self.dev)
+            if self.plans is not None and self.plan_bufs[slot] is None:
+                self.plan_bufs[slot] = torch.zeros(self.plans.nbytes, dtype=torch.uint8, device=self.dev)
         self.q_in.put((nbld, slot, (pts, feats, labs), extras, C.c_void_p(self.side.cuda_stream)))
 
     def _run(self):
@@ -511,10 +518,26 @@ class PyramidPrefetcher:
                     if self.slabs[slot].numel() < nbld.slab_bytes():
                         with torch.cuda.stream(self.side):
                             self.slabs[slot] = torch.empty(int(nbld.slab_bytes() * 1.25), dtype=torch.uint8, device=self.dev)
+                nbld.plans_ok = False
+                if self.plans is not None and nbld.n_cap is not None and nbld.no_crop():
+                    nbld.plans_ok = self._run_plans(nbld, slot, sh)
                 nbld.build_s = time.perf_counter() - t0
                 self.q_out.put((nbld, slot, owned, extras))
             except BaseException as e:  # surfaced by get()
                 self.q_out.put((e, None, None, None))
+
+    def _run_plans(self, nbld, slot, sh):
+        """Worker thread: the lists of every KPConv for the batch just built into ring slot ``slot``. The job table holds
+        device addresses only, all fixed for a (slab, buffer) pair, so it is built once per slot."""
+        slab, buf = self.slabs[slot], self.plan_bufs[slot]
+        key = (slab.data_ptr(), buf.data_ptr())
+        if self.plan_jobs[slot] is None or self.plan_jobs[slot][0] != key:
+            P, Nn, Po, Up, Le = nbld.views(slab)
+            self.plan_jobs[slot] = (key, self.plans.jobs(P, Nn, Po, self.dtype == torch.int64, buf))
+        self.plans.run(self.plan_jobs[slot][1], buf, sh)
+        with torch.cuda.stream(self.side):
+            overflow = int(buf[self.plans.flag_off:self.plans.flag_off + 4].view(torch.int32).item())  # syncs the stream
+        return overflow == 0
 
     def get(self):
         t0 = time.perf_counter()
@@ -543,6 +566,11 @@ class PyramidPrefetcher:
         if nbld.n_cap is not None:
             batch.pool_widths = nbld.static_pool_widths(slab)
         batch.n_points = int(nbld.n_out[0])
+        batch.plan_buf = None
+        if getattr(nbld, "plans_ok", False):
+            batch.plan_buf = self.plan_bufs[slot]
+            batch.plan_buf.record_stream(cur)
+            self.plans.attach(batch.plan_buf, batch.neighbors, batch.pools)
         return batch
 
     def close(self):
