@@ -23,7 +23,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "train points/sec"
 UNIT = "points/s"
-N_BATCHES = 8           # distinct pre-extracted sphere batches cycled through the steps
+N_BATCHES = 8           # distinct sphere batches cycled through the timed steps
+N_CALIB = 8             # batches of ANOTHER tile the static capacities are calibrated on (never timed)
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -147,35 +148,29 @@ def search_bytes(batch, idx_bytes=8):
 
 
 # ---------------------------------------------------------------------------------------------------------- our arm
-def run_ours(args):
+def measure_config(args, cfg_name, ctx, K, W, primary):
+    """One workload (``vaihingen_pl`` / ``dales_pl``): K timed steps device-resident, K timed steps end to end; for the
+    primary workload also the per-kernel profile leg. Returns the fields of the JSON line that depend on the workload."""
+    import ctypes as C
     import torch
     import torch.distributed as dist
     import torch.nn.functional as F
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py: no CUDA device; the product path has no CPU fallback "
-                           "(use --impl reference for the CPU reference arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    # the harness network's Linear layers use the same operand precision as the KPConv contraction (TF32 in, fp32 out)
-    torch.backends.cuda.matmul.allow_tf32 = True
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
     from weasal_b200 import _lib, grid_subsampling, pyramid
-    from weasal_b200.kpconv import KPConv
     from weasal_b200.distributed import GradAllReducer
-    from weasal_b200.net import CfgView, KPFCNNHarness, net_config
-    import ctypes as C
+    from weasal_b200.engine import GraphedTrainStep, calibrate_conv_plans, calibrate_static_caps
+    from weasal_b200.kpconv import KPConv
+    from weasal_b200.net import CfgView, KPFCNNHarness, fused_linear_weights, net_config
+    from weasal_b200.plan import WeightPacker
+
+    rank, world, dev, flush = ctx["rank"], ctx["world"], ctx["dev"], ctx["flush"]
 
     def gpu_subsample(p, f, l, dl):
         return grid_subsampling.subsample(p, features=f, classes=l, sampleDl=dl)
 
-    cfg, batches = build_batches(args.config, args.seed + 17 * rank, N_BATCHES, gpu_subsample)
-    ncfg = net_config(args.config)
+    # timed batches and calibration batches come from DIFFERENT synthetic tiles: the capacities never saw the timed spheres
+    cfg, batches = build_batches(cfg_name, args.seed + 17 * rank, N_BATCHES, gpu_subsample)
+    _, calib = build_batches(cfg_name, args.seed + 17 * rank + 7919, N_CALIB, gpu_subsample)
+    ncfg = net_config(cfg_name)
     view = CfgView(ncfg)
     np.random.seed(args.seed + rank)
     torch.manual_seed(args.seed)  # identical initial weights on every rank
@@ -188,32 +183,35 @@ def run_ours(args):
 
     dev_batches = [{k: torch.from_numpy(v).to(dev) for k, v in b.items() if k != "lengths"} for b in batches]
     pin_batches = [{k: torch.from_numpy(v).pin_memory() for k, v in b.items() if k != "lengths"} for b in batches]
-    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+    cal_pts = [torch.from_numpy(b["points"]).to(dev) for b in calib]
+    cal_lens = [b["lengths"] for b in calib]
 
-    from weasal_b200.engine import GraphedTrainStep, calibrate_static_caps
-    # Static shapes + one CUDA graph per step (weasal_b200/engine.py). Capacities come from a calibration pass over
-    # the batches, like the reference's sampler calibration (batch_limit / neighborhood_limits): rows padded to a
-    # per-layer capacity, neighbourhood limits chosen so that no row is cropped (results equal the unlimited pyramid).
+    # Static shapes + one CUDA graph per step (weasal_b200/engine.py). Capacities come from a calibration pass, like the
+    # reference's sampler calibration (batch_limit / neighborhood_limits, datasets/Vaihingen3D_PseudoLabel.py:1098-1404):
+    # rows padded to a per-layer capacity, neighbourhood limits chosen so that no calibration row is cropped. A timed
+    # batch that outgrows a capacity, or has a cropped row, takes the eager step (counted below).
     use_graph = os.environ.get("WEASAL_BENCH_GRAPH", "1") != "0"  # "eager": static batches, eager launches (ncu lists)
     n_cap = limits = plans = None
-    from weasal_b200.engine import calibrate_conv_plans
-    from weasal_b200.net import fused_linear_weights
-    from weasal_b200.plan import WeightPacker
     # weight-only work (TF32 operand images of every KPConv / unary block): one launch per step
     packer = WeightPacker(net, fused_linear_weights(net)) if os.environ.get("WEASAL_BENCH_PACKER", "1") == "1" else None
     if use_graph:
-        n_cap, limits = calibrate_static_caps(view, [b["points"] for b in dev_batches], [b["lengths"] for b in batches])
+        n_cap, limits = calibrate_static_caps(view, cal_pts, cal_lens, row_margin=1.10, width_margin=0.2)
         # geometry-only work (influence lists, transposed tables of all 10 KPConv): built by the prefetch stage
         if os.environ.get("WEASAL_BENCH_PLANS", "1") == "1":
-            plans = calibrate_conv_plans(net, view, [b["points"] for b in dev_batches], [b["lengths"] for b in batches],
-                                         n_cap, limits)
+            plans = calibrate_conv_plans(net, view, cal_pts, cal_lens, n_cap, limits)
+    del cal_pts
     prefetch = pyramid.PyramidPrefetcher(view, dev, neighborhood_limits=limits, n_cap=n_cap, plans=plans)
     trainer = GraphedTrainStep(net, opt, F.cross_entropy, reducer=reducer if world > 1 else None, clip_value=100.0,
                                use_graph=os.environ.get("WEASAL_BENCH_GRAPH", "1") == "1", plans=plans, packer=packer)
     eager = GraphedTrainStep(net, opt, F.cross_entropy, reducer=None, clip_value=100.0, packer=packer)  # profile leg: no collective
     if use_graph:  # capture before the prefetch pipeline runs (nothing else issues CUDA work meanwhile)
-        prefetch.submit(dev_batches[0]["points"], dev_batches[0]["features"], dev_batches[0]["labels"], batches[0]["lengths"], inputs_ready=True)
-        trainer.prepare(prefetch.get())
+        for b in range(N_BATCHES):  # (the first timed batch that fits the capacities)
+            prefetch.submit(dev_batches[b]["points"], dev_batches[b]["features"], dev_batches[b]["labels"],
+                            batches[b]["lengths"], inputs_ready=True)
+            first = prefetch.get()
+            trainer.prepare(first)
+            if trainer.graph is not None:
+                break
         torch.cuda.synchronize()
 
     def net_step(batch, allreduce=True):
@@ -276,7 +274,7 @@ def run_ours(args):
     def timed(n_warm, n_steps, e2e, clocks=None):
         import gc
         gc.collect()
-        gc.disable()  # the step is host-launch bound: a generational GC pause inside a step shows up as a 10 % outlier
+        gc.disable()  # a generational GC pause inside a step shows up as a 10 % outlier
         run_steps(0, n_warm, e2e)
         if world > 1:
             dist.barrier()
@@ -298,7 +296,6 @@ def run_ours(args):
             return float(tmax[0]), float(t[1])
         return float(t[0]), float(t[1])
 
-    W, K = max(args.warmup, 3), args.steps
     L = _lib.lib()
     # set-up, before any warm-up or timed step: every distinct batch once through the real pipeline, so that the
     # worker thread's scratch arena and the allocator pools have seen the largest batch (a first-time cudaMalloc
@@ -306,15 +303,11 @@ def run_ours(args):
     run_steps(0, N_BATCHES, False)
     run_steps(0, N_BATCHES, True)
     torch.cuda.synchronize()
-    clocks = ClockSampler(local)
-    for _ in range(3):  # the first NVML reads of a process take 10-35 ms (seen as a one-off stall in the first timed step)
-        clocks.sample()
-    clocks.rows.clear()
-    launches0 = _lib.launch_count()
+    clocks = ctx["clocks"] if primary else None
     timed(W, 0, False)
     launches0 = _lib.launch_count()
-    g0 = trainer.n_graphed
-    prof_range = os.environ.get("WEASAL_BENCH_PROFILE_RANGE") == "1"  # ncu --profile-from-start off: the timed steps only
+    g0, e0_ = trainer.n_graphed, trainer.n_eager
+    prof_range = primary and os.environ.get("WEASAL_BENCH_PROFILE_RANGE") == "1"  # ncu --profile-from-start off
     if prof_range:
         torch.cuda.profiler.start()
     ms, pts = timed(0, K, False, clocks if rank == 0 else None)
@@ -323,20 +316,17 @@ def run_ours(args):
     iv = np.diff([a[0] for a in stamps]) * 1e3 if len(stamps) > 2 else np.zeros(1)
     pacing = {"launch_interval_ms": {"min": float(iv.min()), "median": float(np.median(iv)), "max": float(iv.max())},
               "pyramid_build_ms_median": float(np.median([a[1] for a in stamps]) * 1e3) if stamps else None,
-              "get_wait_ms_median": float(np.median([a[2] for a in stamps]) * 1e3) if stamps else None,
-              "launch_intervals_ms": [round(float(v), 2) for v in iv]}
+              "get_wait_ms_median": float(np.median([a[2] for a in stamps]) * 1e3) if stamps else None}
     # library kernels launched in the timed region: the pyramid's (counted live) + those inside the replayed graphs
     gpu_launches = _lib.launch_count() - launches0 + (trainer.n_graphed - g0) * trainer.launches_per_replay
-    graphed_steps = trainer.n_graphed - g0
+    graphed_steps, eager_steps = trainer.n_graphed - g0, trainer.n_eager - e0_
     e2e_ms, e2e_pts = timed(W, K, True, clocks if rank == 0 else None)
-    clk = clocks.summary() if rank == 0 else None
 
     # per-kernel device times (CUDA events on the launching stream, recorded inside the library)
     roof, kernels = None, {}
-    if rank == 0:
+    if rank == 0 and primary:
         L.kp_profile_enable(1)
         psteps = min(K, 8)
-        shapes, sbytes = None, 0
         seen = []
 
         def first_shapes(batch):
@@ -353,11 +343,7 @@ def run_ours(args):
             tag, cnt, tot = line.split()
             kernels[tag] = {"launches_per_step": int(cnt) / psteps, "ms_per_step": float(tot) / psteps}
         alg = algorithmic(shapes)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
+        peaks = ctx["peaks"]
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         alg_bytes = {"kp_fwd": alg["kp_fwd"], "kp_fwd_dx": alg["kp_fwd_dx"], "kp_dw": alg["kp_dw"],
@@ -366,6 +352,7 @@ def run_ours(args):
             if tag in kernels and kernels[tag]["ms_per_step"] > 0:
                 kernels[tag]["algorithmic_mb_per_step"] = b / 1e6
                 kernels[tag]["achieved_gbs"] = b / 1e9 / (kernels[tag]["ms_per_step"] / 1e3)
+                kernels[tag]["frac_of_hbm_peak"] = kernels[tag]["achieved_gbs"] / hbm_peak
         if "kp_fwd" in kernels:
             kernels["kp_fwd"]["contraction_tflops"] = alg["mma_flops"] / 1e12 / (kernels["kp_fwd"]["ms_per_step"] / 1e3)
             kernels["kp_fwd"]["tensor_frac_of_bf16_sustained"] = kernels["kp_fwd"]["contraction_tflops"] / tf_peak
@@ -387,127 +374,361 @@ def run_ours(args):
                     "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                     "bytes_per_launch": alg_bytes[dom] / max(kernels[dom]["launches_per_step"], 1),
                     "launch_ms": kernels[dom]["ms_per_step"] / max(kernels[dom]["launches_per_step"], 1)}
+    prefetch.close()
+    n0 = float(np.mean([b["points"].shape[0] for b in batches]))
+    h2d = int(np.mean([sum(v.nbytes for k, v in b.items()) for b in batches]))
+    res = {
+        "value": pts / (ms / 1e3), "ms_per_step": ms / K,
+        "config": {"workload": f"{cfg_name}: pyramid precompute + KPFCNN fwd+bwd+SGD on {cfg['batch_num']} "
+                               f"synthetic ALS spheres of radius {cfg['in_radius']} m per step",
+                   "points_per_step_per_gpu": n0, "global_points_per_step": n0 * world,
+                   "first_subsampling_dl": cfg["dl"], "first_features_dim": ncfg["first_features_dim"], "layers": 5,
+                   "kpconv_per_forward": 10, "parallelism": f"dp{world}",
+                   "l2": "flushed between steps (256 MB write, inside the timed region)",
+                   "pyramid": "built one step ahead on a side stream by one native call (kp_pyramid_build_static_dev), "
+                              "followed by the influence lists of all KPConv (kp_kpconv_prepare_dev)",
+                   "random_grid_orient": True,
+                   "capacities": f"calibrated on {N_CALIB} batches of another synthetic tile; timed on {N_BATCHES} unseen batches",
+                   "neighborhood_limits": limits,
+                   "step": (f"CUDA graph(s) per step over static-shape batches (rows padded to {n_cap}); "
+                            f"{graphed_steps} of {K} timed steps graphed, {eager_steps} eager (capacity / crop fall-back)")
+                           if use_graph else "eager launches",
+                   "n_graphed": graphed_steps, "n_eager": eager_steps,
+                   "harness_linear_precision": "tf32"},
+        "e2e": {"value": e2e_pts / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms / K},
+        "pacing": pacing, "gpu_launches": int(gpu_launches), "gpu_launches_per_step": gpu_launches / max(K, 1),
+        "roofline": roof, "kernels": kernels, "grad_allreduce_bytes": reducer.bytes() if world > 1 else 0,
+    }
+    del trainer, eager, prefetch, net, opt, dev_batches, pin_batches
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
 
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the product path has no CPU fallback "
+                           "(use --impl reference for the CPU reference arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    # the harness network's Linear layers use the same operand precision as the KPConv contraction (TF32 in, fp32 out)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    clocks = ClockSampler(local)
+    for _ in range(3):  # the first NVML reads of a process take 10-35 ms (seen as a one-off stall in the first timed step)
+        clocks.sample()
+    clocks.rows.clear()
+    ctx = {"rank": rank, "world": world, "dev": dev, "peaks": peaks, "clocks": clocks,
+           "flush": torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)}
+    W, K = max(args.warmup, 3), args.steps
+    main = measure_config(args, args.config, ctx, K, W, primary=True)
+    clk = clocks.summary() if rank == 0 else None
+
+    # the other workload north_star names, in the same line (DALES-shaped PseudoLabel: dl 0.4, first_features_dim 128,
+    # KPConv up to 512 -> 512), at every N, so that the scaling run carries it too
+    extra = {}
+    other = "dales_pl" if args.config == "vaihingen_pl" else "vaihingen_pl"
+    if not args.no_extra_configs:
+        r = measure_config(args, other, ctx, min(K, 10), 3, primary=False)
+        extra[other] = {"metric": METRIC, "unit": UNIT, "value": r["value"], "ms_per_step": r["ms_per_step"],
+                        "steps": min(K, 10), "e2e": r["e2e"], "config": r["config"],
+                        "gpu_launches_per_step": r["gpu_launches_per_step"]}
+    sweep = None
+    if rank == 0 and world == 1 and not args.no_sweep:
+        try:
+            sweep = operator_sweep(dev, peaks)
+        except Exception as e:  # the sweep must never cost the headline line
+            sweep = {"error": repr(e)[:300]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = run_reference(args, budget_s=25.0, as_leg=True)
 
     if rank == 0:
-        n0 = float(np.mean([b["points"].shape[0] for b in batches]))
-        h2d = int(np.mean([sum(v.nbytes for k, v in b.items()) for b in batches]))
         line = {
-            "metric": METRIC, "value": pts / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32 (fp32 gather, TF32 tensor-core contraction, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": f"{args.config}: pyramid precompute + KPFCNN fwd+bwd+SGD on {cfg['batch_num']} "
-                                   f"synthetic ALS spheres of radius {cfg['in_radius']} m per step",
-                       "points_per_step_per_gpu": n0, "global_points_per_step": n0 * world,
-                       "first_subsampling_dl": cfg["dl"], "layers": 5, "kpconv_per_forward": 10,
-                       "parallelism": f"dp{world}", "l2": "flushed between steps (256 MB write, inside the timed region)",
-                       "pyramid": "built one step ahead on a side stream by one native call (kp_pyramid_build_dev)",
-                       "random_grid_orient": True,
-                       "neighborhood_limits": limits if limits is None else f"calibrated, no row cropped: {limits}",
-                       "step": (f"one CUDA graph per step over static-shape batches (rows padded to {n_cap}); "
-                                f"{graphed_steps} of {K} timed steps graphed") if use_graph else "eager launches",
-                       "harness_linear_precision": "tf32"},
-            "e2e": {"value": e2e_pts / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": e2e_ms / K},
-            "pacing": pacing, "gpu_launches": int(gpu_launches), "gpu_launches_per_step": gpu_launches / max(K, 1),
-            "clocks": clk, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
-            "grad_allreduce_bytes": reducer.bytes() if world > 1 else 0,
+            "config": main["config"], "e2e": main["e2e"], "pacing": main["pacing"], "gpu_launches": main["gpu_launches"],
+            "gpu_launches_per_step": main["gpu_launches_per_step"], "clocks": clk, "roofline": main["roofline"],
+            "kernels": main["kernels"], "cpu_baseline": cpu, "grad_allreduce_bytes": main["grad_allreduce_bytes"],
+            "configs": {**extra, **({"operator_sweep": sweep} if sweep is not None else {})},
         }
         emit(line)
-    prefetch.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+# -------------------------------------------------------------------------------------------------- operator sweep
+def operator_sweep(dev, peaks, budget_s=75.0):
+    """BASELINE.json configs[4]: batch radius search + grid subsampling on 1e5 .. 1e7 raw points (B = 1 and 8) and KPConv
+    K = 15 at Cin = Cout in {64, 128, 256, 512}, H in {16, 32, 64}, each row next to the reference's CPU implementation
+    (compiled reference cores oracle/_ref; the reference's aten chain on PyTorch CPU) timed on a bounded sample, with the
+    achieved GB/s against the SURVEY.md section-8d algorithmic bytes. Rank 0, one GPU."""
+    import torch
+    import oracle
+    from oracle.kpconv_torch import kpconv_reference_ops
+    from weasal_b200 import ops
+    from weasal_b200.synthetic import make_als_tile
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    tf = float(peaks.get("bf16_tflops", 1590.0))
+    have_ref = oracle.ref_available()
+    t_start = time.time()
+    rows = []
+
+    def timeit(fn, warm=2, reps=5):
+        for _ in range(warm):
+            out = fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts)), out
+
+    def cpu_rate(fn, units):
+        t0 = time.time()
+        fn()
+        return units / max(time.time() - t0, 1e-9)
+
+    geo = {}
+    for n_raw in (100_000, 1_000_000, 10_000_000):
+        if time.time() - t_start > budget_s * 0.5 and n_raw > 1_000_000:
+            rows.append({"op": "precompute", "N_raw": n_raw, "skipped": "sweep time budget"})
+            continue
+        extent = float(np.sqrt(n_raw / 40.0))  # DALES-like raw density, 40 pts/m^2
+        pts, _, _ = make_als_tile(1, extent, 40.0)
+        order = np.argsort(pts[:, 0], kind="stable")
+        for B in (1, 8):
+            if B == 8 and n_raw != 1_000_000:
+                continue
+            P_np = pts if B == 1 else pts[order]   # B = 8: eight x-slabs as batch elements
+            L = np.array([len(pts)], np.int32) if B == 1 else np.diff(np.linspace(0, len(pts), B + 1).astype(np.int64)).astype(np.int32)
+            P = torch.from_numpy(np.ascontiguousarray(P_np)).to(dev)
+            for mode in ("reference", "first"):
+                ms, (sp, sl) = timeit(lambda: ops.grid_subsample(P, L, sampleDl=0.4, order=mode), warm=1, reps=3)
+                nbytes = 12 * len(pts) + 12 * len(sp) + 8 * B
+                row = {"op": "grid_subsample", "order": mode, "N": len(pts), "B": B, "M": int(len(sp)), "ms": ms,
+                       "Mpts_per_s": len(pts) / ms / 1e3, "algorithmic_GBs": nbytes / ms / 1e6, "frac_hbm": nbytes / ms / 1e6 / hbm}
+                if mode == "reference" and have_ref and B == 1:
+                    ns = min(len(pts), 1_000_000)
+                    row["cpu_Mpts_per_s"] = cpu_rate(lambda: oracle.ref_subsample(P_np[:ns], sampleDl=0.4), ns) / 1e6
+                    row["cpu_sample"] = f"reference grid_subsampling on the first {ns} points, 1 thread"
+                rows.append(row)
+            S = sp.contiguous()
+            Ls = np.asarray(sl, np.int32)
+            ms, nb = timeit(lambda: ops.batch_query(S, S, Ls, Ls, 1.0, dtype=torch.int32, cap_hint=64), warm=1, reps=3)
+            nbytes = 24 * len(S) + 8 * B + 4 * len(S) * nb.shape[1]
+            row = {"op": "batch_query", "N": int(len(S)), "B": B, "radius": 1.0, "Hmax": int(nb.shape[1]), "ms": ms,
+                   "Mqueries_per_s": len(S) / ms / 1e3, "algorithmic_GBs": nbytes / ms / 1e6, "frac_hbm": nbytes / ms / 1e6 / hbm}
+            if have_ref and B == 1:
+                S_np = S.cpu().numpy()
+                nq = min(len(S_np), 100_000)
+                row["cpu_Mqueries_per_s"] = cpu_rate(lambda: oracle.ref_batch_neighbors(S_np[:nq], S_np, np.array([nq], np.int32), Ls, 1.0), nq) / 1e6
+                row["cpu_sample"] = f"reference batch_nanoflann_neighbors, first {nq} queries against all supports, 1 thread"
+            rows.append(row)
+            if B == 1 and n_raw <= 1_000_000:
+                geo[n_raw] = (S, Ls)
+            del P
+    # KPConv: geometry = the subsampled clouds above; H = the `limit` closest neighbours of a radius-1.3 search
+    for n_raw, Cs, Hs in ((100_000, (64, 128, 256, 512), (16, 32, 64)), (1_000_000, (64, 128), (32,))):
+        if n_raw not in geo:
+            continue
+        S, Ls = geo[n_raw]
+        n = len(S)
+        for H in Hs:
+            nb = ops.batch_query(S, S, Ls, Ls, 1.3, limit=H, dtype=torch.int32).contiguous()
+            shadow = float((nb == n).float().mean())
+            for Cc in Cs:
+                if time.time() - t_start > budget_s:
+                    rows.append({"op": "kpconv", "N": n, "H": H, "C": Cc, "skipped": "sweep time budget"})
+                    continue
+                x = torch.randn(n, Cc, device=dev, requires_grad=True)
+                w = (torch.randn(15, Cc, Cc, device=dev) / Cc ** 0.5).requires_grad_(True)
+                v = torch.randn(15, 3, device=dev)
+                kp = v / v.norm(dim=1, keepdim=True) * 0.66 * 0.5
+                kp[0] = 0
+                ms_f, y = timeit(lambda: ops.kpconv(S, S, nb, x, w, kp, 0.5), warm=2, reps=3)
+                g = torch.randn_like(y)
+
+                def fb():
+                    yy = ops.kpconv(S, S, nb, x, w, kp, 0.5)
+                    yy.backward(g)
+                    return yy
+                ms_fb, _ = timeit(fb, warm=2, reps=3)
+                bytes_f = 4 * n * H + 24 * n + 4 * n * Cc * 2 + 4 * 15 * Cc * Cc
+                flops = 2 * n * 15 * Cc * Cc
+                row = {"op": "kpconv", "N": n, "H": H, "shadow_frac": shadow, "C": Cc, "fwd_ms": ms_f, "fwd_bwd_ms": ms_fb,
+                       "fwd_algorithmic_GBs": bytes_f / ms_f / 1e6, "fwd_frac_hbm": bytes_f / ms_f / 1e6 / hbm,
+                       "fwd_contraction_TFLOPs": flops / ms_f / 1e9, "fwd_frac_bf16_peak": flops / ms_f / 1e9 / tf,
+                       "fwd_Mpts_per_s": n / ms_f / 1e3, "fwd_bwd_Mpts_per_s": n / ms_fb / 1e3}
+                if n_raw == 100_000:
+                    ns = 2048
+                    q_c, nb_c = S[:ns].cpu(), nb[:ns].long().cpu()
+                    s_c, x_c, w_c, kp_c = S.cpu(), x.detach().cpu().requires_grad_(True), w.detach().cpu().requires_grad_(True), kp.cpu()
+
+                    def cpu_fb():
+                        yy = kpconv_reference_ops(q_c, s_c, nb_c, x_c, w_c, kp_c, 0.5)
+                        yy.backward(torch.ones_like(yy))
+                    cpu_fb()
+                    row["cpu_fwd_bwd_Mpts_per_s"] = cpu_rate(cpu_fb, ns) / 1e6
+                    row["cpu_sample"] = f"the reference's aten chain (models/blocks.py:277-374) fwd+bwd on {ns} query points, PyTorch CPU, all host threads"
+                rows.append(row)
+                del x, w, y, g
+            del nb
+    return {"rows": rows, "seconds": time.time() - t_start,
+            "peaks": {"hbm_gbs": hbm, "bf16_tflops_burst": tf, "source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+
+
 # ---------------------------------------------------------------------------------------------------- reference arm
 def run_reference(args, budget_s=150.0, as_leg=False):
-    """The reference's CPU implementation of the path: C++ cores (oracle/_ref, or the C restatement when the
-    reference sources were not available at build time) for the pyramid, prefetched by worker threads the way the
-    reference's DataLoader workers do, and the PyTorch CPU operator chain for the network, all host threads."""
+    """The reference's CPU implementation of the path on the box's host cores, same config as our arm (4 of 4 spheres per
+    step). When a copy of the reference is on the machine (baseline/_ref, tools/install_reference.py) this is the
+    reference ITSELF: its compiled C++ cores (oracle/_ref) behind its own ``segmentation_inputs``
+    (datasets/common.py:461-577), its ``<DS>CustomBatch``, its ``models.architectures.KPFCNN`` built by its own config
+    class, and the training step of utils/trainer_PseudoLabel.py:195-222 (forward, loss, backward, clip_grad_value_, SGD),
+    the pyramid prefetched by ``input_threads`` worker threads like its DataLoader workers. Otherwise the restatements
+    under oracle/ (``kind: "port"``)."""
+    import importlib
     import torch
     import torch.nn.functional as F
     from concurrent.futures import ThreadPoolExecutor
 
     import oracle
-    from oracle.kpconv_torch import KPConvTorch
-    from oracle.pyramid_ref import segmentation_inputs_cpu
-    from weasal_b200.net import CfgView, KPFCNNHarness, net_config
-    from weasal_b200.pyramid import DeviceBatch
+    from oracle import ref_harness
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    kind = "reference" if oracle.ref_available() else "port"
+    threads = min(10, cores)   # the reference's input_threads = 10 (train_*_PseudoLabel.py)
+    root = ref_harness.find_root() if oracle.ref_available() else None
+    kind = "reference" if root is not None else "port"
+    cfg_name = args.config
 
     def cpu_subsample(p, f, l, dl):
-        fn = oracle.ref_subsample if kind == "reference" else oracle.grid_subsample
+        fn = oracle.ref_subsample if oracle.ref_available() else oracle.grid_subsample
         return fn(p, features=f, classes=l, sampleDl=dl)
 
-    cfg, batches = build_batches(args.config, args.seed, N_BATCHES, cpu_subsample)
-    ncfg = net_config(args.config)
-    view = CfgView(ncfg)
+    cfg, batches = build_batches(cfg_name, args.seed, N_BATCHES, cpu_subsample)
+    n_cls = int(cfg["num_classes"])
     np.random.seed(args.seed)
     torch.manual_seed(args.seed)
-    net = KPFCNNHarness(ncfg, KPConvTorch)
-    net.train()
-    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.98, weight_decay=1e-3)
+    cwd = os.getcwd()
+    if kind == "reference":
+        ref_harness.install(root, backend="oracle_ref")
+        script, cls, ds_mod, batch_cls = {
+            "vaihingen_pl": ("train_Vaihingen3D_PseudoLabel", "Vaihingen3DPLConfig", "datasets.Vaihingen3D_PseudoLabel",
+                             "Vaihingen3DPLCustomBatch"),
+            "dales_pl": ("train_DALES_PseudoLabel", "DALESPLConfig", "datasets.DALES_PseudoLabel", "DALESPLCustomBatch"),
+        }[cfg_name]
+        rcfg = getattr(importlib.import_module(script), cls)()
+        Batch = getattr(importlib.import_module(ds_mod), batch_cls)
+        from datasets.common import PointCloudDataset
+        from models.architectures import KPFCNN
+        rcfg.num_classes = n_cls
+        rcfg.class_w = [1.0] * n_cls
+        ds = PointCloudDataset("x")
+        ds.config = rcfg
+        ds.neighborhood_limits = []
+        net = KPFCNN(rcfg, list(range(n_cls)), [])
+        net.train()
+        opt = torch.optim.SGD(net.parameters(), lr=rcfg.learning_rate, momentum=rcfg.momentum, weight_decay=rcfg.weight_decay)
 
-    def precompute(b):
-        li = segmentation_inputs_cpu(b["points"], b["features"], b["labels"], b["lengths"], view,
-                                     use_ref=(kind == "reference"))
-        return [torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a for a in li]
+        def precompute(b):
+            nb = len(b["lengths"])
+            li = ds.segmentation_inputs(b["points"], b["features"], (b["labels"] % n_cls).astype(np.int64), b["lengths"])
+            li += [np.ones((nb, 3), np.float32), np.tile(np.eye(3, dtype=np.float32), (nb, 1, 1)), np.zeros(nb, np.int32),
+                   np.zeros(nb, np.int32), np.arange(len(b["points"]), dtype=np.int64)]
+            return Batch([li])
 
-    def train(li):
-        batch = DeviceBatch(li)
-        loss = F.cross_entropy(net(batch), batch.labels)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        torch.nn.utils.clip_grad_value_(net.parameters(), 100.0)
-        opt.step()
-        return float(loss)
+        def train(batch):
+            opt.zero_grad()
+            out = net(batch, rcfg)
+            loss = net.loss(out, batch.labels)
+            loss.backward()
+            if rcfg.grad_clip_norm > 0:
+                torch.nn.utils.clip_grad_value_(net.parameters(), rcfg.grad_clip_norm)
+            opt.step()
+            return float(loss)
+        what = ("the reference itself (baseline/_ref): segmentation_inputs on its compiled C++ cores, CustomBatch, "
+                "models.architectures.KPFCNN, training step of utils/trainer_PseudoLabel.py:195-222")
+    else:
+        from oracle.kpconv_torch import KPConvTorch
+        from oracle.pyramid_ref import segmentation_inputs_cpu
+        from weasal_b200.net import CfgView, KPFCNNHarness, net_config
+        from weasal_b200.pyramid import DeviceBatch
+        ncfg = net_config(cfg_name)
+        view = CfgView(ncfg)
+        net = KPFCNNHarness(ncfg, KPConvTorch)
+        net.train()
+        opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.98, weight_decay=1e-3)
 
-    # bounded sample: sub-batches of `bn` spheres so that the whole run fits the budget
-    def sub(b, bn):
-        n = int(b["lengths"][:bn].sum())
-        return dict(points=b["points"][:n], lengths=b["lengths"][:bn], features=b["features"][:n], labels=b["labels"][:n])
+        def precompute(b):
+            li = segmentation_inputs_cpu(b["points"], b["features"], b["labels"] % n_cls, b["lengths"], view,
+                                         use_ref=oracle.ref_available())
+            return DeviceBatch([torch.from_numpy(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a for a in li])
 
+        def train(batch):
+            loss = F.cross_entropy(net(batch), batch.labels)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            torch.nn.utils.clip_grad_value_(net.parameters(), 100.0)
+            opt.step()
+            return float(loss)
+        what = "restatement under oracle/ (no copy of the reference on this machine): C cores + aten chain, harness network"
+
+    # always the full workload (4 of 4 spheres per step); the budget bounds the NUMBER of steps
     t0 = time.time()
-    train(precompute(sub(batches[0], 1)))
-    t_one = time.time() - t0  # one sphere, cold
-    W = 1 if as_leg else max(args.warmup, 1)
-    K = 2 if as_leg else args.steps
-    bn = cfg["batch_num"]
-    while bn > 1 and (W + K) * t_one * bn * 0.6 > budget_s:
-        bn -= 1
-    pool = ThreadPoolExecutor(max_workers=min(4, cores))
-    order = [sub(batches[i % N_BATCHES], bn) for i in range(W + K)]
-    futs = [pool.submit(precompute, b) for b in order[:3]]
-    pts, t_timed = 0, 0.0
+    train(precompute(batches[0]))
+    t_one = time.time() - t0  # one step, cold
+    W = 1
+    K = 2 if as_leg else max(2, min(args.steps, int(budget_s / max(t_one * 0.6, 1e-3)) - W))
+    pool = ThreadPoolExecutor(max_workers=threads)
+    order = [batches[i % N_BATCHES] for i in range(W + K)]
+    depth = min(3, W + K)
+    futs = [pool.submit(precompute, b) for b in order[:depth]]
+    pts = 0
     for i in range(W + K):
         if i == W:
             t_start = time.time()
-        li = futs[i].result()
-        if i + 3 < W + K:
-            futs.append(pool.submit(precompute, order[i + 3]))
-        train(li)
+        batch = futs[i].result()
+        if i + depth < W + K:
+            futs.append(pool.submit(precompute, order[i + depth]))
+        train(batch)
         if i >= W:
             pts += order[i]["points"].shape[0]
     t_timed = time.time() - t_start
     pool.shutdown()
+    os.chdir(cwd)
     value = pts / t_timed
-    sample = (f"{K} steps of {bn} of {cfg['batch_num']} spheres ({pts // K} points/step): pyramid on the "
-              f"{'compiled reference C++ cores (oracle/_ref)' if kind == 'reference' else 'C restatement (oracle/)'} "
-              f"prefetched by {min(4, cores)} worker threads + PyTorch CPU KPConv chain fwd+bwd+SGD")
-    leg = {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+    sample = (f"{K} steps of {cfg['batch_num']} of {cfg['batch_num']} spheres ({pts // K} points/step), pyramid prefetched by "
+              f"{threads} worker threads, network on {cores} host threads: {what}")
+    leg = {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "input_threads": threads}
     if as_leg:
         return leg
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
             "steps": K, "warmup": W, "ms_per_step": t_timed / K * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config}: pyramid precompute + KPFCNN fwd+bwd+SGD, reference CPU path",
-                       "points_per_step": pts / K, "spheres_per_step": bn},
+            "config": {"workload": f"{cfg_name}: pyramid precompute + KPFCNN fwd+bwd+SGD on {cfg['batch_num']} synthetic ALS "
+                                   f"spheres of radius {cfg['in_radius']} m per step, reference CPU path",
+                       "points_per_step_per_gpu": pts / K, "spheres_per_step": int(cfg["batch_num"]),
+                       "first_subsampling_dl": cfg["dl"], "steps_requested": args.steps},
             "cpu_baseline": leg, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -534,6 +755,8 @@ def main():
     ap.add_argument("--config", default="vaihingen_pl", choices=["vaihingen_pl", "dales_pl"])
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the operator sweep (configs[4]) of the N = 1 line")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the second workload (DALES-shaped) of the line")
     args = ap.parse_args()
     if os.environ.get("WEASAL_BENCH_WATCHDOG"):  # debugging aid: dump every thread's stack and exit after N seconds
         import faulthandler

@@ -313,6 +313,42 @@ int kp_closest_pool_dev(const float* src, int ns, int channels, const void* inds
 int kp_closest_pool_strided_dev(const float* src, int src_row_stride, int ns, int channels, const void* inds,
                                 int idx_is_i64, int nq, int idx_stride, float* dst, int backward, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Either side of the network: input spheres and test-time votes.
+ *
+ * kp_extract_spheres_dev
+ *   Replaces: datasets/Vaihingen3D_PseudoLabel.py:345-365 (`input_trees[c].query_radius(center_point, r=in_radius)`, then
+ *             `(points[input_inds] - center_point).astype(np.float32)`), same code in the three sibling datasets.
+ *   cloud [n,3] f32 DEVICE; centres [nb,3] f64 HOST (nb <= 16); membership like sklearn's KDTree: float64 distance <= radius.
+ *   Outputs (DEVICE, capacity `cap` rows): centred points f32 [*,3] and cloud indices int64 [*], spheres stacked in centre
+ *   order, rows of a sphere in ascending cloud index (sklearn returns tree order; only the row order differs).
+ *   lengths [nb] HOST. KP_ERR_CAPACITY when the spheres hold more than `cap` points. Synchronises the stream.
+ * kp_augment_spheres_dev
+ *   Replaces: datasets/common.py:252-334 `augmentation_transform` (points only) and the feature assembly of
+ *             Vaihingen3D_PseudoLabel.py:383, 423-430.
+ *   out = (points . R_b) * scale_b + noise in float32, products and sums in numpy's order (no FMA); R [nb,3,3], scale [nb,3],
+ *   lengths [nb], centre_z [nb], color_keep [nb] are HOST arrays drawn by the caller in the reference's RNG order; noise is a
+ *   DEVICE [n,3] array or NULL. out_features [n,fdim] (or NULL) = [1, colors[inds] * color_keep, z_aug + centre_z, z_aug][:fdim]
+ *   with colors a DEVICE [N_cloud, ncol] array and inds the indices kp_extract_spheres_dev returned.
+ * kp_vote_update_dev
+ *   Replaces: utils/tester_PseudoLabel.py:176-195. mode 0: test_probs[inds] = smooth * test_probs[inds] + (1 - smooth) * probs
+ *   for the points within radius_limit of their sphere centre (radius_limit <= 0: all), spheres applied in order; mode 1:
+ *   the order-independent accumulation used when spheres are sharded over GPUs (test_probs += probs, weight += 1).
+ * kp_vote_reproject_dev
+ *   Replaces: tester_PseudoLabel.py:270-283 (`test_probs[test_proj]`, argmax) and utils/metrics.py:35-118 `fast_confusion`
+ *   for labels 0..C-1. weight = NULL for EMA votes; proj = NULL: identity; any of out_probs [m,C], out_pred [m] int32,
+ *   (truth [m] int32, confusion [C,C] int64, rows = truth) may be NULL. */
+int kp_extract_spheres_dev(const float* cloud, long long n, const double* centres, int nb, double radius,
+                           float* out_points, long long* out_inds, long long cap, int* lengths, void* stream);
+int kp_augment_spheres_dev(const float* points, const int* lengths, int nb, const float* R, const float* scale,
+                           const float* noise, float* out_points, const float* colors, int ncol, const long long* inds,
+                           const float* centre_z, const float* color_keep, float* out_features, int fdim, void* stream);
+int kp_vote_update_dev(const float* probs, const float* points, const long long* inds, const int* lengths, int nb,
+                       int n_classes, float radius_limit, float smooth, int mode, float* test_probs, float* weight,
+                       void* stream);
+int kp_vote_reproject_dev(const float* test_probs, const float* weight, const long long* proj, long long m, int n_classes,
+                          float* out_probs, int* out_pred, const int* truth, long long* confusion, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -729,6 +729,63 @@ def test_graphed_static_step_matches_eager_dynamic_step(prefetched, torch_cuda):
         assert d <= 2e-3 * max(float(pa.abs().max()), 1e-3), (na, d)
 
 
+def test_two_graph_data_parallel_step_and_eager_fallback_in_between(torch_cuda):
+    """The data-parallel form of the step (graph A: forward/backward + gradients gathered into a flat buffer; one collective;
+    graph B: clip + optimizer reading the flat buffer) with a pass-through reducer computes what the single-graph step
+    computes, also when an eager fall-back step (which re-creates every p.grad) runs between two replays — the stale-gradient
+    hazard of a tail that reads p.grad."""
+    torch = torch_cuda
+    import copy
+    import torch.nn.functional as F
+    from weasal_b200 import pyramid
+    from weasal_b200.engine import GraphedTrainStep, calibrate_static_caps
+    from weasal_b200.kpconv import KPConv
+    from weasal_b200.net import CfgView, KPFCNNHarness, net_config
+
+    class PassThroughReducer:   # what GradAllReducer does on one rank
+        calls = 0
+
+        def step(self):
+            pass
+
+        def allreduce_flat(self, flat):
+            PassThroughReducer.calls += 1
+
+    ncfg = dict(net_config("vaihingen_pl"), dropout=0.0)
+    view = CfgView(ncfg)
+    data = [make_batch("vaihingen_pl", seed=s, batch_num=2, in_radius=9.0) for s in (1, 2, 3, 4)]
+    dev = torch.device("cuda")
+    P = [torch.from_numpy(b["points"]).to(dev) for b in data]
+    Fe = [torch.from_numpy(b["features"]).to(dev) for b in data]
+    Lb = [torch.from_numpy(b["labels"] % 9).to(dev) for b in data]
+    n_cap, limits = calibrate_static_caps(view, P, [b["lengths"] for b in data], random_grid_orient=False)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    net_a = KPFCNNHarness(ncfg, KPConv).to(dev)
+    net_b = copy.deepcopy(net_a)
+    losses = []
+    for net, reducer in ((net_a, None), (net_b, PassThroughReducer())):
+        opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-3)
+        tr = GraphedTrainStep(net, opt, F.cross_entropy, reducer=reducer, clip_value=100.0)
+        pf = pyramid.PyramidPrefetcher(view, dev, neighborhood_limits=limits, n_cap=n_cap, random_grid_orient=False)
+        ls = []
+        for i in range(4):
+            pf.submit(P[i], Fe[i], Lb[i], data[i]["lengths"])
+            batch = pf.get()
+            if i == 2:
+                batch.no_crop = False   # force the eager step for this batch
+            ls.append(float(tr.step(batch)))
+        pf.close()
+        assert (tr.n_graphed, tr.n_eager) == (3, 1)
+        assert (tr.graph_tail is not None) == (reducer is not None)
+        losses.append(ls)
+    assert PassThroughReducer.calls == 3
+    assert np.allclose(losses[0], losses[1], rtol=2e-3), losses
+    for (na, pa), (nb_, pb) in zip(net_a.named_parameters(), net_b.named_parameters()):
+        d = float((pa.detach() - pb.detach()).abs().max())
+        assert d <= 2e-3 * max(float(pa.detach().abs().max()), 1e-3), (na, d)
+
+
 def test_static_pyramid_layout_and_overflow_fallback(torch_cuda):
     """Static layout: real rows equal the ordinary pyramid, padded rows are all-shadow / 1e6 / ignore_index; a batch
     that outgrows a capacity comes back in the ordinary layout."""

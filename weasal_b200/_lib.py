@@ -28,7 +28,8 @@ SYMBOLS = ["kp_last_error", "kp_version", "kp_launch_count", "kp_free_host", "kp
            "kp_linear_forward_dev", "kp_linear_backward_dev", "kp_closest_pool_strided_dev", "kp_max_pool_forward_width_dev", "kp_plan_ksplit",
            "kp_kpconv_lists_build_dev", "kp_kpconv_apply_lists_dev", "kp_kpconv_dw_lists_dev", "kp_pack_image_floats",
            "kp_pack_weights_dev", "kp_linear_forward_packed_dev", "kp_linear_dx_packed_dev", "kp_linear_dw_dev",
-           "kp_kpconv_prepare_dev"]
+           "kp_kpconv_prepare_dev", "kp_extract_spheres_dev", "kp_augment_spheres_dev", "kp_vote_update_dev",
+           "kp_vote_reproject_dev"]
 
 
 def lib():
@@ -100,6 +101,10 @@ def lib():
     L.kp_linear_dx_packed_dev.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_float, vp, vp, vp]
     L.kp_linear_dw_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_float, vp, vp, vp]
     L.kp_kpconv_prepare_dev.argtypes = [vp, C.c_int, vp, vp]
+    L.kp_extract_spheres_dev.argtypes = [vp, C.c_longlong, vp, C.c_int, C.c_double, vp, vp, C.c_longlong, vp, vp]
+    L.kp_augment_spheres_dev.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, vp]
+    L.kp_vote_update_dev.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, vp, vp, vp]
+    L.kp_vote_reproject_dev.argtypes = [vp, vp, vp, C.c_longlong, C.c_int, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

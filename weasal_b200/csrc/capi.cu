@@ -59,6 +59,15 @@ int pyramid_build_device(const float* pts0, int n0, const int* lens0, int nb, in
                          int* lens_out, int* widths, int* strides, long long* need_bytes, int* need_cap,
                          const int* n_cap, const float* feats, int fdim, const long long* labels, long long label_pad,
                          cudaStream_t stream);
+int extract_spheres_device(const float* cloud, long long n, const double* centres_host, int nb, double radius,
+                           float* out_pts, long long* out_inds, long long cap, int* lengths_host, cudaStream_t stream);
+int augment_device(const float* pts, const int* lengths_host, int nb, const float* R_host, const float* scale_host,
+                   const float* noise, float* out, const float* colors, int ncol, const long long* inds,
+                   const float* centre_z_host, const float* keep_host, float* feats, int fdim, cudaStream_t stream);
+int vote_device(const float* probs, const float* pts, const long long* inds, const int* lengths_host, int nb, int C,
+                float radius_limit, float smooth, int mode, float* acc, float* weight, cudaStream_t stream);
+int reproject_device(const float* acc, const float* weight, const long long* proj, long long m, int C, float* out_probs,
+                     int* out_pred, const int* truth, long long* conf, cudaStream_t stream);
 int max_pool_fwd_device(const float* x, int ns, int C, const void* idx, int is_i64, int nq, int H, int stride,
                         float* out, int* arg, const int* d_width, cudaStream_t stream);
 int max_pool_bwd_device(const float* dout, const int* arg, int nq, int C, float* dx, int ns, cudaStream_t stream);
@@ -363,6 +372,27 @@ int kp_closest_pool_strided_dev(const float* src, int src_row_stride, int ns, in
                                 int idx_is_i64, int nq, int idx_stride, float* dst, int backward, void* stream) {
     return closest_pool_device(src, ns, channels, inds, idx_is_i64, nq, idx_stride, dst, backward, src_row_stride,
                                (cudaStream_t)stream);
+}
+
+int kp_extract_spheres_dev(const float* cloud, long long n, const double* centres, int nb, double radius,
+                           float* out_points, long long* out_inds, long long cap, int* lengths, void* stream) {
+    return extract_spheres_device(cloud, n, centres, nb, radius, out_points, out_inds, cap, lengths, (cudaStream_t)stream);
+}
+int kp_augment_spheres_dev(const float* points, const int* lengths, int nb, const float* R, const float* scale,
+                           const float* noise, float* out_points, const float* colors, int ncol, const long long* inds,
+                           const float* centre_z, const float* color_keep, float* out_features, int fdim, void* stream) {
+    return augment_device(points, lengths, nb, R, scale, noise, out_points, colors, ncol, inds, centre_z, color_keep,
+                          out_features, fdim, (cudaStream_t)stream);
+}
+int kp_vote_update_dev(const float* probs, const float* points, const long long* inds, const int* lengths, int nb,
+                       int n_classes, float radius_limit, float smooth, int mode, float* test_probs, float* weight,
+                       void* stream) {
+    return vote_device(probs, points, inds, lengths, nb, n_classes, radius_limit, smooth, mode, test_probs, weight,
+                       (cudaStream_t)stream);
+}
+int kp_vote_reproject_dev(const float* test_probs, const float* weight, const long long* proj, long long m, int n_classes,
+                          float* out_probs, int* out_pred, const int* truth, long long* confusion, void* stream) {
+    return reproject_device(test_probs, weight, proj, m, n_classes, out_probs, out_pred, truth, confusion, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -4,15 +4,17 @@
 Per batch of spheres the reference does: extract all cloud points within ``in_radius`` of each centre and re-centre
 them (datasets/Vaihingen3D_PseudoLabel.py:318-365), build the pyramid, run the network, softmax, keep the points
 within ``0.7 * in_radius`` of the centre (tester:188-191) and blend their probabilities into ``test_probs`` (tester:194).
-Here every step stays on the device: sphere extraction is one distance mask per centre, the pyramid comes from the
-prefetch thread (one native call per batch), and votes are accumulated as (sum of probabilities, number of votes) —
+Here every step stays on the device: sphere extraction is three kernels over the cloud (weasal_b200/spheres.py), the
+pyramid comes from the prefetch thread (one native call per batch), and votes are accumulated by a kernel as (sum of
+probabilities, number of votes) —
 the order-independent form of the reference's visit-order dependent EMA (weasal_b200/distributed.py) — so that ranks
 can take disjoint sets of spheres and meet in one all-reduce at the end.
 """
 import numpy as np
 import torch
 
-from .distributed import VoteAccumulator, shard_indices
+from .distributed import shard_indices
+from .spheres import VoteBuffer
 from .pyramid import PyramidPrefetcher
 
 
@@ -34,27 +36,16 @@ def vote_centres(points_xy_min, points_xy_max, in_radius, num_votes, seed=0):
 
 def extract_spheres_device(cloud, feats, centres_xy, in_radius, keep_frac=0.7):
     """All points within ``in_radius`` of each centre (the centre's z is that of its nearest cloud point in xy), stacked
-    and re-centred. Returns (points [N,3], features [N,C], lengths int32 [B] (host), cloud indices [N], keep mask [N]).
-    Spheres that come out empty are dropped."""
-    pts, fts, lens, inds, keep = [], [], [], [], []
-    r2 = float(in_radius) ** 2
-    for c in centres_xy:
-        d_xy = ((cloud[:, :2] - c) ** 2).sum(1)
-        c3 = cloud[int(torch.argmin(d_xy))]
-        d2 = ((cloud - c3) ** 2).sum(1)
-        sel = torch.nonzero(d2 < r2).squeeze(1)
-        if sel.numel() == 0:
-            continue
-        p = cloud[sel] - c3
-        pts.append(p)
-        z_rel = p[:, 2:3]
-        fts.append(torch.cat([feats[sel], z_rel], 1))
-        lens.append(int(sel.numel()))
-        inds.append(sel)
-        keep.append(d2[sel] < (keep_frac ** 2) * r2)
-    if not pts:
+    and re-centred, by the sphere-extraction kernels (spheres.extract_spheres). Returns (points [N,3], features [N,C],
+    lengths int32 [B] (host), cloud indices [N]) or None when every sphere is empty; empty spheres are dropped."""
+    from .spheres import extract_spheres
+    d_xy = ((cloud[:, None, :2] - centres_xy[None, :, :]) ** 2).sum(-1)          # [N, B]
+    c3 = cloud[torch.argmin(d_xy, 0)].double().cpu().numpy()                     # [B, 3]
+    p, lens, inds = extract_spheres(cloud, c3, in_radius)
+    if lens.sum() == 0:
         return None
-    return torch.cat(pts), torch.cat(fts), np.asarray(lens, np.int32), torch.cat(inds), torch.cat(keep)
+    f = torch.cat([feats[inds], p[:, 2:3]], 1)
+    return p, f, lens[lens > 0], inds
 
 
 @torch.no_grad()
@@ -79,8 +70,8 @@ def vote_cloud(net, config, cloud, feats, in_radius, batch_num, num_votes=1, num
         ex = extract_spheres_device(cloud, feats, centres_dev[k], in_radius)
         if ex is None:
             return False
-        p, f, lens, inds, keep = ex
-        pf.submit(p, f, None, lens, extras=dict(input_inds=inds, keep=keep))
+        p, f, lens, inds = ex
+        pf.submit(p, f, None, lens, extras=dict(input_inds=inds, in_points=p, in_lengths=lens))
         return True
 
     todo = iter(range(len(mine)))
@@ -97,12 +88,14 @@ def vote_cloud(net, config, cloud, feats, in_radius, batch_num, num_votes=1, num
         inflight = submit_next()  # the next batch's extraction + pyramid overlap this batch's forward pass
         probs = torch.softmax(net(batch), 1)
         if acc is None:
-            acc = VoteAccumulator(cloud.shape[0], probs.shape[1] if num_classes is None else num_classes, dev)
-        acc.add(batch.input_inds[batch.keep], probs[batch.keep])
+            acc = VoteBuffer(cloud.shape[0], probs.shape[1] if num_classes is None else num_classes, dev, mode="sum")
+        # (tester_PseudoLabel.py:188-194: only the points within 0.7 * in_radius of the sphere centre vote)
+        acc.update(probs, batch.in_points, batch.input_inds, batch.in_lengths, radius_limit=0.7 * in_radius)
         n_spheres += len(batch.lengths[0])
         n_points += batch.points[0].shape[0]
     pf.close()
     if acc is None:
-        acc = VoteAccumulator(cloud.shape[0], num_classes or 1, dev)
-    probs = acc.reduce(group)  # all-reduces (sum of probabilities, votes) in place, then divides
+        acc = VoteBuffer(cloud.shape[0], num_classes or 1, dev, mode="sum")
+    acc.reduce(group)  # all-reduces (sum of probabilities, votes) in place
+    probs, _, _ = acc.reproject()
     return probs, acc.weight, n_spheres, n_points
