@@ -20,7 +20,7 @@ size_t grid_bytes(int ns, int nb);
 int grid_build_device(const float* s, int ns, const int* sb_host, int nb, float radius, void* grid_buf, cudaStream_t stream);
 int grid_query_device_ex(const void* grid_buf, int ns, int nb, float radius, const float* q, int nq, const int* qb_host,
                          void* out, int out_is_i64, int cap, int* hmax_host, int* d_result, int shadow, int nq_rows,
-                         cudaStream_t stream);
+                         cudaStream_t stream, const void* qorder_grid = nullptr);
 int grid_subsample_device(const float* pts, int n, const int* lens_host, int nb, const float* feats, int fdim,
                           const int* classes, int ldim, float dl, int max_p, int order_mode, const float* rot_host,
                           float* out_pts, int* out_lens_host, float* out_feats, int* out_classes, int* m_host,
@@ -125,8 +125,9 @@ int pyramid_build_device(const float* pts0, int n0, const int* lens0, int nb, in
         return rc;
     };
     // (rows, shadow): the matrix has `rows` rows (>= nq) and pads with `shadow`
+    // qorder: a grid over the query points (their cell-sorted order makes the search's warps coherent)
     auto search = [&](int layer, int kind, const void* grid, int ns, float r, const float* q, int nq,
-                      const std::vector<int>& qlens, int limit, int rows, int shadow) -> int {
+                      const std::vector<int>& qlens, int limit, int rows, int shadow, const void* qorder) -> int {
         const int width = limit > 0 ? limit : cap;
         const long long o = sl.take((long long)rows * width * isz);
         offs[(1 + kind) * L + layer] = o;
@@ -138,7 +139,7 @@ int pyramid_build_device(const float* pts0, int n0, const int* lens0, int nb, in
         ps.shadow = shadow; ps.rows = rows;
         pend.push_back(ps);
         return grid_query_device_ex(grid, ns, nb, r, q, nq, qlens.data(), ps.out, idx_is_i64, width, nullptr,
-                                    d_results + 2 * (kind * L + layer), shadow, rows, stream);
+                                    d_results + 2 * (kind * L + layer), shadow, rows, stream, qorder);
     };
 
     int rc;
@@ -174,7 +175,7 @@ int pyramid_build_device(const float* pts0, int n0, const int* lens0, int nb, in
                 cur_grid_r = conv_r[l];
             }
             if ((rc = search(l, 0, cur_grid, cur_n, conv_r[l], cur, cur_n, cur_lens, lim(l), n_cap ? n_cap[l] : cur_n,
-                             n_cap ? n_cap[l] : cur_n)) != KP_OK) return rc;
+                             n_cap ? n_cap[l] : cur_n, cur_grid)) != KP_OK) return rc;
         }
         if (l + 1 >= L || !(dl[l] > 0.f)) break;
         // next layer's points: room for cur_n rows now, trimmed to the voxel count once it is known (static mode: the
@@ -213,13 +214,15 @@ int pyramid_build_device(const float* pts0, int n0, const int* lens0, int nb, in
         if (!pool_grid || cur_grid_r != pool_r[l]) {
             if ((rc = get_grid(cur, cur_n, cur_lens, pool_r[l], &pool_grid)) != KP_OK) return rc;
         }
-        if ((rc = search(l, 1, pool_grid, cur_n, pool_r[l], next, m, next_lens, lim(l), n_cap ? n_cap[l + 1] : m,
-                         n_cap ? n_cap[l] : cur_n)) != KP_OK) return rc;
-        // upsample: queries = this layer, supports = next layer (this grid is the next layer's conv grid when radii agree)
+        // the grid over the next layer (supports of the upsample search; the next layer's conv grid when radii agree) is
+        // built first: it also gives the pool search its query order
         const void* up_grid = nullptr;
         if ((rc = get_grid(next, m, next_lens, up_r[l], &up_grid)) != KP_OK) return rc;
+        if ((rc = search(l, 1, pool_grid, cur_n, pool_r[l], next, m, next_lens, lim(l), n_cap ? n_cap[l + 1] : m,
+                         n_cap ? n_cap[l] : cur_n, up_grid)) != KP_OK) return rc;
+        // upsample: queries = this layer, supports = next layer
         if ((rc = search(l, 2, up_grid, m, up_r[l], cur, cur_n, cur_lens, lim(l + 1), n_cap ? n_cap[l] : cur_n,
-                         n_cap ? n_cap[l + 1] : m)) != KP_OK) return rc;
+                         n_cap ? n_cap[l + 1] : m, pool_grid)) != KP_OK) return rc;
         cur = next; cur_n = m; cur_lens = next_lens;
         cur_grid = up_grid; cur_grid_r = up_r[l];
     }

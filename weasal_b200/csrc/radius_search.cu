@@ -17,6 +17,7 @@
 // datasets/common.py:336-346, does afterwards) and the true maximum count is returned for the caller to slice.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 namespace kp {
@@ -275,6 +276,114 @@ __global__ void __launch_bounds__(WARPS * 32) rs_search_kernel(
     for (int h = count + lane; h < cap; h += 32) row[h] = (OutT)P.shadow;
 }
 
+// ------------------------------------------------------------------------------------------ the fast path: two kernels
+// An experiment, kept for the record and selectable with WEASAL_RS_FAST=1 (results at its call site): the warp-per-query
+// kernel above spends ~600 warp instructions per query on shuffles, ballots and a rank sort (ncu: issue-bound at 57-72 %
+// issue slots with DRAM at 1 %). This path splits the work by what each part is good at:
+//   rs_collect   ONE THREAD per query walks the 27 cells and their candidates with plain loads and compares (~2000 thread
+//                instructions = ~60 warp instructions per query) and appends the hits, as packed 64-bit keys
+//                (d2 bits << 32 | support index: d2 >= 0, so the unsigned order of the keys IS the (d2, index) order of the
+//                stated tie-break), to the query's row of a scratch matrix. Queries are taken in the cell-sorted order
+//                of a grid built over them (`qorder`: for a conv search the support grid itself), so the 32 lanes of a warp
+//                sit in the same or adjacent cells, probe the same hash slots and read the same candidates: their loads
+//                coalesce into broadcasts.
+//   rs_rows      one warp per query sorts its keys (n <= 32: one key per lane, rank by 32 shuffles; else through shared
+//                memory) and writes the row: the `cap` smallest keys' indices, padded with the shadow value.
+// A query with more than RS_FAST_HITS neighbours raises RS_ERR_RETRY: the caller repeats with the 1024-hit kernel.
+constexpr int RS_FAST_HITS = 128;
+
+__global__ void __launch_bounds__(128) rs_collect_kernel(SearchParams P, const unsigned* __restrict__ bbox, float radius,
+                                                        const unsigned long long* __restrict__ tkeys,
+                                                        const int* __restrict__ tcount, const int* __restrict__ tstart,
+                                                        int tmask, const float4* __restrict__ sorted,
+                                                        const float4* __restrict__ qorder,
+                                                        unsigned long long* __restrict__ keys, int* __restrict__ cnt,
+                                                        int* __restrict__ err) {
+    __shared__ float s_plan[2];
+    bool fits;
+    const float inv = block_inv_cell(bbox, P.nb, radius, s_plan, &fits);
+    if (!fits && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, RS_ERR_GRID);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.nq) return;
+    const int qi = qorder ? __float_as_int(qorder[t].w) : t;
+    const float qx = P.q[3 * (size_t)qi], qy = P.q[3 * (size_t)qi + 1], qz = P.q[3 * (size_t)qi + 2];
+    const int b = batch_of(P.q_off, P.nb, qi);
+    unsigned long long* row = keys + (size_t)qi * RS_FAST_HITS;
+    int count = 0;
+    if (P.s_off[b + 1] > P.s_off[b]) {
+        const int cx = cell_coord(qx, ord2f(bbox[b * 6 + 0]), inv);
+        const int cy = cell_coord(qy, ord2f(bbox[b * 6 + 1]), inv);
+        const int cz = cell_coord(qz, ord2f(bbox[b * 6 + 2]), inv);
+        for (int c = 0; c < 27; c++) {
+            const int nx = cx + (c % 3) - 1, ny = cy + ((c / 3) % 3) - 1, nz = cz + (c / 9) - 1;
+            if (nx < 0 || ny < 0 || nz < 0 || nx >= 262144 || ny >= 262144 || nz >= 262144) continue;
+            const unsigned long long key = cell_key(b, nx, ny, nz);
+            unsigned slot = (unsigned)mix64(key) & (unsigned)tmask;
+            int c_start = 0, c_cnt = 0;
+            while (true) {
+                const unsigned long long cur = tkeys[slot];
+                if (cur == key) { c_start = tstart[slot]; c_cnt = tcount[slot]; break; }
+                if (cur == CELL_EMPTY) break;
+                slot = (slot + 1) & (unsigned)tmask;
+            }
+            for (int e0 = 0; e0 < c_cnt; e0 += 4) {   // four candidates in flight
+                float4 sp[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) sp[u] = sorted[c_start + min(e0 + u, c_cnt - 1)];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float d2 = sq_dist_ref(qx, qy, qz, sp[u].x, sp[u].y, sp[u].z);
+                    if (e0 + u < c_cnt && d2 < P.r2) {
+                        if (count < RS_FAST_HITS)
+                            row[count] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(sp[u].w);
+                        count++;
+                    }
+                }
+            }
+        }
+    }
+    if (count > RS_FAST_HITS) {
+        atomicOr(err, RS_ERR_RETRY);
+        count = RS_FAST_HITS;
+    }
+    cnt[qi] = count;
+}
+
+constexpr int RS_ROWS_WARPS = 8;
+template <typename OutT>
+__global__ void __launch_bounds__(RS_ROWS_WARPS * 32) rs_rows_kernel(int nq, int nq_rows, int shadow,
+                                                                    const unsigned long long* __restrict__ keys,
+                                                                    const int* __restrict__ cnt, OutT* __restrict__ out,
+                                                                    int cap, int* __restrict__ hmax) {
+    __shared__ unsigned long long s_keys[RS_ROWS_WARPS][RS_FAST_HITS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qi = blockIdx.x * RS_ROWS_WARPS + warp;
+    if (qi >= nq_rows) return;
+    OutT* row = out + (size_t)qi * cap;
+    const int n = qi < nq ? cnt[qi] : 0;
+    if (n > 0) {
+        const unsigned long long* src = keys + (size_t)qi * RS_FAST_HITS;
+        if (lane == 0 && n > *(volatile int*)hmax) atomicMax(hmax, n);
+        if (n <= 32) {
+            const unsigned long long mine = lane < n ? src[lane] : ~0ULL;
+            int rank = 0;
+            for (int j = 0; j < n; j++) rank += (__shfl_sync(0xffffffffu, mine, j) < mine) ? 1 : 0;   // keys are distinct
+            if (lane < n && rank < cap) row[rank] = (OutT)(unsigned)(mine & 0xffffffffULL);
+        } else {
+            unsigned long long* sk = s_keys[warp];
+            for (int i = lane; i < n; i += 32) sk[i] = src[i];
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {
+                const unsigned long long mine = sk[i];
+                int rank = 0;
+                for (int j = 0; j < n; j++) rank += (sk[j] < mine) ? 1 : 0;
+                if (rank < cap) row[rank] = (OutT)(unsigned)(mine & 0xffffffffULL);
+            }
+        }
+    }
+    for (int h = n + lane; h < cap; h += 32) row[h] = (OutT)shadow;
+}
+
 // ---------------------------------------------------------------------------------------------------------- host side
 // A search grid lives in ONE caller-owned device buffer (grid_bytes) so that it can outlive the call that built it: in
 // the pyramid the grid over layer l+1 at radius 2r serves the upsample search of layer l and the conv and pool
@@ -365,17 +474,19 @@ int grid_build_device(const float* s, int ns, const int* sb_host, int nb, float 
 // escalates to the 1024-hit kernel if needed and stores the true max count in *hmax_host.
 int grid_query_device_ex(const void* grid_buf, int ns, int nb, float radius, const float* q, int nq, const int* qb_host,
                          void* out, int out_is_i64, int cap, int* hmax_host, int* d_result, int shadow, int nq_rows,
-                         cudaStream_t stream);
+                         cudaStream_t stream, const void* qorder_grid = nullptr);
 int grid_query_device(const void* grid_buf, int ns, int nb, float radius, const float* q, int nq, const int* qb_host,
                       void* out, int out_is_i64, int cap, int* hmax_host, int* d_result, cudaStream_t stream) {
     return grid_query_device_ex(grid_buf, ns, nb, radius, q, nq, qb_host, out, out_is_i64, cap, hmax_host, d_result, ns, nq,
                                 stream);
 }
 
-// shadow: the value rows are padded with; nq_rows >= nq: rows of `out` (the extra ones are filled with `shadow`)
+// shadow: the value rows are padded with; nq_rows >= nq: rows of `out` (the extra ones are filled with `shadow`).
+// qorder_grid: a grid built over the QUERY points themselves (any radius; the support grid itself when queries are the
+// supports): its cell-sorted point order is the order queries are processed in (coherent warps). Null: index order.
 int grid_query_device_ex(const void* grid_buf, int ns, int nb, float radius, const float* q, int nq, const int* qb_host,
                          void* out, int out_is_i64, int cap, int* hmax_host, int* d_result, int shadow, int nq_rows,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const void* qorder_grid) {
     if (nq < 0 || cap < 0 || nq_rows < nq) return fail(KP_ERR_ARG, "batch_query: bad sizes");
     std::vector<int> qoff;
     int rc = check_batches(qb_host, nb, nq, qoff);
@@ -399,9 +510,29 @@ int grid_query_device_ex(const void* grid_buf, int ns, int nb, float radius, con
     P.q = q; P.nq = nq; P.s = nullptr; P.ns = ns; P.q_off = d_qoff; P.s_off = g.s_off; P.nb = nb;
     P.r2 = radius * radius;  // neighbors.cpp:226, f32
     P.shadow = shadow; P.nq_rows = nq_rows;
+    // Measured on B200 (profiles/r2_radius_search_ab.txt): the thread-per-query path is NOT faster than the warp-per-query
+    // kernel (0.49 vs 0.50 ms at 420 k queries, 0.17 vs 0.14 ms at 42 k, 0.89 vs 0.39 ms over the 13 searches of a training
+    // batch, where 38 k threads cannot fill the device), so it stays an opt-in experiment (WEASAL_RS_FAST=1).
+    static const bool fast_off = !(getenv("WEASAL_RS_FAST") && atoi(getenv("WEASAL_RS_FAST")) == 1);
+    unsigned long long* d_keys = nullptr;
+    int* d_cnt = nullptr;
+    if (!fast_off && nq > 0) {
+        d_keys = S.alloc<unsigned long long>((size_t)nq * RS_FAST_HITS);
+        d_cnt = S.alloc<int>(nq);
+        if (S.status != KP_OK) return S.status;
+    }
+    const float4* qorder = qorder_grid ? grid_view(const_cast<void*>(qorder_grid), nq, nb, 1.f).sorted : nullptr;
     auto launch = [&](bool big) {
         ProfileScope ps2("rs_search", stream);
-        if (!big) {
+        if (!big && d_keys) {
+            rs_collect_kernel<<<ceil_div(nq, 128), 128, 0, stream>>>(P, g.bbox, radius, g.tkeys, g.tcount, g.tstart, g.tsize - 1,
+                                                                    g.sorted, qorder, d_keys, d_cnt, d_err);
+            const int grid = ceil_div(nq_rows, RS_ROWS_WARPS);
+            if (out_is_i64)
+                rs_rows_kernel<long long><<<grid, RS_ROWS_WARPS * 32, 0, stream>>>(nq, nq_rows, shadow, d_keys, d_cnt, (long long*)out, cap, d_hmax);
+            else
+                rs_rows_kernel<int><<<grid, RS_ROWS_WARPS * 32, 0, stream>>>(nq, nq_rows, shadow, d_keys, d_cnt, (int*)out, cap, d_hmax);
+        } else if (!big) {
             const int grid = ceil_div(nq_rows, RS_WARPS_SMALL);
             if (out_is_i64)
                 rs_search_kernel<long long, RS_HITS_SMALL, RS_WARPS_SMALL><<<grid, RS_WARPS_SMALL * 32, 0, stream>>>(
@@ -453,7 +584,8 @@ int batch_query_device(const float* q, int nq, const float* s, int ns, const int
         ArenaHold hold(S);
         int rc = grid_build_device(s, ns, sb_host, nb, radius, buf, stream);
         if (rc != KP_OK) return rc;
-        return grid_query_device(buf, ns, nb, radius, q, nq, qb_host, out, out_is_i64, cap, hmax_host, d_result, stream);
+        return grid_query_device_ex(buf, ns, nb, radius, q, nq, qb_host, out, out_is_i64, cap, hmax_host, d_result, ns, nq,
+                                    stream, (q == s && nq == ns) ? buf : nullptr);
     }
 }
 
