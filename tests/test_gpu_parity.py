@@ -132,7 +132,8 @@ def test_subsample_golden(pre_golden, torch_cuda):
     assert c2.shape == g["sub0.9_classes"].shape and np.array_equal(c2, g["sub0.9_classes"])
 
 
-@pytest.mark.parametrize("seed,dl,n_side", [(0, 0.24, 25.0), (1, 0.4, 40.0), (2, 1.3, 40.0), (3, 2.4, 60.0)])
+@pytest.mark.parametrize("seed,dl,n_side", [(0, 0.24, 25.0), (1, 0.4, 40.0), (2, 1.3, 40.0), (3, 2.4, 60.0),
+                                           (4, 0.3, 90.0), (5, 0.8, 130.0)])  # the last two: > 60k points, the device-wide order replay
 def test_subsample_vs_oracle(seed, dl, n_side, torch_cuda):
     from weasal_b200 import grid_subsampling as gs
     pts, inten, lab = make_als_tile(seed, n_side, 12.0)

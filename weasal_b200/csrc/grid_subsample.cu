@@ -15,6 +15,9 @@
 // the same libstdc++ (the rehash schedule is taken from std::__detail::_Prime_rehash_policy at run time).
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+#include <cstdlib>
+
 #include <climits>
 #include <unordered_map>
 #include <vector>
@@ -276,6 +279,109 @@ __global__ void __launch_bounds__(ORD_THREADS) gs_order_kernel(const unsigned lo
     for (int r = tid; r < m; r += ORD_THREADS) pos_out[s0 + cur[r]] = r;
 }
 
+// The same replay spread over the whole device for large clouds (the dataset-preparation call on a whole tile,
+// datasets/Vaihingen3D_PseudoLabel.py:802-805: 1e5 .. 1e7 points in ONE batch element): a cooperative launch, every phase
+// of a generation a grid-stride loop, grid-wide barriers where the single-CTA kernel has __syncthreads. The work of a
+// generation is embarrassingly parallel apart from one prefix sum; generations remain sequential (a rehash re-inserts the
+// list in list order) but their sizes form a geometric series, so the last two carry most of the work. Batch elements
+// are processed one after the other.
+namespace cg = cooperative_groups;
+
+__global__ void __launch_bounds__(ORD_THREADS) gs_order_coop_kernel(const unsigned long long* __restrict__ seq_key,
+                                                                   const int* __restrict__ seq_start, int nb, Sched sched,
+                                                                   int* __restrict__ scratch,
+                                                                   const long long* __restrict__ scratch_off,
+                                                                   const int* __restrict__ in_offsets,
+                                                                   int* __restrict__ block_sums,
+                                                                   int* __restrict__ pos_out) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int s_warp[33];
+    __shared__ int s_base;
+    const int tid = threadIdx.x;
+    const long long gtid = (long long)blockIdx.x * ORD_THREADS + tid;
+    const long long gsize = (long long)gridDim.x * ORD_THREADS;
+    for (int b = 0; b < nb; b++) {
+        const int s0 = seq_start[b];
+        const int m = seq_start[b + 1] - s0;
+        if (m <= 0) continue;
+        const unsigned long long* keys = seq_key + s0;
+        const int cap = in_offsets[b + 1] - in_offsets[b];
+        int* cur = scratch + scratch_off[b];
+        int* nxt = cur + cap;
+        int* mem = nxt + cap;
+        int* wsum = mem + cap;
+        int* bkt = wsum + cap;
+        int* bfirst = bkt + cap;
+        long long pcap = sched.bkt[0];
+        for (int i = 0; i < sched.n; i++) if (sched.elt[i] < cap || i == 0) pcap = sched.bkt[i];
+        int* bcnt = bfirst + pcap;
+        int* bbase = bcnt + pcap;
+        for (int g = 0; g < sched.n; g++) {
+            const int e0 = (int)sched.elt[g];
+            if (e0 >= m && g > 0) break;
+            const unsigned long long Pn = (unsigned long long)sched.bkt[g];
+            const int end = (g + 1 < sched.n && sched.elt[g + 1] < m) ? (int)sched.elt[g + 1] : m;
+            const int len0 = e0;
+            const int ns = len0 + (end - e0);
+            for (long long j = gtid; j < (long long)Pn; j += gsize) { bfirst[j] = INT_MAX; bcnt[j] = 0; }
+            grid.sync();
+            for (long long t = gtid; t < ns; t += gsize) {
+                const unsigned long long key = keys[ord_elem(cur, len0, e0, (int)t)];
+                const int bk = (key >> 32) ? (int)(key % Pn) : (int)((unsigned)key % (unsigned)Pn);
+                bkt[t] = bk;
+                atomicMin(&bfirst[bk], (int)t);
+                atomicAdd(&bcnt[bk], 1);
+            }
+            grid.sync();
+            // suffix sums of the first-toucher weights: every thread owns a contiguous range, blocks meet through block_sums
+            const long long chunk = (ns + gsize - 1) / gsize;
+            const long long lo = min(gtid * chunk, (long long)ns), hi = min(lo + chunk, (long long)ns);
+            int local = 0;
+            for (long long t = lo; t < hi; t++) {
+                const int bk = bkt[t];
+                const int w = (bfirst[bk] == (int)t) ? bcnt[bk] : 0;
+                wsum[t] = w;
+                local += w;
+            }
+            int btotal;
+            int excl = block_exclusive_scan(local, s_warp, &btotal);
+            if (tid == 0) block_sums[blockIdx.x] = btotal;
+            grid.sync();
+            if (tid == 0) {
+                int before = 0;
+                for (int j = 0; j < (int)blockIdx.x; j++) before += block_sums[j];
+                s_base = before;
+            }
+            __syncthreads();
+            excl += s_base;   // weights before this thread's range; total = ns (every node is counted once)
+            for (long long t = lo; t < hi; t++) {
+                const int w = wsum[t];
+                excl += w;
+                if (w) bbase[bkt[t]] = ns - excl;  // nodes in buckets first touched after this one
+            }
+            for (long long j = gtid; j < (long long)Pn; j += gsize) bfirst[j] = 0;  // reuse as fill cursor (not read above)
+            grid.sync();
+            for (long long t = gtid; t < ns; t += gsize) {
+                const int bk = bkt[t];
+                mem[bbase[bk] + atomicAdd(&bfirst[bk], 1)] = (int)t;
+            }
+            grid.sync();
+            for (long long t = gtid; t < ns; t += gsize) {
+                const int bk = bkt[t];
+                const int r0 = bbase[bk], c = bcnt[bk];
+                int later = 0;
+                for (int u = 0; u < c; u++) later += (mem[r0 + u] > (int)t) ? 1 : 0;
+                nxt[r0 + later] = ord_elem(cur, len0, e0, (int)t);
+            }
+            grid.sync();
+            int* sw = cur; cur = nxt; nxt = sw;
+            if (end >= m) break;
+        }
+        for (long long r = gtid; r < m; r += gsize) pos_out[s0 + cur[r]] = (int)r;
+        grid.sync();
+    }
+}
+
 // per voxel (sequence index) -> global output position, honouring max_p truncation (grid_subsampling.cpp:181-204)
 __global__ void __launch_bounds__(256) gs_outpos_kernel(int nb, const int* __restrict__ seq_start,
                                                        const int* __restrict__ seq_slot,
@@ -503,9 +609,39 @@ int grid_subsample_device(const float* pts, int n, const int* lens_host, int nb,
         if (S.status != KP_OK) return S.status;
         { int rc0 = upload_small(soff.data(), nb * sizeof(long long), d_soff, stream); if (rc0 != KP_OK) return rc0; }
         ProfileScope pso("gs_order", stream);
-        gs_order_kernel<<<nb, ORD_THREADS, 0, stream>>>(d_seq_key, d_seq_start, sched, d_scratch, d_soff, d_offs,
-                                                       d_pos_local);
-        KP_CHECK_LAUNCH();
+        int max_len = 0;
+        for (int b = 0; b < nb; b++) max_len = lens_host[b] > max_len ? lens_host[b] : max_len;
+        static int coop_ctas = -1;   // co-resident CTAs of the cooperative kernel (0: cooperative launch not available)
+        if (coop_ctas < 0) {
+            int dev = 0, sms = 0, per_sm = 0, can = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_order_coop_kernel, ORD_THREADS, 0);
+            coop_ctas = can ? sms * per_sm : 0;
+        }
+        static const int coop_min = getenv("WEASAL_GS_COOP_MIN") ? atoi(getenv("WEASAL_GS_COOP_MIN")) : 60000;
+        if (coop_ctas > 1 && max_len >= coop_min) {
+            // large elements: the replay on every SM (grid-wide barriers cost a few microseconds each, ~100 of them)
+            int* d_bsums = S.alloc<int>(coop_ctas);
+            if (S.status != KP_OK) return S.status;
+            int ctas = ceil_div(max_len, ORD_THREADS);
+            if (ctas > coop_ctas) ctas = coop_ctas;
+            const unsigned long long* a0 = d_seq_key;
+            const int* a1 = d_seq_start;
+            int a2 = nb;
+            int* a4 = d_scratch;
+            const long long* a5 = d_soff;
+            const int* a6 = d_offs;
+            int* a8 = d_pos_local;
+            void* args[] = {&a0, &a1, &a2, &sched, &a4, &a5, &a6, &d_bsums, &a8};
+            KP_CUDA(cudaLaunchCooperativeKernel((const void*)gs_order_coop_kernel, dim3(ctas), dim3(ORD_THREADS), args, 0, stream));
+            g_launch_count.fetch_add(1);
+        } else {
+            gs_order_kernel<<<nb, ORD_THREADS, 0, stream>>>(d_seq_key, d_seq_start, sched, d_scratch, d_soff, d_offs,
+                                                           d_pos_local);
+            KP_CHECK_LAUNCH();
+        }
     }
     ProfileScope* ps3 = new ProfileScope("gs_sort", stream);
     const int invalid = n;  // sort key of points whose voxel was truncated by max_p

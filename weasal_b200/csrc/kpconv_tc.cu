@@ -61,6 +61,9 @@ constexpr int FWD_CK = 64;        // reduction columns per forward stage
 constexpr int DW_CK = 128;        // reduction columns (= UMMA M) per dW CTA
 constexpr int DW_PT = 64;         // points per dW stage
 constexpr int MAX_STAGES = 4;
+#ifndef KP_U
+#define KP_U 4            // entries (gathers) in flight per producer lane
+#endif
 
 // forward A stage [128 rows x 64 cols], UMMA canonical K-major no-swizzle layout: element (row p, col c) at
 //   (c/4)*A_LBO + (p/8)*A_SBO + (p%8)*16 + (c%4)*4     (8 rows x 16 bytes core matrices)
@@ -650,7 +653,7 @@ __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_fwd_kerne
             unsigned char* a = sA + (size_t)s * A_STAGE;
             const int col_base = (c0 + it) * FWD_CK;
             if (DENSE) produce_dense<LayoutKMajor, NRB, RPL>(a, warp, lane, col_base, tile_base, P.nq, P.x, P.gg.cin_p, P.mask, P.slope_in);
-            else produce_sparse<LayoutKMajor, NRB, 4, RPL>(a, warp, lane, P.gg, col_base, 0, toff_tile, ent, P.x);
+            else produce_sparse<LayoutKMajor, NRB, KP_U, RPL>(a, warp, lane, P.gg, col_base, 0, toff_tile, ent, P.x);
             fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->a_full[s]);
@@ -845,7 +848,7 @@ __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_dw_kernel
             } else {
                 const int* toff_tile = P.toff + (size_t)tile * TOFF_PER_TILE;
                 const int2* ent = P.entries + __ldg(toff_tile + 15 * TOFF_RB);
-                produce_sparse<LayoutMNMajor, DW_PT / RB, 4, RPL>(a, warp, lane, P.gg, chunk * DW_CK, half * (DW_PT / RB), toff_tile, ent, P.x);
+                produce_sparse<LayoutMNMajor, DW_PT / RB, KP_U, RPL>(a, warp, lane, P.gg, chunk * DW_CK, half * (DW_PT / RB), toff_tile, ent, P.x);
             }
             fence_proxy_async();
             __syncwarp();
