@@ -200,7 +200,8 @@ def measure_config(args, cfg_name, ctx, K, W, primary):
         if os.environ.get("WEASAL_BENCH_PLANS", "1") == "1":
             plans = calibrate_conv_plans(net, view, cal_pts, cal_lens, n_cap, limits)
     del cal_pts
-    prefetch = pyramid.PyramidPrefetcher(view, dev, neighborhood_limits=limits, n_cap=n_cap, plans=plans)
+    n_workers = int(os.environ.get("WEASAL_BENCH_WORKERS", "2"))  # builds in flight (= batches submitted ahead)
+    prefetch = pyramid.PyramidPrefetcher(view, dev, neighborhood_limits=limits, n_cap=n_cap, plans=plans, workers=n_workers)
     trainer = GraphedTrainStep(net, opt, F.cross_entropy, reducer=reducer if world > 1 else None, clip_value=100.0,
                                use_graph=os.environ.get("WEASAL_BENCH_GRAPH", "1") == "1", plans=plans, packer=packer)
     eager = GraphedTrainStep(net, opt, F.cross_entropy, reducer=None, clip_value=100.0, packer=packer)  # profile leg: no collective
@@ -234,8 +235,9 @@ def measure_config(args, cfg_name, ctx, K, W, primary):
         stamps.clear()
         done = []  # one event per launched step: the host stays at most two steps ahead of the GPU
         ahead = os.environ.get("WEASAL_BENCH_PREFETCH", "1") != "0"  # 0: build each pyramid when its step starts (A/B)
-        if n > 0 and ahead:
-            submit(first)
+        depth = n_workers if ahead else 0
+        for k in range(min(depth, n)):
+            submit(first + k)
         for it in range(first, first + n):
             flush.zero_()  # evict L2 between steps (256 MB > 126 MB L2)
             if not ahead:
@@ -254,8 +256,8 @@ def measure_config(args, cfg_name, ctx, K, W, primary):
             ev = torch.cuda.Event()
             ev.record()
             done.append((ev, it % 4))
-            if ahead and it + 1 < first + n:
-                submit(it + 1)  # after this step's launch: the GPU starts on step t while the host prepares batch t+1
+            if ahead and it + depth < first + n:
+                submit(it + depth)  # after this step's launch: the GPU starts on step t while the next batches are built
             if os.environ.get("WEASAL_DEBUG") and rank == 0:
                 print(f"[bench] {'e2e' if e2e else 'dev'} step {it}: build {prefetch.stats[-1][0] * 1e3:.2f} ms, get() waited "
                       f"{prefetch.stats[-1][1] * 1e3:.2f} ms, net launches {(time.perf_counter() - t_l0) * 1e3:.2f} ms",
@@ -385,8 +387,9 @@ def measure_config(args, cfg_name, ctx, K, W, primary):
                    "first_subsampling_dl": cfg["dl"], "first_features_dim": ncfg["first_features_dim"], "layers": 5,
                    "kpconv_per_forward": 10, "parallelism": f"dp{world}",
                    "l2": "flushed between steps (256 MB write, inside the timed region)",
-                   "pyramid": "built one step ahead on a side stream by one native call (kp_pyramid_build_static_dev), "
-                              "followed by the influence lists of all KPConv (kp_kpconv_prepare_dev)",
+                   "pyramid": f"built {n_workers} step(s) ahead by {n_workers} prefetch thread(s), each on its own side stream: one "
+                              "native call (kp_pyramid_build_static_dev), then the influence lists of all KPConv "
+                              "(kp_kpconv_prepare_dev)",
                    "random_grid_orient": True,
                    "capacities": f"calibrated on {N_CALIB} batches of another synthetic tile; timed on {N_BATCHES} unseen batches",
                    "neighborhood_limits": limits,

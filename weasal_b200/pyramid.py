@@ -430,7 +430,7 @@ class PyramidPrefetcher:
     Grid orientations are drawn from ``np.random`` at submit time, in submission order."""
 
     def __init__(self, config, device="cuda", neighborhood_limits=None, random_grid_orient=True, order="reference",
-                 index_dtype=torch.int64, slots=3, n_cap=None, plans=None):
+                 index_dtype=torch.int64, slots=None, n_cap=None, plans=None, workers=1):
         """``n_cap``: per-layer row capacities -> batches come in the static layout of kp_pyramid_build_static_dev
         (features and labels inside the slab; ``batch.static_slab`` set) for :class:`weasal_b200.engine.GraphedTrainStep`;
         a batch that does not fit falls back to the ordinary layout."""
@@ -445,22 +445,32 @@ class PyramidPrefetcher:
         # plans (weasal_b200.plan.ConvPlans, static layout only): the influence lists / transposed tables of every KPConv
         # of the network are built right behind the pyramid, by the same worker on the same stream
         self.plans = plans if n_cap is not None else None
+        # ``workers`` build threads, each with its own side stream: batch t goes to worker t % workers, get() returns the
+        # batches in submission order. One build is a chain of ~200 small kernels and a few host synchronisations (layer
+        # sizes, search widths), ~3 ms of latency for ~2 ms of kernels: two builds in flight double the throughput of the
+        # stage when the consumer submits two batches ahead.
+        self.workers = max(1, int(workers))
+        slots = slots if slots is not None else self.workers + 2
         self.plan_bufs = [None] * slots
         self.plan_jobs = [None] * slots      # (slab address, buffer address, ctypes job table) per ring slot
         # high priority: the pyramid's ~150 small kernels slot in between the training stream's big ones instead of
         # queueing behind them (a build took 4.2 ms instead of 2.0 ms when the training stream ran ahead)
-        self.side = torch.cuda.Stream(self.dev, priority=-1)
+        self.sides = [torch.cuda.Stream(self.dev, priority=-1) for _ in range(self.workers)]
+        self.side = self.sides[0]
         self.slabs = [None] * slots          # ring of output slabs (uint8 tensors allocated on the side stream)
         self.free_ev = [None] * slots        # recorded on the consumer's stream when a slot's batch has been consumed
-        self.n_sub, self.last_slot = 0, None
+        self.n_sub, self.n_got, self.last_slot = 0, 0, None
         self.stats = []  # per batch: (seconds the native call took in the worker, seconds get() waited for it)
-        self.q_in, self.q_out = queue.Queue(), queue.Queue()
+        self.q_in = [queue.Queue() for _ in range(self.workers)]
+        self.q_out = [queue.Queue() for _ in range(self.workers)]
         # the worker holds the GIL for microseconds per batch but must get it promptly when its call returns: with the
         # default 5 ms switch interval every hand-over from the launch-bound training thread would stall that long
         if sys.getswitchinterval() > 2e-4:
             sys.setswitchinterval(2e-4)
-        self.thread = threading.Thread(target=self._run, name="weasal-pyramid", daemon=True)
-        self.thread.start()
+        self.threads = [threading.Thread(target=self._run, args=(w,), name=f"weasal-pyramid-{w}", daemon=True)
+                        for w in range(self.workers)]
+        for t in self.threads:
+            t.start()
 
     def submit(self, points, features, labels, lengths, extras=None, inputs_ready=False):
         """``inputs_ready``: the caller guarantees that CUDA input tensors were completed long ago (e.g. a resident data
@@ -478,17 +488,19 @@ class PyramidPrefetcher:
             return t.to(dtype) if dtype is not None and t.dtype != dtype else t
 
         slot = self.n_sub % len(self.slabs)
+        w = self.n_sub % self.workers
+        side = self.sides[w]
         self.n_sub += 1
         cuda_inputs = [t for t in (points, features, labels) if torch.is_tensor(t) and t.is_cuda]
         if cuda_inputs and not inputs_ready:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(self.dev))
-            self.side.wait_event(ready)
+            side.wait_event(ready)
         for t in cuda_inputs:  # allocated on the caller's stream, read on the side stream: tell the caching allocator
-            t.record_stream(self.side)
-        with torch.cuda.stream(self.side):
+            t.record_stream(side)
+        with torch.cuda.stream(side):
             if self.free_ev[slot] is not None:
-                self.side.wait_event(self.free_ev[slot])  # the step that read this slot's previous batch has finished
+                side.wait_event(self.free_ev[slot])  # the step that read this slot's previous batch has finished
             pts, feats, labs = to_dev(points, torch.float32), to_dev(features, torch.float32), to_dev(labels)
             nbld = NativeBuild(pts, lens, self.cfg, self.limits, self.orient, self.order, self.dtype, rot=rot,
                                n_cap=self.n_cap, features=feats, labels=labs)
@@ -496,16 +508,16 @@ class PyramidPrefetcher:
                 self.slabs[slot] = torch.empty(int(nbld.slab_bytes() * 1.25), dtype=torch.uint8, device=self.dev)
             if self.plans is not None and self.plan_bufs[slot] is None:
                 self.plan_bufs[slot] = torch.zeros(self.plans.nbytes, dtype=torch.uint8, device=self.dev)
-        self.q_in.put((nbld, slot, (pts, feats, labs), extras, C.c_void_p(self.side.cuda_stream)))
+        self.q_in[w].put((nbld, slot, (pts, feats, labs), extras, C.c_void_p(side.cuda_stream), w))
 
-    def _run(self):
+    def _run(self, w):
         torch.cuda.set_device(self.dev)
         while True:
-            item = self.q_in.get()
+            item = self.q_in[w].get()
             if item is None:
                 return
             try:
-                nbld, slot, owned, extras, sh = item
+                nbld, slot, owned, extras, sh, _ = item
                 t0 = time.perf_counter()
                 while True:
                     try:
@@ -516,17 +528,17 @@ class PyramidPrefetcher:
                                            self.dtype, rot=nbld.rot)
                     # rare: grow the slab / neighbour capacity and repeat
                     if self.slabs[slot].numel() < nbld.slab_bytes():
-                        with torch.cuda.stream(self.side):
+                        with torch.cuda.stream(self.sides[w]):
                             self.slabs[slot] = torch.empty(int(nbld.slab_bytes() * 1.25), dtype=torch.uint8, device=self.dev)
                 nbld.plans_ok = False
                 if self.plans is not None and nbld.n_cap is not None and nbld.no_crop():
-                    nbld.plans_ok = self._run_plans(nbld, slot, sh)
+                    nbld.plans_ok = self._run_plans(nbld, slot, sh, w)
                 nbld.build_s = time.perf_counter() - t0
-                self.q_out.put((nbld, slot, owned, extras))
+                self.q_out[w].put((nbld, slot, owned, extras))
             except BaseException as e:  # surfaced by get()
-                self.q_out.put((e, None, None, None))
+                self.q_out[w].put((e, None, None, None))
 
-    def _run_plans(self, nbld, slot, sh):
+    def _run_plans(self, nbld, slot, sh, w=0):
         """Worker thread: the lists of every KPConv for the batch just built into ring slot ``slot``. The job table holds
         device addresses only, all fixed for a (slab, buffer) pair, so it is built once per slot."""
         slab, buf = self.slabs[slot], self.plan_bufs[slot]
@@ -535,13 +547,14 @@ class PyramidPrefetcher:
             P, Nn, Po, Up, Le = nbld.views(slab)
             self.plan_jobs[slot] = (key, self.plans.jobs(P, Nn, Po, self.dtype == torch.int64, buf))
         self.plans.run(self.plan_jobs[slot][1], buf, sh)
-        with torch.cuda.stream(self.side):
+        with torch.cuda.stream(self.sides[w]):
             overflow = int(buf[self.plans.flag_off:self.plans.flag_off + 4].view(torch.int32).item())  # syncs the stream
         return overflow == 0
 
     def get(self):
         t0 = time.perf_counter()
-        nbld, slot, owned, extras = self.q_out.get()
+        nbld, slot, owned, extras = self.q_out[self.n_got % self.workers].get()
+        self.n_got += 1
         if slot is None:
             raise nbld
         self.stats.append((nbld.build_s, time.perf_counter() - t0))
@@ -574,8 +587,10 @@ class PyramidPrefetcher:
         return batch
 
     def close(self):
-        self.q_in.put(None)
-        self.thread.join(timeout=10)
+        for q in self.q_in:
+            q.put(None)
+        for t in self.threads:
+            t.join(timeout=10)
 
 
 class DeviceBatch:
