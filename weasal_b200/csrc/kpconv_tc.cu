@@ -504,6 +504,13 @@ __device__ __forceinline__ void produce_sparse(unsigned char* sA, int warp, int 
     const int n = b - a;
     const float* __restrict__ xc = x + c0;
     const int p0 = rb * RB;
+    // The lane's cells are zeroed first, so that a finished row is ONE unconditional store and rows without entries need
+    // no bookkeeping: the earlier version, which stored zeros for the gaps between rows on the way, spent ~200 SASS
+    // instructions per entry slot on unrolled gap loops, and this loop is bound by its instruction count (the warps of an
+    // SM sub-partition run it in the same phase; ncu: issue slots, not memory).
+#pragma unroll
+    for (int r = 0; r < RPL; r++)
+        *reinterpret_cast<float4*>(sA + LAY::off(p0 + r_lo + r, cg)) = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int cur = r_lo;
     int2 rec[U];
@@ -515,7 +522,6 @@ __device__ __forceinline__ void produce_sparse(unsigned char* sA, int warp, int 
         int rv[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             wv[u] = __int_as_float(rec[u].y);
             rv[u] = (int)(((unsigned)rec[u].x >> ROW_SHIFT) & (RB - 1));
             if (e0 + u >= n || (RPL != RB && (rv[u] < r_lo || rv[u] >= r_hi))) rv[u] = -1;   // not mine
@@ -528,8 +534,6 @@ __device__ __forceinline__ void produce_sparse(unsigned char* sA, int warp, int 
             if (rv[u] >= 0) {
                 if (rv[u] != cur) {
                     *reinterpret_cast<float4*>(sA + LAY::off(p0 + cur, cg)) = to_tf32(acc);
-                    for (int r = cur + 1; r < rv[u]; r++)
-                        *reinterpret_cast<float4*>(sA + LAY::off(p0 + r, cg)) = make_float4(0.f, 0.f, 0.f, 0.f);
                     acc = make_float4(0.f, 0.f, 0.f, 0.f);
                     cur = rv[u];
                 }
@@ -539,8 +543,6 @@ __device__ __forceinline__ void produce_sparse(unsigned char* sA, int warp, int 
         }
     }
     *reinterpret_cast<float4*>(sA + LAY::off(p0 + cur, cg)) = to_tf32(acc);
-    for (int r = cur + 1; r < r_hi; r++)
-        *reinterpret_cast<float4*>(sA + LAY::off(p0 + r, cg)) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // Dense variant (linear layers next to KPConv: the A operand is a plain row-major matrix a[n, ld]): the lane's 8 cells
