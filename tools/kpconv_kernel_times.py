@@ -1,5 +1,5 @@
 """Per-kernel device times (the library's own CUDA-event timers, kp_profile_enable) of one KPConv forward + backward on
-a subsampled synthetic tile, C = 64 / 128, random and shell-shaped kernel points. WEASAL_B200_LIB selects an experiment
+a subsampled synthetic tile, C = 64 / 128 (KP_TIMES_C=64,256,... for other widths), random and shell-shaped kernel points. WEASAL_B200_LIB selects an experiment
 build of the library (e.g. one compiled with -DKP_ASSEMBLE_V=1) for A/B comparisons.
 
     python tools/kpconv_kernel_times.py
@@ -18,8 +18,8 @@ S = sp.contiguous(); Ls = np.array([len(S)], np.int32)
 nb = ops.batch_query(S, S, Ls, Ls, 1.0, dtype=torch.int32, cap_hint=64)
 n = len(S)
 lib = _lib.lib()
-for Cc in (64, 128):
-    for kpmode in ("randn", "shell"):
+for Cc in [int(c) for c in os.environ.get("KP_TIMES_C", "64,128").split(",")]:
+    for kpmode in os.environ.get("KP_TIMES_KP", "randn,shell").split(","):
         x = torch.randn(n, Cc, device=dev, requires_grad=True)
         w = (torch.randn(15, Cc, Cc, device=dev) / Cc ** 0.5).requires_grad_(True)
         if kpmode == "randn":

@@ -34,6 +34,7 @@
 //                  across a CTA's point tiles, then added to dW.
 #include "common.cuh"
 
+#include <cuda.h>  // CUtensorMap (the encoder itself is fetched through cudaGetDriverEntryPoint: no libcuda link)
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -118,6 +119,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// 2-D tiled tensor copy (TMA): box of the tensor map at (c0 = innermost coordinate, c1) -> shared memory
+__device__ __forceinline__ void tma_g2s_2d(void* dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -610,7 +619,7 @@ struct FwdBars {
 
 template <bool DENSE, int NPW>
 __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_fwd_kernel(const __grid_constant__ FwdParams P) {
-    constexpr int LOADER_WARP = NPW, MMA_WARP = NPW + 1, RPL = RB * 8 / NPW;
+    constexpr int LOADER_WARP = NPW, MMA_WARP = NPW + 1, NGRP = NPW / 8;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int S = P.stages;
     const int b_bytes = P.NB * FWD_CK * 4;
@@ -627,7 +636,7 @@ __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_fwd_kerne
 
     if (tid == 0) {
         for (int s = 0; s < S; s++) {
-            mbar_init(&bars->a_full[s], NPW);
+            mbar_init(&bars->a_full[s], 8);
             mbar_init(&bars->a_empty[s], 1);
             mbar_init(&bars->b_full[s], 1);
             mbar_init(&bars->b_empty[s], 1);
@@ -649,13 +658,16 @@ __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_fwd_kerne
             toff_tile = P.toff + (size_t)tile * TOFF_PER_TILE;
             ent = P.entries + __ldg(toff_tile + 15 * TOFF_RB);
         }
-        for (int it = 0; it < n_loc; it++) {
+        // a stage is always filled by 8 warps; with 16 producer warps (one CTA per SM) the two groups of 8 take
+        // alternate chunks, so two stages are being assembled at any time
+        const int pw = warp & 7;
+        for (int it = warp >> 3; it < n_loc; it += NGRP) {
             const int s = it % S, use = it / S;
             if (use > 0) mbar_wait(&bars->a_empty[s], (uint32_t)((use - 1) & 1));
             unsigned char* a = sA + (size_t)s * A_STAGE;
             const int col_base = (c0 + it) * FWD_CK;
-            if (DENSE) produce_dense<LayoutKMajor, NRB, RPL>(a, warp, lane, col_base, tile_base, P.nq, P.x, P.gg.cin_p, P.mask, P.slope_in);
-            else produce_sparse<LayoutKMajor, NRB, KP_U, RPL>(a, warp, lane, P.gg, col_base, 0, toff_tile, ent, P.x);
+            if (DENSE) produce_dense<LayoutKMajor, NRB, RB>(a, pw, lane, col_base, tile_base, P.nq, P.x, P.gg.cin_p, P.mask, P.slope_in);
+            else produce_sparse<LayoutKMajor, NRB, KP_U, RB>(a, pw, lane, P.gg, col_base, 0, toff_tile, ent, P.x);
             fence_proxy_async();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->a_full[s]);
@@ -761,6 +773,7 @@ struct DwParams {
     const float* dout;   // [nq, cout]
     int cout, NB;        // NB = output columns handled per CTA (<= 256), slice index = blockIdx.z
     int n_tiles, n_splits, stages;
+    int b_tma;           // dOut stages are filled by the loader warp with tensor copies (else by the producer warps)
     float* dw;           // [K, cin, cout], pre-zeroed
     uint32_t tmem_cols;
     // dense mode: A = x[nq, cin_p] itself (times the LeakyReLU derivative read from mask), see produce_dense
@@ -774,8 +787,9 @@ struct DwBars {
 };
 
 template <bool DENSE, int NPW>
-__global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_dw_kernel(const __grid_constant__ DwParams P) {
-    constexpr int LOADER_WARP = NPW, MMA_WARP = NPW + 1, RPL = RB * 8 / NPW;
+__global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_dw_kernel(const __grid_constant__ DwParams P,
+                                                                               const __grid_constant__ CUtensorMap dout_map) {
+    constexpr int LOADER_WARP = NPW, MMA_WARP = NPW + 1, NGRP = NPW / 8;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int S = P.stages;
     const int b_bytes = dw_b_bytes(P.NB);
@@ -790,7 +804,7 @@ __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_dw_kernel
 
     if (tid == 0) {
         for (int s = 0; s < S; s++) {
-            mbar_init(&bars->full[s], NPW);
+            mbar_init(&bars->full[s], P.b_tma ? 9 : 8);  // 8 producer warps (+ the loader's expect_tx arrival)
             mbar_init(&bars->empty[s], 1);
         }
         mbar_init(&bars->acc_full, 1);
@@ -806,7 +820,8 @@ __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_dw_kernel
         // ===== producers: step t = (tile, half): A stage [64 points x 128 columns] + dOut stage [64 points x NB] =====
         const int nv = P.NB >> 2;
         const bool vec4 = (P.cout & 3) == 0;
-        for (int t = 0; t < n_steps; t++) {
+        const int pw = warp & 7;  // (groups of 8 warps take alternate steps, as in the forward kernel)
+        for (int t = warp >> 3; t < n_steps; t += NGRP) {
             const int s = t % S, use = t / S;
             const int tile = split + (t >> 1) * P.n_splits, half = t & 1;
             const int row_base = tile * TILE_M + half * DW_PT;
@@ -814,12 +829,13 @@ __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_dw_kernel
             unsigned char* a = smem + (size_t)s * stage_bytes;
             unsigned char* b = a + DW_A_STAGE;
             // dOut rows -> B stage (TF32): 64 rows x NB/4 float4 items dealt over the 256 lanes, 4 loads in flight
-            const int items = DW_PT * nv;
-            for (int base = warp * 32 + lane; base < items; base += 4 * NPW * 32) {
+            // (only when the loader warp cannot do it: row pitch of dOut not a multiple of 16 bytes)
+            const int items = P.b_tma ? 0 : DW_PT * nv;
+            for (int base = pw * 32 + lane; base < items; base += 4 * 256) {
                 float4 v[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const int q = base + u * NPW * 32;
+                    const int q = base + u * 256;
                     v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (q < items) {
                         const int r = q / nv, n4 = q - r * nv;
@@ -838,7 +854,7 @@ __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_dw_kernel
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const int q = base + u * NPW * 32;
+                    const int q = base + u * 256;
                     if (q < items) {
                         const int r = q / nv, n4 = q - r * nv;
                         *reinterpret_cast<float4*>(b + LayoutMNMajor::off(r, n4)) = to_tf32(v[u]);
@@ -846,15 +862,31 @@ __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_dw_kernel
                 }
             }
             if (DENSE) {
-                produce_dense<LayoutMNMajor, DW_PT / RB, RPL>(a, warp, lane, chunk * DW_CK, row_base, P.nq, P.x, P.gg.cin_p, P.mask, P.slope_in);
+                produce_dense<LayoutMNMajor, DW_PT / RB, RB>(a, pw, lane, chunk * DW_CK, row_base, P.nq, P.x, P.gg.cin_p, P.mask, P.slope_in);
             } else {
                 const int* toff_tile = P.toff + (size_t)tile * TOFF_PER_TILE;
                 const int2* ent = P.entries + __ldg(toff_tile + 15 * TOFF_RB);
-                produce_sparse<LayoutMNMajor, DW_PT / RB, KP_U, RPL>(a, warp, lane, P.gg, chunk * DW_CK, half * (DW_PT / RB), toff_tile, ent, P.x);
+                produce_sparse<LayoutMNMajor, DW_PT / RB, KP_U, RB>(a, pw, lane, P.gg, chunk * DW_CK, half * (DW_PT / RB), toff_tile, ent, P.x);
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->full[s]);
+        }
+    } else if (warp == LOADER_WARP) {
+        // ===== loader: dOut[64 points x NB] -> B stage, one tensor copy per 32 output columns; the copy engine applies
+        //       the 32-byte-atom swizzle and the fp32 -> tf32 conversion (tensor map data type TFLOAT32), rows and
+        //       columns past the end of dOut arrive as zeros =====
+        if (lane == 0 && P.b_tma) {
+            const int n_box = (P.NB + 31) / 32;
+            for (int t = 0; t < n_steps; t++) {
+                const int s = t % S, use = t / S;
+                const int tile = split + (t >> 1) * P.n_splits, half = t & 1;
+                const int row_base = tile * TILE_M + half * DW_PT;
+                if (use > 0) mbar_wait(&bars->empty[s], (uint32_t)((use - 1) & 1));
+                unsigned char* b = smem + (size_t)s * stage_bytes + DW_A_STAGE;
+                mbar_expect_tx(&bars->full[s], (uint32_t)(n_box * MN_LBO));
+                for (int j = 0; j < n_box; j++) tma_g2s_2d(b + (size_t)j * MN_LBO, &dout_map, n0 + 32 * j, row_base, &bars->full[s]);
+            }
         }
     } else if (warp == MMA_WARP) {
         if (lane == 0) {
@@ -1124,6 +1156,36 @@ static int launch_fwd(const char* tag, bool dense, int nc, const float* x, const
     return KP_OK;
 }
 
+// tensor map of a row-major fp32 matrix m[rows, cols] for boxes of [64 rows x 32 columns] in the dW stage layout
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+static bool dw_stage_map(const float* m, long long rows, int cols, CUtensorMap* map) {
+    static const bool off = getenv("WEASAL_DW_TMA") && atoi(getenv("WEASAL_DW_TMA")) == 0;
+    memset(map, 0, sizeof(*map));
+    if (off || (cols & 3) != 0 || ((uintptr_t)m & 15) != 0 || rows <= 0) return false;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    const cuuint32_t box[2] = {32, (cuuint32_t)DW_PT};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(m), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // dw[K, cin, cout] (+)= A^T · dout, A as above; dw must be zeroed by the caller
 static int launch_dw(const char* tag, bool dense, int nq, const float* x, const GatherGeom& gg, int cin, const int* toff,
                      const int2* entries, const float* dout, int cout, float* dw, const float* mask, float slope_in,
@@ -1144,6 +1206,8 @@ static int launch_dw(const char* tag, bool dense, int nq, const float* x, const 
     if (splits < 1) splits = 1;
     if (splits > P.n_tiles) splits = P.n_tiles;
     P.n_splits = splits;
+    alignas(64) CUtensorMap dout_map;
+    P.b_tma = dw_stage_map(dout, nq, cout, &dout_map) ? 1 : 0;
     P.dw = dw;
     P.mask = mask; P.slope_in = slope_in;
     uint32_t cols = 32;
@@ -1155,7 +1219,7 @@ static int launch_dw(const char* tag, bool dense, int nq, const float* x, const 
 #define KP_LAUNCH_DW(D, W)                                                      \
     do {                                                                        \
         KP_CUDA(set_smem(kp_dw_kernel<D, W>, smem));                            \
-        kp_dw_kernel<D, W><<<grid, (W + 2) * 32, smem, stream>>>(P);            \
+        kp_dw_kernel<D, W><<<grid, (W + 2) * 32, smem, stream>>>(P, dout_map);  \
     } while (0)
     if (dense) { if (two) KP_LAUNCH_DW(true, 8); else KP_LAUNCH_DW(true, 16); }
     else { if (two) KP_LAUNCH_DW(false, 8); else KP_LAUNCH_DW(false, 16); }
