@@ -324,6 +324,41 @@ def measure_config(args, cfg_name, ctx, K, W, primary):
     graphed_steps, eager_steps = trainer.n_graphed - g0, trainer.n_eager - e0_
     e2e_ms, e2e_pts = timed(W, K, True, clocks if rank == 0 else None)
 
+    # diagnostic, outside every timed region: the two halves of the pipeline each on an otherwise idle GPU. Their sum
+    # against ms_per_step says how much of the side stream's work the step hides.
+    if rank == 0 and primary and world == 1 and use_graph and trainer.graph is not None:
+        def build_only(n):
+            last = None
+            for it in range(n):
+                b = it % N_BATCHES
+                prefetch.submit(dev_batches[b]["points"], dev_batches[b]["features"], dev_batches[b]["labels"],
+                                batches[b]["lengths"], inputs_ready=True)
+                last = prefetch.get()
+            torch.cuda.synchronize()
+            return last
+        last = build_only(2)
+        t0 = time.perf_counter()
+        last = build_only(10)
+        t_pyr = (time.perf_counter() - t0) / 10 * 1e3
+        for _ in range(3):
+            trainer.step(last)
+        torch.cuda.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(10):
+            trainer.step(last)
+        eb.record()
+        torch.cuda.synchronize()
+        t_graph = ea.elapsed_time(eb) / 10
+        ea.record()
+        for _ in range(10):
+            flush.zero_()
+            trainer.step(last)
+        eb.record()
+        torch.cuda.synchronize()
+        pacing["alone_ms"] = {"pyramid_and_lists_one_at_a_time": t_pyr, "training_graph": t_graph,
+                              "training_graph_after_l2_flush": ea.elapsed_time(eb) / 10}
+
     # per-kernel device times (CUDA events on the launching stream, recorded inside the library)
     roof, kernels = None, {}
     if rank == 0 and primary:

@@ -20,7 +20,9 @@ n = len(S)
 torch.manual_seed(0)
 x = torch.randn(n, C_, device=dev, requires_grad=True)
 w = (torch.randn(15, C_, C_, device=dev) / C_ ** 0.5).requires_grad_(True)
-v = torch.randn(15, 3, device=dev); kp = v / v.norm(dim=1, keepdim=True) * 0.66 * 0.4; kp[0] = 0
+# kernel points as the reference lays them out: one at the centre, 14 on a shell of 0.66 x the conv radius (1.0 here),
+# influence extent 0.4 (KP_extent 1.2 x radius / conv_radius 2.5 = 0.48 in the configs): ~1 kernel point per neighbour
+v = torch.randn(15, 3, device=dev); kp = v / v.norm(dim=1, keepdim=True) * 0.66; kp[0] = 0
 g = torch.randn(n, C_, device=dev)
 for it in range(reps):
     x.grad = w.grad = None

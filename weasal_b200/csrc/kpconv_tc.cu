@@ -207,49 +207,23 @@ __device__ __forceinline__ float influence_w(float rx, float ry, float rz, float
 
 constexpr int LST_WARPS = 16;     // warps per list-building CTA: 8 rows of the tile each
 constexpr int LST_ROWS = TILE_M / LST_WARPS;
-constexpr int INF_MAX_ROW = 128;  // real neighbours staged per centre in shared memory (longer rows: two-pass path)
-
-// any row length (rare: more than INF_MAX_ROW neighbours): one pass over the row per kernel point, lanes = neighbours;
-// the groups come out in kernel-point order, each in table-column order (scratch format)
-__device__ __noinline__ void influence_long_row(const float* __restrict__ others, int no, const Table& T, size_t pos0,
-                                                int cnt_row, float cx, float cy, float cz, const float* s_kp, int K,
-                                                float inv_ext, unsigned short* koff_row, int2* __restrict__ my_entries,
-                                                int lane) {
-    const unsigned lt_mask = (1u << lane) - 1u;
-    int run = 0;
-    for (int k = 0; k < 15; k++) {
-        if (lane == 0) koff_row[k] = (unsigned short)run;
-        if (k >= K) continue;
-        const float kx = s_kp[3 * k], ky = s_kp[3 * k + 1], kz = s_kp[3 * k + 2];
-        for (int hb = 0; hb < cnt_row; hb += 32) {
-            const int h = hb + lane;
-            long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
-            const bool valid = j >= 0 && j < no;
-            float w = 0.f;
-            if (valid) w = influence_w(others[3 * j] - cx, others[3 * j + 1] - cy, others[3 * j + 2] - cz, kx, ky, kz, inv_ext);
-            const unsigned m = __ballot_sync(0xffffffffu, w > 0.f);
-            if (w > 0.f) {
-                int2 e;
-                e.x = (int)((unsigned)j | ((unsigned)k << K_SHIFT));
-                e.y = __float_as_int(w);
-                my_entries[run + __popc(m & lt_mask)] = e;
-            }
-            run += __popc(m);
-        }
-    }
-    if (lane == 0) koff_row[15] = (unsigned short)run;
-    __syncwarp();
-}
+constexpr int LST_G = 4;          // rows a warp has in flight
+constexpr int LST_CELLS = 8;      // candidate table: LST_CELLS^3 cells over the cube that holds every kernel point's ball
 
 // One CTA per tile of 128 centres.
-//   Phase A (one warp per centre at a time, 8 centres per warp): the real neighbours of the row are compacted into
-//     shared memory (shadow entries dropped), then the warp sweeps the (kernel point, neighbour) pairs in kernel-point-
-//     major order, 32 pairs per step, one influence evaluation per lane; ballot-compacting the non-zero weights yields the
-//     row's list grouped by kernel point, written to the row's slot of a scratch buffer (15 entries per table cell is the
-//     exact worst case, so no allocation), with the group starts kept in shared memory.
-//   Scan: per kernel point, the exclusive prefix of the group sizes over the 128 rows = each row's place in the tile's
-//     flat list of that kernel point; the tile takes its range of the compact entry buffer with one atomicAdd.
-//   Phase B: the rows' groups are copied from the scratch slots (still in L2) to their place in the flat lists.
+//   Candidate table (per CTA, 512 cells, a few thousand instructions): which kernel points can reach a relative position,
+//     by cell of a coarse grid over the cube [-b, b]^3, b = max |kernel point coordinate| + extent (conservative
+//     point-to-box test). A neighbour lies within the extent of ~1.03 kernel points and its cell names ~3 candidates, so
+//     the exact influence (the same expression as before: the set of entries and their weights do not change) is
+//     evaluated ~3 times per neighbour instead of 15.
+//   Phase A (one warp per centre at a time, 8 centres per warp; lanes = columns of the neighbour table): every lane looks
+//     its neighbour's candidates up and the warp walks them, one candidate per lane per pass; non-zero weights are ballot-
+//     compacted into the row's slot of a scratch buffer (15 entries per table cell is the exact worst case, so no
+//     allocation), tagged with the kernel point, and counted per (row, kernel point) in shared memory.
+//   Scan: per kernel point, the exclusive prefix of the counts over the 128 rows = each row's place in the tile's flat
+//     list of that kernel point; the tile takes its range of the compact entry buffer with one atomicAdd.
+//   Phase B: the rows' entries are copied from the scratch slots (still in L2) to their place in the flat lists; the rank
+//     of an entry among the row's entries of the same kernel point comes from __match_any_sync (deterministic order).
 struct ListsOut {
     int* toff;        // [n_tiles][16][17]
     int2* entries;    // compact, `cap` entries
@@ -258,83 +232,156 @@ struct ListsOut {
     int* overflow;    // optional: one flag shared by all lists of a batch (set together with ctl[1])
 };
 
-__global__ void __launch_bounds__(LST_WARPS * 32, 2) kp_lists_kernel(const float* __restrict__ centres, int nc,
-                                                                 const float* __restrict__ others, int no, Table T,
-                                                                 const float* __restrict__ kp, int K, float kp_sign,
-                                                                 float inv_ext, int2* __restrict__ scratch, ListsOut L) {
-    __shared__ float s_kp[16 * 3];
-    __shared__ float4 s_nb[LST_WARPS][INF_MAX_ROW];
-    __shared__ unsigned short s_koff[TILE_M][16];  // per row: start of kernel point k's group in the row's slot; [15] = count
-    __shared__ int s_pos[15][TILE_M + 1];          // per kernel point: exclusive prefix of the group sizes over the rows
+// One launch builds the lists of several (centres, table, kernel points) jobs: the 20 lists of a training step's 10
+// KPConv (forward + dX each) are one grid of ~1700 tiles instead of 20 launches that each end in a partial wave (the
+// deep layers have 4-16 tiles).
+struct ListJob {
+    const float* centres;
+    const float* others;
+    Table T;
+    const float* kp;
+    int2* scratch;
+    ListsOut L;
+    int nc, no, K;
+    float kp_sign, inv_ext;
+    int first_tile;   // of this job inside the grid
+};
+constexpr int LST_MAX_JOBS = 24;
+struct ListJobs {
+    ListJob job[LST_MAX_JOBS];
+    int n;
+};
+
+__global__ void __launch_bounds__(128) kp_lists_ctl_kernel(const __grid_constant__ ListJobs J) {
+    if ((int)threadIdx.x < 4 * J.n)  // the 4 control ints of every job's header (cursor, overflow flag, 2 spare)
+        J.job[threadIdx.x >> 2].L.ctl[threadIdx.x & 3] = 0;
+}
+
+__global__ void __launch_bounds__(LST_WARPS * 32, 2) kp_lists_kernel(const __grid_constant__ ListJobs J) {
+    int ji = 0;
+    while (ji + 1 < J.n && (int)blockIdx.x >= J.job[ji + 1].first_tile) ji++;
+    const float* __restrict__ centres = J.job[ji].centres;
+    const float* __restrict__ others = J.job[ji].others;
+    const Table T = J.job[ji].T;
+    const float* __restrict__ kp = J.job[ji].kp;
+    int2* __restrict__ scratch = J.job[ji].scratch;
+    const ListsOut L = J.job[ji].L;
+    const int nc = J.job[ji].nc, no = J.job[ji].no, K = J.job[ji].K;
+    const float kp_sign = J.job[ji].kp_sign, inv_ext = J.job[ji].inv_ext;
+    const int tile = (int)blockIdx.x - J.job[ji].first_tile;
+    constexpr int NCELL = LST_CELLS * LST_CELLS * LST_CELLS;
+    __shared__ float4 s_kp[16];
+    __shared__ unsigned short s_tab[NCELL];        // bit k: kernel point k may influence positions of the cell
+    __shared__ unsigned short s_cnt[TILE_M][16];   // per row: entries per kernel point; [15] = the row's total
+    __shared__ int s_pos[15][TILE_M + 1];          // per kernel point: exclusive prefix of the counts over the rows
     __shared__ int s_start[17];                    // list starts inside the tile's range; [15] = tile total; [16] = range base
-    if (threadIdx.x < 48) s_kp[threadIdx.x] = (threadIdx.x < 3 * K) ? kp_sign * kp[threadIdx.x] : 1e30f;
+    if (threadIdx.x < 16) {
+        const int k = threadIdx.x;
+        s_kp[k] = k < K ? make_float4(kp_sign * kp[3 * k], kp_sign * kp[3 * k + 1], kp_sign * kp[3 * k + 2], 0.f)
+                        : make_float4(1e30f, 1e30f, 1e30f, 0.f);
+    }
+    for (int t = threadIdx.x; t < TILE_M * 16 / 2; t += LST_WARPS * 32) reinterpret_cast<unsigned*>(&s_cnt[0][0])[t] = 0u;
+    __syncthreads();
+    const float ext = 1.f / inv_ext;
+    float box = 0.f;
+    for (int k = 0; k < K; k++) box = fmaxf(box, fmaxf(fabsf(s_kp[k].x), fmaxf(fabsf(s_kp[k].y), fabsf(s_kp[k].z))));
+    box += ext;
+    const float cell = 2.f * box / LST_CELLS, inv_cell = LST_CELLS / (2.f * box);
+    {
+        // the half edge is padded: a position within rounding distance of a cell face may be binned on either side
+        const float half = 0.5f * cell * 1.001f + 1e-6f * box, reach2 = ext * ext * 1.0001f;
+        for (int c = threadIdx.x; c < NCELL; c += LST_WARPS * 32) {
+            const int ix = c % LST_CELLS, iy = (c / LST_CELLS) % LST_CELLS, iz = c / (LST_CELLS * LST_CELLS);
+            const float ccx = -box + (ix + 0.5f) * cell, ccy = -box + (iy + 0.5f) * cell, ccz = -box + (iz + 0.5f) * cell;
+            unsigned m = 0;
+            for (int k = 0; k < K; k++) {
+                const float4 q = s_kp[k];
+                const float dx = fmaxf(0.f, fabsf(q.x - ccx) - half), dy = fmaxf(0.f, fabsf(q.y - ccy) - half),
+                            dz = fmaxf(0.f, fabsf(q.z - ccz) - half);
+                if (dx * dx + dy * dy + dz * dz < reach2) m |= 1u << k;
+            }
+            s_tab[c] = (unsigned short)m;
+        }
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile = blockIdx.x;
     const unsigned lt_mask = (1u << lane) - 1u;
-    float4* nb = s_nb[warp];
 
-    for (int rr = 0; rr < LST_ROWS; rr++) {
-        const int row = warp * LST_ROWS + rr;
-        const int i = tile * TILE_M + row;
-        unsigned short* koff_row = s_koff[row];
-        if (i >= nc) {
-            if (lane < 16) koff_row[lane] = 0;
-            continue;
+    // rows are taken LST_G at a time: the table reads and the coordinate gathers of the group are issued together (the
+    // kernel is bound by the latency of the chain table entry -> coordinates, not by its instruction count)
+    for (int g0 = 0; g0 < LST_ROWS; g0 += LST_G) {
+        const int row_g = warp * LST_ROWS + g0;
+        int cnt_r[LST_G], run[LST_G];
+        size_t pos0[LST_G], row0[LST_G];
+        float cx[LST_G], cy[LST_G], cz[LST_G];
+        int max_cnt = 0;
+#pragma unroll
+        for (int rr = 0; rr < LST_G; rr++) {
+            const int i = tile * TILE_M + row_g + rr;
+            cnt_r[rr] = 0; run[rr] = 0; pos0[rr] = 0; row0[rr] = 0;
+            cx[rr] = cy[rr] = cz[rr] = 0.f;
+            if (i < nc) {
+                cx[rr] = centres[3 * (size_t)i]; cy[rr] = centres[3 * (size_t)i + 1]; cz[rr] = centres[3 * (size_t)i + 2];
+                if (T.rowptr) { row0[rr] = (size_t)T.rowptr[i]; pos0[rr] = row0[rr]; cnt_r[rr] = T.rowptr[i + 1] - T.rowptr[i]; }
+                else { row0[rr] = (size_t)i * T.H; pos0[rr] = (size_t)i * T.stride; cnt_r[rr] = T.H; }
+            }
+            max_cnt = max(max_cnt, cnt_r[rr]);
         }
-        const float cx = centres[3 * (size_t)i], cy = centres[3 * (size_t)i + 1], cz = centres[3 * (size_t)i + 2];
-        size_t row0, pos0;
-        int cnt_row;
-        if (T.rowptr) { row0 = (size_t)T.rowptr[i]; pos0 = row0; cnt_row = T.rowptr[i + 1] - T.rowptr[i]; }
-        else { row0 = (size_t)i * T.H; pos0 = (size_t)i * T.stride; cnt_row = T.H; }
-        int2* my_entries = scratch + 15 * row0;
-        if (cnt_row > INF_MAX_ROW) {
-            influence_long_row(others, no, T, pos0, cnt_row, cx, cy, cz, s_kp, K, inv_ext, koff_row, my_entries, lane);
-            continue;
-        }
-        int hn = 0;
-        for (int hb = 0; hb < cnt_row; hb += 32) {
+        for (int hb = 0; hb < max_cnt; hb += 32) {
             const int h = hb + lane;
-            long long j = (h < cnt_row) ? table_get(T, pos0 + h) : -1;
-            const bool valid = j >= 0 && j < no;
-            const unsigned m = __ballot_sync(0xffffffffu, valid);
-            if (valid)
-                nb[hn + __popc(m & lt_mask)] = make_float4(others[3 * j] - cx, others[3 * j + 1] - cy, others[3 * j + 2] - cz,
-                                                           __int_as_float((int)j));
-            hn += __popc(m);
-        }
-        __syncwarp();
-        const int npairs = K * hn;
-        const int my_first = min(lane * hn, npairs);  // first pair of kernel point `lane` (lanes 0..15)
-        int myoff = 0, run = 0;
-        // pair p = (kernel point p / hn, neighbour p % hn). hn <= 128 and p < 1920, so the quotient comes exactly from one
-        // float multiply: (p + 0.5) / hn stays at least 0.5 / 128 away from an integer, far above the rounding error
-        const float inv_hn = hn > 0 ? 1.f / (float)hn : 0.f;
-        int base = 0;
-        for (; base < npairs; base += 32) {
-            const int p = base + lane;
-            const bool valid = p < npairs;
-            const int k = (int)(((float)p + 0.5f) * inv_hn);
-            const int h = p - k * hn;
-            float w = 0.f;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) {
-                v = nb[h];
-                w = influence_w(v.x, v.y, v.z, s_kp[3 * k], s_kp[3 * k + 1], s_kp[3 * k + 2], inv_ext);
+            int jv[LST_G];
+            float rx[LST_G], ry[LST_G], rz[LST_G];
+#pragma unroll
+            for (int rr = 0; rr < LST_G; rr++) {
+                const long long j = (h < cnt_r[rr]) ? table_get(T, pos0[rr] + h) : -1;
+                jv[rr] = (j >= 0 && j < no) ? (int)j : -1;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, w > 0.f);
-            if (w > 0.f) {
-                int2 e;
-                e.x = (int)((unsigned)__float_as_int(v.w) | ((unsigned)k << K_SHIFT));
-                e.y = __float_as_int(w);
-                my_entries[run + __popc(m & lt_mask)] = e;
+#pragma unroll
+            for (int rr = 0; rr < LST_G; rr++) {
+                rx[rr] = ry[rr] = rz[rr] = 0.f;
+                if (jv[rr] >= 0) {
+                    rx[rr] = others[3 * (size_t)jv[rr]] - cx[rr]; ry[rr] = others[3 * (size_t)jv[rr] + 1] - cy[rr];
+                    rz[rr] = others[3 * (size_t)jv[rr] + 2] - cz[rr];
+                }
             }
-            if (my_first >= base && my_first < base + 32) myoff = run + __popc(m & ((1u << (my_first - base)) - 1u));
-            run += __popc(m);
+#pragma unroll
+            for (int rr = 0; rr < LST_G; rr++) {
+                unsigned short* cnt = s_cnt[row_g + rr];
+                int2* my_entries = scratch + 15 * row0[rr];
+                unsigned cand = 0;
+                if (jv[rr] >= 0) {
+                    const float fx = (rx[rr] + box) * inv_cell, fy = (ry[rr] + box) * inv_cell, fz = (rz[rr] + box) * inv_cell;
+                    if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)LST_CELLS && fy < (float)LST_CELLS && fz < (float)LST_CELLS)
+                        cand = s_tab[((int)fz * LST_CELLS + (int)fy) * LST_CELLS + (int)fx];
+                }
+                while (__any_sync(0xffffffffu, cand != 0u)) {
+                    const bool act = cand != 0u;
+                    const int k = act ? __ffs((int)cand) - 1 : 0;
+                    cand &= cand - 1u;
+                    float w = 0.f;
+                    if (act) {
+                        const float4 q = s_kp[k];
+                        w = influence_w(rx[rr], ry[rr], rz[rr], q.x, q.y, q.z, inv_ext);
+                    }
+                    const bool hit = w > 0.f;
+                    const unsigned hm = __ballot_sync(0xffffffffu, hit);
+                    if (hm == 0u) continue;
+                    if (hit) {
+                        const unsigned peers = __match_any_sync(hm, k);
+                        int2 e;
+                        e.x = (int)((unsigned)jv[rr] | ((unsigned)k << K_SHIFT));
+                        e.y = __float_as_int(w);
+                        my_entries[run[rr] + __popc(hm & lt_mask)] = e;
+                        if ((peers & lt_mask) == 0u) cnt[k] = (unsigned short)(cnt[k] + __popc(peers));
+                    }
+                    run[rr] += __popc(hm);
+                    __syncwarp();  // the next pass may count the same kernel point from another lane
+                }
+            }
         }
-        if (my_first >= base) myoff = run;  // kernel points that start at or after the end of the sweep
-        if (lane < 16) koff_row[lane] = (unsigned short)myoff;
-        __syncwarp();  // the staging row is reused by the next centre
+#pragma unroll
+        for (int rr = 0; rr < LST_G; rr++)
+            if (lane == 0 && tile * TILE_M + row_g + rr < nc) s_cnt[row_g + rr][15] = (unsigned short)(run[rr] < 65535 ? run[rr] : 65535);
     }
     __syncthreads();
 
@@ -343,7 +390,7 @@ __global__ void __launch_bounds__(LST_WARPS * 32, 2) kp_lists_kernel(const float
         int carry = 0;
         for (int r0 = 0; r0 < TILE_M; r0 += 32) {
             const int r = r0 + lane;
-            const int c = (int)s_koff[r][k + 1] - (int)s_koff[r][k];
+            const int c = (int)s_cnt[r][k];
             int incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -389,20 +436,57 @@ __global__ void __launch_bounds__(LST_WARPS * 32, 2) kp_lists_kernel(const float
     }
     if (base < 0) return;
     int2* dst = L.entries + base;
-    for (int rr = 0; rr < LST_ROWS; rr++) {
-        const int row = warp * LST_ROWS + rr;
-        const int i = tile * TILE_M + row;
-        if (i >= nc) break;
-        const unsigned short* ko = s_koff[row];
-        const int total = ko[15];
-        if (total == 0) continue;
-        const size_t row0 = T.rowptr ? (size_t)T.rowptr[i] : (size_t)i * T.H;
-        const int2* src = scratch + 15 * row0;
-        for (int e = lane; e < total; e += 32) {
-            int2 rec = src[e];
-            const int k = (int)((unsigned)rec.x >> K_SHIFT);
-            rec.x = (int)(((unsigned)rec.x & JS_MASK) | ((unsigned)row << ROW_SHIFT));
-            dst[s_start[k] + s_pos[k][row] + (e - (int)ko[k])] = rec;
+    // the first 32 entries of every row of a group are read together (most rows have fewer), the rest row by row
+    for (int g0 = 0; g0 < LST_ROWS; g0 += LST_G) {
+        const int row_g = warp * LST_ROWS + g0;
+        int total[LST_G];
+        const int2* src[LST_G];
+        int2 first[LST_G];
+#pragma unroll
+        for (int rr = 0; rr < LST_G; rr++) {
+            const int row = row_g + rr, i = tile * TILE_M + row;
+            total[rr] = 0;
+            src[rr] = scratch;
+            if (i < nc) {
+                total[rr] = s_cnt[row][15];
+                if (total[rr] == 65535) {  // (a row of more than 4369 table cells: recount)
+                    total[rr] = 0;
+                    for (int k = 0; k < 15; k++) total[rr] += (int)s_cnt[row][k];
+                }
+                src[rr] = scratch + 15 * (T.rowptr ? (size_t)T.rowptr[i] : (size_t)i * T.H);
+            }
+            first[rr] = make_int2(0, 0);
+            if (lane < total[rr]) first[rr] = src[rr][lane];
+        }
+#pragma unroll
+        for (int rr = 0; rr < LST_G; rr++) {
+            const int row = row_g + rr;
+            if (total[rr] == 0) continue;
+            unsigned short* cnt = s_cnt[row];
+            const bool multi = total[rr] > 32;
+            if (multi) {  // the counts become the number of entries already placed, per kernel point
+                __syncwarp();
+                if (lane < 15) cnt[lane] = 0;
+                __syncwarp();
+            }
+            for (int e0 = 0; e0 < total[rr]; e0 += 32) {
+                const int e = e0 + lane;
+                const bool act = e < total[rr];
+                const unsigned am = __ballot_sync(0xffffffffu, act);
+                if (act) {
+                    int2 rec = e0 == 0 ? first[rr] : src[rr][e];
+                    const int k = (int)((unsigned)rec.x >> K_SHIFT);
+                    const unsigned peers = __match_any_sync(am, k);
+                    const int rank = (multi ? (int)cnt[k] : 0) + __popc(peers & lt_mask);
+                    rec.x = (int)(((unsigned)rec.x & JS_MASK) | ((unsigned)row << ROW_SHIFT));
+                    dst[s_start[k] + s_pos[k][row] + rank] = rec;
+                    if (multi) {
+                        __syncwarp(am);
+                        if ((peers & lt_mask) == 0u) cnt[k] = (unsigned short)(cnt[k] + __popc(peers));
+                        __syncwarp(am);
+                    }
+                }
+            }
         }
     }
 }
@@ -1019,9 +1103,38 @@ void kpconv_lists_bytes(int nc, long long n_pairs, long long* hdr_bytes, long lo
     *entries_bytes = (n_pairs > 0 ? n_pairs : 1) * 15 * 8;  // exact worst case; callers with calibrated bounds pass less
 }
 
-static int build_lists(Scratch& S, const float* centres, int nc, const float* others, int no, const Table& T,
-                       long long n_pairs, const float* kp, int K, float kp_sign, float extent, Lists* L,
-                       cudaStream_t stream, int* overflow = nullptr) {
+// host side of a batch of list jobs: add_list_job() per job, then launch_list_jobs()
+struct ListBatch {
+    ListJobs J;
+    int n_tiles;
+    long long cost[LST_MAX_JOBS];  // table cells per tile (long rows first: they finish last)
+    ListBatch() : n_tiles(0) { J.n = 0; }
+};
+static int launch_list_jobs(ListBatch& B, cudaStream_t stream) {
+    if (B.J.n == 0) return KP_OK;
+    // jobs with the longest rows go first in the grid, so the last wave is made of cheap tiles
+    for (int a = 1; a < B.J.n; a++)
+        for (int b = a; b > 0 && B.cost[b] > B.cost[b - 1]; b--) {
+            std::swap(B.cost[b], B.cost[b - 1]);
+            std::swap(B.J.job[b], B.J.job[b - 1]);
+        }
+    int first = 0;
+    for (int a = 0; a < B.J.n; a++) {
+        B.J.job[a].first_tile = first;
+        first += ceil_div(B.J.job[a].nc, TILE_M);
+    }
+    ProfileScope ps("kp_lists", stream);
+    kp_lists_ctl_kernel<<<1, 128, 0, stream>>>(B.J);
+    KP_CHECK_LAUNCH();
+    kp_lists_kernel<<<first, LST_WARPS * 32, 0, stream>>>(B.J);
+    KP_CHECK_LAUNCH();
+    B.J.n = 0;
+    B.n_tiles = 0;
+    return KP_OK;
+}
+static int add_list_job(ListBatch& B, Scratch& S, const float* centres, int nc, const float* others, int no, const Table& T,
+                        long long n_pairs, const float* kp, int K, float kp_sign, float extent, Lists* L,
+                        cudaStream_t stream, int* overflow = nullptr) {
     if (n_pairs * 15 >= (1LL << 31)) return fail(KP_ERR_UNSUPPORTED, "kpconv: neighbour table too large (Nq*H*15 >= 2^31)");
     const int n_tiles = ceil_div(nc, TILE_M);
     if (!L->hdr) {
@@ -1031,13 +1144,25 @@ static int build_lists(Scratch& S, const float* centres, int nc, const float* ot
     }
     int2* scratch = S.alloc<int2>((size_t)(n_pairs > 0 ? n_pairs : 1) * 15);
     if (S.status != KP_OK) return S.status;
-    ProfileScope ps("kp_lists", stream);
-    KP_CUDA(cudaMemsetAsync(L->hdr, 0, LISTS_CTL_INTS * sizeof(int), stream));
-    ListsOut O;
-    O.toff = L->hdr + LISTS_CTL_INTS; O.entries = L->entries; O.ctl = L->hdr; O.cap = L->cap; O.overflow = overflow;
-    kp_lists_kernel<<<n_tiles, LST_WARPS * 32, 0, stream>>>(centres, nc, others, no, T, kp, K, kp_sign, 1.f / extent, scratch, O);
-    KP_CHECK_LAUNCH();
+    if (B.J.n == LST_MAX_JOBS) {
+        const int rc = launch_list_jobs(B, stream);
+        if (rc != KP_OK) return rc;
+    }
+    ListJob& j = B.J.job[B.J.n];
+    j.centres = centres; j.others = others; j.T = T; j.kp = kp; j.scratch = scratch;
+    j.L.toff = L->hdr + LISTS_CTL_INTS; j.L.entries = L->entries; j.L.ctl = L->hdr; j.L.cap = L->cap; j.L.overflow = overflow;
+    j.nc = nc; j.no = no; j.K = K; j.kp_sign = kp_sign; j.inv_ext = 1.f / extent; j.first_tile = 0;
+    B.cost[B.J.n] = nc > 0 ? n_pairs / nc : 0;
+    B.J.n++;
+    B.n_tiles += n_tiles;
     return KP_OK;
+}
+static int build_lists(Scratch& S, const float* centres, int nc, const float* others, int no, const Table& T,
+                       long long n_pairs, const float* kp, int K, float kp_sign, float extent, Lists* L,
+                       cudaStream_t stream, int* overflow = nullptr) {
+    ListBatch B;
+    const int rc = add_list_job(B, S, centres, nc, others, no, T, n_pairs, kp, K, kp_sign, extent, L, stream, overflow);
+    return rc != KP_OK ? rc : launch_list_jobs(B, stream);
 }
 
 // How many CTAs share the reduction axis of one 128-point tile. A CTA costs (its chunks + ~1 chunk of fixed work:
@@ -1311,34 +1436,39 @@ int kpconv_prepare_device(const kp_list_job* jobs, int n_jobs, int* overflow_fla
     Scratch S(stream);
     ArenaHold hold(S);  // every job's scratch stays valid until the call returns (jobs overlap on the stream)
     if (overflow_flag) KP_CUDA(cudaMemsetAsync(overflow_flag, 0, sizeof(int), stream));
+    // the transposed tables first (the lists over them need them), then every list of the batch in one launch
     for (int i = 0; i < n_jobs; i++) {
         const kp_list_job& J = jobs[i];
-        int rc;
-        if (J.kind == 1) {
-            if (J.nc < 0 || J.no <= 0 || J.H <= 0 || J.idx_stride < J.H || !J.rowptr || !J.col)
-                return fail(KP_ERR_ARG, "kpconv_prepare: bad transpose job");
-            rc = transpose_table_device(S, J.neighb_inds, J.idx_is_i64, J.nc, J.H, J.idx_stride, J.no, J.rowptr, J.col, stream);
-        } else if (J.kind == 0 || J.kind == 2) {
-            if (J.nc <= 0 || J.no <= 0 || J.K <= 0 || J.K > 15 || !(J.KP_extent > 0.f) || !J.hdr || !J.entries || J.entries_cap <= 0)
-                return fail(KP_ERR_ARG, "kpconv_prepare: bad list job");
-            Table T;
-            long long n_pairs;
-            if (J.kind == 2) {
-                T.idx = J.col; T.rowptr = J.rowptr; T.H = 0; T.stride = 0; T.is_i64 = 0;
-                n_pairs = J.n_pairs;
-            } else {
-                if (J.H <= 0 || J.idx_stride < J.H) return fail(KP_ERR_ARG, "kpconv_prepare: bad table");
-                T.idx = J.neighb_inds; T.rowptr = nullptr; T.H = J.H; T.stride = J.idx_stride; T.is_i64 = J.idx_is_i64;
-                n_pairs = (long long)J.nc * J.H;
-            }
-            Lists L;
-            L.hdr = (int*)J.hdr; L.entries = (int2*)J.entries; L.cap = J.entries_cap;
-            rc = build_lists(S, J.centres, J.nc, J.others, J.no, T, n_pairs, J.kernel_points, J.K, J.kp_sign, J.KP_extent, &L,
-                             stream, overflow_flag);
-        } else return fail(KP_ERR_ARG, "kpconv_prepare: unknown job kind");
+        if (J.kind != 1) continue;
+        if (J.nc < 0 || J.no <= 0 || J.H <= 0 || J.idx_stride < J.H || !J.rowptr || !J.col)
+            return fail(KP_ERR_ARG, "kpconv_prepare: bad transpose job");
+        const int rc = transpose_table_device(S, J.neighb_inds, J.idx_is_i64, J.nc, J.H, J.idx_stride, J.no, J.rowptr, J.col, stream);
         if (rc != KP_OK) return rc;
     }
-    return KP_OK;
+    ListBatch B;
+    for (int i = 0; i < n_jobs; i++) {
+        const kp_list_job& J = jobs[i];
+        if (J.kind == 1) continue;
+        if (J.kind != 0 && J.kind != 2) return fail(KP_ERR_ARG, "kpconv_prepare: unknown job kind");
+        if (J.nc <= 0 || J.no <= 0 || J.K <= 0 || J.K > 15 || !(J.KP_extent > 0.f) || !J.hdr || !J.entries || J.entries_cap <= 0)
+            return fail(KP_ERR_ARG, "kpconv_prepare: bad list job");
+        Table T;
+        long long n_pairs;
+        if (J.kind == 2) {
+            T.idx = J.col; T.rowptr = J.rowptr; T.H = 0; T.stride = 0; T.is_i64 = 0;
+            n_pairs = J.n_pairs;
+        } else {
+            if (J.H <= 0 || J.idx_stride < J.H) return fail(KP_ERR_ARG, "kpconv_prepare: bad table");
+            T.idx = J.neighb_inds; T.rowptr = nullptr; T.H = J.H; T.stride = J.idx_stride; T.is_i64 = J.idx_is_i64;
+            n_pairs = (long long)J.nc * J.H;
+        }
+        Lists L;
+        L.hdr = (int*)J.hdr; L.entries = (int2*)J.entries; L.cap = J.entries_cap;
+        const int rc = add_list_job(B, S, J.centres, J.nc, J.others, J.no, T, n_pairs, J.kernel_points, J.K, J.kp_sign,
+                                    J.KP_extent, &L, stream, overflow_flag);
+        if (rc != KP_OK) return rc;
+    }
+    return launch_list_jobs(B, stream);
 }
 
 // lists_hdr / lists_entries (optional, caller-owned device buffers of kpconv_lists_bytes): the forward pass leaves

@@ -24,6 +24,8 @@ A batch that does not fit the capacities, or whose rows were cropped by a limit 
 conv matrices then does not hold), takes the ordinary eager step with the same kernels.
 """
 import numpy as np
+import os
+
 import torch
 
 from . import _lib
@@ -148,7 +150,9 @@ class GraphedTrainStep:
         saved = [p.detach().clone() for p in params]
         had_state = {id(p) for p in params if self.opt.state.get(p)}
         cur = torch.cuda.current_stream(dev)
-        s = torch.cuda.Stream(dev)
+        # capture stream of high priority: kernel nodes keep the priority of the stream they were captured on, and the
+        # step must win SM slots against the prefetch streams' builds (WEASAL_TRAIN_PRIORITY=0: no preference)
+        s = torch.cuda.Stream(dev, priority=int(os.environ.get("WEASAL_TRAIN_PRIORITY", "-1")))
         s.wait_stream(cur)
         with torch.cuda.stream(s):
             self.slab.copy_(batch.static_slab)

@@ -343,7 +343,7 @@ _SIDE = {}
 def _side_stream(dev):
     key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
     if key not in _SIDE:
-        _SIDE[key] = torch.cuda.Stream(dev)
+        _SIDE[key] = torch.cuda.Stream(dev, priority=int(os.environ.get("WEASAL_TRAIN_PRIORITY", "-1")))
     return _SIDE[key]
 
 

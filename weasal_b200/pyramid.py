@@ -8,6 +8,7 @@ in the main process on the training stream and returns the same flat list
 (indices int64 as collated by the reference, common.py:551-553). :class:`DeviceBatch` exposes that list with the
 field names of ``<DS>CustomBatch`` (datasets/Vaihingen3D_PseudoLabel.py:1407-1481) so the unchanged networks consume it.
 """
+import os
 import time
 
 import numpy as np
@@ -453,9 +454,13 @@ class PyramidPrefetcher:
         slots = slots if slots is not None else self.workers + 2
         self.plan_bufs = [None] * slots
         self.plan_jobs = [None] * slots      # (slab address, buffer address, ctypes job table) per ring slot
-        # high priority: the pyramid's ~150 small kernels slot in between the training stream's big ones instead of
-        # queueing behind them (a build took 4.2 ms instead of 2.0 ms when the training stream ran ahead)
-        self.sides = [torch.cuda.Stream(self.dev, priority=-1) for _ in range(self.workers)]
+        # Stream priority (WEASAL_PREFETCH_PRIORITY, default 0 = low): with batches submitted two ahead nothing waits
+        # for a build, so the builds run underneath the training step, whose graph is captured on a high-priority
+        # stream (engine.GraphedTrainStep): its chain of ~400 small dependent kernels then gets SM slots as soon as a
+        # node becomes ready instead of queueing behind the builds' CTAs. (With a single build in flight and the
+        # consumer waiting for it, -1 is the better choice.)
+        prio = int(os.environ.get("WEASAL_PREFETCH_PRIORITY", "0"))
+        self.sides = [torch.cuda.Stream(self.dev, priority=prio) for _ in range(self.workers)]
         self.side = self.sides[0]
         self.slabs = [None] * slots          # ring of output slabs (uint8 tensors allocated on the side stream)
         self.free_ev = [None] * slots        # recorded on the consumer's stream when a slot's batch has been consumed
