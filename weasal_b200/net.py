@@ -16,7 +16,10 @@ import torch.nn.functional as F
 
 import os
 
-UNARY_FUSED_MAX_CHANNELS = int(os.environ.get("WEASAL_UNARY_MAX_C", "64"))
+# Unary blocks up to this many channels (in and out) run on the fused tcgen05 linear kernels; wider ones are plain large
+# GEMMs where the library kernel wins. Measured in the training step (bench.py, ms/step Vaihingen / DALES): 64: 3.64 /
+# 4.07, 128: 3.59 / 3.85, 256: 3.58 / 3.88, 512: 3.66 / 3.98, all: 3.98 / 4.67.
+UNARY_FUSED_MAX_CHANNELS = int(os.environ.get("WEASAL_UNARY_MAX_C", "256"))
 
 
 def max_pool(x, inds, width=None):
