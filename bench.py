@@ -582,17 +582,21 @@ def operator_sweep(dev, peaks, budget_s=75.0):
                 row["cpu_Mqueries_per_s"] = cpu_rate(lambda: oracle.ref_batch_neighbors(S_np[:nq], S_np, np.array([nq], np.int32), Ls, 1.0), nq) / 1e6
                 row["cpu_sample"] = f"reference batch_nanoflann_neighbors, first {nq} queries against all supports, 1 thread"
             rows.append(row)
-            if B == 1 and n_raw <= 1_000_000:
+            if B == 1:
                 geo[n_raw] = (S, Ls)
             del P
-    # KPConv: geometry = the subsampled clouds above; H = the `limit` closest neighbours of a radius-1.3 search
-    for n_raw, Cs, Hs in ((100_000, (64, 128, 256, 512), (16, 32, 64)), (1_000_000, (64, 128), (32,))):
+    # KPConv: geometry = the subsampled clouds above (dl 0.4); H = the `limit` closest neighbours of a search of radius
+    # 1.0 = conv_radius 2.5 x dl; kernel points as the reference lays them out (one at the centre, 14 on a shell of 0.66 x
+    # that radius, kernel_points.py:484) with influence extent KP_extent 1.0 x dl (blocks.py:533-535)
+    R_CONV, EXTENT = 1.0, 0.4
+    for n_raw, Cs, Hs in ((100_000, (64, 128, 256, 512), (16, 32, 64)), (1_000_000, (64, 128, 256, 512), (32,)),
+                          (10_000_000, (64,), (32,))):
         if n_raw not in geo:
             continue
         S, Ls = geo[n_raw]
         n = len(S)
         for H in Hs:
-            nb = ops.batch_query(S, S, Ls, Ls, 1.3, limit=H, dtype=torch.int32).contiguous()
+            nb = ops.batch_query(S, S, Ls, Ls, R_CONV, limit=H, dtype=torch.int32).contiguous()
             shadow = float((nb == n).float().mean())
             for Cc in Cs:
                 if time.time() - t_start > budget_s:
@@ -601,13 +605,13 @@ def operator_sweep(dev, peaks, budget_s=75.0):
                 x = torch.randn(n, Cc, device=dev, requires_grad=True)
                 w = (torch.randn(15, Cc, Cc, device=dev) / Cc ** 0.5).requires_grad_(True)
                 v = torch.randn(15, 3, device=dev)
-                kp = v / v.norm(dim=1, keepdim=True) * 0.66 * 0.5
+                kp = v / v.norm(dim=1, keepdim=True) * 0.66 * R_CONV
                 kp[0] = 0
-                ms_f, y = timeit(lambda: ops.kpconv(S, S, nb, x, w, kp, 0.5), warm=2, reps=3)
+                ms_f, y = timeit(lambda: ops.kpconv(S, S, nb, x, w, kp, EXTENT), warm=2, reps=3)
                 g = torch.randn_like(y)
 
                 def fb():
-                    yy = ops.kpconv(S, S, nb, x, w, kp, 0.5)
+                    yy = ops.kpconv(S, S, nb, x, w, kp, EXTENT)
                     yy.backward(g)
                     return yy
                 ms_fb, _ = timeit(fb, warm=2, reps=3)
@@ -623,7 +627,7 @@ def operator_sweep(dev, peaks, budget_s=75.0):
                     s_c, x_c, w_c, kp_c = S.cpu(), x.detach().cpu().requires_grad_(True), w.detach().cpu().requires_grad_(True), kp.cpu()
 
                     def cpu_fb():
-                        yy = kpconv_reference_ops(q_c, s_c, nb_c, x_c, w_c, kp_c, 0.5)
+                        yy = kpconv_reference_ops(q_c, s_c, nb_c, x_c, w_c, kp_c, EXTENT)
                         yy.backward(torch.ones_like(yy))
                     cpu_fb()
                     row["cpu_fwd_bwd_Mpts_per_s"] = cpu_rate(cpu_fb, ns) / 1e6

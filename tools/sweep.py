@@ -60,7 +60,9 @@ def kpconv_sweep(S, Ls, nb):
     for C in (64, 128, 256):
         x = torch.randn(n, C, device=dev, requires_grad=True)
         w = (torch.randn(15, C, C, device=dev) / C ** 0.5).requires_grad_(True)
-        kp = torch.randn(15, 3, device=dev) * 0.4
+        v = torch.randn(15, 3, device=dev)  # the reference's layout: centre + shell at 0.66 x conv radius (1.0), extent 0.4
+        kp = v / v.norm(dim=1, keepdim=True) * 0.66
+        kp[0] = 0
         ms_f, y = timeit(lambda: ops.kpconv(S, S, nb, x, w, kp, 0.4), warm=3, reps=5)
         g = torch.randn_like(y)
 

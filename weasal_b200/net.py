@@ -20,6 +20,7 @@ import os
 # GEMMs where the library kernel wins. Measured in the training step (bench.py, ms/step Vaihingen / DALES): 64: 3.64 /
 # 4.07, 128: 3.59 / 3.85, 256: 3.58 / 3.88, 512: 3.66 / 3.98, all: 3.98 / 4.67.
 UNARY_FUSED_MAX_CHANNELS = int(os.environ.get("WEASAL_UNARY_MAX_C", "256"))
+FORK_SHORTCUT = os.environ.get("WEASAL_FORK_SHORTCUT", "1") != "0"
 
 
 def max_pool(x, inds, width=None):
@@ -93,9 +94,29 @@ class ConvBlock(nn.Module):
             q, s, idx = batch.points[l], batch.points[l], batch.neighbors[l]
         if self.kind == 'simple':
             return F.leaky_relu(self.conv(q, s, idx, x), 0.1)
-        y = self.unary2(F.leaky_relu(self.conv(q, s, idx, self.unary1(x)), 0.1))
         widths = getattr(batch, "pool_widths", None)
-        sc = self.shortcut(max_pool(x, idx, widths[l] if widths is not None else None) if self.strided else x)
+
+        def shortcut():
+            return self.shortcut(max_pool(x, idx, widths[l] if widths is not None else None) if self.strided else x)
+
+        # The shortcut branch (max-pool and / or a Linear) does not depend on the conv branch: it runs on a second stream
+        # beside unary1 -> KPConv -> unary2, forward and (autograd keeps an op's backward on its forward's stream)
+        # backward; inside a captured step this becomes a fork / join of the graph. The deep layers' kernels are a few
+        # CTAs each, so the two branches share the SMs instead of queueing.
+        fork = FORK_SHORTCUT and x.is_cuda and (self.strided or not isinstance(self.shortcut, nn.Identity))
+        if fork:
+            from . import ops
+            cur, side = torch.cuda.current_stream(x.device), ops._side_stream(x.device, 1)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                sc = shortcut()
+            x.record_stream(side)
+        y = self.unary2(F.leaky_relu(self.conv(q, s, idx, self.unary1(x)), 0.1))
+        if fork:
+            cur.wait_stream(side)
+            sc.record_stream(cur)
+        else:
+            sc = shortcut()
         return F.leaky_relu(y + sc, 0.1)
 
 

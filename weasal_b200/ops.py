@@ -340,8 +340,9 @@ _FORK_BACKWARD = os.environ.get("WEASAL_FORK_BACKWARD", "1") != "0"
 _SIDE = {}
 
 
-def _side_stream(dev):
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+def _side_stream(dev, which=0):
+    """``which``: 0 = the stream dW runs on beside dX, 1 = the shortcut branch of a residual block (net.ConvBlock)"""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), which)
     if key not in _SIDE:
         _SIDE[key] = torch.cuda.Stream(dev, priority=int(os.environ.get("WEASAL_TRAIN_PRIORITY", "-1")))
     return _SIDE[key]
