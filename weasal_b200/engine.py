@@ -153,7 +153,8 @@ class GraphedTrainStep:
         # capture stream of high priority: kernel nodes keep the priority of the stream they were captured on, and the
         # step must win SM slots against the prefetch streams' builds (WEASAL_TRAIN_PRIORITY=0: no preference)
         s = torch.cuda.Stream(dev, priority=int(os.environ.get("WEASAL_TRAIN_PRIORITY", "-1")))
-        s.wait_stream(cur)
+        self._capture_stream = s  # kept for the trainer's lifetime: the library's scratch arena is keyed by (thread,
+        s.wait_stream(cur)        # stream) and the captured graph holds pointers into this stream's arena
         with torch.cuda.stream(s):
             self.slab.copy_(batch.static_slab)
             if self.plan_buf is not None:
