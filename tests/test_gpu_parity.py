@@ -897,6 +897,12 @@ def test_sharded_sphere_voting_equals_single_rank(torch_cuda):
     net = KPFCNNHarness(ncfg, KPConv).to(dev)
     view = CfgView(ncfg)
     p1, v1, s1, n1 = vote_cloud(net, view, cloud, feats, R, 2, num_votes=1, random_grid_orient=False)
+    stats = dict(vote_cloud.last_stats)
+    assert stats["graphed"] > 0 and stats["graphed"] >= 4 * stats["eager"], stats  # the CUDA-graph path is the one that ran
+    # ... and it equals the eager path (same kernels; the padded layout changes nothing for the real rows)
+    p0, v0, s0, n0 = vote_cloud(net, view, cloud, feats, R, 2, num_votes=1, random_grid_orient=False, graph=False)
+    assert (s0, n0) == (s1, n1) and torch.equal(v0, v1)
+    assert float((p0 - p1).abs().max()) < 1e-3
     sums, votes, spheres = 0, 0, 0
     for r in range(2):
         p, v, s, n = vote_cloud(net, view, cloud, feats, R, 2, num_votes=1, rank=r, world_size=2,

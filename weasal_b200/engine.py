@@ -60,7 +60,8 @@ def calibrate_static_caps(config, point_sets, length_sets, row_margin=1.05, row_
     return n_cap, limits
 
 
-def calibrate_conv_plans(net, config, point_sets, length_sets, n_cap, limits, random_grid_orient=True, margin=1.3):
+def calibrate_conv_plans(net, config, point_sets, length_sets, n_cap, limits, random_grid_orient=True, margin=1.3,
+                         forward_only=False):
     """The fixed layout of the prefetched KPConv lists (weasal_b200.plan.ConvPlans) for ``net``: capacities of the entry
     buffers from a calibration pass over the given batches (records actually needed, plus a margin; a batch that
     outgrows them takes the eager step)."""
@@ -74,7 +75,7 @@ def calibrate_conv_plans(net, config, point_sets, length_sets, n_cap, limits, ra
         used = measure_entries(specs, DeviceBatch(li))
         need = used if need is None else [max(a, b) for a, b in zip(need, used)]
     caps = [int(v * margin) + 4096 for v in need]
-    return ConvPlans(specs, n_cap, limits, limits, caps)
+    return ConvPlans(specs, n_cap, limits, limits, caps, forward_only=forward_only)
 
 
 class GraphedTrainStep:
@@ -239,3 +240,72 @@ class GraphedTrainStep:
             self.graph_tail.replay()
         self.n_graphed += 1
         return self.loss
+
+
+class GraphedForward:
+    """Inference counterpart of :class:`GraphedTrainStep` (sphere voting, utils/tester_PseudoLabel.py:149-195):
+    ``post(net(batch))`` under ``no_grad`` captured once on a static-shape batch and replayed per batch; a batch that does
+    not fit the captured layout runs eagerly. The weights must not change after construction (their operand images are
+    packed once). ``run(batch)`` returns the rows of the batch's real points ``[batch.n_points, C]`` — for graphed batches a
+    view of the graph's static output, valid until the next ``run``."""
+
+    def __init__(self, net, post=None, plans=None, packer=None, warmup=2):
+        self.net, self.post, self.plans, self.packer, self.warmup = net, post, plans, packer, warmup
+        self.graph = self.slab = self.plan_buf = self.layout = self.out = None
+        self.n_graphed = self.n_eager = 0
+        if packer is not None:
+            packer.pack()
+
+    _static_batch = GraphedTrainStep._static_batch
+
+    def _forward(self, batch):
+        with torch.no_grad():
+            y = self.net(batch)
+            return self.post(y) if self.post is not None else y
+
+    def _fits(self, batch):
+        if getattr(batch, "static_slab", None) is None or not batch.no_crop:
+            return False
+        if self.plans is not None and getattr(batch, "plan_buf", None) is None:
+            return False
+        if self.layout is None:
+            return True
+        nbld = batch.build
+        return (np.array_equal(nbld.offs, self.layout[0]) and np.array_equal(nbld.n_cap, self.layout[1])
+                and np.array_equal(nbld.strides, self.layout[2]) and batch.static_slab.numel() == self.slab.numel())
+
+    def _capture(self, batch):
+        nbld, dev = batch.build, batch.static_slab.device
+        self.slab = torch.empty_like(batch.static_slab)
+        self.plan_buf = torch.empty_like(batch.plan_buf) if (self.plans is not None and batch.plan_buf is not None) else None
+        self.layout = (nbld.offs.copy(), nbld.n_cap.copy(), nbld.strides.copy())
+        cur = torch.cuda.current_stream(dev)
+        s = torch.cuda.Stream(dev, priority=int(os.environ.get("WEASAL_TRAIN_PRIORITY", "-1")))
+        self._capture_stream = s
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            self.slab.copy_(batch.static_slab)
+            if self.plan_buf is not None:
+                self.plan_buf.copy_(batch.plan_buf)
+            for _ in range(self.warmup):
+                self._forward(self._static_batch(nbld))
+        cur.wait_stream(s)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
+            self.out = self._forward(self._static_batch(nbld))
+        self.graph = g
+        torch.cuda.synchronize(dev)
+
+    def run(self, batch):
+        if not self._fits(batch):
+            self.n_eager += 1
+            return self._forward(batch)[:batch.n_points]
+        if self.graph is None:
+            self._capture(batch)
+        self.slab.copy_(batch.static_slab, non_blocking=True)
+        if self.plan_buf is not None:
+            self.plan_buf.copy_(batch.plan_buf, non_blocking=True)
+        self.graph.replay()
+        self.n_graphed += 1
+        return self.out[:batch.n_points]

@@ -72,7 +72,8 @@ class ConvPlans:
     ``entry_caps[i]``: capacity of conv i's lists in records (forward and dX lists hold exactly the same number of
     records: one per (query, neighbour, kernel point) triple with a non-zero weight)."""
 
-    def __init__(self, specs, n_cap, conv_widths, pool_widths, entry_caps):
+    def __init__(self, specs, n_cap, conv_widths, pool_widths, entry_caps, forward_only=False):
+        self.forward_only = bool(forward_only)  # inference: no dX lists, no transposed tables
         self.specs, self.n_cap = list(specs), [int(v) for v in n_cap]
         self.conv_w, self.pool_w = [int(v) for v in conv_widths], [int(v) for v in pool_widths]
         self.caps = [int(v) for v in entry_caps]
@@ -123,6 +124,8 @@ class ConvPlans:
             jobs.append(_lib.ListJob(kind=0, centres=q.data_ptr(), nc=it["nq"], others=s.data_ptr(), no=it["ns"],
                                      neighb_inds=idx.data_ptr(), kp_sign=1.0, hdr=base + it["f_hdr"],
                                      entries=base + it["f_ent"], **common))
+            if self.forward_only:
+                continue
             if not sp.strided:
                 # conv matrix of a layer against itself, no crop: its own transpose (the f32 distance is symmetric)
                 jobs.append(_lib.ListJob(kind=0, centres=s.data_ptr(), nc=it["ns"], others=q.data_ptr(), no=it["nq"],

@@ -50,10 +50,20 @@ def extract_spheres_device(cloud, feats, centres_xy, in_radius, keep_frac=0.7):
 
 @torch.no_grad()
 def vote_cloud(net, config, cloud, feats, in_radius, batch_num, num_votes=1, num_classes=None, rank=0, world_size=1,
-               seed=0, group=None, neighborhood_limits=None, random_grid_orient=True):
+               seed=0, group=None, neighborhood_limits=None, random_grid_orient=True, graph=True, calib_batches=8,
+               workers=3, state=None):
     """Votes of this rank's share of the spheres, all-reduced: returns (probabilities [N, classes], votes [N],
     spheres this rank ran, points this rank pushed through the network). ``cloud`` [N,3] / ``feats`` [N,C-1] are CUDA
-    tensors holding the whole (subsampled) cloud on every rank; the network sees ``[feats, z_rel]`` per point."""
+    tensors holding the whole (subsampled) cloud on every rank; the network sees ``[feats, z_rel]`` per point.
+
+    ``graph`` (default, needs no ``neighborhood_limits``): row capacities, matrix widths and list capacities are
+    calibrated on ``calib_batches`` batches spread over this rank's schedule (like the reference's sampler calibration),
+    the batches come in the static layout with their forward influence lists prepared by the prefetch workers, and the
+    forward pass + softmax is ONE CUDA graph replay per batch (engine.GraphedForward); a batch that does not fit runs
+    eagerly. Sphere extraction runs on its own stream, so its host read-backs (sphere sizes) never wait for the network.
+    ``state``: the calibration + captured graph of an earlier call on the same network and cloud density
+    (``vote_cloud.last_state``), reused instead of calibrating again (the reference calibrates once per dataset and then
+    runs many voting passes, tester_PseudoLabel.py:149-160)."""
     dev = cloud.device
     lo, hi = cloud[:, :2].min(0)[0].cpu().numpy(), cloud[:, :2].max(0)[0].cpu().numpy()
     centres = vote_centres(lo, hi, in_radius, num_votes, seed)
@@ -62,16 +72,46 @@ def vote_cloud(net, config, cloud, feats, in_radius, batch_num, num_votes=1, num
     centres_dev = [torch.from_numpy(b).to(dev) for b in mine]
     net.eval()
     acc = None
-    pf = PyramidPrefetcher(config, dev, neighborhood_limits=neighborhood_limits, random_grid_orient=random_grid_orient)
-    pending = []
+    softmax = lambda y: torch.softmax(y, 1)
+    fwd = None
+    graph = graph and neighborhood_limits is None and len(mine) > 0
+    if graph:
+        from .engine import GraphedForward, calibrate_conv_plans, calibrate_static_caps
+        from .net import fused_linear_weights
+        from .plan import WeightPacker
+        if state is None:
+            picks = sorted(set(int(round(v)) for v in np.linspace(0, len(mine) - 1, min(calib_batches, len(mine)))))
+            cal = [extract_spheres_device(cloud, feats, centres_dev[k], in_radius) for k in picks]
+            cal = [c for c in cal if c is not None]
+            if cal:
+                n_cap, limits = calibrate_static_caps(config, [c[0] for c in cal], [c[2] for c in cal], row_margin=1.25,
+                                                      width_margin=0.25, random_grid_orient=random_grid_orient)
+                plans = calibrate_conv_plans(net, config, [c[0] for c in cal], [c[2] for c in cal], n_cap, limits,
+                                             random_grid_orient=random_grid_orient, margin=1.5, forward_only=True)
+                state = dict(n_cap=n_cap, limits=limits, plans=plans, net=net,
+                             fwd=GraphedForward(net, post=softmax, plans=plans,
+                                                packer=WeightPacker(net, fused_linear_weights(net))))
+            del cal
+        if state is not None:
+            assert state["net"] is net, "vote_cloud: state belongs to another network"
+            fwd = state["fwd"]
+            pf = PyramidPrefetcher(config, dev, neighborhood_limits=state["limits"], random_grid_orient=random_grid_orient,
+                                   n_cap=state["n_cap"], plans=state["plans"], workers=workers)
+    vote_cloud.last_state = state
+    if fwd is None:
+        workers = 1
+        pf = PyramidPrefetcher(config, dev, neighborhood_limits=neighborhood_limits, random_grid_orient=random_grid_orient)
     n_spheres = n_points = 0
+    ex_stream = torch.cuda.Stream(dev)
+    ex_stream.wait_stream(torch.cuda.current_stream(dev))
 
     def submit(k):
-        ex = extract_spheres_device(cloud, feats, centres_dev[k], in_radius)
-        if ex is None:
-            return False
-        p, f, lens, inds = ex
-        pf.submit(p, f, None, lens, extras=dict(input_inds=inds, in_points=p, in_lengths=lens))
+        with torch.cuda.stream(ex_stream):
+            ex = extract_spheres_device(cloud, feats, centres_dev[k], in_radius)
+            if ex is None:
+                return False
+            p, f, lens, inds = ex
+            pf.submit(p, f, None, lens, extras=dict(input_inds=inds, in_points=p, in_lengths=lens))
         return True
 
     todo = iter(range(len(mine)))
@@ -82,18 +122,28 @@ def vote_cloud(net, config, cloud, feats, in_radius, batch_num, num_votes=1, num
                 return True
         return False
 
-    inflight = submit_next()
+    inflight = sum(1 for _ in range(workers) if submit_next())
     while inflight:
         batch = pf.get()
-        inflight = submit_next()  # the next batch's extraction + pyramid overlap this batch's forward pass
-        probs = torch.softmax(net(batch), 1)
+        inflight -= 1
+        if submit_next():  # the next batches' extraction + pyramid overlap this batch's forward pass
+            inflight += 1
+        cur = torch.cuda.current_stream(dev)
+        for t in (batch.in_points, batch.input_inds):  # allocated on the extraction stream, read on this one
+            t.record_stream(cur)
+        probs = fwd.run(batch) if fwd is not None else softmax(net(batch))
         if acc is None:
             acc = VoteBuffer(cloud.shape[0], probs.shape[1] if num_classes is None else num_classes, dev, mode="sum")
         # (tester_PseudoLabel.py:188-194: only the points within 0.7 * in_radius of the sphere centre vote)
         acc.update(probs, batch.in_points, batch.input_inds, batch.in_lengths, radius_limit=0.7 * in_radius)
-        n_spheres += len(batch.lengths[0])
-        n_points += batch.points[0].shape[0]
+        n_spheres += len(batch.in_lengths)
+        n_points += int(batch.in_points.shape[0])
     pf.close()
+    g0, e0 = getattr(vote_cloud, "_seen", {}).get(id(fwd), (0, 0)) if fwd is not None else (0, 0)
+    vote_cloud.last_stats = dict(graphed=fwd.n_graphed - g0 if fwd is not None else 0,
+                                 eager=fwd.n_eager - e0 if fwd is not None else -(-n_spheres // max(batch_num, 1)))
+    if fwd is not None:
+        vote_cloud._seen = {id(fwd): (fwd.n_graphed, fwd.n_eager)}
     if acc is None:
         acc = VoteBuffer(cloud.shape[0], num_classes or 1, dev, mode="sum")
     acc.reduce(group)  # all-reduces (sum of probabilities, votes) in place
