@@ -526,3 +526,47 @@ print("OK")
 """
     out = subprocess.run([sys.executable, "-c", code, ROOT, root], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stderr[-2000:]
+
+
+def test_conv_plan_layout_and_job_table():
+    """plan.ConvPlans (host logic of kp_kpconv_prepare_dev's job table): one forward list job per KPConv, plus for
+    training a dX list job per KPConv (over the same table for the symmetric same-layer matrices, over a transposed CSR
+    copy built once per strided layer); buffers of one plan do not overlap; forward_only drops dX jobs and transposes."""
+    import torch
+    from weasal_b200 import plan
+    from weasal_b200.kpconv import KPConv
+    from weasal_b200.net import KPFCNNHarness, net_config
+    np.random.seed(0)
+    torch.manual_seed(0)
+    net = KPFCNNHarness(net_config("vaihingen_pl"), KPConv)
+    specs = plan.conv_specs(net)
+    assert len(specs) == 10 and sum(s.strided for s in specs) == 4
+    n_cap, widths = [1024, 512, 256, 128, 128], [20, 30, 40, 50, 60]
+    caps = [5000 + 100 * i for i in range(len(specs))]
+    full = plan.ConvPlans(specs, n_cap, widths, widths, caps)
+    fwd = plan.ConvPlans(specs, n_cap, widths, widths, caps, forward_only=True)
+    assert full.nbytes == fwd.nbytes  # same layout either way (a plan buffer serves both)
+    # ranges inside the buffer are disjoint and inside it
+    spans = []
+    for it in full.items:
+        for side in ("f", "d"):
+            spans.append((it[side + "_hdr"], it[side + "_hdr_bytes"]))
+            spans.append((it[side + "_ent"], it[side + "_ent_bytes"]))
+    for l, (rp, col) in full.tr.items():
+        spans.append((rp, (n_cap[l] + 2) * 4))
+        spans.append((col, n_cap[l + 1] * widths[l] * 4))
+    spans.sort()
+    assert spans[0][0] >= 256 and all(a + n <= b for (a, n), (b, _) in zip(spans, spans[1:]))
+    assert spans[-1][0] + spans[-1][1] <= full.nbytes
+    pts = [torch.zeros(n, 3) for n in n_cap]
+    nbr = [torch.zeros(n, w, dtype=torch.int64) for n, w in zip(n_cap, widths)]
+    pool = [torch.zeros(n_cap[l + 1], widths[l], dtype=torch.int64) for l in range(4)] + [torch.zeros(0, 1, dtype=torch.int64)]
+    buf = torch.zeros(full.nbytes, dtype=torch.uint8)
+    kinds = [j.kind for j in full.jobs(pts, nbr, pool, True, buf)]
+    assert kinds.count(0) == 10 + 6 and kinds.count(1) == 4 and kinds.count(2) == 4
+    jf = fwd.jobs(pts, nbr, pool, True, buf)
+    assert [j.kind for j in jf] == [0] * 10 and all(j.kp_sign == 1.0 for j in jf)
+    base = buf.data_ptr()
+    for j, it, sp in zip(jf, fwd.items, specs):
+        assert j.hdr == base + it["f_hdr"] and j.entries == base + it["f_ent"] and j.entries_cap == it["cap"]
+        assert j.nc == (n_cap[sp.layer + 1] if sp.strided else n_cap[sp.layer]) and j.no == n_cap[sp.layer]
