@@ -47,6 +47,13 @@ int kp_profile_read(char* buf, int buflen);
  * unary kernels split the reduction axis of one 128-point tile, given the tiles, the 128-column chunks of that axis and
  * the CTAs the device holds at once (296 for the 8-warp kernels, 148 for the 16-warp ones). */
 int kp_plan_ksplit(int n_tiles, int n_chunks, int slots);
+/* Streams confined to a partition of the device's SMs (CUDA green context, driver API): `n_streams` non-blocking streams
+ * of the given priority whose kernels run on a group of at least `min_sms` SMs (rounded up to the architecture's
+ * granularity, 8 on sm_100) and on no others. The training step's prefetch stage (the reference's DataLoader workers,
+ * datasets/Vaihingen3D_PseudoLabel.py:243-252) runs on such streams, so that its kernels do not take SM slots from the
+ * training step on the rest of the device. streams_out receives cudaStream_t handles (they live as long as the process),
+ * *sms_granted the partition's size. KP_ERR_UNSUPPORTED when the driver lacks the API. */
+int kp_sm_partition_streams(int min_sms, int n_streams, int priority, void** streams_out, int* sms_granted);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Batch radius search.

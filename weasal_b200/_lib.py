@@ -25,7 +25,7 @@ SYMBOLS = ["kp_last_error", "kp_version", "kp_launch_count", "kp_free_host", "kp
            "kp_kpconv_backward_kept_dev", "kp_transpose_table_dev", "kp_kpconv_wf_dev", "kp_kpconv_dx_atomic_dev", "kp_profile_enable",
            "kp_profile_read", "kp_max_pool_forward_dev", "kp_max_pool_backward_dev", "kp_closest_pool_dev",
            "kp_pyramid_build_dev", "kp_pyramid_build_static_dev", "kp_kpconv_backward_sym_dev",
-           "kp_linear_forward_dev", "kp_linear_backward_dev", "kp_closest_pool_strided_dev", "kp_max_pool_forward_width_dev", "kp_plan_ksplit",
+           "kp_linear_forward_dev", "kp_linear_backward_dev", "kp_closest_pool_strided_dev", "kp_max_pool_forward_width_dev", "kp_plan_ksplit", "kp_sm_partition_streams",
            "kp_kpconv_lists_build_dev", "kp_kpconv_apply_lists_dev", "kp_kpconv_dw_lists_dev", "kp_pack_image_floats",
            "kp_pack_weights_dev", "kp_linear_forward_packed_dev", "kp_linear_dx_packed_dev", "kp_linear_dw_dev",
            "kp_kpconv_prepare_dev", "kp_extract_spheres_dev", "kp_augment_spheres_dev", "kp_vote_update_dev",
@@ -87,6 +87,7 @@ def lib():
                                               vp, vp, vp, vp, vp]
     L.kp_closest_pool_strided_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
     L.kp_plan_ksplit.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.kp_sm_partition_streams.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
     L.kp_linear_forward_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_float, vp, vp]
     L.kp_linear_backward_dev.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_float, vp, vp, vp, vp]
     L.kp_kpconv_lists_build_dev.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_longlong, vp,

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["primitives.cu", "grid_subsample.cu", "radius_search.cu", "kpconv_simt.cu", "kpconv_tc.cu", "pool_ops.cu", "pyramid.cu", "sphere_vote.cu", "capi.cu"]
+SOURCES = ["primitives.cu", "grid_subsample.cu", "radius_search.cu", "kpconv_simt.cu", "kpconv_tc.cu", "pool_ops.cu", "pyramid.cu", "sphere_vote.cu", "sm_partition.cu", "capi.cu"]
 LIB = os.path.join(HERE, "libweasal_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -49,6 +49,7 @@ int transpose_table_entry(const void* idx, int idx_is_i64, int nq, int H, int id
                           int* col_sorted, cudaStream_t stream);
 int profile_read(char* buf, int buflen);
 int plan_ksplit(int n_tiles, int n_chunks, int slots);
+int sm_partition_streams(int min_sms, int n_streams, int priority, void** streams_out, int* sms_granted);
 int linear_forward_device(const float* x, int n, int cin, const float* w, int w_packed, const float* bias, int cout,
                           float slope, float* y, cudaStream_t stream);
 int linear_backward_device(const float* x, int n, int cin, const float* w, int w_packed, int cout, const float* y,
@@ -96,6 +97,10 @@ long long kp_launch_count(void) { return g_launch_count.load(); }
 void kp_free_host(void* p) { free(p); }
 void kp_profile_enable(int on) { g_profile_on = on != 0; }
 int kp_profile_read(char* buf, int buflen) { return profile_read(buf, buflen); }
+int kp_sm_partition_streams(int min_sms, int n_streams, int priority, void** streams_out, int* sms_granted) {
+    return kp::sm_partition_streams(min_sms, n_streams, priority, streams_out, sms_granted);
+}
+
 int kp_plan_ksplit(int n_tiles, int n_chunks, int slots) {
     if (n_tiles <= 0 || n_chunks <= 0 || slots <= 0) return fail(KP_ERR_ARG, "plan_ksplit: bad sizes");
     return plan_ksplit(n_tiles, n_chunks, slots);

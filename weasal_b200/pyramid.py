@@ -431,7 +431,7 @@ class PyramidPrefetcher:
     Grid orientations are drawn from ``np.random`` at submit time, in submission order."""
 
     def __init__(self, config, device="cuda", neighborhood_limits=None, random_grid_orient=True, order="reference",
-                 index_dtype=torch.int64, slots=None, n_cap=None, plans=None, workers=1):
+                 index_dtype=torch.int64, slots=None, n_cap=None, plans=None, workers=1, sm_partition=0):
         """``n_cap``: per-layer row capacities -> batches come in the static layout of kp_pyramid_build_static_dev
         (features and labels inside the slab; ``batch.static_slab`` set) for :class:`weasal_b200.engine.GraphedTrainStep`;
         a batch that does not fit falls back to the ordinary layout."""
@@ -460,7 +460,22 @@ class PyramidPrefetcher:
         # node becomes ready instead of queueing behind the builds' CTAs. (With a single build in flight and the
         # consumer waiting for it, -1 is the better choice.)
         prio = int(os.environ.get("WEASAL_PREFETCH_PRIORITY", "0"))
-        self.sides = [torch.cuda.Stream(self.dev, priority=prio) for _ in range(self.workers)]
+        # WEASAL_PREFETCH_SMS=n (n > 0): the build streams are confined to a partition of >= n SMs (CUDA green context,
+        # kp_sm_partition_streams), so that their CTAs never hold slots on the other SMs, where the training step runs
+        n_sms = int(os.environ.get("WEASAL_PREFETCH_SMS", str(sm_partition)))
+        self.sm_partition = 0
+        self.sides = None
+        if n_sms > 0:
+            import ctypes as C
+            from . import _lib
+            handles, granted = (C.c_void_p * self.workers)(), C.c_int(0)
+            with torch.cuda.device(self.dev):
+                rc = _lib.lib().kp_sm_partition_streams(n_sms, self.workers, prio, handles, C.byref(granted))
+            if rc == 0:
+                self.sides = [torch.cuda.ExternalStream(int(h), device=self.dev) for h in handles]
+                self.sm_partition = int(granted.value)
+        if self.sides is None:
+            self.sides = [torch.cuda.Stream(self.dev, priority=prio) for _ in range(self.workers)]
         self.side = self.sides[0]
         self.slabs = [None] * slots          # ring of output slabs (uint8 tensors allocated on the side stream)
         self.free_ev = [None] * slots        # recorded on the consumer's stream when a slot's batch has been consumed
