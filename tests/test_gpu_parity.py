@@ -494,6 +494,29 @@ def test_native_pyramid_equals_operator_driver_and_prefetcher(torch_cuda):
     assert all((j, i) in fwd for i, j in list(fwd)[:20000])
 
 
+def test_prefetcher_on_an_sm_partition(torch_cuda):
+    """Build streams confined to a green-context SM partition (kp_sm_partition_streams): same pyramid, bit for bit."""
+    torch = torch_cuda
+    from weasal_b200 import pyramid
+    cfg = _vaihingen_cfg()
+    b = make_batch("vaihingen_pl", seed=6, batch_num=2, in_radius=10.0)
+    feats = np.ones((len(b["points"]), 1), np.float32)
+    labels = (np.arange(len(b["points"])) % 5).astype(np.int64)
+    outs = []
+    for part in (0, 64):
+        pf = pyramid.PyramidPrefetcher(cfg, "cuda", workers=2, sm_partition=part)
+        assert (pf.sm_partition >= 64) if part else (pf.sm_partition == 0)
+        np.random.seed(21)
+        pf.submit(b["points"], feats, labels, b["lengths"])
+        pf.submit(b["points"], feats, labels, b["lengths"])
+        g0, g1 = pf.get(), pf.get()
+        pf.close()
+        outs.append([t.clone() for g in (g0, g1) for t in g.points + g.neighbors + g.pools + g.upsamples + [g.features, g.labels]])
+    assert len(outs[0]) == len(outs[1])
+    for a, c in zip(*outs):
+        assert torch.equal(a, c)
+
+
 def test_native_pyramid_grows_cap_and_slab(torch_cuda):
     """A first call with a neighbour capacity / slab that is too small reports what it needs and the wrapper repeats."""
     torch = torch_cuda
