@@ -243,13 +243,16 @@ def measure_config(args, cfg_name, ctx, K, W, primary):
             if not ahead:
                 submit(it)
             batch = prefetch.get()
+            t_w = 0.0
             if len(done) >= 2:
                 ev0, slot0 = done.pop(0)
+                t_w0 = time.perf_counter()
                 ev0.synchronize()
+                t_w = time.perf_counter() - t_w0   # host idle, waiting for the GPU: ~0 would mean the HOST paces the loop
                 if e2e:
                     loss_host = float(loss_pinned[slot0])  # the device -> host read of that step's result
             t_l0 = time.perf_counter()
-            stamps.append((t_l0, prefetch.stats[-1][0], prefetch.stats[-1][1]))
+            stamps.append((t_l0, prefetch.stats[-1][0], prefetch.stats[-1][1], t_w))
             loss = net_step(batch, allreduce)
             if e2e:  # the step's result travels to pinned host memory behind the step; it is read two steps later, so
                 loss_pinned[it % 4].copy_(loss, non_blocking=True)  # the host never drains the GPU inside the loop
@@ -318,7 +321,8 @@ def measure_config(args, cfg_name, ctx, K, W, primary):
     iv = np.diff([a[0] for a in stamps]) * 1e3 if len(stamps) > 2 else np.zeros(1)
     pacing = {"launch_interval_ms": {"min": float(iv.min()), "median": float(np.median(iv)), "max": float(iv.max())},
               "pyramid_build_ms_median": float(np.median([a[1] for a in stamps]) * 1e3) if stamps else None,
-              "get_wait_ms_median": float(np.median([a[2] for a in stamps]) * 1e3) if stamps else None}
+              "get_wait_ms_median": float(np.median([a[2] for a in stamps]) * 1e3) if stamps else None,
+              "host_waits_for_gpu_ms_median": float(np.median([a[3] for a in stamps]) * 1e3) if stamps else None}
     # library kernels launched in the timed region: the pyramid's (counted live) + those inside the replayed graphs
     gpu_launches = _lib.launch_count() - launches0 + (trainer.n_graphed - g0) * trainer.launches_per_replay
     graphed_steps, eager_steps = trainer.n_graphed - g0, trainer.n_eager - e0_
