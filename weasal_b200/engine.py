@@ -160,8 +160,13 @@ class GraphedTrainStep:
             self.slab.copy_(batch.static_slab)
             if self.plan_buf is not None:
                 self.plan_buf.copy_(batch.plan_buf)
-            for _ in range(self.warmup):  # sizes the allocator pools, the library's scratch arena (per stream) and the
-                self._body(self._static_batch(nbld))  # optimizer's momentum buffers before anything is recorded
+            from . import ops
+            ops.CAPTURE_WARMUP[0] = True   # (side-stream forks that exist only in a captured step run here too)
+            try:
+                for _ in range(self.warmup):  # sizes the allocator pools, the library's scratch arenas (per thread and
+                    self._body(self._static_batch(nbld))  # stream) and the optimizer's momentum buffers before recording
+            finally:
+                ops.CAPTURE_WARMUP[0] = False
         cur.wait_stream(s)
         torch.cuda.synchronize(dev)
         self.opt.zero_grad(set_to_none=True)
@@ -287,8 +292,13 @@ class GraphedForward:
             self.slab.copy_(batch.static_slab)
             if self.plan_buf is not None:
                 self.plan_buf.copy_(batch.plan_buf)
-            for _ in range(self.warmup):
-                self._forward(self._static_batch(nbld))
+            from . import ops
+            ops.CAPTURE_WARMUP[0] = True
+            try:
+                for _ in range(self.warmup):
+                    self._forward(self._static_batch(nbld))
+            finally:
+                ops.CAPTURE_WARMUP[0] = False
         cur.wait_stream(s)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()

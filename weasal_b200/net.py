@@ -104,8 +104,10 @@ class ConvBlock(nn.Module):
         # backward; inside a captured step this becomes a fork / join of the graph. The deep layers' kernels are a few
         # CTAs each, so the two branches share the SMs instead of queueing.
         # (only while a step is being captured: launched eagerly, the extra stream hand-overs cost host time instead)
-        fork = (FORK_SHORTCUT and x.is_cuda and (self.strided or not isinstance(self.shortcut, nn.Identity))
-                and torch.cuda.is_current_stream_capturing())
+        fork = FORK_SHORTCUT and x.is_cuda and (self.strided or not isinstance(self.shortcut, nn.Identity))
+        if fork:
+            from . import ops
+            fork = ops.forking_for_capture()
         if fork:
             from . import ops
             cur, side = torch.cuda.current_stream(x.device), ops._side_stream(x.device, 1)

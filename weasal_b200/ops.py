@@ -338,6 +338,14 @@ KPConvFunction._backward_planned = staticmethod(_backward_planned)
 
 _FORK_BACKWARD = os.environ.get("WEASAL_FORK_BACKWARD", "1") != "0"
 _SIDE = {}
+# True while a step engine runs its warm-up passes before a capture: code that forks onto side streams only inside a
+# captured step must take the same streams during the warm-up, so that every (thread, stream) scratch arena of the
+# library has its final size before recording starts (cudaMalloc is illegal during capture).
+CAPTURE_WARMUP = [False]
+
+
+def forking_for_capture():
+    return CAPTURE_WARMUP[0] or torch.cuda.is_current_stream_capturing()
 
 
 def _side_stream(dev, which=0):
