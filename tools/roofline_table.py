@@ -30,7 +30,10 @@ def main():
     print("|---|---|---|---|---|---|---|")
     tot = 0.0
     for name, v in sorted(k.items(), key=lambda kv: -kv[1]["ms_per_step"]):
-        tot += v["ms_per_step"]
+        if "tags" in v:  # an aggregate of other rows (kp_fwd_kernel = forward + dX launches of the same kernel)
+            name += " = " + " + ".join(v["tags"])
+        else:
+            tot += v["ms_per_step"]
         mb = v.get("algorithmic_mb_per_step")
         g = v.get("achieved_gbs")
         print(f"| `{name}` | {v['launches_per_step']:.0f} | {v['ms_per_step']:.3f} | "
