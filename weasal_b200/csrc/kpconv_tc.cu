@@ -120,6 +120,30 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// thread-block clusters: a weight chunk is fetched ONCE per cluster, every CTA copies its slice into the shared memory
+// of all CTAs of the cluster (multicast) and signals each CTA's own barrier at the same offset
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {  // arrives on `bar` of every CTA in the mask
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
 // 2-D tiled tensor copy (TMA): box of the tensor map at (c0 = innermost coordinate, c1) -> shared memory
 __device__ __forceinline__ void tma_g2s_2d(void* dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
     asm volatile(
@@ -683,6 +707,8 @@ struct FwdParams {
     int NB, n_nblk, n_chunks;
     int ksplit;          // CTAs along the reduction (blockIdx.y); > 1 => partial sums are added atomically into out
     int stages;
+    int cluster;         // CTAs per cluster along x (tiles): 1, or 2 / 4 = the weight chunks are multicast inside the cluster
+    int n_tiles;         // real tiles (gridDim.x is rounded up to the cluster size; the extra CTAs only take part in the copies)
     float* out;          // [nq, cout] with row stride ldo (pre-zeroed when ksplit > 1)
     int cout, ldo;
     uint32_t tmem_cols;
@@ -715,15 +741,19 @@ __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_fwd_kerne
     const int tile = blockIdx.x, tile_base = tile * TILE_M;
     const int cps = (P.n_chunks + P.ksplit - 1) / P.ksplit;
     const int c0 = blockIdx.y * cps, c1 = min(P.n_chunks, c0 + cps);
-    if (c0 >= c1) return;
+    if (c0 >= c1) return;   // (uniform over a cluster: its CTAs share blockIdx.y)
     const int n_loc = c1 - c0;
+    const int CL = P.cluster;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+    const bool ghost = tile >= P.n_tiles;   // padding CTA of the last cluster: copies its weight slices, nothing else
 
     if (tid == 0) {
         for (int s = 0; s < S; s++) {
             mbar_init(&bars->a_full[s], 8);
             mbar_init(&bars->a_empty[s], 1);
             mbar_init(&bars->b_full[s], 1);
-            mbar_init(&bars->b_empty[s], 1);
+            mbar_init(&bars->b_empty[s], CL);   // every CTA of the cluster must have consumed a stage before it is refilled
         }
         mbar_init(&bars->acc_full, 1);
         fence_mbar_init();
@@ -731,6 +761,7 @@ __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_fwd_kerne
     if (warp == MMA_WARP) tmem_alloc(&bars->tmem, P.tmem_cols);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // barriers of all CTAs initialised before anyone copies into / arrives on them
     tc_fence_after();
     const uint32_t tmem = bars->tmem;
 
@@ -738,14 +769,14 @@ __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_fwd_kerne
         // ===== producers: A chunk `it` -> stage it % S =====
         const int* toff_tile = nullptr;
         const int2* ent = nullptr;
-        if (!DENSE) {
+        if (!DENSE && !ghost) {
             toff_tile = P.toff + (size_t)tile * TOFF_PER_TILE;
             ent = P.entries + __ldg(toff_tile + 15 * TOFF_RB);
         }
         // a stage is always filled by 8 warps; with 16 producer warps (one CTA per SM) the two groups of 8 take
         // alternate chunks, so two stages are being assembled at any time
         const int pw = warp & 7;
-        for (int it = warp >> 3; it < n_loc; it += NGRP) {
+        for (int it = warp >> 3; it < n_loc && !ghost; it += NGRP) {
             const int s = it % S, use = it / S;
             if (use > 0) mbar_wait(&bars->a_empty[s], (uint32_t)((use - 1) & 1));
             unsigned char* a = sA + (size_t)s * A_STAGE;
@@ -765,8 +796,14 @@ __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_fwd_kerne
                 if (use > 0) mbar_wait(&bars->b_empty[s], (uint32_t)((use - 1) & 1));
                 const int chunk = c0 + t / P.n_nblk, nblk = t % P.n_nblk;
                 mbar_expect_tx(&bars->b_full[s], (uint32_t)b_bytes);
-                bulk_g2s(sB + (size_t)s * b_bytes, P.images + ((size_t)chunk * P.n_nblk + nblk) * (size_t)P.NB * FWD_CK,
-                         (uint32_t)b_bytes, &bars->b_full[s]);
+                const float* src = P.images + ((size_t)chunk * P.n_nblk + nblk) * (size_t)P.NB * FWD_CK;
+                if (CL == 1) bulk_g2s(sB + (size_t)s * b_bytes, src, (uint32_t)b_bytes, &bars->b_full[s]);
+                else {
+                    const uint32_t slice = (uint32_t)b_bytes / (uint32_t)CL;
+                    bulk_g2s_multicast(sB + (size_t)s * b_bytes + (size_t)crank * slice,
+                                       reinterpret_cast<const unsigned char*>(src) + (size_t)crank * slice, slice,
+                                       &bars->b_full[s], cmask);
+                }
             }
         }
     } else {
@@ -775,7 +812,13 @@ __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_fwd_kerne
             const uint32_t idesc = make_idesc(TILE_M, P.NB, 0, 0);
             const uint32_t b_lbo = (uint32_t)P.NB * 16u;
             int t = 0;
-            for (int it = 0; it < n_loc; it++) {
+            if (ghost) {  // release every stage as soon as it has arrived (no MMAs outstanding: the commit arrives at once)
+                for (int tt = 0; tt < n_loc * P.n_nblk; tt++) {
+                    mbar_wait(&bars->b_full[tt % S], (uint32_t)((tt / S) & 1));
+                    umma_commit_multicast(&bars->b_empty[tt % S], cmask);
+                }
+            }
+            for (int it = 0; it < n_loc && !ghost; it++) {
                 const int s = it % S;
                 mbar_wait(&bars->a_full[s], (uint32_t)((it / S) & 1));
                 const uint32_t a_addr = smem_u32(sA + (size_t)s * A_STAGE);
@@ -790,16 +833,17 @@ __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_fwd_kerne
                         const uint64_t bd = make_desc(b_addr + kk * 2 * b_lbo, b_lbo, B_SBO);
                         umma_tf32(tmem + (uint32_t)(nblk * P.NB), ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
                     }
-                    umma_commit(&bars->b_empty[sb]);
+                    if (CL == 1) umma_commit(&bars->b_empty[sb]);
+                    else umma_commit_multicast(&bars->b_empty[sb], cmask);
                 }
                 umma_commit(&bars->a_empty[s]);
             }
-            umma_commit(&bars->acc_full);
+            if (!ghost) umma_commit(&bars->acc_full);
         }
     }
 
     // ===== epilogue: the producer warps drain TMEM (warp w: lanes 32*(w%4).., column blocks of 16 dealt over w/4) =====
-    if (warp < NPW) {
+    if (warp < NPW && !ghost) {
         mbar_wait(&bars->acc_full, 0u);
         __syncwarp();
         tc_fence_after();
@@ -840,6 +884,7 @@ __global__ void __launch_bounds__((NPW + 2) * 32, NPW == 8 ? 2 : 1) kp_fwd_kerne
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // nobody leaves while a peer may still copy into its stages or arrive on its barriers
     if (warp == MMA_WARP) tmem_dealloc(tmem, P.tmem_cols);
 }
 
@@ -1266,13 +1311,29 @@ static int launch_fwd(const char* tag, bool dense, int nc, const float* x, const
     uint32_t cols = 32;
     while ((int)cols < sh.n_nblk * sh.NB) cols <<= 1;
     P.tmem_cols = cols;
+    // clusters (WEASAL_FWD_CLUSTER = 2 / 4): the CTAs of `cl` neighbouring tiles fetch every weight chunk once and
+    // multicast it, for layers whose weight stream is a large part of the L2 traffic (wide layers, many tiles)
+    static const int cl_env = getenv("WEASAL_FWD_CLUSTER") ? atoi(getenv("WEASAL_FWD_CLUSTER")) : 1;
+    int cl = (cl_env == 2 || cl_env == 4) ? cl_env : 1;
+    if (sh.NB * FWD_CK * 4 / cl < 4096 || n_tiles < 4 * cl || sh.NB < 128) cl = 1;
+    P.cluster = cl;
+    P.n_tiles = n_tiles;
     ProfileScope ps(tag, stream);
-    const dim3 grid(n_tiles, ksplit);
+    const dim3 grid(ceil_div(n_tiles, cl) * cl, ksplit);
     const bool two = smem <= SMEM_TWO_CTAS;
-#define KP_LAUNCH_FWD(D, W)                                                     \
-    do {                                                                        \
-        KP_CUDA(set_smem(kp_fwd_kernel<D, W>, smem));                           \
-        kp_fwd_kernel<D, W><<<grid, (W + 2) * 32, smem, stream>>>(P);           \
+#define KP_LAUNCH_FWD(D, W)                                                                  \
+    do {                                                                                     \
+        KP_CUDA(set_smem(kp_fwd_kernel<D, W>, smem));                                        \
+        if (cl == 1) kp_fwd_kernel<D, W><<<grid, (W + 2) * 32, smem, stream>>>(P);           \
+        else {                                                                               \
+            cudaLaunchConfig_t cfg = {};                                                     \
+            cfg.gridDim = grid; cfg.blockDim = dim3((W + 2) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = stream; \
+            cudaLaunchAttribute at[1];                                                       \
+            at[0].id = cudaLaunchAttributeClusterDimension;                                  \
+            at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1; \
+            cfg.attrs = at; cfg.numAttrs = 1;                                                \
+            KP_CUDA(cudaLaunchKernelEx(&cfg, kp_fwd_kernel<D, W>, P));                       \
+        }                                                                                    \
     } while (0)
     if (dense) { if (two) KP_LAUNCH_FWD(true, 8); else KP_LAUNCH_FWD(true, 16); }
     else { if (two) KP_LAUNCH_FWD(false, 8); else KP_LAUNCH_FWD(false, 16); }
