@@ -14,24 +14,28 @@
 //     is bound by how many gathers the producer warps keep in flight; the pipeline exists to keep them issuing.
 //
 // Kernels
-//   kp_lists       one CTA per tile of 128 centre points: influence weights of every (neighbour, kernel point) pair,
-//                  compacted into ONE FLAT LIST PER (tile, kernel point), sorted by row: entry = (neighbour index | row
-//                  in tile << 25, weight). A tile header holds, per kernel point, the list's start at every 8-row block.
-//                  The lists depend on the geometry and the (frozen) kernel points only: a training step builds them in
-//                  its prefetch stage, off the training stream.
+//   kp_lists       one CTA per tile of 128 centre points, ALL list jobs of a call in one grid: a per-CTA candidate table
+//                  (8^3 cells -> kernel points that can reach the cell) cuts the influence evaluations to ~3 per
+//                  neighbour; hits are compacted into ONE FLAT LIST PER (tile, kernel point), sorted by row: entry =
+//                  (neighbour index | row in tile << 25, weight). A tile header holds, per kernel point, the list's start
+//                  at every 8-row block. The lists depend on the geometry and the (frozen) kernel points only: a
+//                  training step builds them in its prefetch stage, off the training stream.
 //   kp_pack_w      W[k,c,o] -> TF32-rounded B-operand images, one per 64-column chunk of the (k,c) reduction axis,
-//                  already in the UMMA K-major core-matrix layout (a CTA fetches a chunk with one bulk copy).
+//                  already in the UMMA K-major core-matrix layout (a CTA fetches a chunk with one bulk copy); all
+//                  layers of a step in one launch.
 //   kp_fwd         one CTA per 128-point tile (x a slice of the reduction axis on deep layers). Warp roles: 8 PRODUCER
-//                  warps assemble A chunks [128 x 64] into a ring of shared-memory stages (each lane group walks one flat
-//                  list segment: U independent float4 gathers in flight, accumulation in registers, one store per row);
-//                  1 LOADER warp streams the packed weight chunks with cp.async.bulk into its own ring; 1 MMA warp
-//                  issues tcgen05.mma.kind::tf32 (M128 x N x K8) into TMEM and releases stages with tcgen05.commit;
-//                  the producer warps drain TMEM at the end (fused bias / LeakyReLU / split-reduction atomics).
-//                  Backward-dX is the same kernel run on the transposed neighbour table with W^T and -kp
+//                  warps per stage assemble A chunks [128 x 64] into a ring of shared-memory stages (each lane group
+//                  walks one flat list segment: U independent float4 gathers in flight, accumulation in registers, one
+//                  store per row; with one CTA per SM two groups of 8 warps fill alternate stages); 1 LOADER warp streams
+//                  the packed weight chunks with cp.async.bulk into its own ring (opt-in: multicast inside a cluster);
+//                  1 MMA warp issues tcgen05.mma.kind::tf32 (M128 x N x K8) into TMEM and releases stages with
+//                  tcgen05.commit; the producer warps drain TMEM at the end (fused bias / LeakyReLU / split-reduction
+//                  atomics). Backward-dX is the same kernel run on the transposed neighbour table with W^T and -kp
 //                  (atomics-free segmented scatter).
 //   kp_dw          dW[(k,c),o] = sum_i WF[i,(k,c)] * dOut[i,o]: stages of 64 points, the A tile consumed MN-major
-//                  (M = (k,c) rows, K = points) against the dOut tile, same producer / MMA roles, accumulated in TMEM
-//                  across a CTA's point tiles, then added to dW.
+//                  (M = (k,c) rows, K = points) against the dOut tile, which the loader warp fetches with TMA tensor
+//                  copies (cp.async.bulk.tensor.2d, TFLOAT32 conversion and 32-byte-atom swizzle done by the copy
+//                  engine); same producer / MMA roles, accumulated in TMEM across a CTA's point tiles, then added to dW.
 #include "common.cuh"
 
 #include <cuda.h>  // CUtensorMap (the encoder itself is fetched through cudaGetDriverEntryPoint: no libcuda link)
