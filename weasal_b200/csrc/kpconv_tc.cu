@@ -59,9 +59,9 @@ constexpr int K_SHIFT = 27;       // scratch lists (per row, grouped by kernel p
 constexpr unsigned JS_MASK = (1u << K_SHIFT) - 1u;
 
 // Producer warps per CTA (template parameter NPW of the kernels; they are also the epilogue warps): 8 where two CTAs
-// share an SM (every lane owns 8 rows of one column group), 16 where the stages of a wide layer leave room for one CTA
-// only (4 rows per lane): the gather is latency bound, so an SM wants ~16 producer warps either way. Two more warps
-// follow them: the weight loader and the MMA issuer.
+// share an SM, 16 where the stages of a wide layer leave room for one CTA only. A stage is always filled by 8 warps
+// (every lane owns 8 rows of one column group); with 16 warps the two groups of 8 fill alternate stages. The gather is
+// latency bound, so an SM wants ~16 producer warps either way. Two more warps follow them: the loader and the MMA issuer.
 constexpr int FWD_CK = 64;        // reduction columns per forward stage
 constexpr int DW_CK = 128;        // reduction columns (= UMMA M) per dW CTA
 constexpr int DW_PT = 64;         // points per dW stage
@@ -600,8 +600,8 @@ struct GatherGeom {
     int cin_p, K;
 };
 
-// RPL = rows per lane: 8 (8 producer warps), or 4 (16 warps: two lane groups share a unit, each walks the unit's entries
-// and takes the rows of its half).
+// RPL = rows per lane: 8 in every current instantiation (a stage is filled by 8 warps); 4 = two lane groups share a
+// unit, each walks the unit's entries and takes the rows of its half (kept for experiments with 16 warps per stage).
 template <class LAY, int NRBS, int U, int RPL>
 __device__ __forceinline__ void produce_sparse(unsigned char* sA, int warp, int lane, const GatherGeom& gg, int col_base,
                                                int rb_base, const int* __restrict__ toff_tile,
